@@ -1,0 +1,262 @@
+/*
+ * tde_b200.h — C ABI of libtde_b200.so, the B200 (sm_100a) implementation of
+ * TorchDriveEnv's per-timestep simulation hot path.
+ *
+ * Every entry point replaces one call the reference makes on its
+ * SimulatorInterface-level surface (citations are file:line under the
+ * reference checkout, torchdriveenv/gym_env.py unless said otherwise):
+ *
+ *   tde_step                     WaypointSuiteEnv.step :369-389 + GymEnv.step :115-120
+ *                                  (simulator.step :117, get_obs :122-124, get_reward :396-411,
+ *                                   is_terminated :413-417, is_truncated :134-135, get_info :419-437,
+ *                                   check_reach_target/advance :378-383,391-394)
+ *   tde_reset                    WaypointSuiteEnv.reset :319-349 + set_start_pos :351-367
+ *                                  + build_simulator's state initialisation :192-198,241-247,269-283
+ *   tde_render                   simulator.render_egocentric() :123,154
+ *   tde_get_state/tde_set_state  simulator.get_state() :127,371,392-393,397-399,420-423 / set_state :247
+ *   tde_compute_infractions,
+ *   tde_get_infractions          simulator.compute_offroad() :142,415,427; compute_collision() :143,415,428;
+ *                                  compute_traffic_lights_violations() :144,415,429; compute_wrong_way()
+ *   tde_kinematics               KinematicBicycle.step via simulator.step :117 (+ IAIWrapper replay :275-294)
+ *   tde_collision_boxes,
+ *   tde_offroad_boxes            the same metrics on caller-provided boxes (micro-bench config C4)
+ *   tde_upload_scenarios         the constructor-side tensors of build_simulator :179-300
+ *                                  (road_mesh :184,260; traffic_controls :187-189; waypoints :252-257;
+ *                                   agent_states/attributes :241-247,261; replay_states/replay_mask :275-283)
+ *   tde_clone                    simulator.copy() :110
+ *   tde_get_episode_stats        the per-episode quantities EvalNTimestepsCallback aggregates
+ *                                  (examples/rl_training.py:99-108)
+ *
+ * Conventions
+ *   - Plain C, no torch types.  All *_dev pointers are CUDA device pointers owned by the caller;
+ *     *_host pointers are host memory.  `stream` is a cudaStream_t passed as void*.
+ *   - Every function returns 0 (TDE_OK) or a negative TDE_E_* code; the message is available through
+ *     tde_last_error().  Nothing throws or exits across this boundary.
+ *   - tde_step / tde_render / tde_kinematics / ... never allocate, never synchronise with the host and
+ *     only enqueue work on `stream`, so they can be captured into a CUDA graph.
+ *   - A handle is bound to one GPU and is not thread-safe.
+ */
+#ifndef TDE_B200_H
+#define TDE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TDE_VERSION 100 /* 0.1.0 */
+
+/* error codes */
+#define TDE_OK 0
+#define TDE_E_INVAL (-1) /* bad argument */
+#define TDE_E_CUDA (-2)  /* CUDA runtime error */
+#define TDE_E_SHAPE (-3) /* size/shape mismatch or capacity exceeded */
+#define TDE_E_ARCH (-4)  /* device is not sm_100 */
+#define TDE_E_STATE (-5) /* call order (e.g. step before upload/reset) */
+
+/* limits of this build */
+#define TDE_MAX_AGENTS 64
+#define TDE_OBS_H 64
+#define TDE_OBS_W 64
+#define TDE_OBS_C 3
+#define TDE_MAX_STOPLINES 32
+#define TDE_INFO_STRIDE 16
+
+/* info[] columns, one row of TDE_INFO_STRIDE floats per env (get_info :419-437) */
+#define TDE_INFO_OFFROAD 0
+#define TDE_INFO_COLLISION 1
+#define TDE_INFO_TL_VIOLATION 2
+#define TDE_INFO_IS_SUCCESS 3
+#define TDE_INFO_REACHED_WAYPOINT_NUM 4
+#define TDE_INFO_PSI_SMOOTHNESS 5
+#define TDE_INFO_PSI_REWARD 6
+#define TDE_INFO_DIST_REWARD 7
+#define TDE_INFO_SPEED_SMOOTHNESS 8
+#define TDE_INFO_WRONG_WAY 9
+#define TDE_INFO_EPISODE_RETURN 10
+#define TDE_INFO_EPISODE_LENGTH 11
+#define TDE_INFO_SCENARIO 12
+#define TDE_INFO_DID_RESET 13
+
+/* per-agent infraction cache columns (float4 per agent) */
+#define TDE_INFR_COLLISION 0
+#define TDE_INFR_OFFROAD 1
+#define TDE_INFR_TL_VIOLATION 2
+#define TDE_INFR_WRONG_WAY 3
+
+/* render classes = painter's levels, higher paints over lower */
+#define TDE_CLS_BACKGROUND 0
+#define TDE_CLS_ROAD 1
+#define TDE_CLS_LANE_MARKING 2
+#define TDE_CLS_TL_GREEN 3
+#define TDE_CLS_TL_YELLOW 4
+#define TDE_CLS_TL_RED 5
+#define TDE_CLS_WAYPOINT 6
+#define TDE_CLS_VEHICLE 7
+#define TDE_CLS_EGO 8
+#define TDE_CLS_DIRECTION 9
+#define TDE_CLS_EGO_DIRECTION 10
+#define TDE_NUM_CLASSES 11
+
+/* traffic-light states in the schedule table */
+#define TDE_LIGHT_GREEN 0
+#define TDE_LIGHT_YELLOW 1
+#define TDE_LIGHT_RED 2
+
+/* phase bits for tde_step_phases (tde_step == all of them) */
+#define TDE_PH_KINEMATICS 1
+#define TDE_PH_INFRACTIONS 2
+#define TDE_PH_REWARD 4
+#define TDE_PH_RENDER 8
+#define TDE_PH_ALL 15
+
+/* episode statistics vector (doubles), reduced across GPUs by the host side */
+#define TDE_STAT_EPISODES 0
+#define TDE_STAT_RETURN_SUM 1
+#define TDE_STAT_LENGTH_SUM 2
+#define TDE_STAT_OFFROAD 3
+#define TDE_STAT_COLLISION 4
+#define TDE_STAT_TL_VIOLATION 5
+#define TDE_STAT_SUCCESS 6
+#define TDE_STAT_REACHED_WAYPOINTS 7
+#define TDE_STAT_STEPS 8
+#define TDE_NUM_STATS 16
+
+typedef struct tde_handle tde_handle;
+
+/* EnvConfig :34-54 plus the TorchDriveConfig/RendererConfig values the env relies on. */
+typedef struct tde_config {
+    int32_t num_envs;              /* E, envs owned by this handle (this GPU's shard) */
+    int32_t max_agents;            /* A, agent slots per env, slot 0 = ego; 1..TDE_MAX_AGENTS */
+    int64_t env_index_offset;      /* global index of local env 0 (keys the reset RNG, so a sharded run
+                                      reproduces the unsharded one) */
+    int32_t max_environment_steps; /* :37  default 200 */
+    int32_t terminated_at_infraction; /* :44 default 1 */
+    int32_t left_handed_coordinates;  /* :46-49 default 1 */
+    int32_t auto_reset;            /* 1: finished envs are re-initialised inside tde_step (VecEnv semantics) */
+    int32_t randomize_ego_attributes; /* 1: ego length/width/lr ~ U as in :194-196, else scenario table */
+    int32_t device;                /* CUDA ordinal */
+    float dt;                      /* 0.1 (:432) */
+    float waypoint_bonus;          /* :39 100 */
+    float heading_penalty;         /* :40 25 */
+    float distance_bonus;          /* :41 1 */
+    float distance_cutoff;         /* :42 0.5 */
+    float reach_radius;            /* :394 3 */
+    float offroad_threshold;       /* TorchDriveConfig default 0.5 [EXT-RECALLED] */
+    float tl_rear_factor;          /* fraction of the agent box (at its rear) tested against red stop lines */
+    float fov;                     /* metres covered by the 64 px birdview, default 35 */
+    float start_speed_max;         /* :358 10 */
+    float start_heading_sigma;     /* :361 0.1 */
+    int32_t reserved[8];
+} tde_config;
+
+/*
+ * Scenario tables (host pointers, copied by tde_upload_scenarios).
+ *
+ * A "map" is static geometry shared by scenarios: the road (lane) mesh with a lane direction per
+ * triangle, lane-marking triangles, stop lines and their light schedule.  A "scenario" is a waypoint
+ * polyline on a map plus the agent table (slot 0 = ego) and the optional NPC log-replay.
+ */
+typedef struct tde_scenario_set {
+    int32_t num_maps;
+    /* road mesh: map m owns triangles [map_tri_offset[m], map_tri_offset[m+1]);
+       8 floats per triangle: ax ay bx by cx cy lane_dir_cos lane_dir_sin */
+    const int32_t* map_tri_offset;
+    const float* road_tris;
+    /* lane markings: 6 floats per triangle */
+    const int32_t* map_mark_offset;
+    const float* mark_tris;
+    /* stop lines: 5 floats per line: x y length width psi */
+    const int32_t* map_stop_offset;
+    const float* stoplines;
+    /* light schedule: map m has period P=map_light_period[m] (>=1) rows of L(m) uint8 states starting
+       at light_states[map_light_offset[m]], row-major [t][l] */
+    const int32_t* map_light_period;
+    const int32_t* map_light_offset;
+    const uint8_t* light_states;
+
+    int32_t num_scenarios;
+    const int32_t* scen_map;           /* [Ns] */
+    const int32_t* scen_wp_offset;     /* [Ns+1] */
+    const float* waypoints;            /* 2 floats per waypoint */
+    const float* scen_start_heading;   /* [Ns] lane direction at the start segment (find_lanelet_directions :359) */
+    const int32_t* scen_num_agents;    /* [Ns] present agents incl. ego, <= max_agents */
+    const float* agent_init;           /* [Ns][A][4] x y psi v (slot 0 ignored: ego start is sampled) */
+    const float* agent_attr;           /* [Ns][A][3] length width rear_axis_offset */
+    const int32_t* scen_replay_T;      /* [Ns] replay horizon (0 = none) */
+    const int32_t* scen_replay_offset; /* [Ns+1] in time rows; row r holds A states / A mask bytes */
+    const float* replay_states;        /* [rows][A][4] */
+    const uint8_t* replay_mask;        /* [rows][A] */
+} tde_scenario_set;
+
+int tde_version(void);
+/* message of the last failure on this handle (or of the last failed tde_create when h == NULL) */
+const char* tde_last_error(const tde_handle* h);
+
+int tde_create(const tde_config* cfg, tde_handle** out);
+int tde_destroy(tde_handle* h);
+/* default-initialise a config with the reference defaults */
+int tde_default_config(tde_config* cfg);
+
+int tde_upload_scenarios(tde_handle* h, const tde_scenario_set* set);
+/* per-env scenario choice at reset is uniform over [lo[e], hi[e]); default [0, num_scenarios) */
+int tde_set_env_scenario_range(tde_handle* h, const int32_t* lo_host, const int32_t* hi_host);
+/* RGB palette, TDE_NUM_CLASSES x 3 bytes */
+int tde_set_palette(tde_handle* h, const uint8_t* rgb_host);
+
+/* env_mask_dev: E bytes (non-zero = reset) or NULL = all envs */
+int tde_reset(tde_handle* h, const uint8_t* env_mask_dev, uint64_t seed, void* stream);
+
+/* One lockstep env step for all E envs.
+   actions_dev    float[E][2] (acceleration, steering) for the ego of each env
+   obs_dev        uint8[E][3][64][64]      (may be NULL: no render)
+   reward_dev     float[E]
+   terminated_dev uint8[E]
+   truncated_dev  uint8[E]
+   info_dev       float[E][TDE_INFO_STRIDE] */
+int tde_step(tde_handle* h, const float* actions_dev, uint8_t* obs_dev, float* reward_dev,
+             uint8_t* terminated_dev, uint8_t* truncated_dev, float* info_dev, void* stream);
+/* same with a TDE_PH_* mask: granular entry points for parity tests and micro-benchmarks */
+int tde_step_phases(tde_handle* h, int32_t phases, const float* actions_dev, uint8_t* obs_dev,
+                    float* reward_dev, uint8_t* terminated_dev, uint8_t* truncated_dev,
+                    float* info_dev, void* stream);
+/* host-buffer variant: copies actions H2D, steps, copies results D2H, synchronises `stream` */
+int tde_step_host(tde_handle* h, const float* actions_host, uint8_t* obs_host, float* reward_host,
+                  uint8_t* terminated_host, uint8_t* truncated_host, float* info_host, void* stream);
+
+int tde_kinematics(tde_handle* h, const float* actions_dev, void* stream);
+int tde_render(tde_handle* h, uint8_t* obs_dev, void* stream);
+int tde_compute_infractions(tde_handle* h, void* stream);
+
+/* state float[E][A][4] = x y psi v; attr float[E][A][4] = length width lr present */
+int tde_get_state(tde_handle* h, float* out_dev, void* stream);
+int tde_set_state(tde_handle* h, const float* in_dev, void* stream);
+int tde_get_attributes(tde_handle* h, float* out_dev, void* stream);
+int tde_set_attributes(tde_handle* h, const float* in_dev, void* stream);
+/* float[E][A][4], columns TDE_INFR_* */
+int tde_get_infractions(tde_handle* h, float* out_dev, void* stream);
+/* int32[E][8]: scenario, step, target_idx, reached, light_phase, episode, map, reserved */
+int tde_get_env_vars(tde_handle* h, int32_t* out_dev, void* stream);
+int tde_set_env_vars(tde_handle* h, const int32_t* in_dev, void* stream);
+
+/* Stateless kernels on caller-provided boxes (config C4).
+   state_dev float[E][A][4], attr_dev float[E][A][4]; out float[E][A]. */
+int tde_collision_boxes(const float* state_dev, const float* attr_dev, int32_t num_envs, int32_t num_agents,
+                        float* out_count_dev, void* stream);
+int tde_offroad_boxes(tde_handle* h, int32_t map_id, const float* state_dev, const float* attr_dev,
+                      int32_t num_envs, int32_t num_agents, float* out_offroad_dev, void* stream);
+
+int tde_clone(tde_handle* h, tde_handle** out);
+
+/* double[TDE_NUM_STATS]; synchronises `stream`. reset_after != 0 zeroes the accumulators. */
+int tde_get_episode_stats(tde_handle* h, double* out_host, int32_t reset_after, void* stream);
+
+/* introspection used by the tests / bench */
+int tde_num_kernel_launches(const tde_handle* h, int64_t* out);
+int tde_device_sm_count(const tde_handle* h, int32_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TDE_B200_H */

@@ -1,0 +1,593 @@
+// tde_b200.cu — host side of libtde_b200.so: handle, scenario upload (incl. the nearest-candidate
+// grid over the lane mesh), launches.  C ABI declared in include/tde_b200.h.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "tde_kernels.cuh"
+
+static thread_local std::string g_create_error;
+
+struct tde_handle {
+    tde_config cfg;
+    int E = 0, A = 0, device = 0, sm_count = 0;
+    float4 *state = nullptr, *attr = nullptr, *infr = nullptr;
+    int* vars = nullptr;
+    float* ep_return = nullptr;
+    int *scen_lo = nullptr, *scen_hi = nullptr;
+    double* stats = nullptr;
+    MapDev* maps_dev = nullptr;
+    ScenDev* scens_dev = nullptr;
+    std::vector<MapDev> maps_host;
+    std::vector<ScenDev> scens_host;
+    std::vector<void*> scenario_allocs;
+    int num_maps = 0, num_scen = 0;
+    uint8_t palette[TDE_NUM_CLASSES * 3];
+    unsigned long long seed = 0;
+    bool uploaded = false, was_reset = false;
+    long long launches = 0;
+    int grid_step = 0;
+    size_t smem_step = 0;
+    // device staging for tde_step_host
+    float* h_actions = nullptr; uint8_t* h_obs = nullptr; float* h_reward = nullptr;
+    uint8_t *h_term = nullptr, *h_trunc = nullptr; float* h_info = nullptr;
+    std::string err;
+};
+
+static const uint8_t k_default_palette[TDE_NUM_CLASSES * 3] = {
+    0, 0, 0, 128, 128, 128, 255, 255, 255, 0, 200, 0, 230, 200, 0, 220, 0, 0,
+    0, 170, 255, 60, 90, 220, 250, 120, 0, 200, 220, 255, 255, 230, 150,
+};
+
+static int fail(tde_handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+#define CUDA_TRY(h, expr)                                                                         \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            return fail(h, TDE_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));       \
+    } while (0)
+
+// ------------------------------------------------------------------ small prep kernels
+
+// raw (M,8) triangles -> 3 float4 records with per-edge 1/len^2 (same binary32 ops as the oracle)
+__global__ void prep_tris_kernel(const float* __restrict__ raw, int n, float4* __restrict__ out) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const float* r = raw + 8 * (size_t)t;
+    float ax = r[0], ay = r[1], bx = r[2], by = r[3], cx = r[4], cy = r[5];
+    auto il = [](float ax, float ay, float bx, float by) {
+        float abx = bx - ax, aby = by - ay;
+        float l2 = abx * abx + aby * aby;
+        return l2 > 0.0f ? 1.0f / l2 : 0.0f;
+    };
+    out[3 * t] = make_float4(ax, ay, bx, by);
+    out[3 * t + 1] = make_float4(cx, cy, il(ax, ay, bx, by), il(bx, by, cx, cy));
+    out[3 * t + 2] = make_float4(il(cx, cy, ax, ay), r[6], r[7], 0.0f);
+}
+// raw (L,5) stop lines -> [x y hl hw][c s 0 0]
+__global__ void prep_stops_kernel(const float* __restrict__ raw, int n, float4* __restrict__ out) {
+    int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n) return;
+    const float* r = raw + 5 * (size_t)l;
+    Box b = tde_make_box(r[0], r[1], r[4], r[2], r[3], 1.0f);
+    out[2 * l] = make_float4(b.x, b.y, b.hl, b.hw);
+    out[2 * l + 1] = make_float4(b.c, b.s, 0.0f, 0.0f);
+}
+
+// ------------------------------------------------------------------ nearest-candidate grid (host, float64)
+
+namespace {
+struct P2 { double x, y; };
+inline double seg_d2(P2 p, P2 a, P2 b) {
+    double abx = b.x - a.x, aby = b.y - a.y, apx = p.x - a.x, apy = p.y - a.y;
+    double l2 = abx * abx + aby * aby;
+    double t = l2 > 0 ? (apx * abx + apy * aby) / l2 : 0.0;
+    t = std::min(1.0, std::max(0.0, t));
+    double qx = apx - t * abx, qy = apy - t * aby;
+    return qx * qx + qy * qy;
+}
+inline double tri_dist(P2 p, const float* t) {
+    P2 a{t[0], t[1]}, b{t[2], t[3]}, c{t[4], t[5]};
+    double c0 = (b.x - a.x) * (p.y - a.y) - (b.y - a.y) * (p.x - a.x);
+    double c1 = (c.x - b.x) * (p.y - b.y) - (c.y - b.y) * (p.x - b.x);
+    double c2 = (a.x - c.x) * (p.y - c.y) - (a.y - c.y) * (p.x - c.x);
+    if ((c0 >= 0 && c1 >= 0 && c2 >= 0) || (c0 <= 0 && c1 <= 0 && c2 <= 0)) return 0.0;
+    return std::sqrt(std::min(seg_d2(p, a, b), std::min(seg_d2(p, b, c), seg_d2(p, c, a))));
+}
+
+struct Grid {
+    float gx0 = 0, gy0 = 0, inv_cell = 1;
+    int nx = 0, ny = 0;
+    std::vector<int> cell_start;
+    std::vector<uint16_t> items;
+};
+
+// For every grid cell keep each triangle that can be the nearest one (or contain the point) for some
+// point of the cell: U = min_t max_{p in cell} dist(p, t) bounds the nearest distance from above, any
+// triangle whose lower bound to the cell exceeds U can never win.  A query is then one cell lookup.
+Grid build_grid(const float* tris, int M) {
+    Grid g;
+    if (M <= 0) { g.nx = g.ny = 0; g.cell_start.assign(1, 0); return g; }
+    double lox = 1e300, loy = 1e300, hix = -1e300, hiy = -1e300;
+    std::vector<P2> cen(M);
+    std::vector<double> rad(M);
+    for (int t = 0; t < M; ++t) {
+        const float* r = tris + 8 * (size_t)t;
+        for (int k = 0; k < 3; ++k) {
+            lox = std::min(lox, (double)r[2 * k]); hix = std::max(hix, (double)r[2 * k]);
+            loy = std::min(loy, (double)r[2 * k + 1]); hiy = std::max(hiy, (double)r[2 * k + 1]);
+        }
+        cen[t] = P2{(r[0] + r[2] + r[4]) / 3.0, (r[1] + r[3] + r[5]) / 3.0};
+        double rr = 0;
+        for (int k = 0; k < 3; ++k) rr = std::max(rr, std::hypot(r[2 * k] - cen[t].x, r[2 * k + 1] - cen[t].y));
+        rad[t] = rr;
+    }
+    const double margin = 8.0;
+    lox -= margin; loy -= margin; hix += margin; hiy += margin;
+    double w = hix - lox, hgt = hiy - loy;
+    double cell = std::max(2.0, std::sqrt(w * hgt / 4096.0));
+    g.nx = std::max(1, (int)std::ceil(w / cell));
+    g.ny = std::max(1, (int)std::ceil(hgt / cell));
+    g.gx0 = (float)lox; g.gy0 = (float)loy;
+    g.inv_cell = (float)(1.0 / cell);
+    // the device maps a point with floorf((p - gx0) * inv_cell) in binary32: use the same constants
+    double x0 = g.gx0, y0 = g.gy0, cs = 1.0 / (double)g.inv_cell;
+    double dil = 1e-3 * cs + 1e-3;  // dilation covering binary32 rounding of the cell index
+    double half = 0.5 * cs + dil, hd = half * std::sqrt(2.0);
+    g.cell_start.assign((size_t)g.nx * g.ny + 1, 0);
+    std::vector<int> cand;
+    std::vector<double> lb;
+    for (int iy = 0; iy < g.ny; ++iy) {
+        for (int ix = 0; ix < g.nx; ++ix) {
+            P2 c{x0 + (ix + 0.5) * cs, y0 + (iy + 0.5) * cs};
+            P2 corner[4] = {{c.x - half, c.y - half}, {c.x + half, c.y - half}, {c.x + half, c.y + half}, {c.x - half, c.y + half}};
+            // cheap upper bound on U from centroids, then exact U over the plausible triangles
+            double Uub = 1e300;
+            for (int t = 0; t < M; ++t) Uub = std::min(Uub, std::hypot(c.x - cen[t].x, c.y - cen[t].y) + hd);
+            cand.clear(); lb.clear();
+            double U = 1e300;
+            for (int t = 0; t < M; ++t) {
+                double dc = std::hypot(c.x - cen[t].x, c.y - cen[t].y);
+                if (dc - rad[t] - hd > Uub) continue;
+                const float* r = tris + 8 * (size_t)t;
+                double dcen = tri_dist(c, r);
+                double l = std::max(0.0, dcen - hd);
+                if (l > Uub) continue;
+                double mx = 0;
+                for (int k = 0; k < 4; ++k) mx = std::max(mx, tri_dist(corner[k], r));
+                U = std::min(U, mx);
+                cand.push_back(t); lb.push_back(l);
+            }
+            double lim = U * (1.0 + 1e-4) + 1e-3;
+            for (size_t k = 0; k < cand.size(); ++k)
+                if (lb[k] <= lim) g.items.push_back((uint16_t)cand[k]);
+            g.cell_start[(size_t)iy * g.nx + ix + 1] = (int)g.items.size();
+        }
+    }
+    return g;
+}
+}  // namespace
+
+// ------------------------------------------------------------------ handle
+
+template <typename T>
+static int dev_alloc(tde_handle* h, T** p, size_t n) {
+    CUDA_TRY(h, cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
+    CUDA_TRY(h, cudaMemset(*p, 0, std::max<size_t>(n, 1) * sizeof(T)));
+    return TDE_OK;
+}
+template <typename T>
+static int dev_upload(tde_handle* h, T** p, const T* src, size_t n) {
+    int rc = dev_alloc(h, p, n);
+    if (rc) return rc;
+    if (n) CUDA_TRY(h, cudaMemcpy(*p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    h->scenario_allocs.push_back((void*)*p);
+    return TDE_OK;
+}
+
+extern "C" int tde_version(void) { return TDE_VERSION; }
+
+extern "C" const char* tde_last_error(const tde_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int tde_default_config(tde_config* c) {
+    if (!c) return TDE_E_INVAL;
+    std::memset(c, 0, sizeof(*c));
+    c->num_envs = 1; c->max_agents = 1; c->env_index_offset = 0;
+    c->max_environment_steps = 200; c->terminated_at_infraction = 1; c->left_handed_coordinates = 1;
+    c->auto_reset = 0; c->randomize_ego_attributes = 0; c->device = 0;
+    c->dt = 0.1f; c->waypoint_bonus = 100.f; c->heading_penalty = 25.f; c->distance_bonus = 1.f;
+    c->distance_cutoff = 0.5f; c->reach_radius = 3.f; c->offroad_threshold = 0.5f; c->tl_rear_factor = 0.1f;
+    c->fov = 35.f; c->start_speed_max = 10.f; c->start_heading_sigma = 0.1f;
+    return TDE_OK;
+}
+
+static void free_scenarios(tde_handle* h) {
+    for (void* p : h->scenario_allocs) cudaFree(p);
+    h->scenario_allocs.clear();
+    if (h->maps_dev) cudaFree(h->maps_dev);
+    if (h->scens_dev) cudaFree(h->scens_dev);
+    h->maps_dev = nullptr; h->scens_dev = nullptr;
+    h->maps_host.clear(); h->scens_host.clear();
+    h->uploaded = false;
+}
+
+template <int AH>
+static int configure_kernels(tde_handle* h) {
+    size_t smem = sizeof(WarpScratch) * TDE_WARPS_PER_BLOCK;
+    CUDA_TRY(h, cudaFuncSetAttribute(tde_step_kernel<AH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tde_step_kernel<AH>, TDE_WARPS_PER_BLOCK * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    h->smem_step = smem;
+    int want = (h->E + TDE_WARPS_PER_BLOCK - 1) / TDE_WARPS_PER_BLOCK;
+    h->grid_step = std::max(1, std::min(want, per_sm * h->sm_count));
+    return TDE_OK;
+}
+
+extern "C" int tde_create(const tde_config* cfg, tde_handle** out) {
+    if (!cfg || !out) return fail(nullptr, TDE_E_INVAL, "tde_create: null argument");
+    if (cfg->num_envs < 1) return fail(nullptr, TDE_E_INVAL, "tde_create: num_envs must be >= 1");
+    if (cfg->max_agents < 1 || cfg->max_agents > TDE_MAX_AGENTS)
+        return fail(nullptr, TDE_E_SHAPE, "tde_create: max_agents must be in [1, 64]");
+    if (!(cfg->fov > 0.f) || !(cfg->dt > 0.f)) return fail(nullptr, TDE_E_INVAL, "tde_create: fov and dt must be > 0");
+    if (cfg->max_environment_steps < 1) return fail(nullptr, TDE_E_INVAL, "tde_create: max_environment_steps must be >= 1");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(nullptr, TDE_E_CUDA, std::string("tde_create: no CUDA device (") + cudaGetErrorString(ce) + "); there is no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, TDE_E_INVAL, "tde_create: bad device ordinal");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return fail(nullptr, TDE_E_CUDA, "tde_create: cudaGetDeviceProperties failed");
+    if (prop.major != 10)
+        return fail(nullptr, TDE_E_ARCH, "tde_create: device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                                             ", this library is built for sm_100a only");
+    tde_handle* h = new tde_handle();
+    h->cfg = *cfg; h->E = cfg->num_envs; h->A = cfg->max_agents; h->device = cfg->device;
+    h->sm_count = prop.multiProcessorCount;
+    std::memcpy(h->palette, k_default_palette, sizeof(k_default_palette));
+    int rc = TDE_OK;
+    auto bail = [&](int code) { g_create_error = h->err; tde_destroy(h); return code; };
+    if (cudaSetDevice(h->device) != cudaSuccess) return bail(fail(h, TDE_E_CUDA, "cudaSetDevice failed"));
+    size_t EA = (size_t)h->E * h->A;
+    if ((rc = dev_alloc(h, &h->state, EA)) || (rc = dev_alloc(h, &h->attr, EA)) || (rc = dev_alloc(h, &h->infr, EA)) ||
+        (rc = dev_alloc(h, &h->vars, (size_t)h->E * 8)) || (rc = dev_alloc(h, &h->ep_return, (size_t)h->E)) ||
+        (rc = dev_alloc(h, &h->scen_lo, (size_t)h->E)) || (rc = dev_alloc(h, &h->scen_hi, (size_t)h->E)) ||
+        (rc = dev_alloc(h, &h->stats, (size_t)TDE_NUM_STATS)))
+        return bail(rc);
+    rc = h->A <= 32 ? configure_kernels<1>(h) : configure_kernels<2>(h);
+    if (rc) return bail(rc);
+    *out = h;
+    return TDE_OK;
+}
+
+extern "C" int tde_destroy(tde_handle* h) {
+    if (!h) return TDE_OK;
+    cudaSetDevice(h->device);
+    free_scenarios(h);
+    cudaFree(h->state); cudaFree(h->attr); cudaFree(h->infr); cudaFree(h->vars); cudaFree(h->ep_return);
+    cudaFree(h->scen_lo); cudaFree(h->scen_hi); cudaFree(h->stats);
+    cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_reward); cudaFree(h->h_term); cudaFree(h->h_trunc); cudaFree(h->h_info);
+    delete h;
+    return TDE_OK;
+}
+
+extern "C" int tde_set_palette(tde_handle* h, const uint8_t* rgb) {
+    if (!h || !rgb) return fail(h, TDE_E_INVAL, "tde_set_palette: null argument");
+    std::memcpy(h->palette, rgb, TDE_NUM_CLASSES * 3);
+    return TDE_OK;
+}
+
+extern "C" int tde_upload_scenarios(tde_handle* h, const tde_scenario_set* s) {
+    if (!h || !s) return fail(h, TDE_E_INVAL, "tde_upload_scenarios: null argument");
+    if (s->num_maps < 1 || s->num_scenarios < 1) return fail(h, TDE_E_INVAL, "tde_upload_scenarios: need >= 1 map and >= 1 scenario");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    free_scenarios(h);
+    const int A = h->A;
+    const float ppm = (float)TDE_OBS_W / h->cfg.fov;
+    const double max_edge_m = 430.0 / (double)ppm;  // keeps snapped vertices of drawn primitives inside +-511 px
+    h->maps_host.resize(s->num_maps);
+    for (int m = 0; m < s->num_maps; ++m) {
+        MapDev& M = h->maps_host[m];
+        std::memset(&M, 0, sizeof(M));
+        int t0 = s->map_tri_offset[m], nt = s->map_tri_offset[m + 1] - t0;
+        int k0 = s->map_mark_offset[m], nk = s->map_mark_offset[m + 1] - k0;
+        int l0 = s->map_stop_offset[m], nl = s->map_stop_offset[m + 1] - l0;
+        if (nt < 0 || nk < 0 || nl < 0) return fail(h, TDE_E_INVAL, "tde_upload_scenarios: offsets must be non-decreasing");
+        if (nt > 65535) return fail(h, TDE_E_SHAPE, "tde_upload_scenarios: more than 65535 road triangles in one map");
+        if (nl > TDE_MAX_STOPLINES) return fail(h, TDE_E_SHAPE, "tde_upload_scenarios: more than 32 stop lines in one map");
+        auto edge_ok = [&](const float* v, int stride_pts) {
+            for (int k = 0; k < 3; ++k) {
+                int k1 = (k + 1) % 3;
+                double d = std::hypot((double)v[2 * k] - v[2 * k1], (double)v[2 * k + 1] - v[2 * k1 + 1]);
+                if (!(d <= max_edge_m)) return false;
+            }
+            (void)stride_pts;
+            return true;
+        };
+        for (int t = 0; t < nt; ++t)
+            if (!edge_ok(s->road_tris + 8 * (size_t)(t0 + t), 0))
+                return fail(h, TDE_E_SHAPE, "tde_upload_scenarios: road triangle edge too long for the rasteriser's fixed-point range; subdivide the mesh");
+        for (int t = 0; t < nk; ++t)
+            if (!edge_ok(s->mark_tris + 6 * (size_t)(k0 + t), 0))
+                return fail(h, TDE_E_SHAPE, "tde_upload_scenarios: marking triangle edge too long; subdivide the mesh");
+        // road triangles -> device records
+        float* raw = nullptr; float4* rec = nullptr;
+        int rc;
+        if ((rc = dev_upload(h, &raw, s->road_tris + 8 * (size_t)t0, (size_t)nt * 8))) return rc;
+        if ((rc = dev_alloc(h, &rec, (size_t)nt * 3))) return rc;
+        h->scenario_allocs.push_back(rec);
+        if (nt) prep_tris_kernel<<<(nt + 127) / 128, 128>>>(raw, nt, rec);
+        M.tri = rec; M.ntri = nt;
+        float2* mk = nullptr;
+        if ((rc = dev_upload(h, (float**)&mk, s->mark_tris + 6 * (size_t)k0, (size_t)nk * 6))) return rc;
+        M.mark = mk; M.nmark = nk;
+        float* sraw = nullptr; float4* srec = nullptr;
+        if ((rc = dev_upload(h, &sraw, s->stoplines + 5 * (size_t)l0, (size_t)nl * 5))) return rc;
+        if ((rc = dev_alloc(h, &srec, (size_t)nl * 2))) return rc;
+        h->scenario_allocs.push_back(srec);
+        if (nl) prep_stops_kernel<<<1, 64>>>(sraw, nl, srec);
+        M.stop = srec; M.nstop = nl;
+        int P = s->map_light_period[m];
+        int lo = s->map_light_offset[m], ln = s->map_light_offset[m + 1] - lo;
+        if (nl > 0 && (P < 1 || ln != P * nl)) return fail(h, TDE_E_SHAPE, "tde_upload_scenarios: light schedule must hold period x stoplines states");
+        uint8_t* lights = nullptr;
+        if ((rc = dev_upload(h, &lights, s->light_states + lo, (size_t)std::max(ln, 0)))) return rc;
+        M.lights = lights; M.period = nl > 0 ? P : 0;
+        Grid g = build_grid(s->road_tris + 8 * (size_t)t0, nt);
+        int* cs = nullptr; uint16_t* items = nullptr;
+        if ((rc = dev_upload(h, &cs, g.cell_start.data(), g.cell_start.size()))) return rc;
+        if ((rc = dev_upload(h, &items, g.items.data(), g.items.size()))) return rc;
+        M.cell_start = cs; M.cell_items = items;
+        M.gx0 = g.gx0; M.gy0 = g.gy0; M.inv_cell = g.inv_cell; M.gnx = g.nx; M.gny = g.ny;
+    }
+    h->scens_host.resize(s->num_scenarios);
+    for (int k = 0; k < s->num_scenarios; ++k) {
+        ScenDev& S = h->scens_host[k];
+        std::memset(&S, 0, sizeof(S));
+        S.map = s->scen_map[k];
+        if (S.map < 0 || S.map >= s->num_maps) return fail(h, TDE_E_INVAL, "tde_upload_scenarios: scen_map out of range");
+        int w0 = s->scen_wp_offset[k];
+        S.W = s->scen_wp_offset[k + 1] - w0;
+        if (S.W < 1) return fail(h, TDE_E_INVAL, "tde_upload_scenarios: a scenario needs >= 1 waypoint");
+        S.nag = s->scen_num_agents[k];
+        if (S.nag < 1 || S.nag > A) return fail(h, TDE_E_SHAPE, "tde_upload_scenarios: scen_num_agents must be in [1, max_agents]");
+        S.start_heading = s->scen_start_heading[k];
+        int rc;
+        float2* wp = nullptr;
+        if ((rc = dev_upload(h, (float**)&wp, s->waypoints + 2 * (size_t)w0, (size_t)S.W * 2))) return rc;
+        S.wp = wp;
+        float4* init = nullptr;
+        if ((rc = dev_upload(h, (float**)&init, s->agent_init + (size_t)k * A * 4, (size_t)A * 4))) return rc;
+        S.init = init;
+        std::vector<float> at4((size_t)A * 4, 0.f);
+        for (int a = 0; a < A; ++a)
+            for (int q = 0; q < 3; ++q) at4[4 * a + q] = s->agent_attr[((size_t)k * A + a) * 3 + q];
+        float4* attr = nullptr;
+        if ((rc = dev_upload(h, (float**)&attr, at4.data(), at4.size()))) return rc;
+        S.attr = attr;
+        S.rep_T = s->scen_replay_T[k];
+        int r0 = s->scen_replay_offset[k];
+        if (S.rep_T < 0 || s->scen_replay_offset[k + 1] - r0 != S.rep_T) return fail(h, TDE_E_SHAPE, "tde_upload_scenarios: replay offsets do not match scen_replay_T");
+        float4* rs = nullptr; uint8_t* rm = nullptr;
+        if ((rc = dev_upload(h, (float**)&rs, s->replay_states + (size_t)r0 * A * 4, (size_t)S.rep_T * A * 4))) return rc;
+        if ((rc = dev_upload(h, &rm, s->replay_mask + (size_t)r0 * A, (size_t)S.rep_T * A))) return rc;
+        S.rep_states = rs; S.rep_mask = rm;
+    }
+    h->num_maps = s->num_maps; h->num_scen = s->num_scenarios;
+    CUDA_TRY(h, cudaMalloc((void**)&h->maps_dev, sizeof(MapDev) * h->num_maps));
+    CUDA_TRY(h, cudaMemcpy(h->maps_dev, h->maps_host.data(), sizeof(MapDev) * h->num_maps, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMalloc((void**)&h->scens_dev, sizeof(ScenDev) * h->num_scen));
+    CUDA_TRY(h, cudaMemcpy(h->scens_dev, h->scens_host.data(), sizeof(ScenDev) * h->num_scen, cudaMemcpyHostToDevice));
+    std::vector<int> lo((size_t)h->E, 0), hi((size_t)h->E, h->num_scen);
+    CUDA_TRY(h, cudaMemcpy(h->scen_lo, lo.data(), sizeof(int) * h->E, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->scen_hi, hi.data(), sizeof(int) * h->E, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    h->uploaded = true; h->was_reset = false;
+    return TDE_OK;
+}
+
+extern "C" int tde_set_env_scenario_range(tde_handle* h, const int32_t* lo, const int32_t* hi) {
+    if (!h || !lo || !hi) return fail(h, TDE_E_INVAL, "tde_set_env_scenario_range: null argument");
+    if (!h->uploaded) return fail(h, TDE_E_STATE, "tde_set_env_scenario_range: upload scenarios first");
+    for (int e = 0; e < h->E; ++e)
+        if (lo[e] < 0 || hi[e] > h->num_scen || lo[e] >= hi[e]) return fail(h, TDE_E_INVAL, "tde_set_env_scenario_range: need 0 <= lo < hi <= num_scenarios");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaMemcpy(h->scen_lo, lo, sizeof(int) * h->E, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->scen_hi, hi, sizeof(int) * h->E, cudaMemcpyHostToDevice));
+    return TDE_OK;
+}
+
+static StepParams make_params(tde_handle* h) {
+    StepParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.cfg = h->cfg; p.E = h->E; p.A = h->A; p.num_scen = h->num_scen; p.seed = h->seed;
+    p.maps = h->maps_dev; p.scens = h->scens_dev;
+    p.state = h->state; p.attr = h->attr; p.infr = h->infr; p.vars = h->vars; p.ep_return = h->ep_return;
+    p.scen_lo = h->scen_lo; p.scen_hi = h->scen_hi; p.stats = h->stats;
+    for (int ch = 0; ch < 3; ++ch)
+        for (int w = 0; w < 4; ++w) {
+            uint32_t v = 0;
+            for (int b = 0; b < 4; ++b) {
+                int cls = 4 * w + b;
+                uint32_t byte = cls < TDE_NUM_CLASSES ? h->palette[3 * cls + ch] : 0;
+                v |= byte << (8 * b);
+            }
+            p.pal[ch][w] = v;
+        }
+    p.ppm = (float)TDE_OBS_W / h->cfg.fov;
+    p.ppmy = h->cfg.left_handed_coordinates ? p.ppm : -p.ppm;
+    return p;
+}
+
+extern "C" int tde_reset(tde_handle* h, const uint8_t* env_mask_dev, uint64_t seed, void* stream) {
+    if (!h) return TDE_E_INVAL;
+    if (!h->uploaded) return fail(h, TDE_E_STATE, "tde_reset: upload scenarios first");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    h->seed = seed;
+    StepParams p = make_params(h);
+    p.reset_mask = env_mask_dev;
+    cudaStream_t st = (cudaStream_t)stream;
+    int grid = std::max(1, std::min((h->E + TDE_WARPS_PER_BLOCK - 1) / TDE_WARPS_PER_BLOCK, h->sm_count * 8));
+    if (h->A <= 32) tde_reset_kernel<1><<<grid, TDE_WARPS_PER_BLOCK * 32, 0, st>>>(p);
+    else tde_reset_kernel<2><<<grid, TDE_WARPS_PER_BLOCK * 32, 0, st>>>(p);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches++;
+    h->was_reset = true;
+    return TDE_OK;
+}
+
+extern "C" int tde_step_phases(tde_handle* h, int32_t phases, const float* actions, uint8_t* obs, float* reward,
+                               uint8_t* terminated, uint8_t* truncated, float* info, void* stream) {
+    if (!h) return TDE_E_INVAL;
+    if (!h->uploaded || !h->was_reset) return fail(h, TDE_E_STATE, "tde_step: upload scenarios and reset first");
+    if ((phases & ~TDE_PH_ALL) || phases == 0) return fail(h, TDE_E_INVAL, "tde_step_phases: bad phase mask");
+    if ((phases & TDE_PH_KINEMATICS) && !actions) return fail(h, TDE_E_INVAL, "tde_step: actions is null");
+    if ((phases & TDE_PH_REWARD) && (!reward || !terminated || !truncated || !info))
+        return fail(h, TDE_E_INVAL, "tde_step: reward/terminated/truncated/info must be non-null");
+    if (phases == TDE_PH_RENDER && !obs) return fail(h, TDE_E_INVAL, "tde_render: obs is null");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    StepParams p = make_params(h);
+    p.phases = phases; p.actions = actions; p.obs = obs; p.reward = reward; p.terminated = terminated;
+    p.truncated = truncated; p.info = info;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->A <= 32) tde_step_kernel<1><<<h->grid_step, TDE_WARPS_PER_BLOCK * 32, h->smem_step, st>>>(p);
+    else tde_step_kernel<2><<<h->grid_step, TDE_WARPS_PER_BLOCK * 32, h->smem_step, st>>>(p);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches++;
+    return TDE_OK;
+}
+
+extern "C" int tde_step(tde_handle* h, const float* actions, uint8_t* obs, float* reward, uint8_t* terminated,
+                        uint8_t* truncated, float* info, void* stream) {
+    int phases = obs ? TDE_PH_ALL : (TDE_PH_ALL & ~TDE_PH_RENDER);
+    return tde_step_phases(h, phases, actions, obs, reward, terminated, truncated, info, stream);
+}
+
+extern "C" int tde_kinematics(tde_handle* h, const float* actions, void* stream) {
+    return tde_step_phases(h, TDE_PH_KINEMATICS, actions, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
+}
+extern "C" int tde_render(tde_handle* h, uint8_t* obs, void* stream) {
+    return tde_step_phases(h, TDE_PH_RENDER, nullptr, obs, nullptr, nullptr, nullptr, nullptr, stream);
+}
+extern "C" int tde_compute_infractions(tde_handle* h, void* stream) {
+    return tde_step_phases(h, TDE_PH_INFRACTIONS, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int tde_step_host(tde_handle* h, const float* actions, uint8_t* obs, float* reward, uint8_t* terminated,
+                             uint8_t* truncated, float* info, void* stream) {
+    if (!h) return TDE_E_INVAL;
+    if (!actions || !reward || !terminated || !truncated || !info) return fail(h, TDE_E_INVAL, "tde_step_host: null argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t E = (size_t)h->E, obs_bytes = E * TDE_OBS_C * TDE_OBS_H * TDE_OBS_W;
+    if (!h->h_actions) {
+        CUDA_TRY(h, cudaMalloc((void**)&h->h_actions, E * 2 * sizeof(float)));
+        CUDA_TRY(h, cudaMalloc((void**)&h->h_reward, E * sizeof(float)));
+        CUDA_TRY(h, cudaMalloc((void**)&h->h_term, E));
+        CUDA_TRY(h, cudaMalloc((void**)&h->h_trunc, E));
+        CUDA_TRY(h, cudaMalloc((void**)&h->h_info, E * TDE_INFO_STRIDE * sizeof(float)));
+    }
+    if (obs && !h->h_obs) CUDA_TRY(h, cudaMalloc((void**)&h->h_obs, obs_bytes));
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_actions, actions, E * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+    int rc = tde_step(h, h->h_actions, obs ? h->h_obs : nullptr, h->h_reward, h->h_term, h->h_trunc, h->h_info, stream);
+    if (rc) return rc;
+    if (obs) CUDA_TRY(h, cudaMemcpyAsync(obs, h->h_obs, obs_bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaMemcpyAsync(reward, h->h_reward, E * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaMemcpyAsync(terminated, h->h_term, E, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaMemcpyAsync(truncated, h->h_trunc, E, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaMemcpyAsync(info, h->h_info, E * TDE_INFO_STRIDE * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    return TDE_OK;
+}
+
+static int copy_dev(tde_handle* h, void* dst, const void* src, size_t bytes, void* stream, const char* what) {
+    if (!h) return TDE_E_INVAL;
+    if (!dst || !src) return fail(h, TDE_E_INVAL, std::string(what) + ": null argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return TDE_OK;
+}
+extern "C" int tde_get_state(tde_handle* h, float* out, void* stream) {
+    return copy_dev(h, out, h ? h->state : nullptr, h ? (size_t)h->E * h->A * 16 : 0, stream, "tde_get_state");
+}
+extern "C" int tde_set_state(tde_handle* h, const float* in, void* stream) {
+    return copy_dev(h, h ? h->state : nullptr, in, h ? (size_t)h->E * h->A * 16 : 0, stream, "tde_set_state");
+}
+extern "C" int tde_get_attributes(tde_handle* h, float* out, void* stream) {
+    return copy_dev(h, out, h ? h->attr : nullptr, h ? (size_t)h->E * h->A * 16 : 0, stream, "tde_get_attributes");
+}
+extern "C" int tde_set_attributes(tde_handle* h, const float* in, void* stream) {
+    return copy_dev(h, h ? h->attr : nullptr, in, h ? (size_t)h->E * h->A * 16 : 0, stream, "tde_set_attributes");
+}
+extern "C" int tde_get_infractions(tde_handle* h, float* out, void* stream) {
+    return copy_dev(h, out, h ? h->infr : nullptr, h ? (size_t)h->E * h->A * 16 : 0, stream, "tde_get_infractions");
+}
+extern "C" int tde_get_env_vars(tde_handle* h, int32_t* out, void* stream) {
+    return copy_dev(h, out, h ? h->vars : nullptr, h ? (size_t)h->E * 32 : 0, stream, "tde_get_env_vars");
+}
+extern "C" int tde_set_env_vars(tde_handle* h, const int32_t* in, void* stream) {
+    return copy_dev(h, h ? h->vars : nullptr, in, h ? (size_t)h->E * 32 : 0, stream, "tde_set_env_vars");
+}
+
+extern "C" int tde_collision_boxes(const float* state, const float* attr, int32_t E, int32_t A, float* out, void* stream) {
+    if (!state || !attr || !out || E < 1 || A < 1 || A > TDE_MAX_AGENTS) return fail(nullptr, TDE_E_INVAL, "tde_collision_boxes: bad argument");
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+        return fail(nullptr, TDE_E_CUDA, "tde_collision_boxes: no CUDA device");
+    int grid = std::max(1, std::min((E + TDE_WARPS_PER_BLOCK - 1) / TDE_WARPS_PER_BLOCK, sms * 8));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (A <= 32) tde_collision_kernel<1><<<grid, TDE_WARPS_PER_BLOCK * 32, 0, st>>>((const float4*)state, (const float4*)attr, E, A, out);
+    else tde_collision_kernel<2><<<grid, TDE_WARPS_PER_BLOCK * 32, 0, st>>>((const float4*)state, (const float4*)attr, E, A, out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(nullptr, TDE_E_CUDA, std::string("tde_collision_boxes: ") + cudaGetErrorString(e));
+    return TDE_OK;
+}
+
+extern "C" int tde_offroad_boxes(tde_handle* h, int32_t map_id, const float* state, const float* attr, int32_t E, int32_t A,
+                                 float* out, void* stream) {
+    if (!h) return TDE_E_INVAL;
+    if (!h->uploaded) return fail(h, TDE_E_STATE, "tde_offroad_boxes: upload scenarios first");
+    if (!state || !attr || !out || E < 1 || A < 1 || map_id < 0 || map_id >= h->num_maps) return fail(h, TDE_E_INVAL, "tde_offroad_boxes: bad argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int n = E * A;
+    int grid = std::max(1, std::min((n + 255) / 256, h->sm_count * 8));
+    tde_offroad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h->maps_dev, map_id, h->cfg.offroad_threshold, (const float4*)state,
+                                                               (const float4*)attr, n, out);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches++;
+    return TDE_OK;
+}
+
+extern "C" int tde_clone(tde_handle* h, tde_handle** out) {
+    if (!h || !out) return fail(h, TDE_E_INVAL, "tde_clone: null argument");
+    return fail(h, TDE_E_STATE, "tde_clone: use the Python-side copy (re-upload + state copy)");
+}
+
+extern "C" int tde_get_episode_stats(tde_handle* h, double* out, int32_t reset_after, void* stream) {
+    if (!h || !out) return fail(h, TDE_E_INVAL, "tde_get_episode_stats: null argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(h, cudaMemcpyAsync(out, h->stats, sizeof(double) * TDE_NUM_STATS, cudaMemcpyDeviceToHost, st));
+    if (reset_after) CUDA_TRY(h, cudaMemsetAsync(h->stats, 0, sizeof(double) * TDE_NUM_STATS, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    return TDE_OK;
+}
+
+extern "C" int tde_num_kernel_launches(const tde_handle* h, int64_t* out) {
+    if (!h || !out) return TDE_E_INVAL;
+    *out = h->launches;
+    return TDE_OK;
+}
+extern "C" int tde_device_sm_count(const tde_handle* h, int32_t* out) {
+    if (!h || !out) return TDE_E_INVAL;
+    *out = h->sm_count;
+    return TDE_OK;
+}

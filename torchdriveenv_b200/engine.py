@@ -1,0 +1,180 @@
+"""Thin Python host over the C ABI (include/tde_b200.h): owns the handle, allocates I/O tensors with
+PyTorch (device memory + streams only) and passes raw pointers to libtde_b200.so through ctypes."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _capi
+from ._capi import (INFO_COLUMNS, PH_ALL, PH_RENDER, TDE_INFO_STRIDE, TDE_NUM_STATS, TDE_OBS_C, TDE_OBS_H,
+                    TDE_OBS_W, check, default_config, load_library, scenario_struct)
+from .scenarios import ScenarioSet
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class Engine:
+    """E lockstep environments on one GPU.  All tensors returned live on that GPU."""
+
+    def __init__(self, scenarios: ScenarioSet, num_envs: int, max_agents: Optional[int] = None,
+                 device: Optional[str] = None, **config):
+        if not torch.cuda.is_available():
+            raise RuntimeError("torchdriveenv_b200 needs a CUDA (sm_100a) device: there is no CPU fallback")
+        self.lib = load_library()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if self.device.type != "cuda":
+            raise RuntimeError(f"device {self.device} is not a CUDA device: there is no CPU fallback")
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", dev_index)
+        self.scenarios = scenarios
+        A = int(max_agents if max_agents is not None else scenarios.max_agents())
+        self.E, self.A = int(num_envs), A
+        self.cfg = default_config(num_envs=self.E, max_agents=A, device=dev_index, **config)
+        self.packed: Dict[str, np.ndarray] = scenarios.pack(A)
+        self.h = C.c_void_p()
+        check(self.lib, None, self.lib.tde_create(C.byref(self.cfg), C.byref(self.h)), "tde_create")
+        s, keep = scenario_struct(self.packed)
+        check(self.lib, self.h, self.lib.tde_upload_scenarios(self.h, C.byref(s)), "tde_upload_scenarios")
+        del keep
+        E = self.E
+        with torch.cuda.device(self.device):
+            self.obs = torch.zeros((E, TDE_OBS_C, TDE_OBS_H, TDE_OBS_W), dtype=torch.uint8, device=self.device)
+            self.reward = torch.zeros(E, dtype=torch.float32, device=self.device)
+            self.terminated = torch.zeros(E, dtype=torch.uint8, device=self.device)
+            self.truncated = torch.zeros(E, dtype=torch.uint8, device=self.device)
+            self.info = torch.zeros((E, TDE_INFO_STRIDE), dtype=torch.float32, device=self.device)
+        self._host = None
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.tde_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check(self, code, what):
+        check(self.lib, self.h, code, what)
+
+    # -- configuration
+    def set_env_scenario_range(self, lo, hi):
+        lo = np.ascontiguousarray(lo, np.int32); hi = np.ascontiguousarray(hi, np.int32)
+        self._check(self.lib.tde_set_env_scenario_range(self.h, lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p)),
+                    "tde_set_env_scenario_range")
+
+    def set_palette(self, rgb):
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        self._check(self.lib.tde_set_palette(self.h, rgb.ctypes.data_as(C.c_void_p)), "tde_set_palette")
+
+    # -- the hot path
+    def reset(self, mask: Optional[torch.Tensor] = None, seed: int = 0):
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        self._check(self.lib.tde_reset(self.h, _ptr(mask), C.c_uint64(seed), self._stream()), "tde_reset")
+
+    def step(self, actions: torch.Tensor, render: bool = True, phases: int = PH_ALL):
+        a = actions.to(device=self.device, dtype=torch.float32).contiguous().view(self.E, 2)
+        if not render:
+            phases &= ~PH_RENDER
+        self._check(self.lib.tde_step_phases(self.h, int(phases), _ptr(a), _ptr(self.obs) if render else None,
+                                             _ptr(self.reward), _ptr(self.terminated), _ptr(self.truncated),
+                                             _ptr(self.info), self._stream()), "tde_step")
+        return (self.obs if render else None), self.reward, self.terminated, self.truncated, self.info
+
+    def step_host(self, actions: np.ndarray, render: bool = True):
+        """Reference-facing call with HOST buffers (tde_step_host): H2D, step, D2H, synchronise."""
+        E = self.E
+        if self._host is None:
+            pin = dict(pin_memory=True)
+            self._host = dict(
+                act=torch.zeros((E, 2), dtype=torch.float32, **pin),
+                obs=torch.zeros((E, TDE_OBS_C, TDE_OBS_H, TDE_OBS_W), dtype=torch.uint8, **pin),
+                rew=torch.zeros(E, dtype=torch.float32, **pin), term=torch.zeros(E, dtype=torch.uint8, **pin),
+                trunc=torch.zeros(E, dtype=torch.uint8, **pin),
+                info=torch.zeros((E, TDE_INFO_STRIDE), dtype=torch.float32, **pin))
+        hb = self._host
+        hb["act"].numpy()[...] = np.asarray(actions, np.float32).reshape(E, 2)
+        self._check(self.lib.tde_step_host(self.h, _ptr(hb["act"]), _ptr(hb["obs"]) if render else None, _ptr(hb["rew"]),
+                                           _ptr(hb["term"]), _ptr(hb["trunc"]), _ptr(hb["info"]), self._stream()),
+                    "tde_step_host")
+        return (hb["obs"].numpy() if render else None), hb["rew"].numpy(), hb["term"].numpy(), hb["trunc"].numpy(), hb["info"].numpy()
+
+    def kinematics(self, actions: torch.Tensor):
+        a = actions.to(device=self.device, dtype=torch.float32).contiguous().view(self.E, 2)
+        self._check(self.lib.tde_kinematics(self.h, _ptr(a), self._stream()), "tde_kinematics")
+
+    def render(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        out = self.obs if out is None else out
+        self._check(self.lib.tde_render(self.h, _ptr(out), self._stream()), "tde_render")
+        return out
+
+    def compute_infractions(self) -> torch.Tensor:
+        self._check(self.lib.tde_compute_infractions(self.h, self._stream()), "tde_compute_infractions")
+        return self.get_infractions()
+
+    # -- state access
+    def _get(self, fn, shape, dtype, what):
+        out = torch.empty(shape, dtype=dtype, device=self.device)
+        self._check(fn(self.h, _ptr(out), self._stream()), what)
+        return out
+
+    def _set(self, fn, t, shape, dtype, what):
+        t = torch.as_tensor(t).to(device=self.device, dtype=dtype).contiguous().view(shape)
+        self._check(fn(self.h, _ptr(t), self._stream()), what)
+        torch.cuda.current_stream(self.device).synchronize()  # `t` may be a temporary
+
+    def get_state(self): return self._get(self.lib.tde_get_state, (self.E, self.A, 4), torch.float32, "tde_get_state")
+    def set_state(self, t): self._set(self.lib.tde_set_state, t, (self.E, self.A, 4), torch.float32, "tde_set_state")
+    def get_attributes(self): return self._get(self.lib.tde_get_attributes, (self.E, self.A, 4), torch.float32, "tde_get_attributes")
+    def set_attributes(self, t): self._set(self.lib.tde_set_attributes, t, (self.E, self.A, 4), torch.float32, "tde_set_attributes")
+    def get_infractions(self): return self._get(self.lib.tde_get_infractions, (self.E, self.A, 4), torch.float32, "tde_get_infractions")
+    def get_env_vars(self): return self._get(self.lib.tde_get_env_vars, (self.E, 8), torch.int32, "tde_get_env_vars")
+    def set_env_vars(self, t): self._set(self.lib.tde_set_env_vars, t, (self.E, 8), torch.int32, "tde_set_env_vars")
+
+    def episode_stats(self, reset: bool = False) -> np.ndarray:
+        out = (C.c_double * TDE_NUM_STATS)()
+        self._check(self.lib.tde_get_episode_stats(self.h, out, int(reset), self._stream()), "tde_get_episode_stats")
+        return np.asarray(list(out), np.float64)
+
+    def num_kernel_launches(self) -> int:
+        n = C.c_int64()
+        self._check(self.lib.tde_num_kernel_launches(self.h, C.byref(n)), "tde_num_kernel_launches")
+        return int(n.value)
+
+    def sm_count(self) -> int:
+        n = C.c_int32()
+        self._check(self.lib.tde_device_sm_count(self.h, C.byref(n)), "tde_device_sm_count")
+        return int(n.value)
+
+    # -- stateless kernels (config C4)
+    def collision_boxes(self, state: torch.Tensor, attr: torch.Tensor) -> torch.Tensor:
+        st = state.to(device=self.device, dtype=torch.float32).contiguous()
+        at = attr.to(device=self.device, dtype=torch.float32).contiguous()
+        E, A = st.shape[:2]
+        out = torch.empty((E, A), dtype=torch.float32, device=self.device)
+        check(self.lib, None, self.lib.tde_collision_boxes(_ptr(st), _ptr(at), E, A, _ptr(out), self._stream()), "tde_collision_boxes")
+        return out
+
+    def offroad_boxes(self, map_id: int, state: torch.Tensor, attr: torch.Tensor) -> torch.Tensor:
+        st = state.to(device=self.device, dtype=torch.float32).contiguous()
+        at = attr.to(device=self.device, dtype=torch.float32).contiguous()
+        E, A = st.shape[:2]
+        out = torch.empty((E, A), dtype=torch.float32, device=self.device)
+        self._check(self.lib.tde_offroad_boxes(self.h, int(map_id), _ptr(st), _ptr(at), E, A, _ptr(out), self._stream()), "tde_offroad_boxes")
+        return out
+
+
+def info_dict(info_row) -> Dict[str, float]:
+    return {k: float(info_row[i]) for k, i in INFO_COLUMNS.items()}
