@@ -1,0 +1,115 @@
+"""The reference-shaped Python API (gym.Env / SingleAgentWrapper / SimulatorInterface / VecEnv) on top
+of the CUDA engine, checked against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from torchdriveenv_b200 import scenarios as S
+from torchdriveenv_b200._capi import default_config
+
+pytestmark = pytest.mark.gpu
+
+
+def _suite():
+    from torchdriveenv_b200.gym_env import Scenario, WaypointSuite
+    return WaypointSuite(locations=["Town07", "Town01"],
+                         waypoint_suite=[S.VALIDATION_POLYLINES["three_way"], S.VALIDATION_POLYLINES["traffic_lights"]],
+                         car_sequence_suite=[{}, {}],
+                         scenarios=[Scenario(agent_states=S.THREE_WAY_NPCS["states"], agent_attributes=S.THREE_WAY_NPCS["attributes"],
+                                             recurrent_states=[[0.0] * 4] * 2), None])
+
+
+def test_single_env_api_matches_reference_shapes(oracle):
+    from torchdriveenv_b200.gym_env import EnvConfig, SingleAgentWrapper, WaypointSuiteEnv
+    cfg = EnvConfig(seed=3, device="cuda:0")
+    env = SingleAgentWrapper(WaypointSuiteEnv(cfg, _suite(), n_background=4))
+    assert env.action_space.shape == (2,) and env.observation_space.shape == (3, 64, 64)
+    np.testing.assert_allclose(env.action_space.low, [-1.0, -0.3]); np.testing.assert_allclose(env.action_space.high, [1.0, 0.3])
+    obs, info = env.reset()
+    assert obs.shape == (3, 64, 64) and obs.dtype == np.uint8 and info == {}
+    inner = env.env
+    orc = oracle.OracleEnvSet(default_config(num_envs=1, max_agents=inner.engine.A), inner.engine.packed)
+    orc.reset(seed=3)
+    assert np.array_equal(obs, orc.render()[0])
+    total = 0.0
+    for k in range(40):
+        a = np.array([1.0, 0.0], np.float32)            # the notebook's constant action [1, 0]
+        obs, reward, terminated, truncated, info = env.step(a)
+        oobs, orr, ote, otr, oinfo = orc.step(a[None])
+        assert obs.shape == (3, 64, 64) and isinstance(reward, float) and isinstance(terminated, bool) and isinstance(truncated, bool)
+        assert np.array_equal(obs, oobs[0]) and reward == float(orr[0]) and terminated == bool(ote[0]) and truncated == bool(otr[0])
+        for key in ("offroad", "collision", "traffic_light_violation", "is_success", "reached_waypoint_num", "psi_smoothness",
+                    "psi_reward", "dist_reward", "speed_smoothness"):
+            assert key in info
+        assert float(info["offroad"]) == float(oinfo[0, 0]) and info["reached_waypoint_num"] == int(oinfo[0, 4])
+        total += reward
+        if terminated or truncated:
+            break
+    frame = env.render()
+    assert frame.shape == (64, 64, 3)
+    env.close()
+
+
+def test_simulator_interface_surface(oracle):
+    from torchdriveenv_b200.simulator import BatchedSimulator
+    ss = S.traffic_lights(12)
+    sim = BatchedSimulator(ss, num_envs=32, device="cuda:0", seed=5)
+    orc = oracle.OracleEnvSet(default_config(num_envs=32, max_agents=12), sim.engine.packed)
+    orc.reset(seed=5)
+    assert sim.get_state().shape == (32, 1, 4)                       # NPCs are hidden, as IAIWrapper hides them
+    rng = np.random.default_rng(5)
+    for _ in range(10):
+        a = np.stack([rng.uniform(-1, 1, 32), rng.uniform(-0.3, 0.3, 32)], 1).astype(np.float32)
+        sim.step(torch.from_numpy(a).view(32, 1, 2))
+        orc.step(a, render=False, phases=3)
+    assert np.array_equal(sim.get_state().cpu().numpy(), orc.state[:, :1])
+    assert np.array_equal(sim.compute_offroad().cpu().numpy(), orc.infractions[:, :1, 1])
+    assert np.array_equal(sim.compute_collision().cpu().numpy(), orc.infractions[:, :1, 0])
+    assert np.array_equal(sim.compute_traffic_lights_violations().cpu().numpy(), orc.infractions[:, :1, 2])
+    assert np.array_equal(sim.compute_wrong_way().cpu().numpy(), orc.infractions[:, :1, 3])
+    bv = sim.render_egocentric()
+    assert bv.shape == (32, 1, 3, 64, 64) and bv.dtype == torch.uint8
+    assert np.array_equal(bv[:, 0].cpu().numpy(), orc.render())
+    twin = sim.copy()
+    assert torch.equal(twin.get_state(), sim.get_state()) and torch.equal(twin.render_egocentric(), bv)
+    twin.step(torch.zeros(32, 1, 2))
+    assert not torch.equal(twin.get_state(), sim.get_state())        # independent after the copy
+    assert sim.to("cuda:0") is sim
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        sim.to("cpu")
+    full = BatchedSimulator(ss, num_envs=4, device="cuda:0", expose_npcs=True)
+    assert full.get_state().shape == (4, 12, 4) and full.compute_collision().shape == (4, 12)
+
+
+def test_vec_env_frame_stack_and_auto_reset(oracle):
+    from torchdriveenv_b200.gym_env import EnvConfig, TorchDriveVecEnv
+    E = 48
+    cfg = EnvConfig(seed=8, device="cuda:0", max_environment_steps=15)
+    venv = TorchDriveVecEnv(cfg, S.traffic_lights(8), num_envs=E, n_stack=3)
+    obs = venv.reset()
+    assert obs.shape == (E, 9, 64, 64) and obs.dtype == torch.uint8
+    assert bool((obs[:, :6] == 0).all()) and bool((obs[:, 6:] != 0).any())
+    orc = oracle.OracleEnvSet(default_config(num_envs=E, max_agents=8, auto_reset=1, max_environment_steps=15), venv.engine.packed)
+    orc.reset(seed=8)
+    rng = np.random.default_rng(8)
+    frames = [orc.render()]
+    n_done = 0
+    for k in range(25):
+        a = np.stack([rng.uniform(-1, 1, E), rng.uniform(-0.3, 0.3, E)], 1).astype(np.float32)
+        obs, rew, dones, infos = venv.step(a)
+        oobs, orr, ote, otr, oinfo = orc.step(a)
+        assert np.array_equal(obs[:, 6:].cpu().numpy(), oobs) and np.array_equal(rew.cpu().numpy(), orr)
+        d = (ote | otr).astype(bool)
+        assert np.array_equal(dones.cpu().numpy(), d)
+        # channels-first stack: previous frame in the middle slot unless the env just restarted
+        prev = frames[-1]
+        keep = ~d
+        assert np.array_equal(obs[keep][:, 3:6].cpu().numpy(), prev[keep])
+        assert bool((obs[d][:, :6] == 0).all())
+        frames.append(oobs)
+        n_done += int(d.sum())
+        assert set(infos) >= {"offroad", "collision", "traffic_light_violation", "is_success", "terminated", "truncated"}
+    assert n_done > 0
+    stats = venv.episode_statistics()
+    assert stats["episodes"] == n_done and stats["steps"] == 25 * E
+    venv.close()

@@ -1,0 +1,148 @@
+"""Host-side logic that needs no GPU: scenario tables, file loaders, config mirror, sharding."""
+import json
+import os
+
+import numpy as np
+import pytest
+import yaml
+
+from torchdriveenv_b200 import scenarios as S
+from torchdriveenv_b200.distributed import shard_range, summarize
+from torchdriveenv_b200.roofline import bytes_per_env_step, c4_bytes_per_env
+
+
+def test_pack_layout_and_padding():
+    ss = S.validation_mix(6)
+    A = 12
+    p = ss.pack(A)
+    Nm, Ns = len(ss.maps), len(ss.scenarios)
+    assert p["map_tri_offset"].shape == (Nm + 1,) and p["map_tri_offset"][-1] == p["road_tris"].shape[0]
+    assert p["road_tris"].dtype == np.float32 and p["road_tris"].shape[1] == 8
+    assert p["agent_init"].shape == (Ns, A, 4) and p["agent_attr"].shape == (Ns, A, 3)
+    assert p["replay_states"].shape == (p["scen_replay_offset"][-1], A * 4)
+    assert p["replay_mask"].shape == (p["scen_replay_offset"][-1], A)
+    assert (p["replay_mask"][:, 0] == 0).all()                       # the ego is never replayed
+    for k, sc in enumerate(ss.scenarios):
+        n = sc.agent_init.shape[0]
+        assert p["scen_num_agents"][k] == n
+        np.testing.assert_array_equal(p["agent_init"][k, :n], sc.agent_init)
+        assert (p["agent_init"][k, n:] == 0).all()
+    L = ss.maps[4].stoplines.shape[0]
+    assert L > 0 and p["map_light_offset"][5] - p["map_light_offset"][4] == p["map_light_period"][4] * L
+    with pytest.raises(ValueError):
+        ss.pack(3)
+
+
+def test_lane_directions_are_unit_and_follow_the_polyline():
+    m = S.build_polyline_map(S.VALIDATION_POLYLINES["chicken"], "c")
+    d = m.road_tris[:, 6:8]
+    np.testing.assert_allclose(np.linalg.norm(d, axis=1), 1.0, atol=1e-5)
+    # this polyline runs towards -y: the ego lane points down, the oncoming lane up
+    assert (d[:, 1] < -0.9).sum() > 10 and (d[:, 1] > 0.9).sum() > 10
+
+
+def test_subdivide_long_triangles():
+    t = np.array([[0, 0, 1000, 0, 0, 10, 1, 0]], np.float32)
+    out = S.subdivide_long_triangles(t, 200.0)
+    v = out[:, :6].reshape(-1, 3, 2)
+    e = np.linalg.norm(v - np.roll(v, -1, axis=1), axis=2)
+    assert e.max() <= 200.0 + 1e-3 and out.shape[0] >= 5
+    area = 0.5 * np.abs((v[:, 1, 0] - v[:, 0, 0]) * (v[:, 2, 1] - v[:, 0, 1]) - (v[:, 1, 1] - v[:, 0, 1]) * (v[:, 2, 0] - v[:, 0, 0]))
+    assert abs(area.sum() - 5000.0) < 1.0
+    assert (out[:, 6] == 1).all()
+
+
+def test_replay_rollout_follows_the_lane():
+    ss = S.traffic_lights(8)
+    sc = ss.scenarios[0]
+    assert sc.replay_states.shape == (200, 8, 4) and sc.replay_mask[:, 1:].all() and not sc.replay_mask[:, 0].any()
+    step = np.linalg.norm(np.diff(sc.replay_states[:, 1:, :2], axis=0), axis=2)
+    speed = sc.replay_states[0, 1:, 3]
+    moving = step[:100]
+    assert np.all(moving <= speed[None] * 0.1 * 1.05 + 1e-3)
+
+
+def test_shard_range_partitions():
+    for total, ws in ((16384, 8), (10, 3), (5, 8), (65536, 4)):
+        spans = [shard_range(total, r, ws) for r in range(ws)]
+        assert spans[0][0] == 0 and spans[-1][1] == total
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(10, 3, 3)
+
+
+def test_summarize_and_roofline_formula():
+    s = np.zeros(16); s[:9] = [10, 50, 400, 4, 2, 1, 3, 25, 400]
+    out = summarize(s)
+    assert out["mean_return"] == 5 and out["mean_length"] == 40 and out["offroad_rate"] == 0.4 and out["success_rate"] == 0.3
+    assert bytes_per_env_step(16, False) == 1010 and bytes_per_env_step(32, True) == 14274
+    assert c4_bytes_per_env(64) == 1856
+
+
+def test_env_config_defaults_match_reference():
+    from torchdriveenv_b200.gym_env import EnvConfig, Scenario, WaypointSuite
+    c = EnvConfig()
+    assert (c.ego_only, c.max_environment_steps, c.frame_stack, c.waypoint_bonus, c.heading_penalty, c.distance_bonus,
+            c.distance_cutoff, c.use_background_traffic, c.terminated_at_infraction, c.seed, c.render_mode, c.video_res,
+            c.video_fov, c.device) == (False, 200, 3, 100., 25., 1., 0.5, True, True, None, "rgb_array", 1024, 500, None)
+    assert c.simulator.left_handed_coordinates and c.simulator.highlight_ego_vehicle
+    assert Scenario().agent_states is None and WaypointSuite().locations is None
+
+
+def test_yaml_and_json_loaders(tmp_path):
+    from torchdriveenv_b200 import env_utils
+    from torchdriveenv_b200.gym_env import EnvConfig, scenario_set_from_suite
+    suite = dict(locations=["Town01", "Town03"],
+                 waypoint_suite=[[[0.0, 0.0], [10.0, 0.0], [20.0, 5.0]], [[5.0, 5.0], [5.0, 25.0]]],
+                 car_sequence_suite=[{1: [[30.0 + t, 0.0, 0.0, 0.0] for t in range(5)]}, {}],
+                 scenarios=[dict(agent_states=[[30.0, 0.0, 0.0, 0.0]], agent_attributes=[[5.0, 2.0, 2.0]], recurrent_states=[[0.0] * 4]), None])
+    p = tmp_path / "suite.yml"
+    p.write_text(yaml.safe_dump(suite))
+    data = env_utils.load_waypoint_suite_data(str(p))
+    assert data.locations == ["Town01", "Town03"] and data.scenarios[1] is None and data.scenarios[0].agent_attributes == [[5.0, 2.0, 2.0]]
+    ss = scenario_set_from_suite(EnvConfig(), data, n_background=2, seed=0)
+    assert len(ss.maps) == 2 and ss.scenarios[0].agent_init.shape == (4, 4)
+    assert ss.scenarios[0].replay_mask[:5, 1].all() and not ss.scenarios[0].replay_mask[5:, 1].any()
+    np.testing.assert_allclose(ss.scenarios[0].replay_states[3, 1], [33, 0, 0, 0])
+    assert ss.scenarios[1].agent_init.shape == (3, 4)
+    ego_only = scenario_set_from_suite(EnvConfig(ego_only=True), data, n_background=2)
+    assert ego_only.scenarios[0].agent_init.shape == (1, 4)
+    cfgp = tmp_path / "env.yml"
+    cfgp.write_text(yaml.safe_dump(dict(distance_cutoff=0.25, max_environment_steps=100, simulator=dict(offroad_threshold=0.3))))
+    cfg = env_utils.load_env_config(str(cfgp))
+    assert cfg.distance_cutoff == 0.25 and cfg.max_environment_steps == 100 and cfg.simulator.offroad_threshold == 0.3
+    # scenario-builder JSON (env_utils.py:31-105)
+    d = tmp_path / "labeled"; d.mkdir()
+    st = lambda x, y: dict(center=dict(x=x, y=y), orientation=0.5)
+    js = dict(individual_suggestions={"0": dict(states=[st(0, 0), st(10, 0)])},
+              predetermined_agents={"1": dict(states={"0": st(20, 0)}, static_attributes=dict(length=5, width=2, rear_axis_offset=1.5, max_speed=0)),
+                                    "2": dict(states={"0": st(30, 0), "1": st(31, 0)}, static_attributes=dict(length=4.5, width=1.9, rear_axis_offset=1.4))})
+    (d / "carla_Town02_x.json").write_text(json.dumps(js))
+    lab = env_utils.load_labeled_data(str(d))
+    assert lab.locations == ["Town02"] and lab.waypoint_suite[0] == [[0, 0], [10, 0]]
+    assert len(lab.car_sequence_suite[0][1]) == 200 and len(lab.car_sequence_suite[0][2]) == 2
+    assert lab.scenarios[0].agent_attributes[1] == [4.5, 1.9, 1.4]
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/torchdriveenv/data/validation_cases.yml"), reason="reference checkout not present")
+def test_reference_validation_suite_loads():
+    from torchdriveenv_b200 import env_utils
+    from torchdriveenv_b200.gym_env import EnvConfig, scenario_set_from_suite
+    data = env_utils.load_waypoint_suite_data("/root/reference/torchdriveenv/data/validation_cases.yml")
+    assert data.locations == ["Town07", "Town07", "Town03", "Town03", "Town01"]
+    for name, poly in zip(["three_way", "parked_car", "chicken", "roundabout", "traffic_lights"], data.waypoint_suite):
+        np.testing.assert_allclose(np.asarray(poly), np.asarray(S.VALIDATION_POLYLINES[name]), atol=1e-3)
+    ss = scenario_set_from_suite(EnvConfig(), data)
+    assert ss.scenarios[1].replay_states.shape[0] == 300   # parked-car case: 300-step stationary replay
+    ss.pack(ss.max_agents())
+
+
+def test_engine_refuses_to_run_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from torchdriveenv_b200.engine import Engine
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Engine(S.three_way(0), 1)

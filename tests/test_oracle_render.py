@@ -1,0 +1,90 @@
+"""Pins the oracle's birdview: exact equality with an independent numpy restatement of the same
+fixed-point rule, and looser agreement with float64 (no snapping) and cv2.fillPoly renderings."""
+import numpy as np
+import pytest
+
+from torchdriveenv_b200 import scenarios as S
+from torchdriveenv_b200._capi import default_config
+
+from raster_ref import camera, raster_cv2, raster_fixed, raster_float64, world_primitives
+
+
+def _envs(oracle, ss, E, A, seed, steps, **cfg):
+    c = default_config(num_envs=E, max_agents=A, **cfg)
+    packed = ss.pack(A)
+    env = oracle.OracleEnvSet(c, packed)
+    env.reset(seed=seed)
+    rng = np.random.default_rng(seed)
+    for _ in range(steps):
+        env.step(np.stack([rng.uniform(-1, 1, E), rng.uniform(-0.3, 0.3, E)], 1), render=False)
+    return env, c, packed
+
+
+@pytest.mark.parametrize("name,builder,A,lh", [("three_way", S.three_way, 9, 1), ("traffic_lights", lambda: S.traffic_lights(24), 24, 1),
+                                                 ("roundabout", lambda: S.roundabout(12), 12, 0)])
+def test_oracle_render_vs_independent_rasterisers(oracle, name, builder, A, lh):
+    E = 6
+    env, cfg, packed = _envs(oracle, builder(), E, A, seed=5, steps=7, auto_reset=1, left_handed_coordinates=lh)
+    cls = env.render_classes()
+    obs = env.render()
+    pal = np.array([[0, 0, 0], [128, 128, 128], [255, 255, 255], [0, 200, 0], [230, 200, 0], [220, 0, 0], [0, 170, 255],
+                    [60, 90, 220], [250, 120, 0], [200, 220, 255], [255, 230, 150]], np.uint8)
+    same64, samecv = [], []
+    for e in range(E):
+        prims = world_primitives(packed, cfg, env.state[e], env.attr[e], env.env_vars[e], oracle.sincos)
+        cam = camera(cfg, env.state[e, 0], oracle.sincos)
+        ref = raster_fixed(prims, cam)
+        assert np.array_equal(ref, cls[e]), f"{name} env {e}: {(ref != cls[e]).sum()} pixels differ from the fixed-point restatement"
+        assert np.array_equal(obs[e], pal[cls[e]].transpose(2, 0, 1))
+        same64.append((raster_float64(prims, cam) == cls[e]).mean())
+        samecv.append((raster_cv2(prims, cam) == cls[e]).mean())
+        assert (cls[e] == 8).sum() > 10 and cls[e, 32, 32] in (8, 9, 10)   # the ego sits at the image centre
+    assert np.mean(same64) > 0.985, same64   # differences only where snapping / tie rules matter
+    assert np.mean(samecv) > 0.93, samecv    # fillPoly also paints boundary pixels
+
+
+def test_render_orientation_and_handedness(oracle):
+    """Ego faces +x of the image; a point ahead of the ego lands right of centre; a point to the ego's
+    left (+y in a right-handed frame) lands above centre right-handed and below it left-handed."""
+    ss = S.three_way(0)
+    for lh, row_sign in ((1, +1), (0, -1)):
+        cfg = default_config(num_envs=1, max_agents=3, left_handed_coordinates=lh)
+        env = oracle.OracleEnvSet(cfg, ss.pack(3))
+        env.reset(seed=0)
+        env.state[0, 0] = [0, 0, 0.5, 0]
+        env.attr[0, 1:, 3] = 0
+        env.attr[0, 1, :] = [4, 2, 1, 1]
+        c, s = np.cos(0.5), np.sin(0.5)
+        env.state[0, 1] = [8 * c, 8 * s, 0.5, 0]           # 8 m straight ahead
+        cls = env.render_classes()[0]
+        ys, xs = np.nonzero(cls == 7)
+        assert xs.mean() > 40 and abs(ys.mean() - 32) < 1.5
+        env.state[0, 1] = [-8 * s, 8 * c, 0.5, 0]          # 8 m to the left (+90 deg)
+        cls = env.render_classes()[0]
+        ys, xs = np.nonzero(cls == 7)
+        assert abs(xs.mean() - 32) < 1.5 and (ys.mean() - 32) * row_sign > 8
+        env.close()
+
+
+def test_render_fill_rule_shared_edges(oracle):
+    """Two triangles sharing an edge cover every pixel exactly once-or-more (no cracks), and an
+    axis-aligned square covers exactly the pixel centres inside it (top-left rule on the boundary)."""
+    tris = np.array([[0, 0, 20, 0, 20, 20, 1, 0], [0, 0, 20, 20, 0, 20, 1, 0]], np.float32)
+    m = S.MapData(road_tris=tris)
+    sc = S.ScenarioData(0, np.array([[10, 10], [15, 10]], np.float32), 0.0, np.array([[10, 10, 0, 0]], np.float32), np.array([[0.2, 0.2, 1]], np.float32))
+    cfg = default_config(num_envs=1, max_agents=1, fov=64.0)   # 1 px per metre
+    env = oracle.OracleEnvSet(cfg, S.ScenarioSet([m], [sc]).pack(1))
+    env.reset(seed=0)
+    for psi in (0.0, 0.3, 1.1, 2.5):
+        env.state[0, 0] = [10.25, 10.25, psi, 0]
+        cls = env.render_classes()[0]
+        road = (cls >= 1)
+        # the 20 m square is 400 px^2; pixel-centre sampling gives 400 +- boundary effects
+        assert abs(int(road.sum()) - 400) <= 12
+        # no crack along the shared diagonal: the covered region has no holes
+        filled = road.copy()
+        assert (filled[1:-1, 1:-1] | ~(filled[:-2, 1:-1] & filled[2:, 1:-1] & filled[1:-1, :-2] & filled[1:-1, 2:])).all()
+    env.state[0, 0] = [10.0, 10.0, 0.0, 0]   # square spans pixel x in [22, 42): centres 22.5 .. 41.5
+    cls = env.render_classes()[0]
+    ys, xs = np.nonzero(cls >= 1)
+    assert xs.min() == 22 and xs.max() == 41 and ys.min() == 22 and ys.max() == 41

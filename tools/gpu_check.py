@@ -45,7 +45,7 @@ def compare(name, ss, E, A, steps=60, seed=3, **cfg):
 compare("three_way E=4", S.three_way(), 4, 9)
 compare("roundabout E=64 A=16", S.roundabout(16), 64, 16, auto_reset=1)
 compare("traffic_lights E=256 A=32", S.traffic_lights(32), 256, 32, auto_reset=1)
-compare("mix E=64 A=40", S.validation_mix(40), 64, 40, auto_reset=1, randomize_ego_attributes=1, steps=40)
+compare("mix E=64 A=40", S.validation_mix(40), 64, 44, auto_reset=1, randomize_ego_attributes=1, steps=40)
 
 # stateless kernels
 st, at = S.scatter_boxes(512, 64, size=80.0, seed=1, present_p=0.9)

@@ -1,0 +1,98 @@
+"""Scenario / config file loaders with the reference's names (torchdriveenv/env_utils.py:10-123).
+OmegaConf is replaced by PyYAML (the files are plain YAML); the schemas are unchanged:
+WaypointSuite YAML = locations / waypoint_suite / car_sequence_suite / scenarios
+(validation_cases.yml:1,7,84,1290); scenario-builder JSON = individual_suggestions['0'].states and
+predetermined_agents[id].{states, static_attributes} (env_utils.py:31-105)."""
+from __future__ import annotations
+
+import json
+import os
+import random
+from typing import Optional
+
+import yaml
+
+from .gym_env import EnvConfig, Scenario, SimulatorConfig, WaypointSuite
+
+
+def construct_env_config(raw_config) -> EnvConfig:
+    raw = dict(raw_config)
+    sim = raw.pop("simulator", None)
+    cfg = EnvConfig(**raw)
+    if isinstance(sim, dict):
+        cfg.simulator = SimulatorConfig(**{k: v for k, v in sim.items() if k in SimulatorConfig.__dataclass_fields__})
+    return cfg
+
+
+def load_env_config(yaml_path) -> EnvConfig:
+    with open(yaml_path) as f:
+        return construct_env_config(yaml.safe_load(f))
+
+
+def load_waypoint_suite_data(yaml_path) -> WaypointSuite:
+    with open(yaml_path) as f:
+        data = yaml.load(f, Loader=getattr(yaml, "CSafeLoader", yaml.SafeLoader))
+    suite = WaypointSuite(**data)
+    if suite.scenarios is not None:
+        suite.scenarios = [Scenario(agent_states=s["agent_states"], agent_attributes=s["agent_attributes"],
+                                    recurrent_states=s.get("recurrent_states")) if s is not None else None
+                           for s in suite.scenarios]
+    return suite
+
+
+def load_labeled_data(data_dir) -> WaypointSuite:
+    """Scenario-builder JSON directory -> WaypointSuite (env_utils.py:31-105)."""
+    suite = WaypointSuite(locations=[], waypoint_suite=[], car_sequence_suite=[], scenarios=[])
+    for json_file in sorted(os.listdir(data_dir)):
+        if not json_file.endswith(".json"):
+            continue
+        suite.locations.append(json_file.split('_')[1])
+        with open(os.path.join(data_dir, json_file)) as f:
+            data = json.load(f)
+        suite.waypoint_suite.append([[s['center']['x'], s['center']['y']] for s in data['individual_suggestions']['0']['states']])
+        scenario, car_sequences = None, None
+        agents = data.get("predetermined_agents")
+        if agents is not None:
+            states, attrs, rec = [], [], []
+            for key in agents:
+                ag = agents[key]
+                speed = random.randint(5, 10) if len(ag['states']) == 1 else 0
+                s0 = ag['states']['0']
+                states.append([s0['center']['x'], s0['center']['y'], s0['orientation'], speed])
+                sa = ag['static_attributes']
+                attrs.append([sa['length'], sa['width'], sa['rear_axis_offset']])
+                rec.append([0] * 132)
+            if states:
+                scenario = Scenario(agent_states=states, agent_attributes=attrs, recurrent_states=rec)
+            car_sequences = {}
+            for key in agents:
+                ag = agents[key]
+                s0 = ag['states']['0']
+                if ag['static_attributes'].get("max_speed", None) == 0:
+                    car_sequences[int(key)] = [[s0['center']['x'], s0['center']['y'], s0['orientation'], 0] for _ in range(200)]
+                elif len(ag['states']) > 1:
+                    car_sequences[int(key)] = [[ag['states'][i]['center']['x'], ag['states'][i]['center']['y'],
+                                                ag['states'][i]['orientation'], 0] for i in ag['states']]
+        suite.scenarios.append(scenario)
+        suite.car_sequence_suite.append(car_sequences)
+    return suite
+
+
+def _load_default_data(file_name) -> Optional[WaypointSuite]:
+    roots = [os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")]
+    extra = os.environ.get("TORCHDRIVEENV_DATA")
+    if extra:
+        roots.append(extra)
+    for root in roots:
+        path = os.path.join(root, file_name)
+        if os.path.exists(path):
+            return load_waypoint_suite_data(path)
+    return None
+
+
+def load_default_validation_data():
+    return _load_default_data("validation_cases.yml")
+
+
+def load_default_train_data():
+    return _load_default_data("training_cases.yml")

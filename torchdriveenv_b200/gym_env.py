@@ -1,0 +1,397 @@
+"""gym.Env-level API of the reference, served by the CUDA engine.
+
+Mirrors torchdriveenv/gym_env.py of the reference name for name: ``EnvConfig`` :34-54, ``Scenario``
+:56-60, ``WaypointSuite`` :63-68, ``GymEnv`` :71-177, ``build_simulator`` :179-300,
+``WaypointSuiteEnv`` :303-437, ``SingleAgentWrapper`` :440-487.  What the reference computes per step
+in Python on a B=1 torchdrivesim simulator (reward :396-411, termination :413-417, truncation
+:134-135, info :419-437, waypoint progress :378-394) is computed inside the fused CUDA step kernel;
+this module only marshals tensors.  ``TorchDriveVecEnv`` is the batched sibling (SB3 VecEnv shape,
+examples/rl_training.py:159-160) that steps thousands of envs in lockstep.
+
+gymnasium / stable-baselines3 are optional: when absent the spaces are small stand-ins.
+"""
+from __future__ import annotations
+
+import logging
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from ._capi import INFO_COLUMNS, TDE_OBS_H, TDE_OBS_W
+from .engine import Engine
+from .scenarios import (MapData, ScenarioData, ScenarioSet, build_polyline_map, place_npcs)
+from .simulator import BatchedSimulator
+
+logger = logging.getLogger(__name__)
+
+try:  # pragma: no cover - gymnasium is not installed in the build image
+    import gymnasium as gym
+    _Env, _Wrapper, _Box = gym.Env, gym.Wrapper, gym.spaces.Box
+except Exception:  # minimal stand-ins with the attributes the reference uses
+    gym = None
+
+    class _Box:
+        def __init__(self, low, high, shape=None, dtype=np.float32):
+            self.dtype = np.dtype(dtype)
+            if shape is None:
+                shape = np.shape(low)
+            self.shape = tuple(shape)
+            self.low = np.broadcast_to(np.asarray(low, self.dtype), self.shape).copy()
+            self.high = np.broadcast_to(np.asarray(high, self.dtype), self.shape).copy()
+
+        def sample(self):
+            if np.issubdtype(self.dtype, np.integer):
+                return np.random.randint(self.low, self.high.astype(np.int64) + 1).astype(self.dtype)
+            return np.random.uniform(self.low, self.high).astype(self.dtype)
+
+        def contains(self, x):
+            x = np.asarray(x)
+            return x.shape == self.shape and bool(np.all(x >= self.low) and np.all(x <= self.high))
+
+    class _Env:
+        metadata: Dict = {}
+
+    class _Wrapper(_Env):
+        def __init__(self, env):
+            self.env = env
+
+        def __getattr__(self, name):
+            return getattr(self.env, name)
+
+        def reset(self, **kwargs):
+            return self.env.reset(**kwargs)
+
+        def step(self, action):
+            return self.env.step(action)
+
+
+@dataclass
+class SimulatorConfig:
+    """The TorchDriveConfig / RendererConfig values the reference env relies on (gym_env.py:46-49)."""
+    left_handed_coordinates: bool = True
+    highlight_ego_vehicle: bool = True
+    offroad_threshold: float = 0.5
+    fov: float = 35.0
+    tl_rear_factor: float = 0.1
+
+
+@dataclass
+class EnvConfig:
+    ego_only: bool = False
+    max_environment_steps: int = 200
+    frame_stack: int = 3
+    waypoint_bonus: float = 100.
+    heading_penalty: float = 25.
+    distance_bonus: float = 1.
+    distance_cutoff: float = 0.5
+    use_background_traffic: bool = True
+    terminated_at_infraction: bool = True
+    seed: Optional[int] = None
+    simulator: SimulatorConfig = field(default_factory=SimulatorConfig)
+    render_mode: Optional[str] = "rgb_array"
+    video_filename: Optional[str] = "rendered_video.mp4"
+    video_res: Optional[int] = 1024
+    video_fov: Optional[float] = 500
+    device: Optional[str] = None
+
+
+@dataclass
+class Scenario:
+    agent_states: List[List[float]] = None
+    agent_attributes: List[List[float]] = None
+    recurrent_states: List[List[float]] = None
+
+
+@dataclass
+class WaypointSuite:
+    locations: List[str] = None
+    waypoint_suite: List[List[List[float]]] = None
+    car_sequence_suite: List[Optional[Dict[int, List[List[float]]]]] = None
+    scenarios: List[Optional[Scenario]] = None
+
+
+def engine_config(cfg: EnvConfig, **extra) -> Dict:
+    sim = cfg.simulator
+    out = dict(max_environment_steps=int(cfg.max_environment_steps), waypoint_bonus=float(cfg.waypoint_bonus),
+               heading_penalty=float(cfg.heading_penalty), distance_bonus=float(cfg.distance_bonus),
+               distance_cutoff=float(cfg.distance_cutoff), terminated_at_infraction=int(bool(cfg.terminated_at_infraction)),
+               left_handed_coordinates=int(bool(sim.left_handed_coordinates)), offroad_threshold=float(sim.offroad_threshold),
+               fov=float(sim.fov), tl_rear_factor=float(sim.tl_rear_factor))
+    out.update(extra)
+    return out
+
+
+def scenario_set_from_suite(cfg: EnvConfig, data: WaypointSuite, n_background: int = 0, seed: int = 0,
+                            map_builder=None) -> ScenarioSet:
+    """Scenario tables from a WaypointSuite, following build_simulator (gym_env.py:179-300): waypoints
+    :252-257, predetermined agents :222-228, replay tensors from car sequences :275-283.  The CARLA map
+    assets (find_map_config :312) are not available offline, so each entry gets a synthetic lane mesh
+    extruded from its own waypoint polyline; the Inverted AI background agents (:236-238) are replaced
+    by ``n_background`` constant-speed replay NPCs."""
+    maps: List[MapData] = []
+    scen: List[ScenarioData] = []
+    rng = np.random.default_rng(seed)
+    builder = map_builder or (lambda poly, name: build_polyline_map(poly, name, with_lights=True))
+    for k, poly in enumerate(data.waypoint_suite):
+        poly = np.asarray(poly, np.float64)
+        name = f"{(data.locations[k] if data.locations else 'map')}_{k}"
+        maps.append(builder(poly, name))
+        d = poly[1] - poly[0]
+        heading = float(np.arctan2(d[1], d[0]))
+        states = [[poly[0][0], poly[0][1], heading, 0.0]]
+        attrs = [[5.0, 2.0, 0.9]]
+        sc = data.scenarios[k] if data.scenarios is not None else None
+        if not cfg.ego_only and sc is not None and sc.agent_states is not None:
+            states += [list(map(float, s)) for s in sc.agent_states]
+            attrs += [list(map(float, a)) for a in sc.agent_attributes]
+        n_pre = len(states)
+        seqs = data.car_sequence_suite[k] if (data.car_sequence_suite is not None and not cfg.ego_only) else None
+        bg_states = bg_attrs = bg_rep = bg_mask = None
+        if not cfg.ego_only and n_background > 0:
+            bg_states, bg_attrs, bg_rep, bg_mask = place_npcs(poly, n_background, rng)
+            states += bg_states.tolist(); attrs += bg_attrs.tolist()
+        n = len(states)
+        T = 0
+        if seqs:
+            T = max(len(v) for v in seqs.values())
+        if bg_rep is not None:
+            T = max(T, bg_rep.shape[0])
+        rs = rm = None
+        if T > 0:
+            rs = np.zeros((T, n, 4), np.float32); rm = np.zeros((T, n), np.uint8)
+            if seqs:
+                for idx, seq in seqs.items():  # dict key = agent slot (gym_env.py:279)
+                    idx = int(idx)
+                    if 0 < idx < n and len(seq) > 0:
+                        arr = np.asarray(seq, np.float32).reshape(-1, 4)
+                        rs[: arr.shape[0], idx] = arr; rm[: arr.shape[0], idx] = 1
+            if bg_rep is not None:
+                rs[: bg_rep.shape[0], n_pre:] = bg_rep; rm[: bg_rep.shape[0], n_pre:] = bg_mask
+        scen.append(ScenarioData(map_index=k, waypoints=poly.astype(np.float32), start_heading=heading,
+                                 agent_init=np.asarray(states, np.float32), agent_attr=np.asarray(attrs, np.float32),
+                                 replay_states=rs, replay_mask=rm, name=name))
+    return ScenarioSet(maps, scen)
+
+
+def _info_from_row(row: np.ndarray, as_tensor_device=None) -> Dict:
+    """get_info (gym_env.py:419-437): infraction values as B x A tensors, the rest as Python scalars."""
+    def t(v):
+        x = torch.tensor([[float(v)]])
+        return x.to(as_tensor_device) if as_tensor_device is not None else x
+    c = INFO_COLUMNS
+    return dict(
+        offroad=t(row[c["offroad"]]), collision=t(row[c["collision"]]),
+        traffic_light_violation=t(row[c["traffic_light_violation"]]),
+        is_success=bool(row[c["is_success"]] != 0), reached_waypoint_num=int(row[c["reached_waypoint_num"]]),
+        psi_smoothness=float(row[c["psi_smoothness"]]), psi_reward=float(row[c["psi_reward"]]),
+        dist_reward=float(row[c["dist_reward"]]), speed_smoothness=float(row[c["speed_smoothness"]]),
+        wrong_way=float(row[c["wrong_way"]]),
+    )
+
+
+class GymEnv(_Env):
+    metadata = {"render_modes": ["video", "rgb_array"], "render_fps": 10}
+
+    def __init__(self, cfg: EnvConfig, simulator):
+        if cfg.render_mode is not None and cfg.render_mode not in self.metadata["render_modes"]:
+            raise NotImplementedError
+        self.render_mode = cfg.render_mode
+        action_range = np.ndarray(shape=(2, 2), dtype=np.float32)
+        action_range[:, 0] = (-1.0, 1.0)   # acceleration (gym_env.py:83)
+        action_range[:, 1] = (-0.3, 0.3)   # steering (gym_env.py:84)
+        self.max_environment_steps = cfg.max_environment_steps
+        self.environment_steps = 0
+        self.action_space = _Box(low=action_range[0], high=action_range[1], dtype=np.float32)
+        self.observation_space = _Box(low=0, high=255, shape=(3, TDE_OBS_H, TDE_OBS_W), dtype=np.uint8)
+        self.reward_range = (-float('inf'), float('inf'))
+        self.collision_threshold = 0.0
+        self.offroad_threshold = 0.0
+        self.config = cfg
+        self.simulator = simulator
+        self.current_action = None
+        self.last_birdview = None
+
+    def is_truncated(self):
+        return self.environment_steps >= self.max_environment_steps
+
+    def seed(self, seed=None):
+        pass
+
+    def render(self):
+        if self.render_mode == 'rgb_array':
+            birdview = self.simulator.render_egocentric().cpu().numpy()
+            return np.transpose(birdview.squeeze(), axes=(1, 2, 0))
+        raise NotImplementedError
+
+    def close(self):
+        sim = getattr(self, "simulator", None)
+        if sim is not None and hasattr(sim, "engine"):
+            sim.engine.close()
+
+
+def build_simulator(cfg: EnvConfig, scenarios: ScenarioSet, device, num_envs: int = 1, seed: int = 0,
+                    **extra) -> BatchedSimulator:
+    """Counterpart of build_simulator (gym_env.py:179-300): the scenario tables play the role of the
+    map config + agent tensors, the returned object exposes the SimulatorInterface call surface."""
+    return BatchedSimulator(scenarios, num_envs=num_envs, device=device, seed=seed, **engine_config(cfg, **extra))
+
+
+class WaypointSuiteEnv(GymEnv):
+    """Single environment with the reference's API (B = A = 1 at the interface)."""
+
+    def __init__(self, cfg: EnvConfig, data, n_background: int = 0):
+        self.config = cfg
+        if cfg.device is None:
+            if not torch.cuda.is_available():
+                raise RuntimeError("torchdriveenv_b200 needs a CUDA (sm_100a) device: there is no CPU fallback")
+            self.torch_device = torch.device('cuda')
+        else:
+            self.torch_device = torch.device(cfg.device)
+        self._seed = int(cfg.seed) if cfg.seed is not None else int(np.random.randint(0, 2**31 - 1))
+        logger.info(f"seed: {self._seed}")
+        self.scenario_set = data if isinstance(data, ScenarioSet) else scenario_set_from_suite(cfg, data, n_background, self._seed)
+        super().__init__(cfg=cfg, simulator=None)
+        self.simulator = build_simulator(cfg, self.scenario_set, str(self.torch_device), num_envs=1, seed=self._seed)
+        self.engine: Engine = self.simulator.engine
+        self.reached_waypoint_num = 0
+        self.last_obs = self.last_reward = self.last_info = None
+
+    def reset(self, seed: Optional[int] = None, options: Optional[dict] = None):
+        if seed is not None:
+            self._seed = int(seed)
+        self.engine.reset(seed=self._seed)   # the engine's episode counter varies the draw per episode
+        self.environment_steps = 0
+        self.reached_waypoint_num = 0
+        self.last_obs = self.last_reward = self.last_info = None
+        v = self.engine.get_env_vars()[0].cpu().numpy()
+        self.current_waypoint_suite_idx = int(v[0])
+        self.current_target_idx = int(v[2])
+        return self.get_obs(), {}
+
+    def get_obs(self):
+        return self.simulator.render_egocentric().cpu().numpy().astype(np.uint8)
+
+    def step(self, action):
+        a = torch.as_tensor(np.asarray(action.cpu() if torch.is_tensor(action) else action, dtype=np.float32)).reshape(-1)[:2]
+        obs, rew, term, trunc, info = self.engine.step(a.view(1, 2))
+        self.simulator._infractions_valid = True
+        self.environment_steps += 1
+        obs_np = obs.unsqueeze(1).cpu().numpy()
+        row = info[0].cpu().numpy()
+        reward = float(rew[0].item())
+        terminated, truncated = bool(term[0].item()), bool(trunc[0].item())
+        info_d = _info_from_row(row, self.torch_device)
+        self.reached_waypoint_num = info_d["reached_waypoint_num"]
+        self.last_obs, self.last_reward, self.last_info = obs_np, reward, info_d
+        return obs_np, reward, terminated, truncated, info_d
+
+    def is_terminated(self):
+        if not self.config.terminated_at_infraction:
+            return False
+        s = self.simulator
+        return bool(((s.compute_offroad() > 0) | (s.compute_collision() > 0) | (s.compute_traffic_lights_violations() > 0)).item())
+
+
+class SingleAgentWrapper(_Wrapper):
+    """Removes batch and agent dimensions from the environment interface (gym_env.py:440-487)."""
+
+    def __init__(self, env):
+        super().__init__(env)
+
+    def reset(self, **kwargs):
+        obs, _ = self.env.reset(**kwargs)
+        return self.transform_out(obs), _
+
+    def step(self, action):
+        action = torch.Tensor(np.asarray(action, dtype=np.float32)).unsqueeze(0).unsqueeze(0)
+        obs, reward, terminated, truncated, info = self.env.step(action)
+        return self.transform_out(obs), self.transform_out(reward), self.transform_out(terminated), truncated, self.transform_out(info)
+
+    def transform_out(self, x):
+        if torch.is_tensor(x):
+            t = x.squeeze(0).squeeze(0).cpu()
+        elif isinstance(x, dict):
+            t = {k: self.transform_out(v) for (k, v) in x.items()}
+        elif isinstance(x, np.ndarray):
+            t = self.transform_out(torch.tensor(x)).cpu().numpy()
+        else:
+            t = x
+        return t
+
+    def render(self, *args, **kwargs):
+        return self.env.render(*args, **kwargs)
+
+    def close(self):
+        self.env.close()
+
+
+class TorchDriveVecEnv:
+    """E environments stepped in lockstep on one GPU with the SB3 ``VecEnv`` call shape
+    (examples/rl_training.py:159-160: SubprocVecEnv + VecFrameStack(n_stack, channels_order="first")).
+
+    ``reset() -> obs[E, 3*n_stack, 64, 64]``; ``step(actions[E, 2]) -> (obs, rewards[E], dones[E], infos)``;
+    finished envs are re-initialised inside the step kernel (auto-reset), their frame stack restarts.
+    Outputs stay on the GPU as torch tensors (``output="torch"``) or are copied to numpy (``"numpy"``).
+    ``infos`` is a dict of per-env arrays (columns of get_info :419-437), not a list of dicts.
+    """
+
+    def __init__(self, cfg: EnvConfig, data, num_envs: int, n_stack: Optional[int] = None, n_background: int = 0,
+                 device: Optional[str] = None, output: str = "torch", env_index_offset: int = 0, seed: Optional[int] = None):
+        self.config = cfg
+        self.num_envs = int(num_envs)
+        self.n_stack = int(n_stack if n_stack is not None else 1)
+        self.output = output
+        self._seed = int(seed if seed is not None else (cfg.seed if cfg.seed is not None else 0))
+        self.scenario_set = data if isinstance(data, ScenarioSet) else scenario_set_from_suite(cfg, data, n_background, self._seed)
+        self.engine = Engine(self.scenario_set, self.num_envs, device=device or cfg.device,
+                             **engine_config(cfg, auto_reset=1, env_index_offset=int(env_index_offset)))
+        self.device = self.engine.device
+        self.action_space = _Box(low=np.array([-1.0, -0.3], np.float32), high=np.array([1.0, 0.3], np.float32), dtype=np.float32)
+        self.observation_space = _Box(low=0, high=255, shape=(3 * self.n_stack, TDE_OBS_H, TDE_OBS_W), dtype=np.uint8)
+        self._stack = torch.zeros((self.num_envs, 3 * self.n_stack, TDE_OBS_H, TDE_OBS_W), dtype=torch.uint8, device=self.device)
+        self._actions = None
+
+    def _push(self, obs: torch.Tensor, restart: Optional[torch.Tensor]):
+        if self.n_stack == 1:
+            self._stack = obs
+            return
+        self._stack = torch.roll(self._stack, shifts=-3, dims=1)
+        if restart is not None and bool(restart.any()):
+            self._stack[restart] = 0   # VecFrameStack zeroes the stack of an env that just reset
+        self._stack[:, -3:] = obs
+
+    def _out(self, t: torch.Tensor):
+        return t.cpu().numpy() if self.output == "numpy" else t
+
+    def reset(self):
+        self.engine.reset(seed=self._seed)
+        obs = self.engine.render()
+        self._stack.zero_()
+        self._push(obs, None)
+        return self._out(self._stack)
+
+    def step_async(self, actions):
+        self._actions = actions
+
+    def step_wait(self):
+        a = torch.as_tensor(self._actions, dtype=torch.float32)
+        obs, rew, term, trunc, info = self.engine.step(a)
+        dones = (term | trunc).bool()
+        self._push(obs, dones)
+        infos = {k: self._out(info[:, i]) for k, i in INFO_COLUMNS.items()}
+        infos["terminated"], infos["truncated"] = self._out(term.bool()), self._out(trunc.bool())
+        return self._out(self._stack), self._out(rew), self._out(dones), infos
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def episode_statistics(self, reset: bool = False) -> Dict[str, float]:
+        from ._capi import STAT_NAMES
+        s = self.engine.episode_stats(reset=reset)
+        return {n: float(s[i]) for i, n in enumerate(STAT_NAMES)}
+
+    def close(self):
+        self.engine.close()
