@@ -29,7 +29,8 @@ def test_single_env_api_matches_reference_shapes(oracle):
     assert obs.shape == (3, 64, 64) and obs.dtype == np.uint8 and info == {}
     inner = env.env
     orc = oracle.OracleEnvSet(default_config(num_envs=1, max_agents=inner.engine.A), inner.engine.packed)
-    orc.reset(seed=3)
+    orc.reset(seed=3)   # the simulator is reset once when it is built ...
+    orc.reset(seed=3)   # ... and once more by env.reset(): second episode of the same seed
     assert np.array_equal(obs, orc.render()[0])
     total = 0.0
     for k in range(40):

@@ -31,8 +31,8 @@ struct tde_handle {
     unsigned long long seed = 0;
     bool uploaded = false, was_reset = false;
     long long launches = 0;
-    int grid_step = 0;
-    size_t smem_step = 0;
+    int grid_phys = 0, grid_render = 0;
+    size_t smem_render = 0;
     // device staging for tde_step_host
     float* h_actions = nullptr; uint8_t* h_obs = nullptr; float* h_reward = nullptr;
     uint8_t *h_term = nullptr, *h_trunc = nullptr; float* h_info = nullptr;
@@ -219,16 +219,20 @@ static void free_scenarios(tde_handle* h) {
     h->uploaded = false;
 }
 
+// persistent grids: a multiple of the SM count (resident blocks per SM from the occupancy calculator)
 template <int AH>
 static int configure_kernels(tde_handle* h) {
-    size_t smem = sizeof(WarpScratch) * TDE_WARPS_PER_BLOCK;
-    CUDA_TRY(h, cudaFuncSetAttribute(tde_step_kernel<AH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    size_t smem = sizeof(RenderScratch) * TDE_WARPS_PER_BLOCK;
+    CUDA_TRY(h, cudaFuncSetAttribute(tde_render_kernel<AH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tde_step_kernel<AH>, TDE_WARPS_PER_BLOCK * 32, smem));
+    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tde_render_kernel<AH>, TDE_WARPS_PER_BLOCK * 32, smem));
     if (per_sm < 1) per_sm = 1;
-    h->smem_step = smem;
+    h->smem_render = smem;
     int want = (h->E + TDE_WARPS_PER_BLOCK - 1) / TDE_WARPS_PER_BLOCK;
-    h->grid_step = std::max(1, std::min(want, per_sm * h->sm_count));
+    h->grid_render = std::max(1, std::min(want, per_sm * h->sm_count));
+    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tde_physics_kernel<AH>, TDE_WARPS_PER_BLOCK * 32, 0));
+    if (per_sm < 1) per_sm = 1;
+    h->grid_phys = std::max(1, std::min(want, per_sm * h->sm_count));
     return TDE_OK;
 }
 
@@ -341,6 +345,28 @@ extern "C" int tde_upload_scenarios(tde_handle* h, const tde_scenario_set* s) {
         uint8_t* lights = nullptr;
         if ((rc = dev_upload(h, &lights, s->light_states + lo, (size_t)std::max(ln, 0)))) return rc;
         M.lights = lights; M.period = nl > 0 ? P : 0;
+        // bounding boxes of runs of 32 triangles (render-time culling)
+        auto chunk_boxes = [&](const float* base, int count, int stride) {
+            std::vector<float> bb;
+            for (int c0 = 0; c0 < count; c0 += 32) {
+                float lx = INFINITY, ly = INFINITY, hx = -INFINITY, hy = -INFINITY;
+                for (int t = c0; t < std::min(count, c0 + 32); ++t)
+                    for (int k = 0; k < 3; ++k) {
+                        float x = base[(size_t)t * stride + 2 * k], y = base[(size_t)t * stride + 2 * k + 1];
+                        lx = std::min(lx, x); hx = std::max(hx, x); ly = std::min(ly, y); hy = std::max(hy, y);
+                    }
+                bb.insert(bb.end(), {lx, ly, hx, hy});
+            }
+            return bb;
+        };
+        {
+            std::vector<float> tb = chunk_boxes(s->road_tris + 8 * (size_t)t0, nt, 8);
+            std::vector<float> mb = chunk_boxes(s->mark_tris + 6 * (size_t)k0, nk, 6);
+            float *tbd = nullptr, *mbd = nullptr;
+            if ((rc = dev_upload(h, &tbd, tb.data(), tb.size()))) return rc;
+            if ((rc = dev_upload(h, &mbd, mb.data(), mb.size()))) return rc;
+            M.tri_chunk = (const float4*)tbd; M.mark_chunk = (const float4*)mbd;
+        }
         Grid g = build_grid(s->road_tris + 8 * (size_t)t0, nt);
         int* cs = nullptr; uint16_t* items = nullptr;
         if ((rc = dev_upload(h, &cs, g.cell_start.data(), g.cell_start.size()))) return rc;
@@ -458,10 +484,19 @@ extern "C" int tde_step_phases(tde_handle* h, int32_t phases, const float* actio
     p.phases = phases; p.actions = actions; p.obs = obs; p.reward = reward; p.terminated = terminated;
     p.truncated = truncated; p.info = info;
     cudaStream_t st = (cudaStream_t)stream;
-    if (h->A <= 32) tde_step_kernel<1><<<h->grid_step, TDE_WARPS_PER_BLOCK * 32, h->smem_step, st>>>(p);
-    else tde_step_kernel<2><<<h->grid_step, TDE_WARPS_PER_BLOCK * 32, h->smem_step, st>>>(p);
-    CUDA_TRY(h, cudaGetLastError());
-    h->launches++;
+    const int threads = TDE_WARPS_PER_BLOCK * 32;
+    if (phases & (TDE_PH_KINEMATICS | TDE_PH_INFRACTIONS | TDE_PH_REWARD)) {
+        if (h->A <= 32) tde_physics_kernel<1><<<h->grid_phys, threads, 0, st>>>(p);
+        else tde_physics_kernel<2><<<h->grid_phys, threads, 0, st>>>(p);
+        CUDA_TRY(h, cudaGetLastError());
+        h->launches++;
+    }
+    if ((phases & TDE_PH_RENDER) && obs) {
+        if (h->A <= 32) tde_render_kernel<1><<<h->grid_render, threads, h->smem_render, st>>>(p);
+        else tde_render_kernel<2><<<h->grid_render, threads, h->smem_render, st>>>(p);
+        CUDA_TRY(h, cudaGetLastError());
+        h->launches++;
+    }
     return TDE_OK;
 }
 

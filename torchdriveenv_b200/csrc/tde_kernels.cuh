@@ -1,11 +1,14 @@
 // tde_kernels.cuh — the fused per-timestep kernel and its helpers (sm_100a).
 //
-// One warp owns one environment for the whole step: lanes are agents during the physics phases
-// (bicycle step / NPC replay, all-pairs SAT, corner-to-lane-mesh offroad, red-light stop lines,
-// wrong-way, reward + termination + bookkeeping) and primitives / image rows during the birdview
-// phase.  Nothing is exchanged between warps, so there is no block-level synchronisation on the
-// step path except the one-time staging of the lane mesh into shared memory.
+// Two kernels per env step, one warp per environment in both:
+//   tde_physics_kernel  lanes = agents: bicycle step / NPC replay, all-pairs SAT, corner-to-lane-mesh
+//                       offroad, red-light stop lines, wrong-way, reward + termination + bookkeeping,
+//                       episode statistics, in-kernel auto-reset;
+//   tde_render_kernel   lanes = primitives, then image rows: the egocentric 3x64x64 birdview.
+// Nothing is exchanged between warps, so there is no block-level synchronisation on the step path.
 #pragma once
+#include <climits>
+
 #include "tde_device.cuh"
 #include "../../include/tde_b200.h"
 
@@ -19,6 +22,8 @@ struct MapDev {
     const uint8_t* lights;      // [period][nstop]
     const int* cell_start;      // [gnx*gny+1]
     const uint16_t* cell_items; // nearest-candidate triangle ids per grid cell
+    const float4* tri_chunk;    // bbox (lox loy hix hiy) of every run of 32 road triangles
+    const float4* mark_chunk;   // same for lane-marking triangles
     int ntri, nmark, nstop, period;
     float gx0, gy0, inv_cell;
     int gnx, gny;
@@ -62,10 +67,17 @@ struct StepParams {
 
 struct Cam { float ex, ey, ce, se, ppm, ppmy; };
 
-struct WarpScratch {
-    float4 box[TDE_MAX_AGENTS * 2];                  // Box as two float4
-    unsigned long long span[32 * TDE_SPAN_STRIDE];   // one 32-row band, [row][lane]
-    unsigned long long planes[64 * 4];               // [row][bit-plane] class-index image
+#define TDE_BAND_ROWS 16
+
+struct PhysScratch {  // per warp, physics kernel
+    float4 box[TDE_MAX_AGENTS * 2];  // Box as two float4
+};
+
+struct RenderScratch {  // per warp, render kernel
+    uint4 qv[64];                                              // queue of snapped primitives: 4 x (x | y << 16)
+    unsigned long long span[TDE_BAND_ROWS * TDE_SPAN_STRIDE];  // one 16-row band of coverage spans, [row][primitive]
+    unsigned long long planes[TDE_OBS_H * 4];                  // [row][bit-plane] class-index image
+    unsigned char qc[64];                                      // class | n_vertices << 4
 };
 
 __device__ __forceinline__ Box ld_box(const float4* sb, int a) {
@@ -82,7 +94,7 @@ __device__ __forceinline__ void st_box(float4* sb, int a, const Box& b) {
 
 // squared distance from p to the road mesh of map M (0 on the road); exact: the grid cell lists hold
 // every triangle that can be nearest for any point of the cell, points off the grid scan all triangles
-__device__ __forceinline__ float mesh_dist2(const MapDev& M, float px, float py) {
+__device__ __noinline__ float mesh_dist2(const MapDev& M, float px, float py) {
     float best = INFINITY;
     float fx = floorf((px - M.gx0) * M.inv_cell), fy = floorf((py - M.gy0) * M.inv_cell);
     bool in_grid = fx >= 0.0f && fy >= 0.0f && fx < (float)M.gnx && fy < (float)M.gny;
@@ -118,7 +130,7 @@ __device__ __forceinline__ float offroad_box(const MapDev& M, const Box& b, floa
 }
 
 // compute_wrong_way: max(-cos(psi - lane_dir), 0), min over the triangles under the centre
-__device__ __forceinline__ float wrong_way_box(const MapDev& M, const Box& b) {
+__device__ __noinline__ float wrong_way_box(const MapDev& M, const Box& b) {
     float best = INFINITY;
     float fx = floorf((b.x - M.gx0) * M.inv_cell), fy = floorf((b.y - M.gy0) * M.inv_cell);
     bool in_grid = fx >= 0.0f && fy >= 0.0f && fx < (float)M.gnx && fy < (float)M.gny;
@@ -146,7 +158,7 @@ __device__ __forceinline__ int light_state_at(const MapDev& M, int step, int pha
 }
 
 // TrafficLightControl.compute_violation: rear strip of the agent box vs red stop lines
-__device__ __forceinline__ float tl_violation_box(const MapDev& M, const Box& b, float rear_factor, int step, int phase) {
+__device__ __noinline__ float tl_violation_box(const MapDev& M, const Box& b, float rear_factor, int step, int phase) {
     float length = 2.0f * b.hl;  // exact: hl = 0.5f*length
     float len2 = length * rear_factor;
     float back = 0.5f * (length - len2);
@@ -226,23 +238,21 @@ __device__ __forceinline__ void store_vars(const StepParams& p, int e, int lane,
 
 // ---------------------------------------------------------------- birdview rasteriser
 
-struct LanePrim {
-    int x[4], y[4];
-    int n;    // 0 = nothing to draw
-    int cls;
-};
-
 __device__ __forceinline__ int snap16(float f) {
     float r = rintf(f * 16.0f);
     r = fminf(fmaxf(r, -8191.0f), 8191.0f);
     return (int)r;
 }
+__device__ __forceinline__ unsigned pack_xy(int x, int y) { return ((unsigned)x & 0xffffu) | ((unsigned)y << 16); }
+__device__ __forceinline__ int unpack_x(unsigned w) { return (int)(w << 16) >> 16; }
+__device__ __forceinline__ int unpack_y(unsigned w) { return (int)w >> 16; }
 
-// world -> pixel (translate to ego, rotate by -psi, scale) + viewport test + snap to 1/16 px
+// world -> pixel (translate to ego, rotate by -psi, scale), viewport test, snap to the 1/16-px grid.
+// Returns false when the primitive's float bounding box misses the viewport grown by one pixel.
 template <int N>
-__device__ __forceinline__ LanePrim make_prim(const Cam& cam, const float (&wx)[4], const float (&wy)[4], int cls, bool valid) {
-    LanePrim pr;
+__device__ __forceinline__ bool project_prim(const Cam& cam, const float (&wx)[4], const float (&wy)[4], uint4& out) {
     float minx = INFINITY, maxx = -INFINITY, miny = INFINITY, maxy = -INFINITY;
+    unsigned v[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         if (k < N) {
@@ -253,149 +263,155 @@ __device__ __forceinline__ LanePrim make_prim(const Cam& cam, const float (&wx)[
             float fy = cy * cam.ppmy + 0.5f * (float)TDE_OBS_H;
             minx = fminf(minx, fx); maxx = fmaxf(maxx, fx);
             miny = fminf(miny, fy); maxy = fmaxf(maxy, fy);
-            pr.x[k] = snap16(fx); pr.y[k] = snap16(fy);
+            v[k] = pack_xy(snap16(fx), snap16(fy));
         } else {
-            pr.x[k] = 0; pr.y[k] = 0;
+            v[k] = v[0];
         }
     }
-    bool vis = valid && (maxx >= -1.0f && minx <= (float)TDE_OBS_W + 1.0f && maxy >= -1.0f && miny <= (float)TDE_OBS_H + 1.0f);
-    pr.n = vis ? N : 0;
-    pr.cls = cls;
-    return pr;
+    out = make_uint4(v[0], v[1], v[2], v[3]);
+    return maxx >= -1.0f && minx <= (float)TDE_OBS_W + 1.0f && maxy >= -1.0f && miny <= (float)TDE_OBS_H + 1.0f;
 }
 
-// Rasterise up to 32 convex primitives (one per lane) into the warp's class-index bit-planes.
-//   phase 1 (lane = primitive): exact integer edge stepping, one 64-bit coverage span per row,
-//            written to the shared band buffer;
-//   phase 2 (lane = row): OR the spans of each class present (ascending = painter's order) and
-//            update the four bit-planes of the class index.
-// Pixel-centre sampling on the 1/16-px grid with the top-left rule: identical to the oracle's
-// per-pixel edge-function test.
-__device__ __forceinline__ void raster_chunk(const LanePrim& pr, unsigned long long (&P)[2][4],
-                                             unsigned long long* span, int lane) {
-    // orientation
-    int n = pr.n;
-    int X[4], Y[4];
-    {
-        int area2 = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            int k1 = (k + 1 == n) ? 0 : k + 1;
-            if (k < n) area2 += pr.x[k] * pr.y[k1] - pr.x[k1] * pr.y[k];
-        }
-        if (area2 == 0) n = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            int src = area2 > 0 ? k : (n - 1 - k);
-            src = src < 0 ? 0 : src;
-            // reversed order for negative area; entries k >= n are unused
-            int xs = pr.x[0], ys = pr.y[0];
-#pragma unroll
-            for (int q = 1; q < 4; ++q) { if (src == q) { xs = pr.x[q]; ys = pr.y[q]; } }
-            X[k] = xs; Y[k] = ys;
-        }
+// Rasterise the first `count` (<= 32) queued primitives, one per lane, into the class-index planes.
+//   phase 1 (lane = primitive): exact integer edge stepping (a DDA on floor(K/D) per edge), one 64-bit
+//            coverage span per image row, written to a 16-row band buffer in shared memory;
+//   phase 2 (lane = row x half of the primitives): OR the spans of each class present, classes in
+//            ascending = painter's order, and update the four bit-planes of the class index.
+// Pixel-centre sampling on the 1/16-px grid with the top-left rule: the same pixel set as the
+// oracle's per-pixel edge-function test.
+__device__ __noinline__ void raster_batch(RenderScratch* ws, int count, int lane) {
+    const bool have = lane < count;
+    const uint4 q = ws->qv[lane];
+    const int cn = have ? (int)ws->qc[lane] : 0;
+    int n = cn >> 4;
+    const int cls = cn & 15;
+    int X[4] = {unpack_x(q.x), unpack_x(q.y), unpack_x(q.z), unpack_x(q.w)};
+    int Y[4] = {unpack_y(q.x), unpack_y(q.y), unpack_y(q.z), unpack_y(q.w)};
+    if (n == 3) { X[3] = X[0]; Y[3] = Y[0]; }
+    // orientation: make the signed area positive (x right, y down) by swapping vertices 1 and n-1
+    int area2 = (X[0] * Y[1] - X[1] * Y[0]) + (X[1] * Y[2] - X[2] * Y[1]) + (X[2] * Y[3] - X[3] * Y[2]) + (X[3] * Y[0] - X[0] * Y[3]);
+    if (area2 == 0) n = 0;
+    if (area2 < 0) {
+        if (n == 4) { int t = X[1]; X[1] = X[3]; X[3] = t; t = Y[1]; Y[1] = Y[3]; Y[3] = t; }
+        else { int t = X[1]; X[1] = X[2]; X[2] = t; t = Y[1]; Y[1] = Y[2]; Y[2] = t; X[3] = X[0]; Y[3] = Y[0]; }
     }
-    int ymin = Y[0], ymax = Y[0], xmin = X[0], xmax = X[0];
-#pragma unroll
-    for (int k = 1; k < 4; ++k) {
-        if (k < n) { ymin = min(ymin, Y[k]); ymax = max(ymax, Y[k]); xmin = min(xmin, X[k]); xmax = max(xmax, X[k]); }
-    }
-    int j0 = max(0, (ymin - 8 + 15) >> 4);        // ceil((ymin-8)/16)
-    int j1 = min(TDE_OBS_H - 1, (ymax - 8) >> 4); // floor((ymax-8)/16)
-    bool active = n >= 3 && j0 <= j1 && xmax >= 8 && xmin <= 16 * (TDE_OBS_W - 1) + 8;
-    if (!__any_sync(FULL_MASK, active)) return;
-
-    // edge setup: type 0 none, 1 left (dy<0), 2 right (dy>0), 3 horizontal
-    int etype[4], F[4], rem[4], qS[4], rS[4], D[4];
+    int ymin = min(min(Y[0], Y[1]), min(Y[2], Y[3])), ymax = max(max(Y[0], Y[1]), max(Y[2], Y[3]));
+    int xmin = min(min(X[0], X[1]), min(X[2], X[3])), xmax = max(max(X[0], X[1]), max(X[2], X[3]));
+    int j0 = max(0, (ymin - 8 + 15) >> 4);         // ceil((ymin - 8) / 16)
+    int j1 = min(TDE_OBS_H - 1, (ymax - 8) >> 4);  // floor((ymax - 8) / 16)
+    // horizontal edges only restrict the row range (top edges are inclusive, bottom edges exclusive)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        etype[k] = 0; F[k] = 0; rem[k] = 0; qS[k] = 0; rS[k] = 0; D[k] = 1;
-        if (active && k < n) {
-            int k1 = (k + 1 == n) ? 0 : k + 1;
-            int ax = X[k], ay = Y[k];
-            int bx = X[0], by = Y[0];
+        int k1 = (k + 1) & 3;
+        int dx = X[k1] - X[k], dy = Y[k1] - Y[k];
+        if (dy == 0 && dx != 0) {
+            int c = (Y[k] - 8 + 15) >> 4;
+            if (dx > 0) j0 = max(j0, c); else j1 = min(j1, c - 1);
+        }
+    }
+    const bool active = n >= 3 && j0 <= j1 && xmax >= 8 && xmin <= 16 * (TDE_OBS_W - 1) + 8;
+    if (!__any_sync(FULL_MASK, active)) return;
+
+    // slanted edges: V = current bound (left: first covered column, right: one past the last), stepped per row
+    int V[4], dV[4], rem[4], rS[4], D[4], cstep[4], cap[4];
 #pragma unroll
-            for (int q = 1; q < 4; ++q) { if (k1 == q) { bx = X[q]; by = Y[q]; } }
-            int dx = bx - ax, dy = by - ay;
-            if (dx != 0 || dy != 0) {
-                int bias = (dy < 0 || (dy == 0 && dx > 0)) ? 0 : -1;
-                int C0 = dx * (8 - ay) - dy * (8 - ax) + bias;
-                int S = 16 * dx;
-                int K = C0 + S * j0;
-                if (dy == 0) {
-                    etype[k] = 3; F[k] = K; qS[k] = S;
-                } else {
-                    int d = dy > 0 ? 16 * dy : -16 * dy;
-                    etype[k] = dy < 0 ? 1 : 2;
-                    D[k] = d;
-                    F[k] = tde_floordiv(K, d);
-                    rem[k] = K - F[k] * d;
-                    qS[k] = tde_floordiv(S, d);
-                    rS[k] = S - qS[k] * d;
-                }
-            }
+    for (int k = 0; k < 4; ++k) {
+        int k1 = (k + 1) & 3;
+        int ax = X[k], ay = Y[k];
+        int dx = X[k1] - ax, dy = Y[k1] - ay;
+        V[k] = INT_MIN; dV[k] = 0; rem[k] = 0; rS[k] = 0; D[k] = 0x40000000; cstep[k] = 0; cap[k] = INT_MAX;
+        if (active && dy != 0) {
+            int bias = dy < 0 ? 0 : -1;
+            int C0 = dx * (8 - ay) - dy * (8 - ax) + bias;
+            int S = 16 * dx;
+            int K = C0 + S * j0;
+            int d = dy > 0 ? 16 * dy : -16 * dy;
+            int F = tde_floordiv(K, d);
+            int qs = tde_floordiv(S, d);
+            D[k] = d;
+            rem[k] = K - F * d;
+            rS[k] = S - qs * d;
+            if (dy > 0) { V[k] = F + 1; dV[k] = qs; cstep[k] = 1; cap[k] = INT_MIN; }
+            else { V[k] = -F; dV[k] = -qs; cstep[k] = -1; cap[k] = INT_MAX; }
         }
     }
 
+    unsigned long long* span = ws->span;
     int j = j0;
 #pragma unroll 1
-    for (int band = 0; band < 2; ++band) {
-        int b0 = band * 32, b1 = b0 + 31;
-        bool part = active && j0 <= b1 && j1 >= b0;
-        unsigned bm = __ballot_sync(FULL_MASK, part);
+    for (int band = 0; band < TDE_OBS_H / TDE_BAND_ROWS; ++band) {
+        const int b0 = band * TDE_BAND_ROWS, b1 = b0 + TDE_BAND_ROWS - 1;
+        const bool part = active && j0 <= b1 && j1 >= b0;
+        const unsigned bm = __ballot_sync(FULL_MASK, part);
         if (bm == 0) continue;
-        // clear the band buffer
+        {   // clear the band buffer (16 rows x 33 spans)
+            uint4* s4 = reinterpret_cast<uint4*>(span);
 #pragma unroll 1
-        for (int i = lane; i < 32 * TDE_SPAN_STRIDE; i += 32) span[i] = 0ull;
+            for (int i = lane; i < TDE_BAND_ROWS * TDE_SPAN_STRIDE / 2; i += 32) s4[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
         __syncwarp();
         if (part) {
-            int jend = min(j1, b1);
+            const int jend = min(j1, b1);
 #pragma unroll 1
             for (; j <= jend; ++j) {
                 int xl = 0, xr = TDE_OBS_W;
-                bool ok = true;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    if (etype[k] == 1) xl = max(xl, -F[k]);
-                    else if (etype[k] == 2) xr = min(xr, F[k] + 1);
-                    else if (etype[k] == 3) ok = ok && (F[k] >= 0);
+                    xl = max(xl, min(V[k], cap[k]));
+                    xr = min(xr, max(V[k], cap[k]));
+                    V[k] += dV[k];
+                    rem[k] += rS[k];
+                    if (rem[k] >= D[k]) { rem[k] -= D[k]; V[k] += cstep[k]; }
                 }
-                if (ok && xl < xr) {
-                    unsigned long long mk = (~0ull >> (64 - xr)) & (~0ull << xl);
-                    span[(j - b0) * TDE_SPAN_STRIDE + lane] = mk;
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (etype[k] == 3) F[k] += qS[k];
-                    else if (etype[k] != 0) {
-                        F[k] += qS[k];
-                        rem[k] += rS[k];
-                        if (rem[k] >= D[k]) { rem[k] -= D[k]; F[k] += 1; }
-                    }
-                }
+                if (xl < xr) span[(j - b0) * TDE_SPAN_STRIDE + lane] = (~0ull >> (64 - xr)) & (~0ull << xl);
             }
         }
         __syncwarp();
-        // phase 2: lane = row (b0 + lane); classes ascending
+        // phase 2: lane = (row, half of the primitive slots)
+        const int row = lane & (TDE_BAND_ROWS - 1), kh = lane >> 4;
         unsigned remaining = bm;
         while (remaining) {
-            int mycls = ((remaining >> lane) & 1u) ? pr.cls : 0x7fffffff;
+            int mycls = ((remaining >> lane) & 1u) ? cls : 0x7fffffff;
             int c = __reduce_min_sync(FULL_MASK, mycls);
             unsigned mc = __ballot_sync(FULL_MASK, mycls == c);
+            unsigned u = (mc | (mc >> 16)) & 0xffffu;
+            unsigned mine = (mc >> (16 * kh)) & 0xffffu;
             unsigned long long acc = 0ull;
-            unsigned it = mc;
-            while (it) {
-                int k = __ffs(it) - 1;
-                it &= it - 1;
-                acc |= span[lane * TDE_SPAN_STRIDE + k];
+            while (u) {
+                int b = __ffs(u) - 1;
+                u &= u - 1;
+                if ((mine >> b) & 1u) acc |= span[row * TDE_SPAN_STRIDE + b + 16 * kh];
             }
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                unsigned long long keep = ((c >> b) & 1) ? ~0ull : 0ull;
-                P[band][b] = (P[band][b] & ~acc) | (acc & keep);
-            }
+            acc |= __shfl_xor_sync(FULL_MASK, acc, 16);
+            // each half updates two of the four planes of its row
+            ulonglong2* pp = reinterpret_cast<ulonglong2*>(&ws->planes[(b0 + row) * 4 + 2 * kh]);
+            ulonglong2 pv = *pp;
+            unsigned long long keep0 = ((c >> (2 * kh)) & 1) ? ~0ull : 0ull;
+            unsigned long long keep1 = ((c >> (2 * kh + 1)) & 1) ? ~0ull : 0ull;
+            pv.x = (pv.x & ~acc) | (acc & keep0);
+            pv.y = (pv.y & ~acc) | (acc & keep1);
+            *pp = pv;
             remaining &= ~mc;
         }
+        __syncwarp();
+    }
+}
+
+// append the primitives of the lanes with `valid` to the warp's queue; rasterise a batch when 32 are pending
+__device__ __forceinline__ void enqueue(RenderScratch* ws, int& qn, int lane, bool valid, const uint4& v, int cls, int nverts) {
+    unsigned m = __ballot_sync(FULL_MASK, valid);
+    if (m == 0) return;
+    int pos = qn + __popc(m & ((1u << lane) - 1u));
+    if (valid) { ws->qv[pos] = v; ws->qc[pos] = (unsigned char)(cls | (nverts << 4)); }
+    qn += __popc(m);
+    __syncwarp();
+    if (qn >= 32) {
+        raster_batch(ws, 32, lane);
+        uint4 tv = ws->qv[32 + lane];
+        unsigned char tc = ws->qc[32 + lane];
+        __syncwarp();
+        ws->qv[lane] = tv; ws->qc[lane] = tc;
+        qn -= 32;
         __syncwarp();
     }
 }
@@ -424,151 +440,179 @@ __device__ __forceinline__ uint32_t spread8(uint32_t b) {
     return x;
 }
 
-// simulator.render_egocentric() (gym_env.py:122-124) for one env, by one warp.
-template <int AH>
-__device__ __forceinline__ void render_env_warp(const StepParams& p, const MapDev& M, const ScenDev& S, int e, int lane,
-                                                WarpScratch* ws, int step, int lphase, int target) {
-    const float4* sb = ws->box;
-    Box ego = ld_box(sb, 0);
-    Cam cam;
-    cam.ex = ego.x; cam.ey = ego.y; cam.ce = ego.c; cam.se = ego.s; cam.ppm = p.ppm; cam.ppmy = p.ppmy;
-    unsigned long long P[2][4];
-#pragma unroll
-    for (int b = 0; b < 2; ++b)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) P[b][q] = 0ull;
+// static triangle layers (road, lane markings): lanes first test the bounding boxes of 32-triangle
+// runs against the viewport's reach, then only the visible runs are loaded, projected and queued
+template <bool ROAD>
+__device__ __forceinline__ void queue_static_layer(const MapDev& M, const Cam& cam, float reach, RenderScratch* ws, int& qn, int lane) {
+    const int ntri = ROAD ? M.ntri : M.nmark;
+    const float4* chunk = ROAD ? M.tri_chunk : M.mark_chunk;
+    const int nchunk = (ntri + 31) >> 5;
     float wx[4], wy[4];
-
-    // conservative world-space reach of the viewport around the ego (half diagonal + 1 px)
-    float reach = (0.70710678f * (float)(TDE_OBS_W + TDE_OBS_H) * 0.5f + 2.0f) / p.ppm;
-
-    // level 1: road triangles
 #pragma unroll 1
-    for (int base = 0; base < M.ntri; base += 32) {
-        int t = base + lane;
-        bool valid = t < M.ntri;
-        float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
-        if (valid) { t0 = M.tri[3 * t]; t1 = M.tri[3 * t + 1]; }
-        // cheap world-space reject (conservative): triangle bbox vs the viewport's bounding square
-        float lox = fminf(fminf(t0.x, t0.z), t1.x), hix = fmaxf(fmaxf(t0.x, t0.z), t1.x);
-        float loy = fminf(fminf(t0.y, t0.w), t1.y), hiy = fmaxf(fmaxf(t0.y, t0.w), t1.y);
-        valid = valid && hix >= cam.ex - reach && lox <= cam.ex + reach && hiy >= cam.ey - reach && loy <= cam.ey + reach;
-        if (!__any_sync(FULL_MASK, valid)) continue;
-        wx[0] = t0.x; wy[0] = t0.y; wx[1] = t0.z; wy[1] = t0.w; wx[2] = t1.x; wy[2] = t1.y; wx[3] = 0.f; wy[3] = 0.f;
-        LanePrim pr = make_prim<3>(cam, wx, wy, TDE_CLS_ROAD, valid);
-        raster_chunk(pr, P, ws->span, lane);
-    }
-    // level 2: lane markings
-#pragma unroll 1
-    for (int base = 0; base < M.nmark; base += 32) {
-        int t = base + lane;
-        bool valid = t < M.nmark;
-        float2 a = make_float2(0.f, 0.f), b = a, c = a;
-        if (valid) { a = M.mark[3 * t]; b = M.mark[3 * t + 1]; c = M.mark[3 * t + 2]; }
-        float lox = fminf(fminf(a.x, b.x), c.x), hix = fmaxf(fmaxf(a.x, b.x), c.x);
-        float loy = fminf(fminf(a.y, b.y), c.y), hiy = fmaxf(fmaxf(a.y, b.y), c.y);
-        valid = valid && hix >= cam.ex - reach && lox <= cam.ex + reach && hiy >= cam.ey - reach && loy <= cam.ey + reach;
-        if (!__any_sync(FULL_MASK, valid)) continue;
-        wx[0] = a.x; wy[0] = a.y; wx[1] = b.x; wy[1] = b.y; wx[2] = c.x; wy[2] = c.y; wx[3] = 0.f; wy[3] = 0.f;
-        LanePrim pr = make_prim<3>(cam, wx, wy, TDE_CLS_LANE_MARKING, valid);
-        raster_chunk(pr, P, ws->span, lane);
-    }
-    // levels 3-6: stop lines coloured by light state, then the goal waypoint
-    {
-        int nq = M.nstop + 1;
-#pragma unroll 1
-        for (int base = 0; base < nq; base += 32) {
-            int q = base + lane;
-            bool valid = false;
-            int cls = TDE_CLS_TL_GREEN;
-            wx[0] = wx[1] = wx[2] = wx[3] = 0.f; wy[0] = wy[1] = wy[2] = wy[3] = 0.f;
-            if (q < M.nstop) {
-                float4 u = M.stop[2 * q], v = M.stop[2 * q + 1];
-                Box b; b.x = u.x; b.y = u.y; b.hl = u.z; b.hw = u.w; b.c = v.x; b.s = v.y; b.present = 1.f; b.r = 0.f;
-                box_quad(b, wx, wy);
-                int ls = light_state_at(M, step, lphase, q);
-                cls = ls == TDE_LIGHT_RED ? TDE_CLS_TL_RED : (ls == TDE_LIGHT_YELLOW ? TDE_CLS_TL_YELLOW : TDE_CLS_TL_GREEN);
-                valid = true;
-            } else if (q == M.nstop && target < S.W) {
-                float2 w = S.wp[target];
-                float r = 2.0f;
-                wx[0] = w.x + r; wy[0] = w.y; wx[1] = w.x; wy[1] = w.y + r;
-                wx[2] = w.x - r; wy[2] = w.y; wx[3] = w.x; wy[3] = w.y - r;
-                cls = TDE_CLS_WAYPOINT;
-                valid = true;
+    for (int cb = 0; cb < nchunk; cb += 32) {
+        bool see = false;
+        if (cb + lane < nchunk) {
+            float4 bb = chunk[cb + lane];
+            see = bb.z >= cam.ex - reach && bb.x <= cam.ex + reach && bb.w >= cam.ey - reach && bb.y <= cam.ey + reach;
+        }
+        unsigned vis = __ballot_sync(FULL_MASK, see);
+        while (vis) {
+            int c = cb + __ffs(vis) - 1;
+            vis &= vis - 1;
+            int t = c * 32 + lane;
+            bool valid = t < ntri;
+            if (ROAD) {
+                float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
+                if (valid) { t0 = M.tri[3 * t]; t1 = M.tri[3 * t + 1]; }
+                wx[0] = t0.x; wy[0] = t0.y; wx[1] = t0.z; wy[1] = t0.w; wx[2] = t1.x; wy[2] = t1.y;
+            } else {
+                float2 a = make_float2(0.f, 0.f), b = a, d = a;
+                if (valid) { a = M.mark[3 * t]; b = M.mark[3 * t + 1]; d = M.mark[3 * t + 2]; }
+                wx[0] = a.x; wy[0] = a.y; wx[1] = b.x; wy[1] = b.y; wx[2] = d.x; wy[2] = d.y;
             }
-            if (!__any_sync(FULL_MASK, valid)) continue;
-            LanePrim pr = make_prim<4>(cam, wx, wy, cls, valid);
-            raster_chunk(pr, P, ws->span, lane);
-        }
-    }
-    // levels 7-8: agent rectangles (ego highlighted), levels 9-10: direction triangles.
-    // The chunk holding the ego goes last so that classes stay ascending across chunks.
-#pragma unroll 1
-    for (int h = AH - 1; h >= 0; --h) {
-        int a = h * 32 + lane;
-        Box b = ld_box(sb, a < p.A ? a : 0);
-        bool valid = a < p.A && b.present != 0.0f;
-        box_quad(b, wx, wy);
-        LanePrim pr = make_prim<4>(cam, wx, wy, a == 0 ? TDE_CLS_EGO : TDE_CLS_VEHICLE, valid);
-        raster_chunk(pr, P, ws->span, lane);
-    }
-#pragma unroll 1
-    for (int h = AH - 1; h >= 0; --h) {
-        int a = h * 32 + lane;
-        Box b = ld_box(sb, a < p.A ? a : 0);
-        bool valid = a < p.A && b.present != 0.0f;
-        box_dirtri(b, wx, wy);
-        LanePrim pr = make_prim<3>(cam, wx, wy, a == 0 ? TDE_CLS_EGO_DIRECTION : TDE_CLS_DIRECTION, valid);
-        raster_chunk(pr, P, ws->span, lane);
-    }
-
-    // class-index planes -> shared, then palette lookup with byte permutes and 128-bit stores
-#pragma unroll
-    for (int band = 0; band < 2; ++band)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) ws->planes[(band * 32 + lane) * 4 + b] = P[band][b];
-    __syncwarp();
-    const unsigned short* pl16 = reinterpret_cast<const unsigned short*>(ws->planes);
-    uint8_t* out = p.obs + (size_t)e * (TDE_OBS_C * TDE_OBS_H * TDE_OBS_W);
-#pragma unroll 1
-    for (int it = 0; it < TDE_OBS_H / 8; ++it) {
-        int row = it * 8 + (lane >> 2), q = lane & 3;
-        uint32_t b0 = pl16[(row * 4 + 0) * 4 + q], b1 = pl16[(row * 4 + 1) * 4 + q];
-        uint32_t b2 = pl16[(row * 4 + 2) * 4 + q], b3 = pl16[(row * 4 + 3) * 4 + q];
-        uint32_t idx[2];
-        idx[0] = spread8(b0) | (spread8(b1) << 1) | (spread8(b2) << 2) | (spread8(b3) << 3);
-        idx[1] = spread8(b0 >> 8) | (spread8(b1 >> 8) << 1) | (spread8(b2 >> 8) << 2) | (spread8(b3 >> 8) << 3);
-        uint32_t sel7[4], himask[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            uint32_t sel = (idx[g >> 1] >> (16 * (g & 1))) & 0xffffu;
-            sel7[g] = sel & 0x7777u;
-            himask[g] = __byte_perm(0x0000ff00u, 0u, (sel >> 3) & 0x1111u);
-        }
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            uint32_t w[4];
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                uint32_t lo = __byte_perm(p.pal[ch][0], p.pal[ch][1], sel7[g]);
-                uint32_t hi = __byte_perm(p.pal[ch][2], p.pal[ch][3], sel7[g]);
-                w[g] = (lo & ~himask[g]) | (hi & himask[g]);
+            wx[3] = 0.f; wy[3] = 0.f;
+            float lox = fminf(fminf(wx[0], wx[1]), wx[2]), hix = fmaxf(fmaxf(wx[0], wx[1]), wx[2]);
+            float loy = fminf(fminf(wy[0], wy[1]), wy[2]), hiy = fmaxf(fmaxf(wy[0], wy[1]), wy[2]);
+            valid = valid && hix >= cam.ex - reach && lox <= cam.ex + reach && hiy >= cam.ey - reach && loy <= cam.ey + reach;
+            uint4 pv = make_uint4(0u, 0u, 0u, 0u);
+            if (__any_sync(FULL_MASK, valid)) {
+                bool ok = project_prim<3>(cam, wx, wy, pv) && valid;
+                enqueue(ws, qn, lane, ok, pv, ROAD ? TDE_CLS_ROAD : TDE_CLS_LANE_MARKING, 3);
             }
-            uint4 v = make_uint4(w[0], w[1], w[2], w[3]);
-            *reinterpret_cast<uint4*>(out + ch * (TDE_OBS_H * TDE_OBS_W) + row * TDE_OBS_W + q * 16) = v;
         }
     }
-    __syncwarp();
 }
 
-// ---------------------------------------------------------------- the fused step kernel
-
+// simulator.render_egocentric() (gym_env.py:122-124): one warp renders one env's 3x64x64 birdview.
 template <int AH>
-__global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32) tde_step_kernel(const StepParams p) {
+__global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, 3) tde_render_kernel(const StepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpScratch* ws = reinterpret_cast<WarpScratch*>(smem_raw) + warp;
+    RenderScratch* ws = reinterpret_cast<RenderScratch*>(smem_raw) + warp;
+    const int warps_total = gridDim.x * TDE_WARPS_PER_BLOCK;
+    // conservative world-space reach of the viewport around the ego (half diagonal + 2 px)
+    const float reach = (0.70710678f * (float)(TDE_OBS_W + TDE_OBS_H) * 0.5f + 2.0f) / p.ppm;
+
+#pragma unroll 1
+    for (int e = blockIdx.x * TDE_WARPS_PER_BLOCK + warp; e < p.E; e += warps_total) {
+        int myvar = lane < 8 ? p.vars[(size_t)e * 8 + lane] : 0;
+        const int s = __shfl_sync(FULL_MASK, myvar, 0), step = __shfl_sync(FULL_MASK, myvar, 1);
+        const int target = __shfl_sync(FULL_MASK, myvar, 2), lphase = __shfl_sync(FULL_MASK, myvar, 4);
+        const int m = __shfl_sync(FULL_MASK, myvar, 6);
+        const MapDev& M = p.maps[m];
+        const ScenDev& S = p.scens[s];
+        Box mybox[AH];
+#pragma unroll
+        for (int h = 0; h < AH; ++h) {
+            int a = h * 32 + lane;
+            float4 st = make_float4(0.f, 0.f, 0.f, 0.f), at = make_float4(1.f, 1.f, 1.f, 0.f);
+            if (a < p.A) { st = p.state[(size_t)e * p.A + a]; at = p.attr[(size_t)e * p.A + a]; }
+            mybox[h] = tde_make_box(st.x, st.y, st.z, at.x, at.y, at.w);
+        }
+        Cam cam;
+        cam.ex = __shfl_sync(FULL_MASK, mybox[0].x, 0); cam.ey = __shfl_sync(FULL_MASK, mybox[0].y, 0);
+        cam.ce = __shfl_sync(FULL_MASK, mybox[0].c, 0); cam.se = __shfl_sync(FULL_MASK, mybox[0].s, 0);
+        cam.ppm = p.ppm; cam.ppmy = p.ppmy;
+        {   // clear the class-index planes
+            uint4* pz = reinterpret_cast<uint4*>(ws->planes);
+#pragma unroll
+            for (int i = 0; i < TDE_OBS_H * 4 * 8 / 16 / 32; ++i) pz[i * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncwarp();
+        int qn = 0;
+        float wx[4], wy[4];
+        uint4 pv;
+        queue_static_layer<true>(M, cam, reach, ws, qn, lane);    // level 1: road
+        queue_static_layer<false>(M, cam, reach, ws, qn, lane);   // level 2: lane markings
+        // levels 3-5: stop lines by light state (one pass per state keeps the queue in painter's order)
+        if (M.nstop > 0) {
+            bool valid = lane < M.nstop;
+            int ls = TDE_LIGHT_GREEN;
+            wx[0] = wx[1] = wx[2] = wx[3] = 0.f; wy[0] = wy[1] = wy[2] = wy[3] = 0.f;
+            if (valid) {
+                float4 u = M.stop[2 * lane], v = M.stop[2 * lane + 1];
+                Box b; b.x = u.x; b.y = u.y; b.hl = u.z; b.hw = u.w; b.c = v.x; b.s = v.y; b.present = 1.f; b.r = 0.f;
+                box_quad(b, wx, wy);
+                ls = light_state_at(M, step, lphase, lane);
+            }
+            bool ok = project_prim<4>(cam, wx, wy, pv) && valid;
+            enqueue(ws, qn, lane, ok && ls == TDE_LIGHT_GREEN, pv, TDE_CLS_TL_GREEN, 4);
+            enqueue(ws, qn, lane, ok && ls == TDE_LIGHT_YELLOW, pv, TDE_CLS_TL_YELLOW, 4);
+            enqueue(ws, qn, lane, ok && ls == TDE_LIGHT_RED, pv, TDE_CLS_TL_RED, 4);
+        }
+        // level 6: the current goal waypoint, a diamond of circumradius 2 m
+        if (target < S.W) {
+            float2 w = S.wp[target];
+            const float r = 2.0f;
+            wx[0] = w.x + r; wy[0] = w.y; wx[1] = w.x; wy[1] = w.y + r;
+            wx[2] = w.x - r; wy[2] = w.y; wx[3] = w.x; wy[3] = w.y - r;
+            bool ok = project_prim<4>(cam, wx, wy, pv) && lane == 0;
+            enqueue(ws, qn, lane, ok, pv, TDE_CLS_WAYPOINT, 4);
+        }
+        // levels 7-8: vehicle rectangles then the highlighted ego; levels 9-10: direction triangles
+#pragma unroll
+        for (int h = AH - 1; h >= 0; --h) {
+            int a = h * 32 + lane;
+            box_quad(mybox[h], wx, wy);
+            bool ok = project_prim<4>(cam, wx, wy, pv) && a < p.A && mybox[h].present != 0.0f;
+            enqueue(ws, qn, lane, ok && a != 0, pv, TDE_CLS_VEHICLE, 4);
+            if (h == 0) enqueue(ws, qn, lane, ok && a == 0, pv, TDE_CLS_EGO, 4);
+        }
+#pragma unroll
+        for (int h = AH - 1; h >= 0; --h) {
+            int a = h * 32 + lane;
+            box_dirtri(mybox[h], wx, wy);
+            bool ok = project_prim<3>(cam, wx, wy, pv) && a < p.A && mybox[h].present != 0.0f;
+            enqueue(ws, qn, lane, ok && a != 0, pv, TDE_CLS_DIRECTION, 3);
+            if (h == 0) enqueue(ws, qn, lane, ok && a == 0, pv, TDE_CLS_EGO_DIRECTION, 3);
+        }
+        if (qn > 0) raster_batch(ws, qn, lane);
+        __syncwarp();
+
+        // class-index planes -> palette lookup with byte permutes -> 128-bit stores
+        const unsigned short* pl16 = reinterpret_cast<const unsigned short*>(ws->planes);
+        uint8_t* out = p.obs + (size_t)e * (TDE_OBS_C * TDE_OBS_H * TDE_OBS_W);
+#pragma unroll 1
+        for (int it = 0; it < TDE_OBS_H / 8; ++it) {
+            int row = it * 8 + (lane >> 2), qd = lane & 3;
+            uint32_t b0 = pl16[(row * 4 + 0) * 4 + qd], b1 = pl16[(row * 4 + 1) * 4 + qd];
+            uint32_t b2 = pl16[(row * 4 + 2) * 4 + qd], b3 = pl16[(row * 4 + 3) * 4 + qd];
+            uint32_t idx[2];
+            idx[0] = spread8(b0) | (spread8(b1) << 1) | (spread8(b2) << 2) | (spread8(b3) << 3);
+            idx[1] = spread8(b0 >> 8) | (spread8(b1 >> 8) << 1) | (spread8(b2 >> 8) << 2) | (spread8(b3 >> 8) << 3);
+            uint32_t sel7[4], himask[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                uint32_t sel = (idx[g >> 1] >> (16 * (g & 1))) & 0xffffu;
+                sel7[g] = sel & 0x7777u;
+                himask[g] = __byte_perm(0x0000ff00u, 0u, (sel >> 3) & 0x1111u);
+            }
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                uint32_t w[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint32_t lo = __byte_perm(p.pal[ch][0], p.pal[ch][1], sel7[g]);
+                    uint32_t hi = __byte_perm(p.pal[ch][2], p.pal[ch][3], sel7[g]);
+                    w[g] = (lo & ~himask[g]) | (hi & himask[g]);
+                }
+                *reinterpret_cast<uint4*>(out + ch * (TDE_OBS_H * TDE_OBS_W) + row * TDE_OBS_W + qd * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------- physics kernel
+
+// WaypointSuiteEnv.step :369-389 minus the observation: bicycle step / NPC replay, all-pairs SAT,
+// offroad / red-light / wrong-way against the lane mesh, reward, termination, truncation, info,
+// waypoint progress, episode statistics and (optionally) the in-kernel auto-reset.
+template <int AH>
+__global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32) tde_physics_kernel(const StepParams p) {
+    __shared__ PhysScratch scratch[TDE_WARPS_PER_BLOCK];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    PhysScratch* ws = &scratch[warp];
     const int warps_total = gridDim.x * TDE_WARPS_PER_BLOCK;
     const tde_config& c = p.cfg;
     double st_acc = 0.0;  // lane k accumulates statistic k
@@ -599,30 +643,28 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32) tde_step_kernel(cons
             for (int h = 0; h < AH; ++h) {
                 int a = h * 32 + lane;
                 if (a < p.A && at[h].w != 0.0f) {
-                    if (a == 0) {
-                        st[h] = tde_bicycle(st[h], act_a, act_b, at[h].z, c.dt);
-                    } else if (t < S.rep_T && S.rep_mask[(size_t)t * p.A + a]) {
+                    bool replay = a != 0 && t < S.rep_T && S.rep_mask[(size_t)t * p.A + a];
+                    if (replay) {
                         st[h] = S.rep_states[(size_t)t * p.A + a];
                     } else {
-                        st[h] = tde_bicycle(st[h], 0.0f, 0.0f, at[h].z, c.dt);
+                        st[h] = tde_bicycle(st[h], a == 0 ? act_a : 0.0f, a == 0 ? act_b : 0.0f, at[h].z, c.dt);
                     }
                     p.state[(size_t)e * p.A + a] = st[h];
                 }
             }
             step = t;
         }
-        // boxes of this env -> shared
-#pragma unroll
-        for (int h = 0; h < AH; ++h) {
-            int a = h * 32 + lane;
-            if (a < p.A) st_box(ws->box, a, tde_make_box(st[h].x, st[h].y, st[h].z, at[h].x, at[h].y, at[h].w));
-        }
-        __syncwarp();
 
         float4 inf0 = make_float4(0.f, 0.f, 0.f, 0.f);  // ego's infractions, valid on lane 0
         if (p.phases & TDE_PH_INFRACTIONS) {
             const MapDev& M = p.maps[m];
 #pragma unroll
+            for (int h = 0; h < AH; ++h) {
+                int a = h * 32 + lane;
+                if (a < p.A) st_box(ws->box, a, tde_make_box(st[h].x, st[h].y, st[h].z, at[h].x, at[h].y, at[h].w));
+            }
+            __syncwarp();
+#pragma unroll 1
             for (int h = 0; h < AH; ++h) {
                 int a = h * 32 + lane;
                 float4 inf = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -647,6 +689,7 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32) tde_step_kernel(cons
                 if (a < p.A) p.infr[(size_t)e * p.A + a] = inf;
                 if (h == 0) inf0 = inf;
             }
+            __syncwarp();
         } else if (p.phases & TDE_PH_REWARD) {
             if (lane == 0) inf0 = p.infr[(size_t)e * p.A];
         }
@@ -723,18 +766,9 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32) tde_step_kernel(cons
             if (done && c.auto_reset) {
                 __syncwarp();
                 reset_env_warp<AH>(p, e, lane, s, step, target, reached, lphase, episode, m, st, at);
-#pragma unroll
-                for (int h = 0; h < AH; ++h) {
-                    int a = h * 32 + lane;
-                    if (a < p.A) st_box(ws->box, a, tde_make_box(st[h].x, st[h].y, st[h].z, at[h].x, at[h].y, at[h].w));
-                }
-                __syncwarp();
             }
         }
         if (p.phases & (TDE_PH_KINEMATICS | TDE_PH_REWARD)) store_vars(p, e, lane, s, step, target, reached, lphase, episode, m);
-
-        if ((p.phases & TDE_PH_RENDER) && p.obs != nullptr)
-            render_env_warp<AH>(p, p.maps[m], p.scens[s], e, lane, ws, step, lphase, target);
         __syncwarp();
     }
     if ((p.phases & TDE_PH_REWARD) && lane < TDE_NUM_STATS && st_acc != 0.0) atomicAdd(&p.stats[lane], st_acc);
@@ -758,8 +792,7 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32) tde_reset_kernel(con
 // ---------------------------------------------------------------- stateless micro-benchmark kernels (config C4)
 
 // All-pairs oriented-box collision counts on caller-provided boxes: warp per env, boxes tiled in
-// shared memory, every unordered pair tested once (the SAT is bitwise symmetric) along the
-// "diagonals" j = i + k, hits exchanged with warp shuffles / shared counters.
+// shared memory, cheap conservative rejection voted across the warp before the full SAT.
 template <int AH>
 __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32) tde_collision_kernel(const float4* __restrict__ state,
                                                                                   const float4* __restrict__ attr, int E, int A,
