@@ -637,7 +637,10 @@ void orc_compute_infractions(orc_env_set* o) {
 
 void orc_kinematics(orc_env_set* o, const float* actions) {
 #pragma omp parallel for schedule(static)
-    for (int e = 0; e < o->E; ++e) kinematics_env(o, e, actions + 2 * e);
+    for (int e = 0; e < o->E; ++e) {
+        kinematics_env(o, e, actions + 2 * e);
+        o->vars[8 * e + 1] += 1; /* the simulator's time index advances with every simulator.step */
+    }
 }
 
 /* WaypointSuiteEnv.step :369-389 with GymEnv.step :115-120 inlined, for all E envs.

@@ -67,6 +67,7 @@ print("offroad_boxes (off-grid) equal:", np.array_equal(g, o))
 E, A = 16384, 32
 eng = Engine(S.traffic_lights(32), E, A, auto_reset=1)
 eng.reset(seed=0)
+print("map info", eng.map_info(0))
 act = torch.stack([torch.rand(E, device='cuda') * 2 - 1, torch.rand(E, device='cuda') * 0.6 - 0.3], 1)
 for name, render in (("full step", True), ("no render", False)):
     for _ in range(5): eng.step(act, render=render)

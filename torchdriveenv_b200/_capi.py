@@ -126,7 +126,7 @@ EXPORTS = [
     "tde_step_phases", "tde_step_host", "tde_kinematics", "tde_render", "tde_compute_infractions",
     "tde_get_state", "tde_set_state", "tde_get_attributes", "tde_set_attributes", "tde_get_infractions",
     "tde_get_env_vars", "tde_set_env_vars", "tde_collision_boxes", "tde_offroad_boxes", "tde_clone",
-    "tde_get_episode_stats", "tde_num_kernel_launches", "tde_device_sm_count",
+    "tde_get_episode_stats", "tde_num_kernel_launches", "tde_device_sm_count", "tde_get_map_info",
 ]
 
 
@@ -174,6 +174,7 @@ def load_library() -> C.CDLL:
         "tde_get_episode_stats": ([vp, C.POINTER(C.c_double), i32, vp], C.c_int),
         "tde_num_kernel_launches": ([vp, C.POINTER(i64)], C.c_int),
         "tde_device_sm_count": ([vp, C.POINTER(i32)], C.c_int),
+        "tde_get_map_info": ([vp, i32, C.POINTER(i32)], C.c_int),
     }
     for name, (args, res) in sig.items():
         fn = getattr(lib, name)  # AttributeError here = the library does not match the header

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -26,6 +27,7 @@ struct tde_handle {
     std::vector<MapDev> maps_host;
     std::vector<ScenDev> scens_host;
     std::vector<void*> scenario_allocs;
+    std::vector<std::array<int, 8>> map_info;  // ntri nmark nstop gnx gny items safe_cells overlapping_items
     int num_maps = 0, num_scen = 0;
     uint8_t palette[TDE_NUM_CLASSES * 3];
     unsigned long long seed = 0;
@@ -108,12 +110,64 @@ struct Grid {
     int nx = 0, ny = 0;
     std::vector<int> cell_start;
     std::vector<uint16_t> items;
+    std::vector<uint16_t> meta;  // n_overlapping | TDE_CELL_SAFE
 };
 
-// For every grid cell keep each triangle that can be the nearest one (or contain the point) for some
-// point of the cell: U = min_t max_{p in cell} dist(p, t) bounds the nearest distance from above, any
-// triangle whose lower bound to the cell exceeds U can never win.  A query is then one cell lookup.
-Grid build_grid(const float* tris, int M) {
+inline bool tri_contains(P2 p, const float* t) { return tri_dist(p, t) == 0.0; }
+
+// exact distance between the square [c +- half] and a triangle (0 when they intersect)
+double box_tri_mindist(P2 c, double half, const float* t) {
+    P2 v[3] = {{t[0], t[1]}, {t[2], t[3]}, {t[4], t[5]}};
+    bool sep = false;
+    double mnx = std::min(v[0].x, std::min(v[1].x, v[2].x)), mxx = std::max(v[0].x, std::max(v[1].x, v[2].x));
+    double mny = std::min(v[0].y, std::min(v[1].y, v[2].y)), mxy = std::max(v[0].y, std::max(v[1].y, v[2].y));
+    if (mxx < c.x - half || mnx > c.x + half || mxy < c.y - half || mny > c.y + half) sep = true;
+    for (int k = 0; k < 3 && !sep; ++k) {
+        P2 a = v[k], b = v[(k + 1) % 3];
+        double nx = -(b.y - a.y), ny = b.x - a.x;
+        double r = half * (std::fabs(nx) + std::fabs(ny)), pc = c.x * nx + c.y * ny;
+        double lo = 1e300, hi = -1e300;
+        for (int q = 0; q < 3; ++q) { double pr = v[q].x * nx + v[q].y * ny; lo = std::min(lo, pr); hi = std::max(hi, pr); }
+        if (hi < pc - r || lo > pc + r) sep = true;
+    }
+    if (!sep) return 0.0;
+    double d = 1e300;
+    P2 corner[4] = {{c.x - half, c.y - half}, {c.x + half, c.y - half}, {c.x + half, c.y + half}, {c.x - half, c.y + half}};
+    for (int k = 0; k < 4; ++k) d = std::min(d, tri_dist(corner[k], t));
+    for (int k = 0; k < 3; ++k) {
+        double ex = std::max(std::fabs(v[k].x - c.x) - half, 0.0), ey = std::max(std::fabs(v[k].y - c.y) - half, 0.0);
+        d = std::min(d, std::hypot(ex, ey));
+    }
+    return d;
+}
+
+// upper bound on the distance to the mesh over a square: 0 where a single triangle covers the
+// square, otherwise refined by quartering down to `depth`
+double cover_bound(P2 c, double half, const float* tris, const std::vector<int>& cand, int depth) {
+    P2 corner[4] = {{c.x - half, c.y - half}, {c.x + half, c.y - half}, {c.x + half, c.y + half}, {c.x - half, c.y + half}};
+    double best = 1e300;
+    for (int t : cand) {
+        double mx = 0;
+        for (int k = 0; k < 4; ++k) mx = std::max(mx, tri_dist(corner[k], tris + 8 * (size_t)t));
+        best = std::min(best, mx);
+        if (best == 0.0) return 0.0;
+    }
+    if (depth == 0) return best;
+    double worst = 0;
+    for (int q = 0; q < 4; ++q) {
+        P2 cc{c.x + ((q & 1) ? 0.5 : -0.5) * half, c.y + ((q & 2) ? 0.5 : -0.5) * half};
+        worst = std::max(worst, cover_bound(cc, 0.5 * half, tris, cand, depth - 1));
+        if (worst >= best) return best;
+    }
+    return std::min(best, worst);
+}
+
+// Nearest-candidate grid.  For every cell (dilated a little, to absorb the binary32 rounding of the
+// device's cell index) keep (a) the triangles that intersect it, first, and (b) every other triangle
+// that can be the nearest one for some point of the cell: with U = min_t max_{p in cell} dist(p, t) an
+// upper bound of the nearest distance, a triangle further than U from the whole cell can never win.
+// A cell is SAFE when every one of its points is provably closer to the mesh than `threshold`.
+Grid build_grid(const float* tris, int M, double threshold) {
     Grid g;
     if (M <= 0) { g.nx = g.ny = 0; g.cell_start.assign(1, 0); return g; }
     double lox = 1e300, loy = 1e300, hix = -1e300, hiy = -1e300;
@@ -143,36 +197,74 @@ Grid build_grid(const float* tris, int M) {
     double dil = 1e-3 * cs + 1e-3;  // dilation covering binary32 rounding of the cell index
     double half = 0.5 * cs + dil, hd = half * std::sqrt(2.0);
     g.cell_start.assign((size_t)g.nx * g.ny + 1, 0);
-    std::vector<int> cand;
-    std::vector<double> lb;
+    g.meta.assign((size_t)g.nx * g.ny, 0);
+    std::vector<int> plaus, over, near, both;
+    std::vector<double> mind;
     for (int iy = 0; iy < g.ny; ++iy) {
         for (int ix = 0; ix < g.nx; ++ix) {
             P2 c{x0 + (ix + 0.5) * cs, y0 + (iy + 0.5) * cs};
             P2 corner[4] = {{c.x - half, c.y - half}, {c.x + half, c.y - half}, {c.x + half, c.y + half}, {c.x - half, c.y + half}};
-            // cheap upper bound on U from centroids, then exact U over the plausible triangles
-            double Uub = 1e300;
+            double Uub = 1e300;  // cheap upper bound on U from centroids
             for (int t = 0; t < M; ++t) Uub = std::min(Uub, std::hypot(c.x - cen[t].x, c.y - cen[t].y) + hd);
-            cand.clear(); lb.clear();
+            plaus.clear(); mind.clear();
             double U = 1e300;
             for (int t = 0; t < M; ++t) {
                 double dc = std::hypot(c.x - cen[t].x, c.y - cen[t].y);
                 if (dc - rad[t] - hd > Uub) continue;
                 const float* r = tris + 8 * (size_t)t;
-                double dcen = tri_dist(c, r);
-                double l = std::max(0.0, dcen - hd);
-                if (l > Uub) continue;
+                double md = box_tri_mindist(c, half, r);
+                if (md > Uub) continue;
                 double mx = 0;
                 for (int k = 0; k < 4; ++k) mx = std::max(mx, tri_dist(corner[k], r));
                 U = std::min(U, mx);
-                cand.push_back(t); lb.push_back(l);
+                plaus.push_back(t); mind.push_back(md);
             }
             double lim = U * (1.0 + 1e-4) + 1e-3;
-            for (size_t k = 0; k < cand.size(); ++k)
-                if (lb[k] <= lim) g.items.push_back((uint16_t)cand[k]);
+            over.clear(); near.clear();
+            double dmin = 1e300;
+            for (size_t k = 0; k < plaus.size(); ++k) {
+                dmin = std::min(dmin, mind[k]);
+                if (mind[k] <= 1e-9) over.push_back(plaus[k]);
+                else if (mind[k] <= lim) near.push_back(plaus[k]);
+            }
+            bool safe = false;
+            if (threshold > 2e-3 && dmin < threshold) {
+                both = over; both.insert(both.end(), near.begin(), near.end());
+                double bound = U + 1e-3 < threshold ? U : cover_bound(c, half, tris, both, 4);
+                safe = bound + 1e-3 < threshold;
+            }
+            size_t nover = std::min<size_t>(over.size(), 0x7fff);
+            for (int t : over) g.items.push_back((uint16_t)t);
+            for (int t : near) g.items.push_back((uint16_t)t);
+            g.meta[(size_t)iy * g.nx + ix] = (uint16_t)(nover | (safe ? TDE_CELL_SAFE : 0));
             g.cell_start[(size_t)iy * g.nx + ix + 1] = (int)g.items.size();
         }
     }
     return g;
+}
+
+// Morton (Z-order) key of a point, used to order the static triangles so that runs of 32 are compact
+uint32_t morton_key(double x, double y, double lox, double loy, double inv) {
+    auto spread = [](uint32_t v) { v &= 0xffff; v = (v | (v << 8)) & 0x00ff00ff; v = (v | (v << 4)) & 0x0f0f0f0f; v = (v | (v << 2)) & 0x33333333; v = (v | (v << 1)) & 0x55555555; return v; };
+    uint32_t ix = (uint32_t)std::min(65535.0, std::max(0.0, (x - lox) * inv)), iy = (uint32_t)std::min(65535.0, std::max(0.0, (y - loy) * inv));
+    return spread(ix) | (spread(iy) << 1);
+}
+std::vector<float> morton_sorted(const float* tris, int n, int stride) {
+    std::vector<float> out((size_t)n * stride);
+    if (n == 0) return out;
+    double lox = 1e300, loy = 1e300, hix = -1e300, hiy = -1e300;
+    std::vector<P2> cen(n);
+    for (int t = 0; t < n; ++t) {
+        const float* r = tris + (size_t)t * stride;
+        cen[t] = P2{(r[0] + r[2] + r[4]) / 3.0, (r[1] + r[3] + r[5]) / 3.0};
+        lox = std::min(lox, cen[t].x); hix = std::max(hix, cen[t].x); loy = std::min(loy, cen[t].y); hiy = std::max(hiy, cen[t].y);
+    }
+    double inv = 65535.0 / std::max(1e-9, std::max(hix - lox, hiy - loy));
+    std::vector<std::pair<uint32_t, int>> key(n);
+    for (int t = 0; t < n; ++t) key[t] = {morton_key(cen[t].x, cen[t].y, lox, loy, inv), t};
+    std::stable_sort(key.begin(), key.end());
+    for (int k = 0; k < n; ++k) std::memcpy(&out[(size_t)k * stride], tris + (size_t)key[k].second * stride, sizeof(float) * stride);
+    return out;
 }
 }  // namespace
 
@@ -215,7 +307,7 @@ static void free_scenarios(tde_handle* h) {
     if (h->maps_dev) cudaFree(h->maps_dev);
     if (h->scens_dev) cudaFree(h->scens_dev);
     h->maps_dev = nullptr; h->scens_dev = nullptr;
-    h->maps_host.clear(); h->scens_host.clear();
+    h->maps_host.clear(); h->scens_host.clear(); h->map_info.clear();
     h->uploaded = false;
 }
 
@@ -322,16 +414,20 @@ extern "C" int tde_upload_scenarios(tde_handle* h, const tde_scenario_set* s) {
         for (int t = 0; t < nk; ++t)
             if (!edge_ok(s->mark_tris + 6 * (size_t)(k0 + t), 0))
                 return fail(h, TDE_E_SHAPE, "tde_upload_scenarios: marking triangle edge too long; subdivide the mesh");
+        // static triangles in Morton order: runs of 32 are spatially compact (render-time culling); the
+        // order within a layer does not change any result
+        std::vector<float> road_sorted = morton_sorted(s->road_tris + 8 * (size_t)t0, nt, 8);
+        std::vector<float> mark_sorted = morton_sorted(s->mark_tris + 6 * (size_t)k0, nk, 6);
         // road triangles -> device records
         float* raw = nullptr; float4* rec = nullptr;
         int rc;
-        if ((rc = dev_upload(h, &raw, s->road_tris + 8 * (size_t)t0, (size_t)nt * 8))) return rc;
+        if ((rc = dev_upload(h, &raw, road_sorted.data(), (size_t)nt * 8))) return rc;
         if ((rc = dev_alloc(h, &rec, (size_t)nt * 3))) return rc;
         h->scenario_allocs.push_back(rec);
         if (nt) prep_tris_kernel<<<(nt + 127) / 128, 128>>>(raw, nt, rec);
         M.tri = rec; M.ntri = nt;
         float2* mk = nullptr;
-        if ((rc = dev_upload(h, (float**)&mk, s->mark_tris + 6 * (size_t)k0, (size_t)nk * 6))) return rc;
+        if ((rc = dev_upload(h, (float**)&mk, mark_sorted.data(), (size_t)nk * 6))) return rc;
         M.mark = mk; M.nmark = nk;
         float* sraw = nullptr; float4* srec = nullptr;
         if ((rc = dev_upload(h, &sraw, s->stoplines + 5 * (size_t)l0, (size_t)nl * 5))) return rc;
@@ -360,18 +456,24 @@ extern "C" int tde_upload_scenarios(tde_handle* h, const tde_scenario_set* s) {
             return bb;
         };
         {
-            std::vector<float> tb = chunk_boxes(s->road_tris + 8 * (size_t)t0, nt, 8);
-            std::vector<float> mb = chunk_boxes(s->mark_tris + 6 * (size_t)k0, nk, 6);
+            std::vector<float> tb = chunk_boxes(road_sorted.data(), nt, 8);
+            std::vector<float> mb = chunk_boxes(mark_sorted.data(), nk, 6);
             float *tbd = nullptr, *mbd = nullptr;
             if ((rc = dev_upload(h, &tbd, tb.data(), tb.size()))) return rc;
             if ((rc = dev_upload(h, &mbd, mb.data(), mb.size()))) return rc;
             M.tri_chunk = (const float4*)tbd; M.mark_chunk = (const float4*)mbd;
         }
-        Grid g = build_grid(s->road_tris + 8 * (size_t)t0, nt);
-        int* cs = nullptr; uint16_t* items = nullptr;
+        Grid g = build_grid(road_sorted.data(), nt, (double)h->cfg.offroad_threshold);
+        int* cs = nullptr; uint16_t *items = nullptr, *meta = nullptr;
         if ((rc = dev_upload(h, &cs, g.cell_start.data(), g.cell_start.size()))) return rc;
         if ((rc = dev_upload(h, &items, g.items.data(), g.items.size()))) return rc;
-        M.cell_start = cs; M.cell_items = items;
+        if ((rc = dev_upload(h, &meta, g.meta.data(), g.meta.size()))) return rc;
+        M.cell_start = cs; M.cell_items = items; M.cell_meta = meta;
+        {
+            size_t safe = 0, nover = 0;
+            for (uint16_t m : g.meta) { safe += (m & TDE_CELL_SAFE) ? 1 : 0; nover += m & 0x7fff; }
+            h->map_info.push_back({nt, nk, nl, g.nx, g.ny, (int)g.items.size(), (int)safe, (int)nover});
+        }
         M.gx0 = g.gx0; M.gy0 = g.gy0; M.inv_cell = g.inv_cell; M.gnx = g.nx; M.gny = g.ny;
     }
     h->scens_host.resize(s->num_scenarios);
@@ -619,6 +721,11 @@ extern "C" int tde_get_episode_stats(tde_handle* h, double* out, int32_t reset_a
 extern "C" int tde_num_kernel_launches(const tde_handle* h, int64_t* out) {
     if (!h || !out) return TDE_E_INVAL;
     *out = h->launches;
+    return TDE_OK;
+}
+extern "C" int tde_get_map_info(const tde_handle* h, int32_t map_id, int32_t* out8) {
+    if (!h || !out8 || map_id < 0 || map_id >= (int)h->map_info.size()) return TDE_E_INVAL;
+    for (int k = 0; k < 8; ++k) out8[k] = h->map_info[map_id][k];
     return TDE_OK;
 }
 extern "C" int tde_device_sm_count(const tde_handle* h, int32_t* out) {

@@ -119,6 +119,25 @@ __device__ __forceinline__ float tde_point_tri_dist2(const float4* __restrict__ 
     return inside ? 0.0f : fminf(fminf(d0, d1), d2);
 }
 
+// containment only (same edge functions, same operand order as tde_point_tri_dist2)
+__device__ __forceinline__ bool tde_tri_contains(const float4* __restrict__ tri, float px, float py, float& dc, float& ds) {
+    float4 t0 = tri[0], t1 = tri[1], t2 = tri[2];
+    float c0 = (t0.z - t0.x) * (py - t0.y) - (t0.w - t0.y) * (px - t0.x);
+    float c1 = (t1.x - t0.z) * (py - t0.w) - (t1.y - t0.w) * (px - t0.z);
+    float c2 = (t0.x - t1.x) * (py - t1.y) - (t0.y - t1.y) * (px - t1.x);
+    dc = t2.y; ds = t2.z;
+    return (c0 >= 0.0f && c1 >= 0.0f && c2 >= 0.0f) || (c0 <= 0.0f && c1 <= 0.0f && c2 <= 0.0f);
+}
+// min squared distance to the three edges (what tde_point_tri_dist2 returns for a point outside)
+__device__ __forceinline__ float tde_tri_segdist2(const float4* __restrict__ tri, float px, float py) {
+    float4 t0 = tri[0], t1 = tri[1], t2 = tri[2];
+    float d0, d1, d2, c;
+    tde_edge_terms(t0.x, t0.y, t0.z, t0.w, t1.z, px, py, d0, c);
+    tde_edge_terms(t0.z, t0.w, t1.x, t1.y, t1.w, px, py, d1, c);
+    tde_edge_terms(t1.x, t1.y, t0.x, t0.y, t2.x, px, py, d2, c);
+    return fminf(fminf(d0, d1), d2);
+}
+
 // ---- counter-based RNG shared (as a specification) with the oracle
 __host__ __device__ __forceinline__ uint64_t tde_mix64(uint64_t x) {
     x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ULL;

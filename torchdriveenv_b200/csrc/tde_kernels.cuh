@@ -21,7 +21,8 @@ struct MapDev {
     const float4* stop;         // 2 float4 per stop line: [x y hl hw] [c s 0 0]
     const uint8_t* lights;      // [period][nstop]
     const int* cell_start;      // [gnx*gny+1]
-    const uint16_t* cell_items; // nearest-candidate triangle ids per grid cell
+    const uint16_t* cell_items; // per cell: overlapping triangles first, then the other nearest candidates
+    const uint16_t* cell_meta;  // per cell: n_overlapping | TDE_CELL_SAFE
     const float4* tri_chunk;    // bbox (lox loy hix hiy) of every run of 32 road triangles
     const float4* mark_chunk;   // same for lane-marking triangles
     int ntri, nmark, nstop, period;
@@ -92,25 +93,29 @@ __device__ __forceinline__ void st_box(float4* sb, int a, const Box& b) {
 
 // ---------------------------------------------------------------- lane-mesh queries
 
-// squared distance from p to the road mesh of map M (0 on the road); exact: the grid cell lists hold
-// every triangle that can be nearest for any point of the cell, points off the grid scan all triangles
-__device__ __noinline__ float mesh_dist2(const MapDev& M, float px, float py) {
-    float best = INFINITY;
+// Squared distance from p to the road mesh of map M (0 on the road).  Exact: every grid cell lists the
+// triangles overlapping it first (n_over of them, enough to decide containment) and then every other
+// triangle that can be nearest to some point of the cell; points off the grid scan all triangles.
+// `skip_safe`: cells whose every point is provably closer to the road than the offroad threshold are
+// flagged at upload; for those the caller only needs "distance < threshold" and gets 0.
+#define TDE_CELL_SAFE 0x8000
+__device__ __noinline__ float mesh_dist2(const MapDev& M, float px, float py, bool skip_safe) {
     float fx = floorf((px - M.gx0) * M.inv_cell), fy = floorf((py - M.gy0) * M.inv_cell);
     bool in_grid = fx >= 0.0f && fy >= 0.0f && fx < (float)M.gnx && fy < (float)M.gny;
-    bool ins; float dc, ds;
+    float dc, ds;
+    float best = INFINITY;
     if (in_grid) {
         int cell = (int)fy * M.gnx + (int)fx;
-        int i0 = M.cell_start[cell], i1 = M.cell_start[cell + 1];
-        for (int i = i0; i < i1; ++i) {
-            float d2 = tde_point_tri_dist2(M.tri + 3 * (int)M.cell_items[i], px, py, ins, dc, ds);
-            best = fminf(best, d2);
-        }
+        int meta = M.cell_meta[cell];
+        if (skip_safe && (meta & TDE_CELL_SAFE)) return 0.0f;
+        int i0 = M.cell_start[cell], i1 = M.cell_start[cell + 1], nover = meta & 0x7fff;
+        for (int i = i0; i < i0 + nover; ++i)
+            if (tde_tri_contains(M.tri + 3 * (int)M.cell_items[i], px, py, dc, ds)) return 0.0f;
+        for (int i = i0; i < i1; ++i) best = fminf(best, tde_tri_segdist2(M.tri + 3 * (int)M.cell_items[i], px, py));
     } else {
-        for (int t = 0; t < M.ntri; ++t) {
-            float d2 = tde_point_tri_dist2(M.tri + 3 * t, px, py, ins, dc, ds);
-            best = fminf(best, d2);
-        }
+        for (int t = 0; t < M.ntri; ++t)
+            if (tde_tri_contains(M.tri + 3 * t, px, py, dc, ds)) return 0.0f;
+        for (int t = 0; t < M.ntri; ++t) best = fminf(best, tde_tri_segdist2(M.tri + 3 * t, px, py));
     }
     return best;
 }
@@ -123,7 +128,7 @@ __device__ __forceinline__ float offroad_box(const MapDev& M, const Box& b, floa
     for (int k = 0; k < 4; ++k) {
         float px, py;
         tde_box_corner(b, k, px, py);
-        float d = sqrtf(mesh_dist2(M, px, py));
+        float d = sqrtf(mesh_dist2(M, px, py, true));
         sum = sum + fmaxf(d - thr, 0.0f);
     }
     return sum;
@@ -134,19 +139,15 @@ __device__ __noinline__ float wrong_way_box(const MapDev& M, const Box& b) {
     float best = INFINITY;
     float fx = floorf((b.x - M.gx0) * M.inv_cell), fy = floorf((b.y - M.gy0) * M.inv_cell);
     bool in_grid = fx >= 0.0f && fy >= 0.0f && fx < (float)M.gnx && fy < (float)M.gny;
-    bool ins; float dc, ds;
+    float dc, ds;
     if (in_grid) {
         int cell = (int)fy * M.gnx + (int)fx;
-        int i0 = M.cell_start[cell], i1 = M.cell_start[cell + 1];
-        for (int i = i0; i < i1; ++i) {
-            (void)tde_point_tri_dist2(M.tri + 3 * (int)M.cell_items[i], b.x, b.y, ins, dc, ds);
-            if (ins) best = fminf(best, fmaxf(-(b.c * dc + b.s * ds), 0.0f));
-        }
+        int i0 = M.cell_start[cell], nover = M.cell_meta[cell] & 0x7fff;
+        for (int i = i0; i < i0 + nover; ++i)
+            if (tde_tri_contains(M.tri + 3 * (int)M.cell_items[i], b.x, b.y, dc, ds)) best = fminf(best, fmaxf(-(b.c * dc + b.s * ds), 0.0f));
     } else {
-        for (int t = 0; t < M.ntri; ++t) {
-            (void)tde_point_tri_dist2(M.tri + 3 * t, b.x, b.y, ins, dc, ds);
-            if (ins) best = fminf(best, fmaxf(-(b.c * dc + b.s * ds), 0.0f));
-        }
+        for (int t = 0; t < M.ntri; ++t)
+            if (tde_tri_contains(M.tri + 3 * t, b.x, b.y, dc, ds)) best = fminf(best, fmaxf(-(b.c * dc + b.s * ds), 0.0f));
     }
     return best == INFINITY ? 0.0f : best;
 }

@@ -158,6 +158,12 @@ class Engine:
         self._check(self.lib.tde_device_sm_count(self.h, C.byref(n)), "tde_device_sm_count")
         return int(n.value)
 
+    def map_info(self, map_id: int = 0) -> Dict[str, int]:
+        out = (C.c_int32 * 8)()
+        self._check(self.lib.tde_get_map_info(self.h, int(map_id), out), "tde_get_map_info")
+        keys = ["road_tris", "mark_tris", "stoplines", "grid_nx", "grid_ny", "grid_items", "safe_cells", "overlapping_items"]
+        return dict(zip(keys, [int(v) for v in out]))
+
     # -- stateless kernels (config C4)
     def collision_boxes(self, state: torch.Tensor, attr: torch.Tensor) -> torch.Tensor:
         st = state.to(device=self.device, dtype=torch.float32).contiguous()
