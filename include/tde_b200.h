@@ -256,7 +256,8 @@ int tde_get_episode_stats(tde_handle* h, double* out_host, int32_t reset_after, 
 int tde_num_kernel_launches(const tde_handle* h, int64_t* out);
 int tde_device_sm_count(const tde_handle* h, int32_t* out);
 /* int32[8]: road triangles, marking triangles, stop lines, grid nx, grid ny, grid list entries,
-   cells flagged "every point within the offroad threshold", entries that overlap their cell */
+   cells flagged "every point within the offroad threshold", static render primitives after merging
+   triangle pairs into convex quads */
 int tde_get_map_info(const tde_handle* h, int32_t map_id, int32_t* out8);
 
 #ifdef __cplusplus

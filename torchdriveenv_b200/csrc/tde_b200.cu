@@ -4,6 +4,8 @@
 
 #include <algorithm>
 #include <array>
+#include <map>
+#include <tuple>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -249,6 +251,61 @@ uint32_t morton_key(double x, double y, double lox, double loy, double inv) {
     uint32_t ix = (uint32_t)std::min(65535.0, std::max(0.0, (x - lox) * inv)), iy = (uint32_t)std::min(65535.0, std::max(0.0, (y - loy) * inv));
     return spread(ix) | (spread(iy) << 1);
 }
+// Render-only primitives: pairs of triangles that share an edge and form a strictly convex
+// quadrilateral are merged (the fixed-point fill rule is watertight, so a quad covers exactly the
+// union of its two triangles); the rest stay triangles (fourth vertex = first).  8 floats each.
+std::vector<float> merge_into_quads(const float* tris, int n, int stride) {
+    struct Key { float ax, ay, bx, by; bool operator<(const Key& o) const { return std::tie(ax, ay, bx, by) < std::tie(o.ax, o.ay, o.bx, o.by); } };
+    auto mk = [](float ax, float ay, float bx, float by) { return std::tie(ax, ay) < std::tie(bx, by) ? Key{ax, ay, bx, by} : Key{bx, by, ax, ay}; };
+    std::map<Key, std::vector<int>> edges;  // undirected edge -> triangle*3 + edge index
+    for (int t = 0; t < n; ++t) {
+        const float* r = tris + (size_t)t * stride;
+        for (int k = 0; k < 3; ++k) { int k1 = (k + 1) % 3; edges[mk(r[2 * k], r[2 * k + 1], r[2 * k1], r[2 * k1 + 1])].push_back(t * 3 + k); }
+    }
+    std::vector<char> used(n, 0);
+    std::vector<float> out;
+    auto convex = [](const double (&q)[4][2]) {
+        int sgn = 0;
+        for (int k = 0; k < 4; ++k) {
+            const double* a = q[k]; const double* b = q[(k + 1) % 4]; const double* c = q[(k + 2) % 4];
+            double ux = b[0] - a[0], uy = b[1] - a[1], vx = c[0] - b[0], vy = c[1] - b[1];
+            double cr = ux * vy - uy * vx, lu = std::hypot(ux, uy), lv = std::hypot(vx, vy);
+            if (lu < 1e-6 || lv < 1e-6) return false;
+            double sn = cr / (lu * lv);  // sine of the turn: need a clear turn (interior angle <= ~162 deg)
+            if (std::fabs(sn) < 0.3) return false;
+            int s = sn > 0 ? 1 : -1;
+            if (sgn == 0) sgn = s; else if (s != sgn) return false;
+        }
+        return true;
+    };
+    for (int t = 0; t < n; ++t) {
+        if (used[t]) continue;
+        const float* r = tris + (size_t)t * stride;
+        bool merged = false;
+        for (int k = 0; k < 3 && !merged; ++k) {
+            int k1 = (k + 1) % 3, k2 = (k + 2) % 3;
+            for (int ref : edges[mk(r[2 * k], r[2 * k + 1], r[2 * k1], r[2 * k1 + 1])]) {
+                int u = ref / 3, ue = ref % 3;
+                if (u == t || used[u]) continue;
+                const float* w = tris + (size_t)u * stride;
+                int uo = (ue + 2) % 3;  // vertex of u opposite the shared edge
+                // quad: t's opposite vertex, shared a, u's opposite vertex, shared b
+                double q[4][2] = {{r[2 * k2], r[2 * k2 + 1]}, {r[2 * k], r[2 * k + 1]}, {w[2 * uo], w[2 * uo + 1]}, {r[2 * k1], r[2 * k1 + 1]}};
+                if (!convex(q)) continue;
+                for (int v = 0; v < 4; ++v) { out.push_back((float)q[v][0]); out.push_back((float)q[v][1]); }
+                used[t] = used[u] = 1; merged = true;
+                break;
+            }
+        }
+        if (!merged) {
+            used[t] = 1;
+            for (int v = 0; v < 3; ++v) { out.push_back(r[2 * v]); out.push_back(r[2 * v + 1]); }
+            out.push_back(r[0]); out.push_back(r[1]);
+        }
+    }
+    return out;
+}
+
 std::vector<float> morton_sorted(const float* tris, int n, int stride) {
     std::vector<float> out((size_t)n * stride);
     if (n == 0) return out;
@@ -417,7 +474,6 @@ extern "C" int tde_upload_scenarios(tde_handle* h, const tde_scenario_set* s) {
         // static triangles in Morton order: runs of 32 are spatially compact (render-time culling); the
         // order within a layer does not change any result
         std::vector<float> road_sorted = morton_sorted(s->road_tris + 8 * (size_t)t0, nt, 8);
-        std::vector<float> mark_sorted = morton_sorted(s->mark_tris + 6 * (size_t)k0, nk, 6);
         // road triangles -> device records
         float* raw = nullptr; float4* rec = nullptr;
         int rc;
@@ -426,9 +482,17 @@ extern "C" int tde_upload_scenarios(tde_handle* h, const tde_scenario_set* s) {
         h->scenario_allocs.push_back(rec);
         if (nt) prep_tris_kernel<<<(nt + 127) / 128, 128>>>(raw, nt, rec);
         M.tri = rec; M.ntri = nt;
-        float2* mk = nullptr;
-        if ((rc = dev_upload(h, (float**)&mk, mark_sorted.data(), (size_t)nk * 6))) return rc;
-        M.mark = mk; M.nmark = nk;
+        M.nmark = nk;
+        // render-only static primitives: merged quads / leftover triangles, Morton ordered
+        std::vector<float> rp_road = merge_into_quads(s->road_tris + 8 * (size_t)t0, nt, 8);
+        std::vector<float> rp_mark = merge_into_quads(s->mark_tris + 6 * (size_t)k0, nk, 6);
+        rp_road = morton_sorted(rp_road.data(), (int)(rp_road.size() / 8), 8);
+        rp_mark = morton_sorted(rp_mark.data(), (int)(rp_mark.size() / 8), 8);
+        float *rpr = nullptr, *rpm = nullptr;
+        if ((rc = dev_upload(h, &rpr, rp_road.data(), rp_road.size()))) return rc;
+        if ((rc = dev_upload(h, &rpm, rp_mark.data(), rp_mark.size()))) return rc;
+        M.rp_road = (const float4*)rpr; M.n_rp_road = (int)(rp_road.size() / 8);
+        M.rp_mark = (const float4*)rpm; M.n_rp_mark = (int)(rp_mark.size() / 8);
         float* sraw = nullptr; float4* srec = nullptr;
         if ((rc = dev_upload(h, &sraw, s->stoplines + 5 * (size_t)l0, (size_t)nl * 5))) return rc;
         if ((rc = dev_alloc(h, &srec, (size_t)nl * 2))) return rc;
@@ -447,7 +511,7 @@ extern "C" int tde_upload_scenarios(tde_handle* h, const tde_scenario_set* s) {
             for (int c0 = 0; c0 < count; c0 += 32) {
                 float lx = INFINITY, ly = INFINITY, hx = -INFINITY, hy = -INFINITY;
                 for (int t = c0; t < std::min(count, c0 + 32); ++t)
-                    for (int k = 0; k < 3; ++k) {
+                    for (int k = 0; k < 4; ++k) {
                         float x = base[(size_t)t * stride + 2 * k], y = base[(size_t)t * stride + 2 * k + 1];
                         lx = std::min(lx, x); hx = std::max(hx, x); ly = std::min(ly, y); hy = std::max(hy, y);
                     }
@@ -456,8 +520,8 @@ extern "C" int tde_upload_scenarios(tde_handle* h, const tde_scenario_set* s) {
             return bb;
         };
         {
-            std::vector<float> tb = chunk_boxes(road_sorted.data(), nt, 8);
-            std::vector<float> mb = chunk_boxes(mark_sorted.data(), nk, 6);
+            std::vector<float> tb = chunk_boxes(rp_road.data(), M.n_rp_road, 8);
+            std::vector<float> mb = chunk_boxes(rp_mark.data(), M.n_rp_mark, 8);
             float *tbd = nullptr, *mbd = nullptr;
             if ((rc = dev_upload(h, &tbd, tb.data(), tb.size()))) return rc;
             if ((rc = dev_upload(h, &mbd, mb.data(), mb.size()))) return rc;
@@ -472,7 +536,7 @@ extern "C" int tde_upload_scenarios(tde_handle* h, const tde_scenario_set* s) {
         {
             size_t safe = 0, nover = 0;
             for (uint16_t m : g.meta) { safe += (m & TDE_CELL_SAFE) ? 1 : 0; nover += m & 0x7fff; }
-            h->map_info.push_back({nt, nk, nl, g.nx, g.ny, (int)g.items.size(), (int)safe, (int)nover});
+            h->map_info.push_back({nt, nk, nl, g.nx, g.ny, (int)g.items.size(), (int)safe, M.n_rp_road + M.n_rp_mark});
         }
         M.gx0 = g.gx0; M.gy0 = g.gy0; M.inv_cell = g.inv_cell; M.gnx = g.nx; M.gny = g.ny;
     }

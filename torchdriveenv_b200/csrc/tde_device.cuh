@@ -164,8 +164,15 @@ __device__ __forceinline__ float tde_normal8(uint64_t r0, uint64_t r1) {
     return u * 1.22474487139158894f;
 }
 
-__device__ __forceinline__ int tde_floordiv(int a, int b) {  // b > 0
-    int q = a / b;
-    int r = a - q * b;
-    return r < 0 ? q - 1 : q;
+// exact floor(a / d) and remainder for d > 0 from a float estimate refined twice in integers
+// (inv_d ~ 1/d, any approximation good to ~2^-20 relative)
+__device__ __forceinline__ int tde_floordiv(int a, int d, float inv_d, int& rem) {
+    int q = __float2int_rd((float)a * inv_d);
+    int r = a - q * d;                       // |r| <= ~17 d after the first estimate
+    int q2 = __float2int_rd((float)r * inv_d);
+    q += q2; r -= q2 * d;                    // now off by at most one
+    if (r < 0) { q -= 1; r += d; }
+    else if (r >= d) { q += 1; r -= d; }
+    rem = r;
+    return q;
 }

@@ -17,15 +17,17 @@
 
 struct MapDev {
     const float4* tri;          // 3 float4 per road triangle (see tde_point_tri_dist2)
-    const float2* mark;         // 3 float2 per lane-marking triangle
+    const float4* rp_road;      // render primitives of the road layer: 2 float4 = 4 vertices (triangle: v3 == v0)
+    const float4* rp_mark;      // same for the lane-marking layer
     const float4* stop;         // 2 float4 per stop line: [x y hl hw] [c s 0 0]
     const uint8_t* lights;      // [period][nstop]
     const int* cell_start;      // [gnx*gny+1]
     const uint16_t* cell_items; // per cell: overlapping triangles first, then the other nearest candidates
     const uint16_t* cell_meta;  // per cell: n_overlapping | TDE_CELL_SAFE
-    const float4* tri_chunk;    // bbox (lox loy hix hiy) of every run of 32 road triangles
-    const float4* mark_chunk;   // same for lane-marking triangles
+    const float4* tri_chunk;    // bbox (lox loy hix hiy) of every run of 32 road render primitives
+    const float4* mark_chunk;   // same for the lane-marking layer
     int ntri, nmark, nstop, period;
+    int n_rp_road, n_rp_mark;
     float gx0, gy0, inv_cell;
     int gnx, gny;
 };
@@ -68,17 +70,18 @@ struct StepParams {
 
 struct Cam { float ex, ey, ce, se, ppm, ppmy; };
 
-#define TDE_BAND_ROWS 16
+#define TDE_BAND_ROWS 32
+#define TDE_NBANDS (TDE_OBS_H / TDE_BAND_ROWS)
 
 struct PhysScratch {  // per warp, physics kernel
     float4 box[TDE_MAX_AGENTS * 2];  // Box as two float4
 };
 
 struct RenderScratch {  // per warp, render kernel
-    uint4 qv[64];                                              // queue of snapped primitives: 4 x (x | y << 16)
-    unsigned long long span[TDE_BAND_ROWS * TDE_SPAN_STRIDE];  // one 16-row band of coverage spans, [row][primitive]
-    unsigned long long planes[TDE_OBS_H * 4];                  // [row][bit-plane] class-index image
-    unsigned char qc[64];                                      // class | n_vertices << 4
+    uint4 qv[TDE_NBANDS][64];                              // per 32-row band: queue of snapped primitives, 4 x (x | y << 16)
+    unsigned long long planes[TDE_OBS_H * 4];              // [row][bit-plane] class-index image
+    unsigned int span[TDE_BAND_ROWS * TDE_SPAN_STRIDE];    // one band of coverage spans (xl | xr << 8), [row][primitive]
+    unsigned char qc[TDE_NBANDS][64];                      // class | n_vertices << 4
 };
 
 __device__ __forceinline__ Box ld_box(const float4* sb, int a) {
@@ -273,19 +276,40 @@ __device__ __forceinline__ bool project_prim(const Cam& cam, const float (&wx)[4
     return maxx >= -1.0f && minx <= (float)TDE_OBS_W + 1.0f && maxy >= -1.0f && miny <= (float)TDE_OBS_H + 1.0f;
 }
 
-// Rasterise the first `count` (<= 32) queued primitives, one per lane, into the class-index planes.
-//   phase 1 (lane = primitive): exact integer edge stepping (a DDA on floor(K/D) per edge), one 64-bit
-//            coverage span per image row, written to a 16-row band buffer in shared memory;
-//   phase 2 (lane = row x half of the primitives): OR the spans of each class present, classes in
-//            ascending = painter's order, and update the four bit-planes of the class index.
+// phase 1 of raster_band for primitives with at most NE slanted edges: step the edges down the rows
+template <int NE>
+__device__ __forceinline__ void span_rows(int j, int jend, int b0, int lane, int (&V)[4], const int (&dV)[4], int (&rem)[4],
+                                          const int (&rS)[4], const int (&D)[4], const int (&cstep)[4], const int (&cap)[4],
+                                          unsigned int* span) {
+#pragma unroll 1
+    for (; j <= jend; ++j) {
+        int xl = 0, xr = TDE_OBS_W;
+#pragma unroll
+        for (int k = 0; k < NE; ++k) {
+            xl = max(xl, min(V[k], cap[k]));
+            xr = min(xr, max(V[k], cap[k]));
+            V[k] += dV[k];
+            rem[k] += rS[k];
+            if (rem[k] >= D[k]) { rem[k] -= D[k]; V[k] += cstep[k]; }
+        }
+        if (xl < xr) span[(j - b0) * TDE_SPAN_STRIDE + lane] = (unsigned)xl | ((unsigned)xr << 8);
+    }
+}
+
+// Rasterise the first `count` (<= 32) primitives queued for 32-row band `band`, one per lane, into the
+// class-index planes.
+//   phase 1 (lane = primitive): exact integer edge stepping (a DDA on floor(K/D) per edge), one
+//            coverage span [xl, xr) per image row of the band, written to shared memory;
+//   phase 2 (lane = row): walk the primitives in queue (= painter's) order, OR the spans of each run
+//            of equal class and paint the run over the four bit-planes of the class index.
 // Pixel-centre sampling on the 1/16-px grid with the top-left rule: the same pixel set as the
 // oracle's per-pixel edge-function test.
-__device__ __noinline__ void raster_batch(RenderScratch* ws, int count, int lane) {
+__device__ __noinline__ void raster_band(RenderScratch* ws, int band, int count, int lane) {
     const bool have = lane < count;
-    const uint4 q = ws->qv[lane];
-    const int cn = have ? (int)ws->qc[lane] : 0;
+    const uint4 q = ws->qv[band][lane];
+    const int cn = have ? (int)ws->qc[band][lane] : 0;
     int n = cn >> 4;
-    const int cls = cn & 15;
+    if (n == 4 && q.w == q.x) n = 3;  // a static-layer triangle travels as a quad whose last vertex repeats the first
     int X[4] = {unpack_x(q.x), unpack_x(q.y), unpack_x(q.z), unpack_x(q.w)};
     int Y[4] = {unpack_y(q.x), unpack_y(q.y), unpack_y(q.z), unpack_y(q.w)};
     if (n == 3) { X[3] = X[0]; Y[3] = Y[0]; }
@@ -296,10 +320,10 @@ __device__ __noinline__ void raster_batch(RenderScratch* ws, int count, int lane
         if (n == 4) { int t = X[1]; X[1] = X[3]; X[3] = t; t = Y[1]; Y[1] = Y[3]; Y[3] = t; }
         else { int t = X[1]; X[1] = X[2]; X[2] = t; t = Y[1]; Y[1] = Y[2]; Y[2] = t; X[3] = X[0]; Y[3] = Y[0]; }
     }
+    const int b0 = band * TDE_BAND_ROWS, b1 = b0 + TDE_BAND_ROWS - 1;
     int ymin = min(min(Y[0], Y[1]), min(Y[2], Y[3])), ymax = max(max(Y[0], Y[1]), max(Y[2], Y[3]));
-    int xmin = min(min(X[0], X[1]), min(X[2], X[3])), xmax = max(max(X[0], X[1]), max(X[2], X[3]));
-    int j0 = max(0, (ymin - 8 + 15) >> 4);         // ceil((ymin - 8) / 16)
-    int j1 = min(TDE_OBS_H - 1, (ymax - 8) >> 4);  // floor((ymax - 8) / 16)
+    int j0 = max(b0, (ymin - 8 + 15) >> 4);  // ceil((ymin - 8) / 16)
+    int j1 = min(b1, (ymax - 8) >> 4);       // floor((ymax - 8) / 16)
     // horizontal edges only restrict the row range (top edges are inclusive, bottom edges exclusive)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -310,8 +334,9 @@ __device__ __noinline__ void raster_batch(RenderScratch* ws, int count, int lane
             if (dx > 0) j0 = max(j0, c); else j1 = min(j1, c - 1);
         }
     }
-    const bool active = n >= 3 && j0 <= j1 && xmax >= 8 && xmin <= 16 * (TDE_OBS_W - 1) + 8;
-    if (!__any_sync(FULL_MASK, active)) return;
+    const bool active = n >= 3 && j0 <= j1;
+    const unsigned bm = __ballot_sync(FULL_MASK, active);
+    if (bm == 0) return;
 
     // slanted edges: V = current bound (left: first covered column, right: one past the last), stepped per row
     int V[4], dV[4], rem[4], rS[4], D[4], cstep[4], cap[4];
@@ -327,93 +352,89 @@ __device__ __noinline__ void raster_batch(RenderScratch* ws, int count, int lane
             int S = 16 * dx;
             int K = C0 + S * j0;
             int d = dy > 0 ? 16 * dy : -16 * dy;
-            int F = tde_floordiv(K, d);
-            int qs = tde_floordiv(S, d);
+            float inv_d = __fdividef(1.0f, (float)d);
+            int F = tde_floordiv(K, d, inv_d, rem[k]);
+            int qs = tde_floordiv(S, d, inv_d, rS[k]);
             D[k] = d;
-            rem[k] = K - F * d;
-            rS[k] = S - qs * d;
             if (dy > 0) { V[k] = F + 1; dV[k] = qs; cstep[k] = 1; cap[k] = INT_MIN; }
             else { V[k] = -F; dV[k] = -qs; cstep[k] = -1; cap[k] = INT_MAX; }
         }
     }
-
-    unsigned long long* span = ws->span;
-    int j = j0;
+    unsigned int* span = ws->span;
+    {   // clear the band buffer (32 rows x 33 spans)
+        uint4* s4 = reinterpret_cast<uint4*>(span);
 #pragma unroll 1
-    for (int band = 0; band < TDE_OBS_H / TDE_BAND_ROWS; ++band) {
-        const int b0 = band * TDE_BAND_ROWS, b1 = b0 + TDE_BAND_ROWS - 1;
-        const bool part = active && j0 <= b1 && j1 >= b0;
-        const unsigned bm = __ballot_sync(FULL_MASK, part);
-        if (bm == 0) continue;
-        {   // clear the band buffer (16 rows x 33 spans)
-            uint4* s4 = reinterpret_cast<uint4*>(span);
-#pragma unroll 1
-            for (int i = lane; i < TDE_BAND_ROWS * TDE_SPAN_STRIDE / 2; i += 32) s4[i] = make_uint4(0u, 0u, 0u, 0u);
-        }
-        __syncwarp();
-        if (part) {
-            const int jend = min(j1, b1);
-#pragma unroll 1
-            for (; j <= jend; ++j) {
-                int xl = 0, xr = TDE_OBS_W;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    xl = max(xl, min(V[k], cap[k]));
-                    xr = min(xr, max(V[k], cap[k]));
-                    V[k] += dV[k];
-                    rem[k] += rS[k];
-                    if (rem[k] >= D[k]) { rem[k] -= D[k]; V[k] += cstep[k]; }
-                }
-                if (xl < xr) span[(j - b0) * TDE_SPAN_STRIDE + lane] = (~0ull >> (64 - xr)) & (~0ull << xl);
-            }
-        }
-        __syncwarp();
-        // phase 2: lane = (row, half of the primitive slots)
-        const int row = lane & (TDE_BAND_ROWS - 1), kh = lane >> 4;
-        unsigned remaining = bm;
-        while (remaining) {
-            int mycls = ((remaining >> lane) & 1u) ? cls : 0x7fffffff;
-            int c = __reduce_min_sync(FULL_MASK, mycls);
-            unsigned mc = __ballot_sync(FULL_MASK, mycls == c);
-            unsigned u = (mc | (mc >> 16)) & 0xffffu;
-            unsigned mine = (mc >> (16 * kh)) & 0xffffu;
-            unsigned long long acc = 0ull;
-            while (u) {
-                int b = __ffs(u) - 1;
-                u &= u - 1;
-                if ((mine >> b) & 1u) acc |= span[row * TDE_SPAN_STRIDE + b + 16 * kh];
-            }
-            acc |= __shfl_xor_sync(FULL_MASK, acc, 16);
-            // each half updates two of the four planes of its row
-            ulonglong2* pp = reinterpret_cast<ulonglong2*>(&ws->planes[(b0 + row) * 4 + 2 * kh]);
-            ulonglong2 pv = *pp;
-            unsigned long long keep0 = ((c >> (2 * kh)) & 1) ? ~0ull : 0ull;
-            unsigned long long keep1 = ((c >> (2 * kh + 1)) & 1) ? ~0ull : 0ull;
-            pv.x = (pv.x & ~acc) | (acc & keep0);
-            pv.y = (pv.y & ~acc) | (acc & keep1);
-            *pp = pv;
-            remaining &= ~mc;
-        }
-        __syncwarp();
+        for (int i = lane; i < TDE_BAND_ROWS * TDE_SPAN_STRIDE / 4; i += 32) s4[i] = make_uint4(0u, 0u, 0u, 0u);
     }
+    __syncwarp();
+    if (active) {
+        // a triangle's fourth slot is the degenerate edge 3 -> 0: skip it when the whole batch is triangles
+        if (__any_sync(bm, n == 4)) span_rows<4>(j0, j1, b0, lane, V, dV, rem, rS, D, cstep, cap, span);
+        else span_rows<3>(j0, j1, b0, lane, V, dV, rem, rS, D, cstep, cap, span);
+    }
+    __syncwarp();
+    // phase 2: lane = image row b0 + lane
+    ulonglong2* pp = reinterpret_cast<ulonglong2*>(&ws->planes[(b0 + lane) * 4]);
+    ulonglong2 p01 = pp[0], p23 = pp[1];
+    int cur = 0;
+    unsigned long long acc = 0ull;
+    unsigned todo = bm;
+    while (todo) {
+        int k = __ffs(todo) - 1;
+        todo &= todo - 1;
+        int c = (int)ws->qc[band][k] & 15;
+        if (c != cur) {  // warp-uniform: a new run of equal class starts; paint the finished one
+            p01.x = (p01.x & ~acc) | ((cur & 1) ? acc : 0ull);
+            p01.y = (p01.y & ~acc) | ((cur & 2) ? acc : 0ull);
+            p23.x = (p23.x & ~acc) | ((cur & 4) ? acc : 0ull);
+            p23.y = (p23.y & ~acc) | ((cur & 8) ? acc : 0ull);
+            acc = 0ull; cur = c;
+        }
+        unsigned w = span[lane * TDE_SPAN_STRIDE + k];
+        int xl = (int)(w & 0xffu), xr = (int)(w >> 8);
+        if (xr > xl) acc |= (~0ull >> (64 - xr)) & (~0ull << xl);
+    }
+    p01.x = (p01.x & ~acc) | ((cur & 1) ? acc : 0ull);
+    p01.y = (p01.y & ~acc) | ((cur & 2) ? acc : 0ull);
+    p23.x = (p23.x & ~acc) | ((cur & 4) ? acc : 0ull);
+    p23.y = (p23.y & ~acc) | ((cur & 8) ? acc : 0ull);
+    pp[0] = p01; pp[1] = p23;
+    __syncwarp();
 }
 
-// append the primitives of the lanes with `valid` to the warp's queue; rasterise a batch when 32 are pending
-__device__ __forceinline__ void enqueue(RenderScratch* ws, int& qn, int lane, bool valid, const uint4& v, int cls, int nverts) {
-    unsigned m = __ballot_sync(FULL_MASK, valid);
-    if (m == 0) return;
-    int pos = qn + __popc(m & ((1u << lane) - 1u));
-    if (valid) { ws->qv[pos] = v; ws->qc[pos] = (unsigned char)(cls | (nverts << 4)); }
-    qn += __popc(m);
+// Append the primitives of the lanes with `valid` to the queue of every 32-row band they touch
+// (ballot/popc compaction keeps painter's order); a band is rasterised as soon as 32 are pending.
+__device__ __forceinline__ void enqueue(RenderScratch* ws, int (&qn)[TDE_NBANDS], int lane, bool valid, const uint4& v, int cls, int nverts) {
+    int y0 = unpack_y(v.x), y1 = unpack_y(v.y), y2 = unpack_y(v.z), y3 = unpack_y(v.w);
+    int x0 = unpack_x(v.x), x1 = unpack_x(v.y), x2 = unpack_x(v.z), x3 = unpack_x(v.w);
+    int ymin = min(min(y0, y1), min(y2, y3)), ymax = max(max(y0, y1), max(y2, y3));
+    int xmin = min(min(x0, x1), min(x2, x3)), xmax = max(max(x0, x1), max(x2, x3));
+    int j0 = max(0, (ymin - 8 + 15) >> 4), j1 = min(TDE_OBS_H - 1, (ymax - 8) >> 4);
+    valid = valid && j0 <= j1 && xmax >= 8 && xmin <= 16 * (TDE_OBS_W - 1) + 8;  // bbox holds at least one pixel centre
+    if (!__any_sync(FULL_MASK, valid)) return;
+    const int blo = j0 / TDE_BAND_ROWS, bhi = j1 / TDE_BAND_ROWS;
+    const unsigned char cn = (unsigned char)(cls | (nverts << 4));
+#pragma unroll
+    for (int b = 0; b < TDE_NBANDS; ++b) {
+        bool in = valid && blo <= b && b <= bhi;
+        unsigned m = __ballot_sync(FULL_MASK, in);
+        if (m == 0) continue;
+        int pos = qn[b] + __popc(m & ((1u << lane) - 1u));
+        if (in) { ws->qv[b][pos] = v; ws->qc[b][pos] = cn; }
+        qn[b] += __popc(m);
+    }
     __syncwarp();
-    if (qn >= 32) {
-        raster_batch(ws, 32, lane);
-        uint4 tv = ws->qv[32 + lane];
-        unsigned char tc = ws->qc[32 + lane];
-        __syncwarp();
-        ws->qv[lane] = tv; ws->qc[lane] = tc;
-        qn -= 32;
-        __syncwarp();
+#pragma unroll
+    for (int b = 0; b < TDE_NBANDS; ++b) {
+        if (qn[b] >= 32) {
+            raster_band(ws, b, 32, lane);
+            uint4 tv = ws->qv[b][32 + lane];
+            unsigned char tc = ws->qc[b][32 + lane];
+            __syncwarp();
+            ws->qv[b][lane] = tv; ws->qc[b][lane] = tc;
+            qn[b] -= 32;
+            __syncwarp();
+        }
     }
 }
 
@@ -441,13 +462,14 @@ __device__ __forceinline__ uint32_t spread8(uint32_t b) {
     return x;
 }
 
-// static triangle layers (road, lane markings): lanes first test the bounding boxes of 32-triangle
-// runs against the viewport's reach, then only the visible runs are loaded, projected and queued
+// static layers (road, lane markings): lanes first test the bounding boxes of runs of 32 primitives
+// against the viewport's reach, then only the visible runs are loaded, projected and queued
 template <bool ROAD>
-__device__ __forceinline__ void queue_static_layer(const MapDev& M, const Cam& cam, float reach, RenderScratch* ws, int& qn, int lane) {
-    const int ntri = ROAD ? M.ntri : M.nmark;
+__device__ __forceinline__ void queue_static_layer(const MapDev& M, const Cam& cam, float reach, RenderScratch* ws, int (&qn)[TDE_NBANDS], int lane) {
+    const int nprim = ROAD ? M.n_rp_road : M.n_rp_mark;
+    const float4* prim = ROAD ? M.rp_road : M.rp_mark;
     const float4* chunk = ROAD ? M.tri_chunk : M.mark_chunk;
-    const int nchunk = (ntri + 31) >> 5;
+    const int nchunk = (nprim + 31) >> 5;
     float wx[4], wy[4];
 #pragma unroll 1
     for (int cb = 0; cb < nchunk; cb += 32) {
@@ -461,24 +483,31 @@ __device__ __forceinline__ void queue_static_layer(const MapDev& M, const Cam& c
             int c = cb + __ffs(vis) - 1;
             vis &= vis - 1;
             int t = c * 32 + lane;
-            bool valid = t < ntri;
-            if (ROAD) {
-                float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
-                if (valid) { t0 = M.tri[3 * t]; t1 = M.tri[3 * t + 1]; }
-                wx[0] = t0.x; wy[0] = t0.y; wx[1] = t0.z; wy[1] = t0.w; wx[2] = t1.x; wy[2] = t1.y;
-            } else {
-                float2 a = make_float2(0.f, 0.f), b = a, d = a;
-                if (valid) { a = M.mark[3 * t]; b = M.mark[3 * t + 1]; d = M.mark[3 * t + 2]; }
-                wx[0] = a.x; wy[0] = a.y; wx[1] = b.x; wy[1] = b.y; wx[2] = d.x; wy[2] = d.y;
-            }
-            wx[3] = 0.f; wy[3] = 0.f;
-            float lox = fminf(fminf(wx[0], wx[1]), wx[2]), hix = fmaxf(fmaxf(wx[0], wx[1]), wx[2]);
-            float loy = fminf(fminf(wy[0], wy[1]), wy[2]), hiy = fmaxf(fmaxf(wy[0], wy[1]), wy[2]);
+            bool valid = t < nprim;
+            float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
+            if (valid) { p0 = prim[2 * t]; p1 = prim[2 * t + 1]; }
+            wx[0] = p0.x; wy[0] = p0.y; wx[1] = p0.z; wy[1] = p0.w; wx[2] = p1.x; wy[2] = p1.y; wx[3] = p1.z; wy[3] = p1.w;
+            float lox = fminf(fminf(wx[0], wx[1]), fminf(wx[2], wx[3])), hix = fmaxf(fmaxf(wx[0], wx[1]), fmaxf(wx[2], wx[3]));
+            float loy = fminf(fminf(wy[0], wy[1]), fminf(wy[2], wy[3])), hiy = fmaxf(fmaxf(wy[0], wy[1]), fmaxf(wy[2], wy[3]));
             valid = valid && hix >= cam.ex - reach && lox <= cam.ex + reach && hiy >= cam.ey - reach && loy <= cam.ey + reach;
             uint4 pv = make_uint4(0u, 0u, 0u, 0u);
             if (__any_sync(FULL_MASK, valid)) {
-                bool ok = project_prim<3>(cam, wx, wy, pv) && valid;
-                enqueue(ws, qn, lane, ok, pv, ROAD ? TDE_CLS_ROAD : TDE_CLS_LANE_MARKING, 3);
+                const int cls = ROAD ? TDE_CLS_ROAD : TDE_CLS_LANE_MARKING;
+                bool ok = project_prim<4>(cam, wx, wy, pv) && valid;
+                // a merged quad is drawn as one primitive only if it is still strictly convex after
+                // snapping (then it covers exactly its two triangles); otherwise fall back to the pair
+                int x0 = unpack_x(pv.x), y0 = unpack_y(pv.x), x1 = unpack_x(pv.y), y1 = unpack_y(pv.y);
+                int x2 = unpack_x(pv.z), y2 = unpack_y(pv.z), x3 = unpack_x(pv.w), y3 = unpack_y(pv.w);
+                int c0 = (x1 - x0) * (y2 - y1) - (y1 - y0) * (x2 - x1), c1 = (x2 - x1) * (y3 - y2) - (y2 - y1) * (x3 - x2);
+                int c2 = (x3 - x2) * (y0 - y3) - (y3 - y2) * (x0 - x3), c3 = (x0 - x3) * (y1 - y0) - (y0 - y3) * (x1 - x0);
+                bool convex = (c0 > 0 && c1 > 0 && c2 > 0 && c3 > 0) || (c0 < 0 && c1 < 0 && c2 < 0 && c3 < 0);
+                bool is_tri = pv.w == pv.x;
+                enqueue(ws, qn, lane, ok && (is_tri || convex), pv, cls, 4);
+                bool split = ok && !is_tri && !convex;
+                if (__any_sync(FULL_MASK, split)) {
+                    enqueue(ws, qn, lane, split, make_uint4(pv.x, pv.y, pv.w, pv.x), cls, 4);
+                    enqueue(ws, qn, lane, split, make_uint4(pv.y, pv.z, pv.w, pv.y), cls, 4);
+                }
             }
         }
     }
@@ -520,7 +549,9 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, 3) tde_render_kernel
             for (int i = 0; i < TDE_OBS_H * 4 * 8 / 16 / 32; ++i) pz[i * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
         }
         __syncwarp();
-        int qn = 0;
+        int qn[TDE_NBANDS];
+#pragma unroll
+        for (int b = 0; b < TDE_NBANDS; ++b) qn[b] = 0;
         float wx[4], wy[4];
         uint4 pv;
         queue_static_layer<true>(M, cam, reach, ws, qn, lane);    // level 1: road
@@ -567,7 +598,9 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, 3) tde_render_kernel
             enqueue(ws, qn, lane, ok && a != 0, pv, TDE_CLS_DIRECTION, 3);
             if (h == 0) enqueue(ws, qn, lane, ok && a == 0, pv, TDE_CLS_EGO_DIRECTION, 3);
         }
-        if (qn > 0) raster_batch(ws, qn, lane);
+#pragma unroll
+        for (int b = 0; b < TDE_NBANDS; ++b)
+            if (qn[b] > 0) raster_band(ws, b, qn[b], lane);
         __syncwarp();
 
         // class-index planes -> palette lookup with byte permutes -> 128-bit stores

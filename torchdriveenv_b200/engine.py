@@ -161,7 +161,7 @@ class Engine:
     def map_info(self, map_id: int = 0) -> Dict[str, int]:
         out = (C.c_int32 * 8)()
         self._check(self.lib.tde_get_map_info(self.h, int(map_id), out), "tde_get_map_info")
-        keys = ["road_tris", "mark_tris", "stoplines", "grid_nx", "grid_ny", "grid_items", "safe_cells", "overlapping_items"]
+        keys = ["road_tris", "mark_tris", "stoplines", "grid_nx", "grid_ny", "grid_items", "safe_cells", "render_prims"]
         return dict(zip(keys, [int(v) for v in out]))
 
     # -- stateless kernels (config C4)
