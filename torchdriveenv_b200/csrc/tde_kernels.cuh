@@ -82,6 +82,8 @@ struct RenderScratch {  // per warp, render kernel
     unsigned long long planes[TDE_OBS_H * 4];              // [row][bit-plane] class-index image
     unsigned int span[TDE_BAND_ROWS * TDE_SPAN_STRIDE];    // one band of coverage spans (xl | xr << 8), [row][primitive]
     unsigned char qc[TDE_NBANDS][64];                      // class | n_vertices << 4
+    int qn[TDE_NBANDS];                                    // queue fill (warp-uniform)
+    int pad[2];
 };
 
 __device__ __forceinline__ Box ld_box(const float4* sb, int a) {
@@ -252,28 +254,31 @@ __device__ __forceinline__ int unpack_x(unsigned w) { return (int)(w << 16) >> 1
 __device__ __forceinline__ int unpack_y(unsigned w) { return (int)w >> 16; }
 
 // world -> pixel (translate to ego, rotate by -psi, scale), viewport test, snap to the 1/16-px grid.
-// Returns false when the primitive's float bounding box misses the viewport grown by one pixel.
-template <int N>
-__device__ __forceinline__ bool project_prim(const Cam& cam, const float (&wx)[4], const float (&wy)[4], uint4& out) {
+// ok = false when the primitive's float bounding box misses the viewport grown by one pixel.
+// Triangles are passed with their first vertex repeated as the fourth.
+struct Proj { uint4 v; bool ok; };
+__device__ __noinline__ Proj project_quad(Cam cam, float x0, float y0, float x1, float y1, float x2, float y2, float x3, float y3) {
+    const float wx[4] = {x0, x1, x2, x3}, wy[4] = {y0, y1, y2, y3};
     float minx = INFINITY, maxx = -INFINITY, miny = INFINITY, maxy = -INFINITY;
     unsigned v[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        if (k < N) {
-            float dx = wx[k] - cam.ex, dy = wy[k] - cam.ey;
-            float cx = dx * cam.ce + dy * cam.se;
-            float cy = dy * cam.ce - dx * cam.se;
-            float fx = cx * cam.ppm + 0.5f * (float)TDE_OBS_W;
-            float fy = cy * cam.ppmy + 0.5f * (float)TDE_OBS_H;
-            minx = fminf(minx, fx); maxx = fmaxf(maxx, fx);
-            miny = fminf(miny, fy); maxy = fmaxf(maxy, fy);
-            v[k] = pack_xy(snap16(fx), snap16(fy));
-        } else {
-            v[k] = v[0];
-        }
+        float dx = wx[k] - cam.ex, dy = wy[k] - cam.ey;
+        float cx = dx * cam.ce + dy * cam.se;
+        float cy = dy * cam.ce - dx * cam.se;
+        float fx = cx * cam.ppm + 0.5f * (float)TDE_OBS_W;
+        float fy = cy * cam.ppmy + 0.5f * (float)TDE_OBS_H;
+        minx = fminf(minx, fx); maxx = fmaxf(maxx, fx);
+        miny = fminf(miny, fy); maxy = fmaxf(maxy, fy);
+        v[k] = pack_xy(snap16(fx), snap16(fy));
     }
-    out = make_uint4(v[0], v[1], v[2], v[3]);
-    return maxx >= -1.0f && minx <= (float)TDE_OBS_W + 1.0f && maxy >= -1.0f && miny <= (float)TDE_OBS_H + 1.0f;
+    Proj r;
+    r.v = make_uint4(v[0], v[1], v[2], v[3]);
+    r.ok = maxx >= -1.0f && minx <= (float)TDE_OBS_W + 1.0f && maxy >= -1.0f && miny <= (float)TDE_OBS_H + 1.0f;
+    return r;
+}
+__device__ __forceinline__ Proj project_quad(const Cam& cam, const float (&wx)[4], const float (&wy)[4]) {
+    return project_quad(cam, wx[0], wy[0], wx[1], wy[1], wx[2], wy[2], wx[3], wy[3]);
 }
 
 // phase 1 of raster_band for primitives with at most NE slanted edges: step the edges down the rows
@@ -404,7 +409,7 @@ __device__ __noinline__ void raster_band(RenderScratch* ws, int band, int count,
 
 // Append the primitives of the lanes with `valid` to the queue of every 32-row band they touch
 // (ballot/popc compaction keeps painter's order); a band is rasterised as soon as 32 are pending.
-__device__ __forceinline__ void enqueue(RenderScratch* ws, int (&qn)[TDE_NBANDS], int lane, bool valid, const uint4& v, int cls, int nverts) {
+__device__ __noinline__ void enqueue(RenderScratch* ws, int lane, bool valid, uint4 v, int cls) {
     int y0 = unpack_y(v.x), y1 = unpack_y(v.y), y2 = unpack_y(v.z), y3 = unpack_y(v.w);
     int x0 = unpack_x(v.x), x1 = unpack_x(v.y), x2 = unpack_x(v.z), x3 = unpack_x(v.w);
     int ymin = min(min(y0, y1), min(y2, y3)), ymax = max(max(y0, y1), max(y2, y3));
@@ -413,28 +418,27 @@ __device__ __forceinline__ void enqueue(RenderScratch* ws, int (&qn)[TDE_NBANDS]
     valid = valid && j0 <= j1 && xmax >= 8 && xmin <= 16 * (TDE_OBS_W - 1) + 8;  // bbox holds at least one pixel centre
     if (!__any_sync(FULL_MASK, valid)) return;
     const int blo = j0 / TDE_BAND_ROWS, bhi = j1 / TDE_BAND_ROWS;
-    const unsigned char cn = (unsigned char)(cls | (nverts << 4));
-#pragma unroll
+    const unsigned char cn = (unsigned char)(cls | (4 << 4));
+#pragma unroll 1
     for (int b = 0; b < TDE_NBANDS; ++b) {
         bool in = valid && blo <= b && b <= bhi;
         unsigned m = __ballot_sync(FULL_MASK, in);
         if (m == 0) continue;
-        int pos = qn[b] + __popc(m & ((1u << lane) - 1u));
+        int qn = ws->qn[b];
+        int pos = qn + __popc(m & ((1u << lane) - 1u));
         if (in) { ws->qv[b][pos] = v; ws->qc[b][pos] = cn; }
-        qn[b] += __popc(m);
-    }
-    __syncwarp();
-#pragma unroll
-    for (int b = 0; b < TDE_NBANDS; ++b) {
-        if (qn[b] >= 32) {
+        qn += __popc(m);
+        __syncwarp();
+        if (qn >= 32) {
             raster_band(ws, b, 32, lane);
             uint4 tv = ws->qv[b][32 + lane];
             unsigned char tc = ws->qc[b][32 + lane];
             __syncwarp();
             ws->qv[b][lane] = tv; ws->qc[b][lane] = tc;
-            qn[b] -= 32;
-            __syncwarp();
+            qn -= 32;
         }
+        if (lane == 0) ws->qn[b] = qn;
+        __syncwarp();
     }
 }
 
@@ -464,13 +468,12 @@ __device__ __forceinline__ uint32_t spread8(uint32_t b) {
 
 // static layers (road, lane markings): lanes first test the bounding boxes of runs of 32 primitives
 // against the viewport's reach, then only the visible runs are loaded, projected and queued
-template <bool ROAD>
-__device__ __forceinline__ void queue_static_layer(const MapDev& M, const Cam& cam, float reach, RenderScratch* ws, int (&qn)[TDE_NBANDS], int lane) {
-    const int nprim = ROAD ? M.n_rp_road : M.n_rp_mark;
-    const float4* prim = ROAD ? M.rp_road : M.rp_mark;
-    const float4* chunk = ROAD ? M.tri_chunk : M.mark_chunk;
+__device__ __noinline__ void queue_static_layer(const MapDev& M, bool road, Cam cam, float reach, RenderScratch* ws, int lane) {
+    const int nprim = road ? M.n_rp_road : M.n_rp_mark;
+    const float4* prim = road ? M.rp_road : M.rp_mark;
+    const float4* chunk = road ? M.tri_chunk : M.mark_chunk;
+    const int cls = road ? TDE_CLS_ROAD : TDE_CLS_LANE_MARKING;
     const int nchunk = (nprim + 31) >> 5;
-    float wx[4], wy[4];
 #pragma unroll 1
     for (int cb = 0; cb < nchunk; cb += 32) {
         bool see = false;
@@ -486,28 +489,26 @@ __device__ __forceinline__ void queue_static_layer(const MapDev& M, const Cam& c
             bool valid = t < nprim;
             float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
             if (valid) { p0 = prim[2 * t]; p1 = prim[2 * t + 1]; }
-            wx[0] = p0.x; wy[0] = p0.y; wx[1] = p0.z; wy[1] = p0.w; wx[2] = p1.x; wy[2] = p1.y; wx[3] = p1.z; wy[3] = p1.w;
-            float lox = fminf(fminf(wx[0], wx[1]), fminf(wx[2], wx[3])), hix = fmaxf(fmaxf(wx[0], wx[1]), fmaxf(wx[2], wx[3]));
-            float loy = fminf(fminf(wy[0], wy[1]), fminf(wy[2], wy[3])), hiy = fmaxf(fmaxf(wy[0], wy[1]), fmaxf(wy[2], wy[3]));
+            float lox = fminf(fminf(p0.x, p0.z), fminf(p1.x, p1.z)), hix = fmaxf(fmaxf(p0.x, p0.z), fmaxf(p1.x, p1.z));
+            float loy = fminf(fminf(p0.y, p0.w), fminf(p1.y, p1.w)), hiy = fmaxf(fmaxf(p0.y, p0.w), fmaxf(p1.y, p1.w));
             valid = valid && hix >= cam.ex - reach && lox <= cam.ex + reach && hiy >= cam.ey - reach && loy <= cam.ey + reach;
-            uint4 pv = make_uint4(0u, 0u, 0u, 0u);
-            if (__any_sync(FULL_MASK, valid)) {
-                const int cls = ROAD ? TDE_CLS_ROAD : TDE_CLS_LANE_MARKING;
-                bool ok = project_prim<4>(cam, wx, wy, pv) && valid;
-                // a merged quad is drawn as one primitive only if it is still strictly convex after
-                // snapping (then it covers exactly its two triangles); otherwise fall back to the pair
-                int x0 = unpack_x(pv.x), y0 = unpack_y(pv.x), x1 = unpack_x(pv.y), y1 = unpack_y(pv.y);
-                int x2 = unpack_x(pv.z), y2 = unpack_y(pv.z), x3 = unpack_x(pv.w), y3 = unpack_y(pv.w);
-                int c0 = (x1 - x0) * (y2 - y1) - (y1 - y0) * (x2 - x1), c1 = (x2 - x1) * (y3 - y2) - (y2 - y1) * (x3 - x2);
-                int c2 = (x3 - x2) * (y0 - y3) - (y3 - y2) * (x0 - x3), c3 = (x0 - x3) * (y1 - y0) - (y0 - y3) * (x1 - x0);
-                bool convex = (c0 > 0 && c1 > 0 && c2 > 0 && c3 > 0) || (c0 < 0 && c1 < 0 && c2 < 0 && c3 < 0);
-                bool is_tri = pv.w == pv.x;
-                enqueue(ws, qn, lane, ok && (is_tri || convex), pv, cls, 4);
-                bool split = ok && !is_tri && !convex;
-                if (__any_sync(FULL_MASK, split)) {
-                    enqueue(ws, qn, lane, split, make_uint4(pv.x, pv.y, pv.w, pv.x), cls, 4);
-                    enqueue(ws, qn, lane, split, make_uint4(pv.y, pv.z, pv.w, pv.y), cls, 4);
-                }
+            if (!__any_sync(FULL_MASK, valid)) continue;
+            Proj pr = project_quad(cam, p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w);
+            const uint4 pv = pr.v;
+            bool ok = pr.ok && valid;
+            // a merged quad is drawn as one primitive only if it is still strictly convex after
+            // snapping (then it covers exactly its two triangles); otherwise fall back to the pair
+            int x0 = unpack_x(pv.x), y0 = unpack_y(pv.x), x1 = unpack_x(pv.y), y1 = unpack_y(pv.y);
+            int x2 = unpack_x(pv.z), y2 = unpack_y(pv.z), x3 = unpack_x(pv.w), y3 = unpack_y(pv.w);
+            int c0 = (x1 - x0) * (y2 - y1) - (y1 - y0) * (x2 - x1), c1 = (x2 - x1) * (y3 - y2) - (y2 - y1) * (x3 - x2);
+            int c2 = (x3 - x2) * (y0 - y3) - (y3 - y2) * (x0 - x3), c3 = (x0 - x3) * (y1 - y0) - (y0 - y3) * (x1 - x0);
+            bool convex = (c0 > 0 && c1 > 0 && c2 > 0 && c3 > 0) || (c0 < 0 && c1 < 0 && c2 < 0 && c3 < 0);
+            bool is_tri = pv.w == pv.x;
+            enqueue(ws, lane, ok && (is_tri || convex), pv, cls);
+            bool split = ok && !is_tri && !convex;
+            if (__any_sync(FULL_MASK, split)) {
+                enqueue(ws, lane, split, make_uint4(pv.x, pv.y, pv.w, pv.x), cls);
+                enqueue(ws, lane, split, make_uint4(pv.y, pv.z, pv.w, pv.y), cls);
             }
         }
     }
@@ -549,13 +550,11 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, 3) tde_render_kernel
             for (int i = 0; i < TDE_OBS_H * 4 * 8 / 16 / 32; ++i) pz[i * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
         }
         __syncwarp();
-        int qn[TDE_NBANDS];
-#pragma unroll
-        for (int b = 0; b < TDE_NBANDS; ++b) qn[b] = 0;
+        if (lane < TDE_NBANDS) ws->qn[lane] = 0;
+        __syncwarp();
         float wx[4], wy[4];
-        uint4 pv;
-        queue_static_layer<true>(M, cam, reach, ws, qn, lane);    // level 1: road
-        queue_static_layer<false>(M, cam, reach, ws, qn, lane);   // level 2: lane markings
+        queue_static_layer(M, true, cam, reach, ws, lane);    // level 1: road
+        queue_static_layer(M, false, cam, reach, ws, lane);   // level 2: lane markings
         // levels 3-5: stop lines by light state (one pass per state keeps the queue in painter's order)
         if (M.nstop > 0) {
             bool valid = lane < M.nstop;
@@ -567,40 +566,37 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, 3) tde_render_kernel
                 box_quad(b, wx, wy);
                 ls = light_state_at(M, step, lphase, lane);
             }
-            bool ok = project_prim<4>(cam, wx, wy, pv) && valid;
-            enqueue(ws, qn, lane, ok && ls == TDE_LIGHT_GREEN, pv, TDE_CLS_TL_GREEN, 4);
-            enqueue(ws, qn, lane, ok && ls == TDE_LIGHT_YELLOW, pv, TDE_CLS_TL_YELLOW, 4);
-            enqueue(ws, qn, lane, ok && ls == TDE_LIGHT_RED, pv, TDE_CLS_TL_RED, 4);
+            Proj pr = project_quad(cam, wx, wy);
+            bool ok = pr.ok && valid;
+#pragma unroll 1
+            for (int st = TDE_LIGHT_GREEN; st <= TDE_LIGHT_RED; ++st) enqueue(ws, lane, ok && ls == st, pr.v, TDE_CLS_TL_GREEN + st);
         }
         // level 6: the current goal waypoint, a diamond of circumradius 2 m
         if (target < S.W) {
             float2 w = S.wp[target];
             const float r = 2.0f;
-            wx[0] = w.x + r; wy[0] = w.y; wx[1] = w.x; wy[1] = w.y + r;
-            wx[2] = w.x - r; wy[2] = w.y; wx[3] = w.x; wy[3] = w.y - r;
-            bool ok = project_prim<4>(cam, wx, wy, pv) && lane == 0;
-            enqueue(ws, qn, lane, ok, pv, TDE_CLS_WAYPOINT, 4);
+            Proj pr = project_quad(cam, w.x + r, w.y, w.x, w.y + r, w.x - r, w.y, w.x, w.y - r);
+            enqueue(ws, lane, pr.ok && lane == 0, pr.v, TDE_CLS_WAYPOINT);
         }
         // levels 7-8: vehicle rectangles then the highlighted ego; levels 9-10: direction triangles
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
-        for (int h = AH - 1; h >= 0; --h) {
-            int a = h * 32 + lane;
-            box_quad(mybox[h], wx, wy);
-            bool ok = project_prim<4>(cam, wx, wy, pv) && a < p.A && mybox[h].present != 0.0f;
-            enqueue(ws, qn, lane, ok && a != 0, pv, TDE_CLS_VEHICLE, 4);
-            if (h == 0) enqueue(ws, qn, lane, ok && a == 0, pv, TDE_CLS_EGO, 4);
+            for (int h = AH - 1; h >= 0; --h) {
+                int a = h * 32 + lane;
+                if (pass == 0) box_quad(mybox[h], wx, wy);
+                else { box_dirtri(mybox[h], wx, wy); wx[3] = wx[0]; wy[3] = wy[0]; }
+                Proj pr = project_quad(cam, wx, wy);
+                bool ok = pr.ok && a < p.A && mybox[h].present != 0.0f;
+                enqueue(ws, lane, ok && a != 0, pr.v, pass == 0 ? TDE_CLS_VEHICLE : TDE_CLS_DIRECTION);
+                if (h == 0) enqueue(ws, lane, ok && a == 0, pr.v, pass == 0 ? TDE_CLS_EGO : TDE_CLS_EGO_DIRECTION);
+            }
         }
-#pragma unroll
-        for (int h = AH - 1; h >= 0; --h) {
-            int a = h * 32 + lane;
-            box_dirtri(mybox[h], wx, wy);
-            bool ok = project_prim<3>(cam, wx, wy, pv) && a < p.A && mybox[h].present != 0.0f;
-            enqueue(ws, qn, lane, ok && a != 0, pv, TDE_CLS_DIRECTION, 3);
-            if (h == 0) enqueue(ws, qn, lane, ok && a == 0, pv, TDE_CLS_EGO_DIRECTION, 3);
+#pragma unroll 1
+        for (int b = 0; b < TDE_NBANDS; ++b) {
+            int cnt = ws->qn[b];
+            if (cnt > 0) raster_band(ws, b, cnt, lane);
         }
-#pragma unroll
-        for (int b = 0; b < TDE_NBANDS; ++b)
-            if (qn[b] > 0) raster_band(ws, b, qn[b], lane);
         __syncwarp();
 
         // class-index planes -> palette lookup with byte permutes -> 128-bit stores
