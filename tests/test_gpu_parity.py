@@ -162,7 +162,7 @@ def test_collision_flags_bit_exact_outside_epsilon_band(oracle):
     """All-pairs SAT on dense random boxes (config C4's generator at a test size)."""
     for A, size in ((64, 60.0), (32, 30.0), (7, 12.0)):
         st, at = S.scatter_boxes(2048, A, size=size, seed=A, present_p=0.9)
-        eng = _engine(S.three_way(0), 1, 1)
+        eng = _engine(S.three_way(0), 1, 3)
         got = eng.collision_boxes(torch.from_numpy(st), torch.from_numpy(at)).cpu().numpy()
         want = oracle.collision_boxes(st, at)
         margins = oracle.collision_margins(st, at)
