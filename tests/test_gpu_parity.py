@@ -238,7 +238,9 @@ def test_full_size_c3_properties(oracle):
     assert np.array_equal(term.cpu().numpy().astype(bool), any_infr)             # is_terminated :413-417
     assert np.array_equal(inf[:, IC["did_reset"]] != 0, (term | trunc).cpu().numpy().astype(bool))
     st = eng.get_state().cpu().numpy()
-    assert np.isfinite(st).all() and (st[..., 2] >= -np.pi - 1e-6).all() and (st[..., 2] < np.pi + 1e-6).all()
+    stepped = inf[:, IC["did_reset"]] == 0     # a freshly reset ego keeps its unwrapped start heading (set_start_pos :357-361)
+    psi = st[stepped][..., 2]
+    assert np.isfinite(st).all() and (psi >= -np.pi - 1e-6).all() and (psi < np.pi + 1e-6).all()
     stats = eng.episode_stats()
     assert stats[8] == steps * E and stats[0] == stats[3:6].sum() - 0 or stats[0] <= stats[3:7].sum()
 
