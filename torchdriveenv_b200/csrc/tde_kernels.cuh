@@ -13,7 +13,7 @@
 #include "../../include/tde_b200.h"
 
 #define TDE_WARPS_PER_BLOCK 8
-#define TDE_SPAN_STRIDE 33
+#define TDE_RENDER_BLOCKS_PER_SM 4
 
 struct MapDev {
     const float4* tri;          // 3 float4 per road triangle (see tde_point_tri_dist2)
@@ -70,20 +70,18 @@ struct StepParams {
 
 struct Cam { float ex, ey, ce, se, ppm, ppmy; };
 
-#define TDE_BAND_ROWS 32
-#define TDE_NBANDS (TDE_OBS_H / TDE_BAND_ROWS)
-
 struct PhysScratch {  // per warp, physics kernel
     float4 box[TDE_MAX_AGENTS * 2];  // Box as two float4
 };
 
 struct RenderScratch {  // per warp, render kernel
-    uint4 qv[TDE_NBANDS][64];                              // per 32-row band: queue of snapped primitives, 4 x (x | y << 16)
-    unsigned long long planes[TDE_OBS_H * 4];              // [row][bit-plane] class-index image
-    unsigned int span[TDE_BAND_ROWS * TDE_SPAN_STRIDE];    // one band of coverage spans (xl | xr << 8), [row][primitive]
-    unsigned char qc[TDE_NBANDS][64];                      // class | n_vertices << 4
-    int qn[TDE_NBANDS];                                    // queue fill (warp-uniform)
-    int pad[2];
+    // classes 1..10: one 64-bit coverage word per image row (bit x = pixel x); once every primitive is
+    // in, the first 2 KB are reused for the four bit-planes of the class-index image ([row][plane])
+    unsigned long long cover[(TDE_NUM_CLASSES - 1) * TDE_OBS_H];
+    uint4 qv[64];          // ring of snapped primitives waiting for a full batch, 4 x (x | y << 16)
+    unsigned char qc[64];  // their classes
+    unsigned int used;     // classes that received coverage
+    unsigned int pad[3];
 };
 
 __device__ __forceinline__ Box ld_box(const float4* sb, int a) {
@@ -281,11 +279,12 @@ __device__ __forceinline__ Proj project_quad(const Cam& cam, const float (&wx)[4
     return project_quad(cam, wx[0], wy[0], wx[1], wy[1], wx[2], wy[2], wx[3], wy[3]);
 }
 
-// phase 1 of raster_band for primitives with at most NE slanted edges: step the edges down the rows
+// Row loop of raster_batch for primitives with at most NE slanted edges: step the edges down the
+// rows (an exact integer DDA on floor(K/D) per edge) and OR each row's span into the coverage word of
+// the primitive's class.  Lanes own different primitives, so the ORs are shared-memory atomics.
 template <int NE>
-__device__ __forceinline__ void span_rows(int j, int jend, int b0, int lane, int (&V)[4], const int (&dV)[4], int (&rem)[4],
-                                          const int (&rS)[4], const int (&D)[4], const int (&cstep)[4], const int (&cap)[4],
-                                          unsigned int* span) {
+__device__ __forceinline__ void cover_rows(int j, int jend, int (&V)[4], const int (&dV)[4], int (&rem)[4], const int (&rS)[4],
+                                           const int (&D)[4], const int (&cstep)[4], const int (&cap)[4], unsigned int* cov) {
 #pragma unroll 1
     for (; j <= jend; ++j) {
         int xl = 0, xr = TDE_OBS_W;
@@ -297,38 +296,37 @@ __device__ __forceinline__ void span_rows(int j, int jend, int b0, int lane, int
             rem[k] += rS[k];
             if (rem[k] >= D[k]) { rem[k] -= D[k]; V[k] += cstep[k]; }
         }
-        if (xl < xr) span[(j - b0) * TDE_SPAN_STRIDE + lane] = (unsigned)xl | ((unsigned)xr << 8);
+        if (xl < xr) {
+            unsigned long long m = (~0ull >> (64 - xr)) & (~0ull << xl);
+            unsigned int lo = (unsigned int)m, hi = (unsigned int)(m >> 32);
+            if (lo) atomicOr(cov + 2 * j, lo);
+            if (hi) atomicOr(cov + 2 * j + 1, hi);
+        }
     }
 }
 
-// Rasterise the first `count` (<= 32) primitives queued for 32-row band `band`, one per lane, into the
-// class-index planes.
-//   phase 1 (lane = primitive): exact integer edge stepping (a DDA on floor(K/D) per edge), one
-//            coverage span [xl, xr) per image row of the band, written to shared memory;
-//   phase 2 (lane = row): walk the primitives in queue (= painter's) order, OR the spans of each run
-//            of equal class and paint the run over the four bit-planes of the class index.
-// Pixel-centre sampling on the 1/16-px grid with the top-left rule: the same pixel set as the
-// oracle's per-pixel edge-function test.
-__device__ __noinline__ void raster_band(RenderScratch* ws, int band, int count, int lane) {
+// Rasterise `count` (<= 32) queued primitives starting at ring slot `base`, one per lane, into the
+// per-class coverage bitmaps.  The final pixel is the highest class covering it, so neither the order
+// of the primitives nor their grouping matters.  Pixel-centre sampling on the 1/16-px grid with the
+// top-left rule: the same pixel set as the oracle's per-pixel edge-function test.
+__device__ __noinline__ void raster_batch(RenderScratch* ws, int base, int count, int lane) {
     const bool have = lane < count;
-    const uint4 q = ws->qv[band][lane];
-    const int cn = have ? (int)ws->qc[band][lane] : 0;
-    int n = cn >> 4;
-    if (n == 4 && q.w == q.x) n = 3;  // a static-layer triangle travels as a quad whose last vertex repeats the first
+    const uint4 q = ws->qv[base + lane];
+    const int cls = have ? (int)ws->qc[base + lane] : 1;
+    int n = have ? 4 : 0;
+    if (q.w == q.x) n = min(n, 3);  // a triangle travels as a quad whose last vertex repeats the first
     int X[4] = {unpack_x(q.x), unpack_x(q.y), unpack_x(q.z), unpack_x(q.w)};
     int Y[4] = {unpack_y(q.x), unpack_y(q.y), unpack_y(q.z), unpack_y(q.w)};
-    if (n == 3) { X[3] = X[0]; Y[3] = Y[0]; }
     // orientation: make the signed area positive (x right, y down) by swapping vertices 1 and n-1
     int area2 = (X[0] * Y[1] - X[1] * Y[0]) + (X[1] * Y[2] - X[2] * Y[1]) + (X[2] * Y[3] - X[3] * Y[2]) + (X[3] * Y[0] - X[0] * Y[3]);
     if (area2 == 0) n = 0;
     if (area2 < 0) {
         if (n == 4) { int t = X[1]; X[1] = X[3]; X[3] = t; t = Y[1]; Y[1] = Y[3]; Y[3] = t; }
-        else { int t = X[1]; X[1] = X[2]; X[2] = t; t = Y[1]; Y[1] = Y[2]; Y[2] = t; X[3] = X[0]; Y[3] = Y[0]; }
+        else { int t = X[1]; X[1] = X[2]; X[2] = t; t = Y[1]; Y[1] = Y[2]; Y[2] = t; }
     }
-    const int b0 = band * TDE_BAND_ROWS, b1 = b0 + TDE_BAND_ROWS - 1;
     int ymin = min(min(Y[0], Y[1]), min(Y[2], Y[3])), ymax = max(max(Y[0], Y[1]), max(Y[2], Y[3]));
-    int j0 = max(b0, (ymin - 8 + 15) >> 4);  // ceil((ymin - 8) / 16)
-    int j1 = min(b1, (ymax - 8) >> 4);       // floor((ymax - 8) / 16)
+    int j0 = max(0, (ymin - 8 + 15) >> 4);              // ceil((ymin - 8) / 16)
+    int j1 = min(TDE_OBS_H - 1, (ymax - 8) >> 4);       // floor((ymax - 8) / 16)
     // horizontal edges only restrict the row range (top edges are inclusive, bottom edges exclusive)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -342,6 +340,8 @@ __device__ __noinline__ void raster_band(RenderScratch* ws, int band, int count,
     const bool active = n >= 3 && j0 <= j1;
     const unsigned bm = __ballot_sync(FULL_MASK, active);
     if (bm == 0) return;
+    const unsigned touched = __reduce_or_sync(FULL_MASK, active ? (1u << cls) : 0u);
+    if (lane == 0) ws->used |= touched;
 
     // slanted edges: V = current bound (left: first covered column, right: one past the last), stepped per row
     int V[4], dV[4], rem[4], rS[4], D[4], cstep[4], cap[4];
@@ -365,81 +365,33 @@ __device__ __noinline__ void raster_band(RenderScratch* ws, int band, int count,
             else { V[k] = -F; dV[k] = -qs; cstep[k] = -1; cap[k] = INT_MAX; }
         }
     }
-    unsigned int* span = ws->span;
-    {   // clear the band buffer (32 rows x 33 spans)
-        uint4* s4 = reinterpret_cast<uint4*>(span);
-#pragma unroll 1
-        for (int i = lane; i < TDE_BAND_ROWS * TDE_SPAN_STRIDE / 4; i += 32) s4[i] = make_uint4(0u, 0u, 0u, 0u);
-    }
-    __syncwarp();
     if (active) {
+        unsigned int* cov = reinterpret_cast<unsigned int*>(ws->cover + (cls - 1) * TDE_OBS_H);
         // a triangle's fourth slot is the degenerate edge 3 -> 0: skip it when the whole batch is triangles
-        if (__any_sync(bm, n == 4)) span_rows<4>(j0, j1, b0, lane, V, dV, rem, rS, D, cstep, cap, span);
-        else span_rows<3>(j0, j1, b0, lane, V, dV, rem, rS, D, cstep, cap, span);
+        if (__any_sync(bm, n == 4)) cover_rows<4>(j0, j1, V, dV, rem, rS, D, cstep, cap, cov);
+        else cover_rows<3>(j0, j1, V, dV, rem, rS, D, cstep, cap, cov);
     }
-    __syncwarp();
-    // phase 2: lane = image row b0 + lane
-    ulonglong2* pp = reinterpret_cast<ulonglong2*>(&ws->planes[(b0 + lane) * 4]);
-    ulonglong2 p01 = pp[0], p23 = pp[1];
-    int cur = 0;
-    unsigned long long acc = 0ull;
-    unsigned todo = bm;
-    while (todo) {
-        int k = __ffs(todo) - 1;
-        todo &= todo - 1;
-        int c = (int)ws->qc[band][k] & 15;
-        if (c != cur) {  // warp-uniform: a new run of equal class starts; paint the finished one
-            p01.x = (p01.x & ~acc) | ((cur & 1) ? acc : 0ull);
-            p01.y = (p01.y & ~acc) | ((cur & 2) ? acc : 0ull);
-            p23.x = (p23.x & ~acc) | ((cur & 4) ? acc : 0ull);
-            p23.y = (p23.y & ~acc) | ((cur & 8) ? acc : 0ull);
-            acc = 0ull; cur = c;
-        }
-        unsigned w = span[lane * TDE_SPAN_STRIDE + k];
-        int xl = (int)(w & 0xffu), xr = (int)(w >> 8);
-        if (xr > xl) acc |= (~0ull >> (64 - xr)) & (~0ull << xl);
-    }
-    p01.x = (p01.x & ~acc) | ((cur & 1) ? acc : 0ull);
-    p01.y = (p01.y & ~acc) | ((cur & 2) ? acc : 0ull);
-    p23.x = (p23.x & ~acc) | ((cur & 4) ? acc : 0ull);
-    p23.y = (p23.y & ~acc) | ((cur & 8) ? acc : 0ull);
-    pp[0] = p01; pp[1] = p23;
     __syncwarp();
 }
 
-// Append the primitives of the lanes with `valid` to the queue of every 32-row band they touch
-// (ballot/popc compaction keeps painter's order); a band is rasterised as soon as 32 are pending.
-__device__ __noinline__ void enqueue(RenderScratch* ws, int lane, bool valid, uint4 v, int cls) {
+// Append the primitives of the lanes with `valid` (each with its own class) to the ring by ballot/popc
+// compaction; a batch is rasterised as soon as 32 are pending.  `qtot` counts everything queued so
+// far for this env (warp-uniform); the new count is returned.
+__device__ __noinline__ int enqueue(RenderScratch* ws, int lane, bool valid, uint4 v, int cls, int qtot) {
     int y0 = unpack_y(v.x), y1 = unpack_y(v.y), y2 = unpack_y(v.z), y3 = unpack_y(v.w);
     int x0 = unpack_x(v.x), x1 = unpack_x(v.y), x2 = unpack_x(v.z), x3 = unpack_x(v.w);
     int ymin = min(min(y0, y1), min(y2, y3)), ymax = max(max(y0, y1), max(y2, y3));
     int xmin = min(min(x0, x1), min(x2, x3)), xmax = max(max(x0, x1), max(x2, x3));
     int j0 = max(0, (ymin - 8 + 15) >> 4), j1 = min(TDE_OBS_H - 1, (ymax - 8) >> 4);
     valid = valid && j0 <= j1 && xmax >= 8 && xmin <= 16 * (TDE_OBS_W - 1) + 8;  // bbox holds at least one pixel centre
-    if (!__any_sync(FULL_MASK, valid)) return;
-    const int blo = j0 / TDE_BAND_ROWS, bhi = j1 / TDE_BAND_ROWS;
-    const unsigned char cn = (unsigned char)(cls | (4 << 4));
-#pragma unroll 1
-    for (int b = 0; b < TDE_NBANDS; ++b) {
-        bool in = valid && blo <= b && b <= bhi;
-        unsigned m = __ballot_sync(FULL_MASK, in);
-        if (m == 0) continue;
-        int qn = ws->qn[b];
-        int pos = qn + __popc(m & ((1u << lane) - 1u));
-        if (in) { ws->qv[b][pos] = v; ws->qc[b][pos] = cn; }
-        qn += __popc(m);
-        __syncwarp();
-        if (qn >= 32) {
-            raster_band(ws, b, 32, lane);
-            uint4 tv = ws->qv[b][32 + lane];
-            unsigned char tc = ws->qc[b][32 + lane];
-            __syncwarp();
-            ws->qv[b][lane] = tv; ws->qc[b][lane] = tc;
-            qn -= 32;
-        }
-        if (lane == 0) ws->qn[b] = qn;
-        __syncwarp();
-    }
+    const unsigned m = __ballot_sync(FULL_MASK, valid);
+    if (m == 0) return qtot;
+    const int pos = (qtot + __popc(m & ((1u << lane) - 1u))) & 63;
+    if (valid) { ws->qv[pos] = v; ws->qc[pos] = (unsigned char)cls; }
+    const int qnew = qtot + __popc(m);
+    __syncwarp();
+    if ((qnew ^ qtot) & ~31) raster_batch(ws, qtot & 32, 32, lane);  // crossed a multiple of 32: that half of the ring is full
+    return qnew;
 }
 
 __device__ __forceinline__ void box_quad(const Box& b, float (&wx)[4], float (&wy)[4]) {
@@ -468,7 +420,7 @@ __device__ __forceinline__ uint32_t spread8(uint32_t b) {
 
 // static layers (road, lane markings): lanes first test the bounding boxes of runs of 32 primitives
 // against the viewport's reach, then only the visible runs are loaded, projected and queued
-__device__ __noinline__ void queue_static_layer(const MapDev& M, bool road, Cam cam, float reach, RenderScratch* ws, int lane) {
+__device__ __noinline__ int queue_static_layer(const MapDev& M, bool road, Cam cam, float reach, RenderScratch* ws, int lane, int qtot) {
     const int nprim = road ? M.n_rp_road : M.n_rp_mark;
     const float4* prim = road ? M.rp_road : M.rp_mark;
     const float4* chunk = road ? M.tri_chunk : M.mark_chunk;
@@ -504,25 +456,32 @@ __device__ __noinline__ void queue_static_layer(const MapDev& M, bool road, Cam 
             int c2 = (x3 - x2) * (y0 - y3) - (y3 - y2) * (x0 - x3), c3 = (x0 - x3) * (y1 - y0) - (y0 - y3) * (x1 - x0);
             bool convex = (c0 > 0 && c1 > 0 && c2 > 0 && c3 > 0) || (c0 < 0 && c1 < 0 && c2 < 0 && c3 < 0);
             bool is_tri = pv.w == pv.x;
-            enqueue(ws, lane, ok && (is_tri || convex), pv, cls);
+            qtot = enqueue(ws, lane, ok && (is_tri || convex), pv, cls, qtot);
             bool split = ok && !is_tri && !convex;
             if (__any_sync(FULL_MASK, split)) {
-                enqueue(ws, lane, split, make_uint4(pv.x, pv.y, pv.w, pv.x), cls);
-                enqueue(ws, lane, split, make_uint4(pv.y, pv.z, pv.w, pv.y), cls);
+                qtot = enqueue(ws, lane, split, make_uint4(pv.x, pv.y, pv.w, pv.x), cls, qtot);
+                qtot = enqueue(ws, lane, split, make_uint4(pv.y, pv.z, pv.w, pv.y), cls, qtot);
             }
         }
     }
+    return qtot;
 }
 
 // simulator.render_egocentric() (gym_env.py:122-124): one warp renders one env's 3x64x64 birdview.
 template <int AH>
-__global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, 3) tde_render_kernel(const StepParams p) {
+__global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, TDE_RENDER_BLOCKS_PER_SM) tde_render_kernel(const StepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     RenderScratch* ws = reinterpret_cast<RenderScratch*>(smem_raw) + warp;
     const int warps_total = gridDim.x * TDE_WARPS_PER_BLOCK;
     // conservative world-space reach of the viewport around the ego (half diagonal + 2 px)
     const float reach = (0.70710678f * (float)(TDE_OBS_W + TDE_OBS_H) * 0.5f + 2.0f) / p.ppm;
+    uint4* const cz = reinterpret_cast<uint4*>(ws->cover);
+    constexpr int COVER_U4 = (TDE_NUM_CLASSES - 1) * TDE_OBS_H * 8 / 16;  // 320 = 10 per lane
+#pragma unroll
+    for (int i = 0; i < COVER_U4 / 32; ++i) cz[i * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
+    if (lane == 0) ws->used = 0u;
+    __syncwarp();
 
 #pragma unroll 1
     for (int e = blockIdx.x * TDE_WARPS_PER_BLOCK + warp; e < p.E; e += warps_total) {
@@ -544,18 +503,11 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, 3) tde_render_kernel
         cam.ex = __shfl_sync(FULL_MASK, mybox[0].x, 0); cam.ey = __shfl_sync(FULL_MASK, mybox[0].y, 0);
         cam.ce = __shfl_sync(FULL_MASK, mybox[0].c, 0); cam.se = __shfl_sync(FULL_MASK, mybox[0].s, 0);
         cam.ppm = p.ppm; cam.ppmy = p.ppmy;
-        {   // clear the class-index planes
-            uint4* pz = reinterpret_cast<uint4*>(ws->planes);
-#pragma unroll
-            for (int i = 0; i < TDE_OBS_H * 4 * 8 / 16 / 32; ++i) pz[i * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
-        }
-        __syncwarp();
-        if (lane < TDE_NBANDS) ws->qn[lane] = 0;
-        __syncwarp();
         float wx[4], wy[4];
-        queue_static_layer(M, true, cam, reach, ws, lane);    // level 1: road
-        queue_static_layer(M, false, cam, reach, ws, lane);   // level 2: lane markings
-        // levels 3-5: stop lines by light state (one pass per state keeps the queue in painter's order)
+        int qtot = 0;
+        qtot = queue_static_layer(M, true, cam, reach, ws, lane, qtot);    // class 1: road
+        qtot = queue_static_layer(M, false, cam, reach, ws, lane, qtot);   // class 2: lane markings
+        // classes 3-5: stop lines coloured by their light state
         if (M.nstop > 0) {
             bool valid = lane < M.nstop;
             int ls = TDE_LIGHT_GREEN;
@@ -567,40 +519,62 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, 3) tde_render_kernel
                 ls = light_state_at(M, step, lphase, lane);
             }
             Proj pr = project_quad(cam, wx, wy);
-            bool ok = pr.ok && valid;
-#pragma unroll 1
-            for (int st = TDE_LIGHT_GREEN; st <= TDE_LIGHT_RED; ++st) enqueue(ws, lane, ok && ls == st, pr.v, TDE_CLS_TL_GREEN + st);
+            qtot = enqueue(ws, lane, pr.ok && valid, pr.v, TDE_CLS_TL_GREEN + ls, qtot);
         }
-        // level 6: the current goal waypoint, a diamond of circumradius 2 m
+        // class 6: the current goal waypoint, a diamond of circumradius 2 m
         if (target < S.W) {
             float2 w = S.wp[target];
             const float r = 2.0f;
             Proj pr = project_quad(cam, w.x + r, w.y, w.x, w.y + r, w.x - r, w.y, w.x, w.y - r);
-            enqueue(ws, lane, pr.ok && lane == 0, pr.v, TDE_CLS_WAYPOINT);
+            qtot = enqueue(ws, lane, pr.ok && lane == 0, pr.v, TDE_CLS_WAYPOINT, qtot);
         }
-        // levels 7-8: vehicle rectangles then the highlighted ego; levels 9-10: direction triangles
+        // classes 7-8: vehicle rectangles and the highlighted ego; classes 9-10: their direction triangles
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
-            for (int h = AH - 1; h >= 0; --h) {
+            for (int h = 0; h < AH; ++h) {
                 int a = h * 32 + lane;
                 if (pass == 0) box_quad(mybox[h], wx, wy);
                 else { box_dirtri(mybox[h], wx, wy); wx[3] = wx[0]; wy[3] = wy[0]; }
                 Proj pr = project_quad(cam, wx, wy);
                 bool ok = pr.ok && a < p.A && mybox[h].present != 0.0f;
-                enqueue(ws, lane, ok && a != 0, pr.v, pass == 0 ? TDE_CLS_VEHICLE : TDE_CLS_DIRECTION);
-                if (h == 0) enqueue(ws, lane, ok && a == 0, pr.v, pass == 0 ? TDE_CLS_EGO : TDE_CLS_EGO_DIRECTION);
+                int cls = pass == 0 ? (a == 0 ? TDE_CLS_EGO : TDE_CLS_VEHICLE) : (a == 0 ? TDE_CLS_EGO_DIRECTION : TDE_CLS_DIRECTION);
+                qtot = enqueue(ws, lane, ok, pr.v, cls, qtot);
             }
         }
-#pragma unroll 1
-        for (int b = 0; b < TDE_NBANDS; ++b) {
-            int cnt = ws->qn[b];
-            if (cnt > 0) raster_band(ws, b, cnt, lane);
+        if (qtot & 31) raster_batch(ws, qtot & 32, qtot & 31, lane);
+        __syncwarp();
+
+        // composite: lane owns rows lane and lane + 32; ascending classes overwrite the four bit-planes
+        // of the class index, so the highest class covering a pixel wins
+        const unsigned used = ws->used;
+        unsigned long long P[2][4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) P[r][b] = 0ull;
+#pragma unroll
+        for (int c = 1; c < TDE_NUM_CLASSES; ++c) {
+            if (used & (1u << c)) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    unsigned long long mk = ws->cover[(c - 1) * TDE_OBS_H + r * 32 + lane];
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) P[r][b] = (c >> b) & 1 ? (P[r][b] | mk) : (P[r][b] & ~mk);
+                }
+            }
+        }
+        __syncwarp();   // every lane has read its coverage words: the planes may now overwrite them
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            ulonglong2* pp = reinterpret_cast<ulonglong2*>(&ws->cover[(r * 32 + lane) * 4]);
+            pp[0] = make_ulonglong2(P[r][0], P[r][1]);
+            pp[1] = make_ulonglong2(P[r][2], P[r][3]);
         }
         __syncwarp();
 
         // class-index planes -> palette lookup with byte permutes -> 128-bit stores
-        const unsigned short* pl16 = reinterpret_cast<const unsigned short*>(ws->planes);
+        const unsigned short* pl16 = reinterpret_cast<const unsigned short*>(ws->cover);
         uint8_t* out = p.obs + (size_t)e * (TDE_OBS_C * TDE_OBS_H * TDE_OBS_W);
 #pragma unroll 1
         for (int it = 0; it < TDE_OBS_H / 8; ++it) {
@@ -629,6 +603,11 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, 3) tde_render_kernel
                 *reinterpret_cast<uint4*>(out + ch * (TDE_OBS_H * TDE_OBS_W) + row * TDE_OBS_W + qd * 16) = make_uint4(w[0], w[1], w[2], w[3]);
             }
         }
+        __syncwarp();
+        // clear the coverage words for the next env
+#pragma unroll
+        for (int i = 0; i < COVER_U4 / 32; ++i) cz[i * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
+        if (lane == 0) ws->used = 0u;
         __syncwarp();
     }
 }
