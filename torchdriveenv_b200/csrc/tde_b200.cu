@@ -76,14 +76,14 @@ __global__ void prep_tris_kernel(const float* __restrict__ raw, int n, float4* _
     out[3 * t + 1] = make_float4(cx, cy, il(ax, ay, bx, by), il(bx, by, cx, cy));
     out[3 * t + 2] = make_float4(il(cx, cy, ax, ay), r[6], r[7], 0.0f);
 }
-// raw (L,5) stop lines -> [x y hl hw][c s 0 0]
+// raw (L,5) stop lines -> [x y hl hw][c s rr 0], rr = circumradius bound + 5 mm (broad phase)
 __global__ void prep_stops_kernel(const float* __restrict__ raw, int n, float4* __restrict__ out) {
     int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= n) return;
     const float* r = raw + 5 * (size_t)l;
     Box b = tde_make_box(r[0], r[1], r[4], r[2], r[3], 1.0f);
     out[2 * l] = make_float4(b.x, b.y, b.hl, b.hw);
-    out[2 * l + 1] = make_float4(b.c, b.s, 0.0f, 0.0f);
+    out[2 * l + 1] = make_float4(b.c, b.s, b.hl + b.hw + 0.005f, 0.0f);
 }
 
 // ------------------------------------------------------------------ nearest-candidate grid (host, float64)
@@ -114,8 +114,6 @@ struct Grid {
     std::vector<uint16_t> items;
     std::vector<uint16_t> meta;  // n_overlapping | TDE_CELL_SAFE
 };
-
-inline bool tri_contains(P2 p, const float* t) { return tri_dist(p, t) == 0.0; }
 
 // exact distance between the square [c +- half] and a triangle (0 when they intersect)
 double box_tri_mindist(P2 c, double half, const float* t) {
@@ -189,7 +187,7 @@ Grid build_grid(const float* tris, int M, double threshold) {
     const double margin = 8.0;
     lox -= margin; loy -= margin; hix += margin; hiy += margin;
     double w = hix - lox, hgt = hiy - loy;
-    double cell = std::max(2.0, std::sqrt(w * hgt / 4096.0));
+    double cell = std::max(1.0, std::sqrt(w * hgt / 16384.0));
     g.nx = std::max(1, (int)std::ceil(w / cell));
     g.ny = std::max(1, (int)std::ceil(hgt / cell));
     g.gx0 = (float)lox; g.gy0 = (float)loy;
@@ -234,6 +232,19 @@ Grid build_grid(const float* tris, int M, double threshold) {
                 both = over; both.insert(both.end(), near.begin(), near.end());
                 double bound = U + 1e-3 < threshold ? U : cover_bound(c, half, tris, both, 4);
                 safe = bound + 1e-3 < threshold;
+            }
+            // overlapping triangles that cover most of the cell first: a containment loop then ends early
+            if (over.size() > 1) {
+                std::vector<std::pair<int, int>> cov;
+                for (int t : over) {
+                    int hits = 0;
+                    for (int sy = 0; sy < 4; ++sy)
+                        for (int sx = 0; sx < 4; ++sx)
+                            hits += tri_dist(P2{c.x + (sx - 1.5) * 0.25 * cs, c.y + (sy - 1.5) * 0.25 * cs}, tris + 8 * (size_t)t) == 0.0;
+                    cov.push_back({-hits, t});
+                }
+                std::stable_sort(cov.begin(), cov.end());
+                for (size_t k = 0; k < over.size(); ++k) over[k] = cov[k].second;
             }
             size_t nover = std::min<size_t>(over.size(), 0x7fff);
             for (int t : over) g.items.push_back((uint16_t)t);

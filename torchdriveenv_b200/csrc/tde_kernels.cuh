@@ -70,8 +70,12 @@ struct StepParams {
 
 struct Cam { float ex, ey, ce, se, ppm, ppmy; };
 
-struct PhysScratch {  // per warp, physics kernel
-    float4 box[TDE_MAX_AGENTS * 2];  // Box as two float4
+#define TDE_PAIR_CAP 256
+struct SatScratch {  // per warp: staged boxes, candidate pairs and hit counters of the all-pairs SAT
+    float4 pos[TDE_MAX_AGENTS];            // x y rr -   (rr = circumradius bound + 5 mm, NaN for an absent agent)
+    float4 ext[TDE_MAX_AGENTS];            // c s hl hw
+    int cnt[TDE_MAX_AGENTS];               // overlaps found per agent
+    unsigned short pairs[TDE_PAIR_CAP];    // a | j << 8, a < j: pairs that survived the broad phase
 };
 
 struct RenderScratch {  // per warp, render kernel
@@ -84,57 +88,172 @@ struct RenderScratch {  // per warp, render kernel
     unsigned int pad[3];
 };
 
-__device__ __forceinline__ Box ld_box(const float4* sb, int a) {
-    float4 u = sb[2 * a], v = sb[2 * a + 1];
-    Box b; b.x = u.x; b.y = u.y; b.hl = u.z; b.hw = u.w; b.c = v.x; b.s = v.y; b.present = v.z; b.r = v.w;
+__device__ __forceinline__ Box sat_ld(const SatScratch* ws, int a) {
+    float4 u = ws->pos[a], v = ws->ext[a];
+    Box b; b.x = u.x; b.y = u.y; b.hl = v.z; b.hw = v.w; b.c = v.x; b.s = v.y; b.present = 1.0f; b.r = u.z;
     return b;
 }
-__device__ __forceinline__ void st_box(float4* sb, int a, const Box& b) {
-    sb[2 * a] = make_float4(b.x, b.y, b.hl, b.hw);
-    sb[2 * a + 1] = make_float4(b.c, b.s, b.present, b.r);
+
+// compute_collision (gym_env.py:143,415,428): for every agent the number of other present agents whose
+// box overlaps its own.  Broad phase: lane = agent a, box j broadcast from shared memory, circle test
+// with the circumradius bounds (+1 cm, +0.1 %), only pairs a < j are kept as a bit per lane.  The
+// surviving pairs are compacted into a list and the exact 4-axis SAT (bitwise symmetric in its
+// arguments) runs once per pair with all lanes busy; a hit counts for both agents.
+template <int AH>
+__device__ __forceinline__ void sat_counts(SatScratch* ws, const Box (&me)[AH], int A, int lane, float (&cnt_out)[AH]) {
+    float rr[AH];
+#pragma unroll
+    for (int h = 0; h < AH; ++h) {
+        int a = h * 32 + lane;
+        rr[h] = (a < A && me[h].present != 0.0f) ? me[h].r + 0.005f : __int_as_float(0x7fc00000);
+        if (a < A) {
+            ws->pos[a] = make_float4(me[h].x, me[h].y, rr[h], 0.0f);
+            ws->ext[a] = make_float4(me[h].c, me[h].s, me[h].hl, me[h].hw);
+            ws->cnt[a] = 0;
+        }
+    }
+    __syncwarp();
+    unsigned cm[AH][AH];  // [my slot][j / 32]
+#pragma unroll
+    for (int h = 0; h < AH; ++h)
+#pragma unroll
+        for (int g = 0; g < AH; ++g) cm[h][g] = 0u;
+#pragma unroll
+    for (int g = 0; g < AH; ++g) {
+        const int jn = min(A - g * 32, 32);
+#pragma unroll 2
+        for (int jj = 0; jj < jn; ++jj) {
+            const float4 o = ws->pos[g * 32 + jj];
+#pragma unroll
+            for (int h = 0; h < AH; ++h) {
+                if (h > g) continue;  // only pairs a < j
+                float dx = o.x - me[h].x, dy = o.y - me[h].y;
+                float R = rr[h] + o.z;
+                bool cand = (dx * dx + dy * dy <= R * R * 1.001f) && (h < g || jj > lane);  // NaN radius: never
+                if (cand) cm[h][g] |= 1u << jj;
+            }
+        }
+    }
+    int n = 0;
+#pragma unroll
+    for (int h = 0; h < AH; ++h)
+#pragma unroll
+        for (int g = 0; g < AH; ++g) n += __popc(cm[h][g]);
+    int incl = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(FULL_MASK, incl, d);
+        if (lane >= d) incl += t;
+    }
+    const int total = __shfl_sync(FULL_MASK, incl, 31);
+    if (total > 0) {
+        if (total <= TDE_PAIR_CAP) {
+            int pos = incl - n;
+#pragma unroll
+            for (int h = 0; h < AH; ++h)
+#pragma unroll
+                for (int g = 0; g < AH; ++g) {
+                    unsigned m = cm[h][g];
+                    while (m) {
+                        int j = g * 32 + __ffs(m) - 1;
+                        m &= m - 1;
+                        ws->pairs[pos++] = (unsigned short)((h * 32 + lane) | (j << 8));
+                    }
+                }
+            __syncwarp();
+#pragma unroll 1
+            for (int i = lane; i < total; i += 32) {
+                int pr = ws->pairs[i], a = pr & 255, j = pr >> 8;
+                if (tde_overlap(sat_ld(ws, a), sat_ld(ws, j))) { atomicAdd(&ws->cnt[a], 1); atomicAdd(&ws->cnt[j], 1); }
+            }
+        } else {  // more candidate pairs than the list holds (agents piled up): each lane walks its own bits
+#pragma unroll
+            for (int h = 0; h < AH; ++h)
+#pragma unroll
+                for (int g = 0; g < AH; ++g) {
+                    unsigned m = cm[h][g];
+                    while (m) {
+                        int j = g * 32 + __ffs(m) - 1;
+                        m &= m - 1;
+                        if (tde_overlap(me[h], sat_ld(ws, j))) { atomicAdd(&ws->cnt[h * 32 + lane], 1); atomicAdd(&ws->cnt[j], 1); }
+                    }
+                }
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < AH; ++h) {
+        int a = h * 32 + lane;
+        cnt_out[h] = a < A ? (float)ws->cnt[a] : 0.0f;
+    }
+    __syncwarp();
 }
 
 // ---------------------------------------------------------------- lane-mesh queries
 
-// Squared distance from p to the road mesh of map M (0 on the road).  Exact: every grid cell lists the
-// triangles overlapping it first (n_over of them, enough to decide containment) and then every other
-// triangle that can be nearest to some point of the cell; points off the grid scan all triangles.
-// `skip_safe`: cells whose every point is provably closer to the road than the offroad threshold are
-// flagged at upload; for those the caller only needs "distance < threshold" and gets 0.
+// Distance queries against the road mesh of map M are exact: every grid cell lists the triangles
+// overlapping it first (n_over of them, enough to decide containment) and then every other triangle
+// that can be nearest to some point of the cell; points off the grid scan all triangles.  Cells whose
+// every point is provably closer to the road than the offroad threshold are flagged SAFE at upload:
+// there the offroad term is 0 without looking at a triangle.
 #define TDE_CELL_SAFE 0x8000
-__device__ __noinline__ float mesh_dist2(const MapDev& M, float px, float py, bool skip_safe) {
-    float fx = floorf((px - M.gx0) * M.inv_cell), fy = floorf((py - M.gy0) * M.inv_cell);
-    bool in_grid = fx >= 0.0f && fy >= 0.0f && fx < (float)M.gnx && fy < (float)M.gny;
-    float dc, ds;
-    float best = INFINITY;
-    if (in_grid) {
-        int cell = (int)fy * M.gnx + (int)fx;
-        int meta = M.cell_meta[cell];
-        if (skip_safe && (meta & TDE_CELL_SAFE)) return 0.0f;
-        int i0 = M.cell_start[cell], i1 = M.cell_start[cell + 1], nover = meta & 0x7fff;
-        for (int i = i0; i < i0 + nover; ++i)
-            if (tde_tri_contains(M.tri + 3 * (int)M.cell_items[i], px, py, dc, ds)) return 0.0f;
-        for (int i = i0; i < i1; ++i) best = fminf(best, tde_tri_segdist2(M.tri + 3 * (int)M.cell_items[i], px, py));
-    } else {
-        for (int t = 0; t < M.ntri; ++t)
-            if (tde_tri_contains(M.tri + 3 * t, px, py, dc, ds)) return 0.0f;
-        for (int t = 0; t < M.ntri; ++t) best = fminf(best, tde_tri_segdist2(M.tri + 3 * t, px, py));
-    }
-    return best;
-}
 
-// compute_offroad (gym_env.py:142,415,427): sum over corners of max(dist - threshold, 0)
-__device__ __forceinline__ float offroad_box(const MapDev& M, const Box& b, float thr) {
+// compute_offroad (gym_env.py:142,415,427): sum over corners of max(dist - threshold, 0).  Called by the
+// whole warp (lane = agent, `mine` = has a box).  Each lane first settles its corner alone (safe cell,
+// or inside one of the cell's overlapping triangles); the corners that still need a distance are then
+// taken one at a time by the whole warp, lanes striding over the candidate triangles, min by redux.
+__device__ __noinline__ float offroad_box_warp(const MapDev& M, const Box& b, bool mine, float thr, int lane) {
     if (M.ntri <= 0) return 0.0f;
     float sum = 0.0f;
 #pragma unroll 1
     for (int k = 0; k < 4; ++k) {
         float px, py;
         tde_box_corner(b, k, px, py);
-        float d = sqrtf(mesh_dist2(M, px, py, true));
+        float d2 = 0.0f, dc, ds;
+        int i0 = 0, i1 = 0;
+        bool need = false;
+        if (mine) {
+            float fx = floorf((px - M.gx0) * M.inv_cell), fy = floorf((py - M.gy0) * M.inv_cell);
+            bool in_grid = fx >= 0.0f && fy >= 0.0f && fx < (float)M.gnx && fy < (float)M.gny;
+            if (in_grid) {
+                int cell = (int)fy * M.gnx + (int)fx;
+                int meta = M.cell_meta[cell];
+                if (!(meta & TDE_CELL_SAFE)) {
+                    i0 = M.cell_start[cell]; i1 = M.cell_start[cell + 1];
+                    int nover = meta & 0x7fff;
+                    need = true;
+                    for (int i = i0; i < i0 + nover; ++i)
+                        if (tde_tri_contains(M.tri + 3 * (int)M.cell_items[i], px, py, dc, ds)) { need = false; break; }
+                }
+            } else {
+                need = true; i0 = 0; i1 = -M.ntri;  // off the grid: every triangle, containment included
+            }
+        }
+        unsigned nm = __ballot_sync(FULL_MASK, need);
+        while (nm) {
+            const int src = __ffs(nm) - 1;
+            nm &= nm - 1;
+            const float qx = __shfl_sync(FULL_MASK, px, src), qy = __shfl_sync(FULL_MASK, py, src);
+            const int a0 = __shfl_sync(FULL_MASK, i0, src), a1 = __shfl_sync(FULL_MASK, i1, src);
+            float best = INFINITY;
+            bool inside = false;
+            if (a1 < 0) {
+                for (int t = lane; t < -a1; t += 32) {
+                    inside = inside || tde_tri_contains(M.tri + 3 * t, qx, qy, dc, ds);
+                    best = fminf(best, tde_tri_segdist2(M.tri + 3 * t, qx, qy));
+                }
+                inside = __any_sync(FULL_MASK, inside);
+            } else {
+                for (int i = a0 + lane; i < a1; i += 32) best = fminf(best, tde_tri_segdist2(M.tri + 3 * (int)M.cell_items[i], qx, qy));
+            }
+            // non-negative binary32 values order like their bit patterns
+            const unsigned ub = __reduce_min_sync(FULL_MASK, __float_as_uint(best));
+            if (lane == src) d2 = inside ? 0.0f : __uint_as_float(ub);
+        }
+        float d = sqrtf(d2);
         sum = sum + fmaxf(d - thr, 0.0f);
     }
-    return sum;
+    return mine ? sum : 0.0f;
 }
 
 // compute_wrong_way: max(-cos(psi - lane_dir), 0), min over the triangles under the centre
@@ -160,9 +279,15 @@ __device__ __forceinline__ int light_state_at(const MapDev& M, int step, int pha
     int t = (step + phase) % M.period;
     return M.lights[t * M.nstop + l];
 }
+// bit l set = stop line l shows red at this env time (lane l looks its own light up)
+__device__ __forceinline__ unsigned red_lights_mask(const MapDev& M, int step, int phase, int lane) {
+    bool red = lane < M.nstop && light_state_at(M, step, phase, lane) == TDE_LIGHT_RED;
+    return __ballot_sync(FULL_MASK, red);
+}
 
-// TrafficLightControl.compute_violation: rear strip of the agent box vs red stop lines
-__device__ __noinline__ float tl_violation_box(const MapDev& M, const Box& b, float rear_factor, int step, int phase) {
+// TrafficLightControl.compute_violation: rear strip of the agent box vs the stop lines showing red.
+// Called by the whole warp; a circle test votes before the 4-axis SAT.
+__device__ __noinline__ float tl_violation_warp(const MapDev& M, const Box& b, bool mine, float rear_factor, unsigned red) {
     float length = 2.0f * b.hl;  // exact: hl = 0.5f*length
     float len2 = length * rear_factor;
     float back = 0.5f * (length - len2);
@@ -170,12 +295,18 @@ __device__ __noinline__ float tl_violation_box(const MapDev& M, const Box& b, fl
     rear.x = b.x - back * b.c;
     rear.y = b.y - back * b.s;
     rear.hl = 0.5f * len2;
+    const float rr = rear.hl + rear.hw + 0.005f;
     float viol = 0.0f;
-    for (int l = 0; l < M.nstop; ++l) {
-        if (light_state_at(M, step, phase, l) != TDE_LIGHT_RED) continue;
+    while (red) {
+        const int l = __ffs(red) - 1;
+        red &= red - 1;
         float4 u = M.stop[2 * l], v = M.stop[2 * l + 1];
-        Box sb; sb.x = u.x; sb.y = u.y; sb.hl = u.z; sb.hw = u.w; sb.c = v.x; sb.s = v.y; sb.present = 1.0f; sb.r = 0.0f;
-        if (tde_overlap(rear, sb)) viol += 1.0f;
+        float dx = u.x - rear.x, dy = u.y - rear.y, R = rr + v.z;
+        bool cand = mine && dx * dx + dy * dy <= R * R * 1.001f;
+        if (__any_sync(FULL_MASK, cand)) {
+            Box sb; sb.x = u.x; sb.y = u.y; sb.hl = u.z; sb.hw = u.w; sb.c = v.x; sb.s = v.y; sb.present = 1.0f; sb.r = 0.0f;
+            if (cand && tde_overlap(rear, sb)) viol += 1.0f;
+        }
     }
     return viol;
 }
@@ -619,9 +750,9 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, TDE_RENDER_BLOCKS_PE
 // waypoint progress, episode statistics and (optionally) the in-kernel auto-reset.
 template <int AH>
 __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32) tde_physics_kernel(const StepParams p) {
-    __shared__ PhysScratch scratch[TDE_WARPS_PER_BLOCK];
+    __shared__ SatScratch scratch[TDE_WARPS_PER_BLOCK];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    PhysScratch* ws = &scratch[warp];
+    SatScratch* ws = &scratch[warp];
     const int warps_total = gridDim.x * TDE_WARPS_PER_BLOCK;
     const tde_config& c = p.cfg;
     double st_acc = 0.0;  // lane k accumulates statistic k
@@ -667,33 +798,24 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32) tde_physics_kernel(c
         float4 inf0 = make_float4(0.f, 0.f, 0.f, 0.f);  // ego's infractions, valid on lane 0
         if (p.phases & TDE_PH_INFRACTIONS) {
             const MapDev& M = p.maps[m];
+            Box me[AH];
+            float cnt[AH];
+#pragma unroll
+            for (int h = 0; h < AH; ++h) me[h] = tde_make_box(st[h].x, st[h].y, st[h].z, at[h].x, at[h].y, at[h].w);
+            sat_counts<AH>(ws, me, p.A, lane, cnt);
+            const unsigned red = red_lights_mask(M, step, lphase, lane);
 #pragma unroll
             for (int h = 0; h < AH; ++h) {
                 int a = h * 32 + lane;
-                if (a < p.A) st_box(ws->box, a, tde_make_box(st[h].x, st[h].y, st[h].z, at[h].x, at[h].y, at[h].w));
-            }
-            __syncwarp();
-#pragma unroll 1
-            for (int h = 0; h < AH; ++h) {
-                int a = h * 32 + lane;
-                float4 inf = make_float4(0.f, 0.f, 0.f, 0.f);
                 bool mine = a < p.A && at[h].w != 0.0f;
-                Box me = ld_box(ws->box, a < p.A ? a : 0);
-                // all-pairs SAT: every lane tests its box against box j (broadcast from shared)
-                float cnt = 0.0f;
-#pragma unroll 1
-                for (int j = 0; j < p.A; ++j) {
-                    Box o = ld_box(ws->box, j);
-                    bool cand = mine && j != a && o.present != 0.0f && !tde_far_apart(me, o);
-                    if (__any_sync(FULL_MASK, cand)) {
-                        if (cand && tde_overlap(me, o)) cnt += 1.0f;
-                    }
-                }
+                float4 inf = make_float4(0.f, 0.f, 0.f, 0.f);
+                float off = offroad_box_warp(M, me[h], mine, c.offroad_threshold, lane);
+                float tl = tl_violation_warp(M, me[h], mine, c.tl_rear_factor, red);
                 if (mine) {
-                    inf.x = cnt;
-                    inf.y = offroad_box(M, me, c.offroad_threshold);
-                    inf.z = tl_violation_box(M, me, c.tl_rear_factor, step, lphase);
-                    inf.w = wrong_way_box(M, me);
+                    inf.x = cnt[h];
+                    inf.y = off;
+                    inf.z = tl;
+                    inf.w = wrong_way_box(M, me[h]);
                 }
                 if (a < p.A) p.infr[(size_t)e * p.A + a] = inf;
                 if (h == 0) inf0 = inf;
@@ -800,43 +922,32 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32) tde_reset_kernel(con
 
 // ---------------------------------------------------------------- stateless micro-benchmark kernels (config C4)
 
-// All-pairs oriented-box collision counts on caller-provided boxes: warp per env, boxes tiled in
-// shared memory, cheap conservative rejection voted across the warp before the full SAT.
+// All-pairs oriented-box collision counts on caller-provided boxes: warp per env, the same broad phase
+// + compacted exact SAT as the step kernel.
 template <int AH>
 __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32) tde_collision_kernel(const float4* __restrict__ state,
                                                                                   const float4* __restrict__ attr, int E, int A,
                                                                                   float* __restrict__ out) {
-    __shared__ float4 sbox[TDE_WARPS_PER_BLOCK][TDE_MAX_AGENTS * 2];
+    __shared__ SatScratch scratch[TDE_WARPS_PER_BLOCK];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int warps_total = gridDim.x * TDE_WARPS_PER_BLOCK;
-    float4* sb = sbox[warp];
+    SatScratch* ws = &scratch[warp];
     for (int e = blockIdx.x * TDE_WARPS_PER_BLOCK + warp; e < E; e += warps_total) {
         Box me[AH];
+        float cnt[AH];
 #pragma unroll
         for (int h = 0; h < AH; ++h) {
             int a = h * 32 + lane;
             float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), a4 = make_float4(1.f, 1.f, 1.f, 0.f);
             if (a < A) { s4 = state[(size_t)e * A + a]; a4 = attr[(size_t)e * A + a]; }
             me[h] = tde_make_box(s4.x, s4.y, s4.z, a4.x, a4.y, a4.w);
-            if (a < A) st_box(sb, a, me[h]);
         }
-        __syncwarp();
+        sat_counts<AH>(ws, me, A, lane, cnt);
 #pragma unroll
         for (int h = 0; h < AH; ++h) {
             int a = h * 32 + lane;
-            bool mine = a < A && me[h].present != 0.0f;
-            float cnt = 0.0f;
-#pragma unroll 1
-            for (int j = 0; j < A; ++j) {
-                Box o = ld_box(sb, j);
-                bool cand = mine && j != a && o.present != 0.0f && !tde_far_apart(me[h], o);
-                if (__any_sync(FULL_MASK, cand)) {
-                    if (cand && tde_overlap(me[h], o)) cnt += 1.0f;
-                }
-            }
-            if (a < A) out[(size_t)e * A + a] = cnt;
+            if (a < A) out[(size_t)e * A + a] = me[h].present != 0.0f ? cnt[h] : 0.0f;
         }
-        __syncwarp();
     }
 }
 
@@ -844,13 +955,14 @@ __global__ void __launch_bounds__(256) tde_offroad_kernel(const MapDev* maps, in
                                                           const float4* __restrict__ state, const float4* __restrict__ attr,
                                                           int n, float* __restrict__ out) {
     const MapDev& M = maps[map_id];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        float4 s4 = state[i], a4 = attr[i];
-        float val = 0.0f;
-        if (a4.w != 0.0f) {
-            Box b = tde_make_box(s4.x, s4.y, s4.z, a4.x, a4.y, a4.w);
-            val = offroad_box(M, b, thr);
-        }
-        out[i] = val;
+    const int lane = threadIdx.x & 31;
+    const int stride = gridDim.x * blockDim.x;
+    for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < n; base += stride) {  // warp-uniform trip count
+        int i = base + lane;
+        float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), a4 = make_float4(1.f, 1.f, 1.f, 0.f);
+        if (i < n) { s4 = state[i]; a4 = attr[i]; }
+        Box b = tde_make_box(s4.x, s4.y, s4.z, a4.x, a4.y, a4.w);
+        float val = offroad_box_warp(M, b, i < n && a4.w != 0.0f, thr, lane);
+        if (i < n) out[i] = val;
     }
 }
