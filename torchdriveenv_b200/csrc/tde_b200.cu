@@ -382,7 +382,7 @@ static void free_scenarios(tde_handle* h) {
 // persistent grids: a multiple of the SM count (resident blocks per SM from the occupancy calculator)
 template <int AH>
 static int configure_kernels(tde_handle* h) {
-    size_t smem = sizeof(RenderScratch) * TDE_WARPS_PER_BLOCK;
+    size_t smem = sizeof(RenderScratch) * TDE_WARPS_PER_BLOCK + 256 * sizeof(uint32_t);  // + the spread table
     CUDA_TRY(h, cudaFuncSetAttribute(tde_render_kernel<AH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tde_render_kernel<AH>, TDE_WARPS_PER_BLOCK * 32, smem));

@@ -604,6 +604,10 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, TDE_RENDER_BLOCKS_PE
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     RenderScratch* ws = reinterpret_cast<RenderScratch*>(smem_raw) + warp;
+    // spread table: byte of plane bits -> the same bits at the low bit of 8 nibbles
+    uint32_t* const spread_tab = reinterpret_cast<uint32_t*>(smem_raw + sizeof(RenderScratch) * TDE_WARPS_PER_BLOCK);
+    spread_tab[threadIdx.x] = spread8(threadIdx.x);
+    __syncthreads();
     const int warps_total = gridDim.x * TDE_WARPS_PER_BLOCK;
     // conservative world-space reach of the viewport around the ego (half diagonal + 2 px)
     const float reach = (0.70710678f * (float)(TDE_OBS_W + TDE_OBS_H) * 0.5f + 2.0f) / p.ppm;
@@ -705,16 +709,16 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, TDE_RENDER_BLOCKS_PE
         __syncwarp();
 
         // class-index planes -> palette lookup with byte permutes -> 128-bit stores
-        const unsigned short* pl16 = reinterpret_cast<const unsigned short*>(ws->cover);
+        const unsigned char* pl8 = reinterpret_cast<const unsigned char*>(ws->cover);
         uint8_t* out = p.obs + (size_t)e * (TDE_OBS_C * TDE_OBS_H * TDE_OBS_W);
 #pragma unroll 1
         for (int it = 0; it < TDE_OBS_H / 8; ++it) {
             int row = it * 8 + (lane >> 2), qd = lane & 3;
-            uint32_t b0 = pl16[(row * 4 + 0) * 4 + qd], b1 = pl16[(row * 4 + 1) * 4 + qd];
-            uint32_t b2 = pl16[(row * 4 + 2) * 4 + qd], b3 = pl16[(row * 4 + 3) * 4 + qd];
+            const unsigned char* pb = pl8 + row * 32 + qd * 2;   // plane b of this row at +8b, pixels 16qd.. at +2qd
             uint32_t idx[2];
-            idx[0] = spread8(b0) | (spread8(b1) << 1) | (spread8(b2) << 2) | (spread8(b3) << 3);
-            idx[1] = spread8(b0 >> 8) | (spread8(b1 >> 8) << 1) | (spread8(b2 >> 8) << 2) | (spread8(b3 >> 8) << 3);
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf)
+                idx[hf] = spread_tab[pb[hf]] + 2u * spread_tab[pb[8 + hf]] + 4u * spread_tab[pb[16 + hf]] + 8u * spread_tab[pb[24 + hf]];
             uint32_t sel7[4], himask[4];
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -749,7 +753,7 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, TDE_RENDER_BLOCKS_PE
 // offroad / red-light / wrong-way against the lane mesh, reward, termination, truncation, info,
 // waypoint progress, episode statistics and (optionally) the in-kernel auto-reset.
 template <int AH>
-__global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32) tde_physics_kernel(const StepParams p) {
+__global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, 4) tde_physics_kernel(const StepParams p) {
     __shared__ SatScratch scratch[TDE_WARPS_PER_BLOCK];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     SatScratch* ws = &scratch[warp];
