@@ -118,7 +118,7 @@ def scenario_struct(packed: Dict[str, np.ndarray]):
 
 
 _LIB = None
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libtde_b200.so")
+_LIB_PATH = os.environ.get("TDE_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libtde_b200.so")  # the override is for A/B builds of the same CUDA library
 
 EXPORTS = [
     "tde_version", "tde_last_error", "tde_create", "tde_destroy", "tde_default_config",

@@ -317,6 +317,66 @@ std::vector<float> merge_into_quads(const float* tris, int n, int stride) {
     return out;
 }
 
+// Tile index over the static render primitives (both layers).  A primitive belongs to the tile of its
+// bbox min corner; the device finds the tiles of [ego - reach - maxext, ego + reach] and takes, per tile
+// row, one contiguous run.  Tile indices use the same binary32 expression on both sides.
+struct StaticIndex {
+    std::vector<float> prims;      // 8 floats each: oversized first, then tile-sorted
+    std::vector<uint8_t> cls;
+    std::vector<int> tile_start;   // [ny*nx + 1], indices into prims
+    int n_big = 0, nx = 1, ny = 1;
+    float gx0 = 0, gy0 = 0, inv = 1, maxext = 0;
+};
+StaticIndex build_static_index(const std::vector<float>& road, const std::vector<float>& mark, float reach) {
+    StaticIndex si;
+    struct Item { const float* v; uint8_t cls; float lox, loy, ext; int tile; };
+    std::vector<Item> items;
+    auto add = [&](const std::vector<float>& src, uint8_t cls) {
+        for (size_t k = 0; k + 8 <= src.size(); k += 8) {
+            const float* v = &src[k];
+            float lx = std::min(std::min(v[0], v[2]), std::min(v[4], v[6])), hx = std::max(std::max(v[0], v[2]), std::max(v[4], v[6]));
+            float ly = std::min(std::min(v[1], v[3]), std::min(v[5], v[7])), hy = std::max(std::max(v[1], v[3]), std::max(v[5], v[7]));
+            items.push_back(Item{v, cls, lx, ly, std::max(hx - lx, hy - ly), -1});
+        }
+    };
+    add(road, TDE_CLS_ROAD);
+    add(mark, TDE_CLS_LANE_MARKING);
+    if (items.empty()) { si.tile_start.assign(2, 0); return si; }
+    // tile size: 8 m unless the viewport is large; primitives longer than two tiles stay out of the tiles
+    double T = std::max(8.0, (2.0 * reach + 16.0) / 20.0);
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        const float big = (float)(2.0 * T);
+        float lox = INFINITY, loy = INFINITY, hix = -INFINITY, hiy = -INFINITY, maxext = 0.f;
+        for (auto& it : items)
+            if (it.ext <= big) { lox = std::min(lox, it.lox); loy = std::min(loy, it.loy); hix = std::max(hix, it.lox); hiy = std::max(hiy, it.loy); maxext = std::max(maxext, it.ext); }
+        if (!(lox <= hix)) { lox = loy = hix = hiy = 0.f; }
+        si.gx0 = lox; si.gy0 = loy; si.inv = (float)(1.0 / T);
+        si.maxext = maxext * 1.0001f + 1e-3f;
+        si.nx = (int)std::floor((hix - si.gx0) * si.inv) + 1;
+        si.ny = (int)std::floor((hiy - si.gy0) * si.inv) + 1;
+        double rows = (2.0 * reach + si.maxext) / T + 2.0;
+        if ((double)si.nx * si.ny <= 4.0e6 && rows <= 24.0) break;
+        T *= 1.5;
+    }
+    const float big = (float)(2.0 / (double)si.inv);
+    for (auto& it : items) {
+        if (it.ext > big) { it.tile = -1; continue; }
+        int tx = (int)std::floor((it.lox - si.gx0) * si.inv), ty = (int)std::floor((it.loy - si.gy0) * si.inv);
+        tx = std::min(std::max(tx, 0), si.nx - 1); ty = std::min(std::max(ty, 0), si.ny - 1);
+        it.tile = ty * si.nx + tx;
+    }
+    std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.tile < b.tile; });
+    si.tile_start.assign((size_t)si.nx * si.ny + 1, 0);
+    for (auto& it : items) {
+        si.prims.insert(si.prims.end(), it.v, it.v + 8);
+        si.cls.push_back(it.cls);
+        if (it.tile < 0) si.n_big++; else si.tile_start[(size_t)it.tile + 1]++;
+    }
+    si.tile_start[0] = si.n_big;
+    for (size_t k = 1; k < si.tile_start.size(); ++k) si.tile_start[k] += si.tile_start[k - 1];
+    return si;
+}
+
 std::vector<float> morton_sorted(const float* tris, int n, int stride) {
     std::vector<float> out((size_t)n * stride);
     if (n == 0) return out;
@@ -494,16 +554,20 @@ extern "C" int tde_upload_scenarios(tde_handle* h, const tde_scenario_set* s) {
         if (nt) prep_tris_kernel<<<(nt + 127) / 128, 128>>>(raw, nt, rec);
         M.tri = rec; M.ntri = nt;
         M.nmark = nk;
-        // render-only static primitives: merged quads / leftover triangles, Morton ordered
-        std::vector<float> rp_road = merge_into_quads(s->road_tris + 8 * (size_t)t0, nt, 8);
-        std::vector<float> rp_mark = merge_into_quads(s->mark_tris + 6 * (size_t)k0, nk, 6);
-        rp_road = morton_sorted(rp_road.data(), (int)(rp_road.size() / 8), 8);
-        rp_mark = morton_sorted(rp_mark.data(), (int)(rp_mark.size() / 8), 8);
-        float *rpr = nullptr, *rpm = nullptr;
-        if ((rc = dev_upload(h, &rpr, rp_road.data(), rp_road.size()))) return rc;
-        if ((rc = dev_upload(h, &rpm, rp_mark.data(), rp_mark.size()))) return rc;
-        M.rp_road = (const float4*)rpr; M.n_rp_road = (int)(rp_road.size() / 8);
-        M.rp_mark = (const float4*)rpm; M.n_rp_mark = (int)(rp_mark.size() / 8);
+        // render-only static primitives: merged quads / leftover triangles of both layers, indexed by tile
+        {
+            std::vector<float> rp_road = merge_into_quads(s->road_tris + 8 * (size_t)t0, nt, 8);
+            std::vector<float> rp_mark = merge_into_quads(s->mark_tris + 6 * (size_t)k0, nk, 6);
+            const float reach = (0.70710678f * (float)(TDE_OBS_W + TDE_OBS_H) * 0.5f + 2.0f) / ppm;  // as in tde_render_kernel
+            StaticIndex si = build_static_index(rp_road, rp_mark, reach);
+            float* rpd = nullptr; uint8_t* clsd = nullptr; int* tsd = nullptr;
+            if ((rc = dev_upload(h, &rpd, si.prims.data(), si.prims.size()))) return rc;
+            if ((rc = dev_upload(h, &clsd, si.cls.data(), si.cls.size()))) return rc;
+            if ((rc = dev_upload(h, &tsd, si.tile_start.data(), si.tile_start.size()))) return rc;
+            M.rp = (const float4*)rpd; M.rp_cls = clsd; M.tile_start = tsd;
+            M.n_rp = (int)si.cls.size(); M.n_big = si.n_big;
+            M.tgx0 = si.gx0; M.tgy0 = si.gy0; M.tinv = si.inv; M.maxext = si.maxext; M.tnx = si.nx; M.tny = si.ny;
+        }
         float* sraw = nullptr; float4* srec = nullptr;
         if ((rc = dev_upload(h, &sraw, s->stoplines + 5 * (size_t)l0, (size_t)nl * 5))) return rc;
         if ((rc = dev_alloc(h, &srec, (size_t)nl * 2))) return rc;
@@ -516,38 +580,21 @@ extern "C" int tde_upload_scenarios(tde_handle* h, const tde_scenario_set* s) {
         uint8_t* lights = nullptr;
         if ((rc = dev_upload(h, &lights, s->light_states + lo, (size_t)std::max(ln, 0)))) return rc;
         M.lights = lights; M.period = nl > 0 ? P : 0;
-        // bounding boxes of runs of 32 triangles (render-time culling)
-        auto chunk_boxes = [&](const float* base, int count, int stride) {
-            std::vector<float> bb;
-            for (int c0 = 0; c0 < count; c0 += 32) {
-                float lx = INFINITY, ly = INFINITY, hx = -INFINITY, hy = -INFINITY;
-                for (int t = c0; t < std::min(count, c0 + 32); ++t)
-                    for (int k = 0; k < 4; ++k) {
-                        float x = base[(size_t)t * stride + 2 * k], y = base[(size_t)t * stride + 2 * k + 1];
-                        lx = std::min(lx, x); hx = std::max(hx, x); ly = std::min(ly, y); hy = std::max(hy, y);
-                    }
-                bb.insert(bb.end(), {lx, ly, hx, hy});
-            }
-            return bb;
-        };
-        {
-            std::vector<float> tb = chunk_boxes(rp_road.data(), M.n_rp_road, 8);
-            std::vector<float> mb = chunk_boxes(rp_mark.data(), M.n_rp_mark, 8);
-            float *tbd = nullptr, *mbd = nullptr;
-            if ((rc = dev_upload(h, &tbd, tb.data(), tb.size()))) return rc;
-            if ((rc = dev_upload(h, &mbd, mb.data(), mb.size()))) return rc;
-            M.tri_chunk = (const float4*)tbd; M.mark_chunk = (const float4*)mbd;
-        }
         Grid g = build_grid(road_sorted.data(), nt, (double)h->cfg.offroad_threshold);
-        int* cs = nullptr; uint16_t *items = nullptr, *meta = nullptr;
-        if ((rc = dev_upload(h, &cs, g.cell_start.data(), g.cell_start.size()))) return rc;
+        std::vector<int2> crec(g.meta.size());
+        for (size_t c = 0; c < g.meta.size(); ++c) {
+            int cnt = g.cell_start[c + 1] - g.cell_start[c];
+            if (cnt > 65535) return fail(h, TDE_E_SHAPE, "tde_upload_scenarios: more than 65535 candidate triangles in one grid cell");
+            crec[c] = make_int2(g.cell_start[c], (int)(((unsigned)cnt << 16) | g.meta[c]));
+        }
+        int2* crd = nullptr; uint16_t* items = nullptr;
+        if ((rc = dev_upload(h, &crd, crec.data(), crec.size()))) return rc;
         if ((rc = dev_upload(h, &items, g.items.data(), g.items.size()))) return rc;
-        if ((rc = dev_upload(h, &meta, g.meta.data(), g.meta.size()))) return rc;
-        M.cell_start = cs; M.cell_items = items; M.cell_meta = meta;
+        M.cell_rec = crd; M.cell_items = items;
         {
             size_t safe = 0, nover = 0;
             for (uint16_t m : g.meta) { safe += (m & TDE_CELL_SAFE) ? 1 : 0; nover += m & 0x7fff; }
-            h->map_info.push_back({nt, nk, nl, g.nx, g.ny, (int)g.items.size(), (int)safe, M.n_rp_road + M.n_rp_mark});
+            h->map_info.push_back({nt, nk, nl, g.nx, g.ny, (int)g.items.size(), (int)safe, M.n_rp});
         }
         M.gx0 = g.gx0; M.gy0 = g.gy0; M.inv_cell = g.inv_cell; M.gnx = g.nx; M.gny = g.ny;
     }

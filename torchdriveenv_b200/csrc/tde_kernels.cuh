@@ -13,23 +13,29 @@
 #include "../../include/tde_b200.h"
 
 #define TDE_WARPS_PER_BLOCK 8
+#ifndef TDE_RENDER_BLOCKS_PER_SM
 #define TDE_RENDER_BLOCKS_PER_SM 4
+#endif
+#ifndef TDE_PHYS_BLOCKS_PER_SM
+#define TDE_PHYS_BLOCKS_PER_SM 4
+#endif
 
 struct MapDev {
     const float4* tri;          // 3 float4 per road triangle (see tde_point_tri_dist2)
-    const float4* rp_road;      // render primitives of the road layer: 2 float4 = 4 vertices (triangle: v3 == v0)
-    const float4* rp_mark;      // same for the lane-marking layer
-    const float4* stop;         // 2 float4 per stop line: [x y hl hw] [c s 0 0]
+    const float4* rp;           // static render primitives (road + lane markings): 2 float4 = 4 vertices (triangle: v3 == v0);
+                                // the n_big oversized ones first, the rest sorted by tile (row-major) of their bbox min corner
+    const uint8_t* rp_cls;      // class of each static render primitive
+    const int* tile_start;      // [tny*tnx + 1] index into rp of the first primitive of each tile
+    const float4* stop;         // 2 float4 per stop line: [x y hl hw] [c s rr 0]
     const uint8_t* lights;      // [period][nstop]
-    const int* cell_start;      // [gnx*gny+1]
+    const int2* cell_rec;       // [gnx*gny] per cell: x = first item, y = n_items << 16 | TDE_CELL_SAFE | n_overlapping
     const uint16_t* cell_items; // per cell: overlapping triangles first, then the other nearest candidates
-    const uint16_t* cell_meta;  // per cell: n_overlapping | TDE_CELL_SAFE
-    const float4* tri_chunk;    // bbox (lox loy hix hiy) of every run of 32 road render primitives
-    const float4* mark_chunk;   // same for the lane-marking layer
     int ntri, nmark, nstop, period;
-    int n_rp_road, n_rp_mark;
+    int n_rp, n_big;
     float gx0, gy0, inv_cell;
     int gnx, gny;
+    float tgx0, tgy0, tinv, maxext;  // tile grid of the render primitives; maxext = largest bbox extent of a tiled primitive
+    int tnx, tny;
 };
 
 struct ScenDev {
@@ -198,36 +204,43 @@ __device__ __forceinline__ void sat_counts(SatScratch* ws, const Box (&me)[AH], 
 // there the offroad term is 0 without looking at a triangle.
 #define TDE_CELL_SAFE 0x8000
 
-// compute_offroad (gym_env.py:142,415,427): sum over corners of max(dist - threshold, 0).  Called by the
-// whole warp (lane = agent, `mine` = has a box).  Each lane first settles its corner alone (safe cell,
-// or inside one of the cell's overlapping triangles); the corners that still need a distance are then
-// taken one at a time by the whole warp, lanes striding over the candidate triangles, min by redux.
-__device__ __noinline__ float offroad_box_warp(const MapDev& M, const Box& b, bool mine, float thr, int lane) {
-    if (M.ntri <= 0) return 0.0f;
-    float sum = 0.0f;
+// compute_offroad (gym_env.py:142,415,427): sum over corners of max(dist - threshold, 0), and
+// compute_wrong_way: max(-cos(psi - lane_dir), 0), min over the triangles under the centre.  Called by
+// the whole warp (lane = agent, `mine` = has a box).  The cell records of the four corners and the
+// centre are fetched together; each lane then settles its corners alone (safe cell, or inside one of
+// the cell's overlapping triangles); the corners that still need a distance are taken one at a time by
+// the whole warp, lanes striding over the candidate triangles, min by redux.
+struct MeshInfr { float offroad, wrong_way; };
+__device__ __noinline__ MeshInfr mesh_infractions_warp(const MapDev& M, const Box& b, bool mine, float thr, int lane) {
+    MeshInfr out; out.offroad = 0.0f; out.wrong_way = 0.0f;
+    if (M.ntri <= 0) return out;
+    int2 rec[5];   // x = first item (-1: off the grid), y = n_items << 16 | SAFE | n_overlapping
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        float px = b.x, py = b.y;
+        if (k < 4) tde_box_corner(b, k, px, py);
+        float fx = floorf((px - M.gx0) * M.inv_cell), fy = floorf((py - M.gy0) * M.inv_cell);
+        bool in_grid = fx >= 0.0f && fy >= 0.0f && fx < (float)M.gnx && fy < (float)M.gny;
+        rec[k] = make_int2(in_grid ? 0 : -1, in_grid ? TDE_CELL_SAFE : 0);
+        if (mine && in_grid) rec[k] = M.cell_rec[(int)fy * M.gnx + (int)fx];
+        if (!mine) rec[k] = make_int2(0, TDE_CELL_SAFE);
+    }
+    float sum = 0.0f, dc, ds;
 #pragma unroll 1
     for (int k = 0; k < 4; ++k) {
         float px, py;
         tde_box_corner(b, k, px, py);
-        float d2 = 0.0f, dc, ds;
-        int i0 = 0, i1 = 0;
+        const int2 rc = k == 0 ? rec[0] : k == 1 ? rec[1] : k == 2 ? rec[2] : rec[3];
+        float d2 = 0.0f;
+        int i0 = rc.x, i1 = rc.x + (int)((unsigned)rc.y >> 16);
         bool need = false;
-        if (mine) {
-            float fx = floorf((px - M.gx0) * M.inv_cell), fy = floorf((py - M.gy0) * M.inv_cell);
-            bool in_grid = fx >= 0.0f && fy >= 0.0f && fx < (float)M.gnx && fy < (float)M.gny;
-            if (in_grid) {
-                int cell = (int)fy * M.gnx + (int)fx;
-                int meta = M.cell_meta[cell];
-                if (!(meta & TDE_CELL_SAFE)) {
-                    i0 = M.cell_start[cell]; i1 = M.cell_start[cell + 1];
-                    int nover = meta & 0x7fff;
-                    need = true;
-                    for (int i = i0; i < i0 + nover; ++i)
-                        if (tde_tri_contains(M.tri + 3 * (int)M.cell_items[i], px, py, dc, ds)) { need = false; break; }
-                }
-            } else {
-                need = true; i0 = 0; i1 = -M.ntri;  // off the grid: every triangle, containment included
-            }
+        if (rc.x < 0) {
+            need = true; i0 = 0; i1 = -M.ntri;  // off the grid: every triangle, containment included
+        } else if (!(rc.y & TDE_CELL_SAFE)) {
+            const int nover = rc.y & 0x7fff;
+            need = true;
+            for (int i = i0; i < i0 + nover; ++i)
+                if (tde_tri_contains(M.tri + 3 * (int)M.cell_items[i], px, py, dc, ds)) { need = false; break; }
         }
         unsigned nm = __ballot_sync(FULL_MASK, need);
         while (nm) {
@@ -253,25 +266,19 @@ __device__ __noinline__ float offroad_box_warp(const MapDev& M, const Box& b, bo
         float d = sqrtf(d2);
         sum = sum + fmaxf(d - thr, 0.0f);
     }
-    return mine ? sum : 0.0f;
-}
-
-// compute_wrong_way: max(-cos(psi - lane_dir), 0), min over the triangles under the centre
-__device__ __noinline__ float wrong_way_box(const MapDev& M, const Box& b) {
+    out.offroad = mine ? sum : 0.0f;
+    // wrong way: the triangles under the centre
     float best = INFINITY;
-    float fx = floorf((b.x - M.gx0) * M.inv_cell), fy = floorf((b.y - M.gy0) * M.inv_cell);
-    bool in_grid = fx >= 0.0f && fy >= 0.0f && fx < (float)M.gnx && fy < (float)M.gny;
-    float dc, ds;
-    if (in_grid) {
-        int cell = (int)fy * M.gnx + (int)fx;
-        int i0 = M.cell_start[cell], nover = M.cell_meta[cell] & 0x7fff;
+    if (rec[4].x >= 0) {
+        const int i0 = rec[4].x, nover = rec[4].y & 0x7fff;
         for (int i = i0; i < i0 + nover; ++i)
             if (tde_tri_contains(M.tri + 3 * (int)M.cell_items[i], b.x, b.y, dc, ds)) best = fminf(best, fmaxf(-(b.c * dc + b.s * ds), 0.0f));
     } else {
         for (int t = 0; t < M.ntri; ++t)
             if (tde_tri_contains(M.tri + 3 * t, b.x, b.y, dc, ds)) best = fminf(best, fmaxf(-(b.c * dc + b.s * ds), 0.0f));
     }
-    return best == INFINITY ? 0.0f : best;
+    out.wrong_way = best == INFINITY ? 0.0f : best;
+    return out;
 }
 
 __device__ __forceinline__ int light_state_at(const MapDev& M, int step, int phase, int l) {
@@ -549,50 +556,68 @@ __device__ __forceinline__ uint32_t spread8(uint32_t b) {
     return x;
 }
 
-// static layers (road, lane markings): lanes first test the bounding boxes of runs of 32 primitives
-// against the viewport's reach, then only the visible runs are loaded, projected and queued
-__device__ __noinline__ int queue_static_layer(const MapDev& M, bool road, Cam cam, float reach, RenderScratch* ws, int lane, int qtot) {
-    const int nprim = road ? M.n_rp_road : M.n_rp_mark;
-    const float4* prim = road ? M.rp_road : M.rp_mark;
-    const float4* chunk = road ? M.tri_chunk : M.mark_chunk;
-    const int cls = road ? TDE_CLS_ROAD : TDE_CLS_LANE_MARKING;
-    const int nchunk = (nprim + 31) >> 5;
+// static layers (road, lane markings).  The primitives are sorted by the tile of their bbox min corner,
+// so the candidates of a viewport are one contiguous run per tile row: lanes fetch the runs of the
+// rows in reach, a scan numbers the candidates, and they are projected and queued 32 at a time with
+// every lane busy.  Oversized primitives (kept out of the tiles) are always candidates.
+__device__ __noinline__ int queue_static(const MapDev& M, Cam cam, float reach, RenderScratch* ws, int lane, int qtot) {
+    if (M.n_rp <= 0) return qtot;
+    const float lo_reach = reach + M.maxext;
+    const int tx0 = max(0, (int)floorf((cam.ex - lo_reach - M.tgx0) * M.tinv)), tx1 = min(M.tnx - 1, (int)floorf((cam.ex + reach - M.tgx0) * M.tinv));
+    const int ty0 = max(0, (int)floorf((cam.ey - lo_reach - M.tgy0) * M.tinv)), ty1 = min(M.tny - 1, (int)floorf((cam.ey + reach - M.tgy0) * M.tinv));
+    const int nrows = (tx0 <= tx1 && ty0 <= ty1) ? min(ty1 - ty0 + 1, 32) : 0;   // the upload sizes the tiles for <= 24 rows
+    int s = 0, n = 0;
+    if (lane < nrows) {
+        const int* ts = M.tile_start + (ty0 + lane) * M.tnx;
+        s = ts[tx0];
+        n = ts[tx1 + 1] - s;
+    }
+    int incl = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(FULL_MASK, incl, d);
+        if (lane >= d) incl += t;
+    }
+    incl += M.n_big;                                   // candidates are numbered: oversized first, then row by row
+    const int total = __shfl_sync(FULL_MASK, incl, 31);
+    const int excl = incl - n;
 #pragma unroll 1
-    for (int cb = 0; cb < nchunk; cb += 32) {
-        bool see = false;
-        if (cb + lane < nchunk) {
-            float4 bb = chunk[cb + lane];
-            see = bb.z >= cam.ex - reach && bb.x <= cam.ex + reach && bb.w >= cam.ey - reach && bb.y <= cam.ey + reach;
+    for (int base = 0; base < total; base += 32) {
+        const int g = base + lane;
+        int r = 0;   // number of rows that end at or before g (binary search over the lanes' running totals)
+#pragma unroll
+        for (int st = 16; st >= 1; st >>= 1) {
+            const int probe = r + st - 1;
+            const int v = __shfl_sync(FULL_MASK, incl, probe);
+            if (probe < nrows && g >= v) r += st;
         }
-        unsigned vis = __ballot_sync(FULL_MASK, see);
-        while (vis) {
-            int c = cb + __ffs(vis) - 1;
-            vis &= vis - 1;
-            int t = c * 32 + lane;
-            bool valid = t < nprim;
-            float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
-            if (valid) { p0 = prim[2 * t]; p1 = prim[2 * t + 1]; }
-            float lox = fminf(fminf(p0.x, p0.z), fminf(p1.x, p1.z)), hix = fmaxf(fmaxf(p0.x, p0.z), fmaxf(p1.x, p1.z));
-            float loy = fminf(fminf(p0.y, p0.w), fminf(p1.y, p1.w)), hiy = fmaxf(fmaxf(p0.y, p0.w), fmaxf(p1.y, p1.w));
-            valid = valid && hix >= cam.ex - reach && lox <= cam.ex + reach && hiy >= cam.ey - reach && loy <= cam.ey + reach;
-            if (!__any_sync(FULL_MASK, valid)) continue;
-            Proj pr = project_quad(cam, p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w);
-            const uint4 pv = pr.v;
-            bool ok = pr.ok && valid;
-            // a merged quad is drawn as one primitive only if it is still strictly convex after
-            // snapping (then it covers exactly its two triangles); otherwise fall back to the pair
-            int x0 = unpack_x(pv.x), y0 = unpack_y(pv.x), x1 = unpack_x(pv.y), y1 = unpack_y(pv.y);
-            int x2 = unpack_x(pv.z), y2 = unpack_y(pv.z), x3 = unpack_x(pv.w), y3 = unpack_y(pv.w);
-            int c0 = (x1 - x0) * (y2 - y1) - (y1 - y0) * (x2 - x1), c1 = (x2 - x1) * (y3 - y2) - (y2 - y1) * (x3 - x2);
-            int c2 = (x3 - x2) * (y0 - y3) - (y3 - y2) * (x0 - x3), c3 = (x0 - x3) * (y1 - y0) - (y0 - y3) * (x1 - x0);
-            bool convex = (c0 > 0 && c1 > 0 && c2 > 0 && c3 > 0) || (c0 < 0 && c1 < 0 && c2 < 0 && c3 < 0);
-            bool is_tri = pv.w == pv.x;
-            qtot = enqueue(ws, lane, ok && (is_tri || convex), pv, cls, qtot);
-            bool split = ok && !is_tri && !convex;
-            if (__any_sync(FULL_MASK, split)) {
-                qtot = enqueue(ws, lane, split, make_uint4(pv.x, pv.y, pv.w, pv.x), cls, qtot);
-                qtot = enqueue(ws, lane, split, make_uint4(pv.y, pv.z, pv.w, pv.y), cls, qtot);
-            }
+        r = min(r, 31);
+        const int s_r = __shfl_sync(FULL_MASK, s, r), e_r = __shfl_sync(FULL_MASK, excl, r);
+        bool valid = g < total;
+        const int t = g < M.n_big ? g : s_r + (g - e_r);
+        float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
+        int cls = TDE_CLS_ROAD;
+        if (valid) { p0 = M.rp[2 * t]; p1 = M.rp[2 * t + 1]; cls = M.rp_cls[t]; }
+        float lox = fminf(fminf(p0.x, p0.z), fminf(p1.x, p1.z)), hix = fmaxf(fmaxf(p0.x, p0.z), fmaxf(p1.x, p1.z));
+        float loy = fminf(fminf(p0.y, p0.w), fminf(p1.y, p1.w)), hiy = fmaxf(fmaxf(p0.y, p0.w), fmaxf(p1.y, p1.w));
+        valid = valid && hix >= cam.ex - reach && lox <= cam.ex + reach && hiy >= cam.ey - reach && loy <= cam.ey + reach;
+        if (!__any_sync(FULL_MASK, valid)) continue;
+        Proj pr = project_quad(cam, p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w);
+        const uint4 pv = pr.v;
+        bool ok = pr.ok && valid;
+        // a merged quad is drawn as one primitive only if it is still strictly convex after
+        // snapping (then it covers exactly its two triangles); otherwise fall back to the pair
+        int x0 = unpack_x(pv.x), y0 = unpack_y(pv.x), x1 = unpack_x(pv.y), y1 = unpack_y(pv.y);
+        int x2 = unpack_x(pv.z), y2 = unpack_y(pv.z), x3 = unpack_x(pv.w), y3 = unpack_y(pv.w);
+        int c0 = (x1 - x0) * (y2 - y1) - (y1 - y0) * (x2 - x1), c1 = (x2 - x1) * (y3 - y2) - (y2 - y1) * (x3 - x2);
+        int c2 = (x3 - x2) * (y0 - y3) - (y3 - y2) * (x0 - x3), c3 = (x0 - x3) * (y1 - y0) - (y0 - y3) * (x1 - x0);
+        bool convex = (c0 > 0 && c1 > 0 && c2 > 0 && c3 > 0) || (c0 < 0 && c1 < 0 && c2 < 0 && c3 < 0);
+        bool is_tri = pv.w == pv.x;
+        qtot = enqueue(ws, lane, ok && (is_tri || convex), pv, cls, qtot);
+        bool split = ok && !is_tri && !convex;
+        if (__any_sync(FULL_MASK, split)) {
+            qtot = enqueue(ws, lane, split, make_uint4(pv.x, pv.y, pv.w, pv.x), cls, qtot);
+            qtot = enqueue(ws, lane, split, make_uint4(pv.y, pv.z, pv.w, pv.y), cls, qtot);
         }
     }
     return qtot;
@@ -640,8 +665,7 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, TDE_RENDER_BLOCKS_PE
         cam.ppm = p.ppm; cam.ppmy = p.ppmy;
         float wx[4], wy[4];
         int qtot = 0;
-        qtot = queue_static_layer(M, true, cam, reach, ws, lane, qtot);    // class 1: road
-        qtot = queue_static_layer(M, false, cam, reach, ws, lane, qtot);   // class 2: lane markings
+        qtot = queue_static(M, cam, reach, ws, lane, qtot);                 // classes 1-2: road and lane markings
         // classes 3-5: stop lines coloured by their light state
         if (M.nstop > 0) {
             bool valid = lane < M.nstop;
@@ -753,7 +777,7 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, TDE_RENDER_BLOCKS_PE
 // offroad / red-light / wrong-way against the lane mesh, reward, termination, truncation, info,
 // waypoint progress, episode statistics and (optionally) the in-kernel auto-reset.
 template <int AH>
-__global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, 4) tde_physics_kernel(const StepParams p) {
+__global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, TDE_PHYS_BLOCKS_PER_SM) tde_physics_kernel(const StepParams p) {
     __shared__ SatScratch scratch[TDE_WARPS_PER_BLOCK];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     SatScratch* ws = &scratch[warp];
@@ -813,13 +837,13 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, 4) tde_physics_kerne
                 int a = h * 32 + lane;
                 bool mine = a < p.A && at[h].w != 0.0f;
                 float4 inf = make_float4(0.f, 0.f, 0.f, 0.f);
-                float off = offroad_box_warp(M, me[h], mine, c.offroad_threshold, lane);
+                MeshInfr mi = mesh_infractions_warp(M, me[h], mine, c.offroad_threshold, lane);
                 float tl = tl_violation_warp(M, me[h], mine, c.tl_rear_factor, red);
                 if (mine) {
                     inf.x = cnt[h];
-                    inf.y = off;
+                    inf.y = mi.offroad;
                     inf.z = tl;
-                    inf.w = wrong_way_box(M, me[h]);
+                    inf.w = mi.wrong_way;
                 }
                 if (a < p.A) p.infr[(size_t)e * p.A + a] = inf;
                 if (h == 0) inf0 = inf;
@@ -966,7 +990,7 @@ __global__ void __launch_bounds__(256) tde_offroad_kernel(const MapDev* maps, in
         float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), a4 = make_float4(1.f, 1.f, 1.f, 0.f);
         if (i < n) { s4 = state[i]; a4 = attr[i]; }
         Box b = tde_make_box(s4.x, s4.y, s4.z, a4.x, a4.y, a4.w);
-        float val = offroad_box_warp(M, b, i < n && a4.w != 0.0f, thr, lane);
+        float val = mesh_infractions_warp(M, b, i < n && a4.w != 0.0f, thr, lane).offroad;
         if (i < n) out[i] = val;
     }
 }
