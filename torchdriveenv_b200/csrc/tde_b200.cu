@@ -88,6 +88,12 @@ __global__ void prep_stops_kernel(const float* __restrict__ raw, int n, float4* 
 
 // ------------------------------------------------------------------ nearest-candidate grid (host, float64)
 
+#ifndef TDE_GRID_MIN_CELL
+#define TDE_GRID_MIN_CELL 0.7
+#endif
+#ifndef TDE_GRID_MAX_CELLS
+#define TDE_GRID_MAX_CELLS 32768.0
+#endif
 namespace {
 struct P2 { double x, y; };
 inline double seg_d2(P2 p, P2 a, P2 b) {
@@ -187,7 +193,7 @@ Grid build_grid(const float* tris, int M, double threshold) {
     const double margin = 8.0;
     lox -= margin; loy -= margin; hix += margin; hiy += margin;
     double w = hix - lox, hgt = hiy - loy;
-    double cell = std::max(1.0, std::sqrt(w * hgt / 16384.0));
+    double cell = std::max(TDE_GRID_MIN_CELL, std::sqrt(w * hgt / TDE_GRID_MAX_CELLS));
     g.nx = std::max(1, (int)std::ceil(w / cell));
     g.ny = std::max(1, (int)std::ceil(hgt / cell));
     g.gx0 = (float)lox; g.gy0 = (float)loy;

@@ -211,12 +211,13 @@ __device__ __forceinline__ void sat_counts(SatScratch* ws, const Box (&me)[AH], 
 // the cell's overlapping triangles); the corners that still need a distance are taken one at a time by
 // the whole warp, lanes striding over the candidate triangles, min by redux.
 struct MeshInfr { float offroad, wrong_way; };
+template <bool WRONG_WAY>
 __device__ __noinline__ MeshInfr mesh_infractions_warp(const MapDev& M, const Box& b, bool mine, float thr, int lane) {
     MeshInfr out; out.offroad = 0.0f; out.wrong_way = 0.0f;
     if (M.ntri <= 0) return out;
     int2 rec[5];   // x = first item (-1: off the grid), y = n_items << 16 | SAFE | n_overlapping
 #pragma unroll
-    for (int k = 0; k < 5; ++k) {
+    for (int k = 0; k < (WRONG_WAY ? 5 : 4); ++k) {
         float px = b.x, py = b.y;
         if (k < 4) tde_box_corner(b, k, px, py);
         float fx = floorf((px - M.gx0) * M.inv_cell), fy = floorf((py - M.gy0) * M.inv_cell);
@@ -243,6 +244,22 @@ __device__ __noinline__ MeshInfr mesh_infractions_warp(const MapDev& M, const Bo
                 if (tde_tri_contains(M.tri + 3 * (int)M.cell_items[i], px, py, dc, ds)) { need = false; break; }
         }
         unsigned nm = __ballot_sync(FULL_MASK, need);
+        if (__popc(nm) > 4) {   // many lanes are off the road (scattered boxes): each walks its own candidates
+            if (need) {
+                float best = INFINITY;
+                bool inside = false;
+                if (i1 < 0) {
+                    for (int t = 0; t < -i1; ++t) {
+                        inside = inside || tde_tri_contains(M.tri + 3 * t, px, py, dc, ds);
+                        best = fminf(best, tde_tri_segdist2(M.tri + 3 * t, px, py));
+                    }
+                } else {
+                    for (int i = i0; i < i1; ++i) best = fminf(best, tde_tri_segdist2(M.tri + 3 * (int)M.cell_items[i], px, py));
+                }
+                d2 = inside ? 0.0f : best;
+            }
+            nm = 0u;
+        }
         while (nm) {
             const int src = __ffs(nm) - 1;
             nm &= nm - 1;
@@ -267,6 +284,7 @@ __device__ __noinline__ MeshInfr mesh_infractions_warp(const MapDev& M, const Bo
         sum = sum + fmaxf(d - thr, 0.0f);
     }
     out.offroad = mine ? sum : 0.0f;
+    if (!WRONG_WAY) return out;
     // wrong way: the triangles under the centre
     float best = INFINITY;
     if (rec[4].x >= 0) {
@@ -837,7 +855,7 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, TDE_PHYS_BLOCKS_PER_
                 int a = h * 32 + lane;
                 bool mine = a < p.A && at[h].w != 0.0f;
                 float4 inf = make_float4(0.f, 0.f, 0.f, 0.f);
-                MeshInfr mi = mesh_infractions_warp(M, me[h], mine, c.offroad_threshold, lane);
+                MeshInfr mi = mesh_infractions_warp<true>(M, me[h], mine, c.offroad_threshold, lane);
                 float tl = tl_violation_warp(M, me[h], mine, c.tl_rear_factor, red);
                 if (mine) {
                     inf.x = cnt[h];
@@ -990,7 +1008,7 @@ __global__ void __launch_bounds__(256) tde_offroad_kernel(const MapDev* maps, in
         float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), a4 = make_float4(1.f, 1.f, 1.f, 0.f);
         if (i < n) { s4 = state[i]; a4 = attr[i]; }
         Box b = tde_make_box(s4.x, s4.y, s4.z, a4.x, a4.y, a4.w);
-        float val = mesh_infractions_warp(M, b, i < n && a4.w != 0.0f, thr, lane).offroad;
+        float val = mesh_infractions_warp<false>(M, b, i < n && a4.w != 0.0f, thr, lane).offroad;
         if (i < n) out[i] = val;
     }
 }
