@@ -13,6 +13,8 @@
  *   tde_reset                    WaypointSuiteEnv.reset :319-349 + set_start_pos :351-367
  *                                  + build_simulator's state initialisation :192-198,241-247,269-283
  *   tde_render                   simulator.render_egocentric() :123,154
+ *   tde_step_stacked,
+ *   tde_render_stacked           the same with VecFrameStack (examples/rl_training.py:160) fused into the store
  *   tde_get_state/tde_set_state  simulator.get_state() :127,371,392-393,397-399,420-423 / set_state :247
  *   tde_compute_infractions,
  *   tde_get_infractions          simulator.compute_offroad() :142,415,427; compute_collision() :143,415,428;
@@ -224,6 +226,15 @@ int tde_step_phases(tde_handle* h, int32_t phases, const float* actions_dev, uin
 /* host-buffer variant: copies actions H2D, steps, copies results D2H, synchronises `stream` */
 int tde_step_host(tde_handle* h, const float* actions_host, uint8_t* obs_host, float* reward_host,
                   uint8_t* terminated_host, uint8_t* truncated_host, float* info_host, void* stream);
+
+/* VecFrameStack(n_stack, channels_order="first") fused into the observation store
+   (examples/rl_training.py:160): stack_dev is uint8[E][3*n_stack][64][64], oldest frame first.  The
+   render kernel moves frames 1..n-1 of each env down by one slot while it writes the new frame into
+   the last slot; an env that was reset since its previous frame (tde_reset, or the in-kernel
+   auto-reset) has its older slots zeroed instead, as VecFrameStack does.  n_stack in 1..8. */
+int tde_step_stacked(tde_handle* h, const float* actions_dev, uint8_t* stack_dev, int32_t n_stack, float* reward_dev,
+                     uint8_t* terminated_dev, uint8_t* truncated_dev, float* info_dev, void* stream);
+int tde_render_stacked(tde_handle* h, uint8_t* stack_dev, int32_t n_stack, void* stream);
 
 int tde_kinematics(tde_handle* h, const float* actions_dev, void* stream);
 int tde_render(tde_handle* h, uint8_t* obs_dev, void* stream);

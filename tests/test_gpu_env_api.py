@@ -94,6 +94,7 @@ def test_vec_env_frame_stack_and_auto_reset(oracle):
     orc.reset(seed=8)
     rng = np.random.default_rng(8)
     frames = [orc.render()]
+    age = np.zeros(E, np.int64)      # frames since the env (re)started: slot s holds a frame only if age >= 2 - s
     n_done = 0
     for k in range(25):
         a = np.stack([rng.uniform(-1, 1, E), rng.uniform(-0.3, 0.3, E)], 1).astype(np.float32)
@@ -108,6 +109,15 @@ def test_vec_env_frame_stack_and_auto_reset(oracle):
         assert np.array_equal(obs[keep][:, 3:6].cpu().numpy(), prev[keep])
         assert bool((obs[d][:, :6] == 0).all())
         frames.append(oobs)
+        age = np.where(d, 0, age + 1)
+        # the whole stack against VecFrameStack semantics (oldest frame first, zeros before the restart)
+        want = np.zeros((E, 9, 64, 64), np.uint8)
+        for slot in range(3):
+            back = 2 - slot
+            if back < len(frames):
+                have = age >= back
+                want[have, 3 * slot:3 * slot + 3] = frames[-1 - back][have]
+        assert np.array_equal(obs.cpu().numpy(), want), f"step {k}: fused frame stack"
         n_done += int(d.sum())
         assert set(infos) >= {"offroad", "collision", "traffic_light_violation", "is_success", "terminated", "truncated"}
     assert n_done > 0

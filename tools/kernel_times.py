@@ -23,5 +23,7 @@ def timed(fn, n=50):
 t_phys = timed(lambda k: eng.step(acts[k % 64], render=False))
 t_rend = timed(lambda k: eng.render(out=obs))
 t_both = timed(lambda k: eng.step(acts[k % 64]))
-print(f"E={E} A={A} physics {t_phys:.1f} us  render {t_rend:.1f} us  step {t_both:.1f} us  ({E / t_both:.1f} M env-steps/s)")
+stack = torch.zeros((E, 9, 64, 64), dtype=torch.uint8, device="cuda")
+t_stack = timed(lambda k: eng.step_stacked(acts[k % 64], stack, 3))
+print(f"E={E} A={A} physics {t_phys:.1f} us  render {t_rend:.1f} us  step {t_both:.1f} us  ({E / t_both:.1f} M env-steps/s)  step with fused 3-frame stack {t_stack:.1f} us")
 print("map", eng.map_info(0))

@@ -24,6 +24,7 @@ struct tde_handle {
     float* ep_return = nullptr;
     int *scen_lo = nullptr, *scen_hi = nullptr;
     double* stats = nullptr;
+    uint8_t* restart = nullptr;
     MapDev* maps_dev = nullptr;
     ScenDev* scens_dev = nullptr;
     std::vector<MapDev> maps_host;
@@ -449,9 +450,10 @@ static void free_scenarios(tde_handle* h) {
 template <int AH>
 static int configure_kernels(tde_handle* h) {
     size_t smem = sizeof(RenderScratch) * TDE_WARPS_PER_BLOCK + 256 * sizeof(uint32_t);  // + the spread table
-    CUDA_TRY(h, cudaFuncSetAttribute(tde_render_kernel<AH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(h, cudaFuncSetAttribute(tde_render_kernel<AH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(h, cudaFuncSetAttribute(tde_render_kernel<AH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tde_render_kernel<AH>, TDE_WARPS_PER_BLOCK * 32, smem));
+    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tde_render_kernel<AH, false>, TDE_WARPS_PER_BLOCK * 32, smem));
     if (per_sm < 1) per_sm = 1;
     h->smem_render = smem;
     int want = (h->E + TDE_WARPS_PER_BLOCK - 1) / TDE_WARPS_PER_BLOCK;
@@ -490,7 +492,7 @@ extern "C" int tde_create(const tde_config* cfg, tde_handle** out) {
     if ((rc = dev_alloc(h, &h->state, EA)) || (rc = dev_alloc(h, &h->attr, EA)) || (rc = dev_alloc(h, &h->infr, EA)) ||
         (rc = dev_alloc(h, &h->vars, (size_t)h->E * 8)) || (rc = dev_alloc(h, &h->ep_return, (size_t)h->E)) ||
         (rc = dev_alloc(h, &h->scen_lo, (size_t)h->E)) || (rc = dev_alloc(h, &h->scen_hi, (size_t)h->E)) ||
-        (rc = dev_alloc(h, &h->stats, (size_t)TDE_NUM_STATS)))
+        (rc = dev_alloc(h, &h->stats, (size_t)TDE_NUM_STATS)) || (rc = dev_alloc(h, &h->restart, (size_t)h->E)))
         return bail(rc);
     rc = h->A <= 32 ? configure_kernels<1>(h) : configure_kernels<2>(h);
     if (rc) return bail(rc);
@@ -503,7 +505,7 @@ extern "C" int tde_destroy(tde_handle* h) {
     cudaSetDevice(h->device);
     free_scenarios(h);
     cudaFree(h->state); cudaFree(h->attr); cudaFree(h->infr); cudaFree(h->vars); cudaFree(h->ep_return);
-    cudaFree(h->scen_lo); cudaFree(h->scen_hi); cudaFree(h->stats);
+    cudaFree(h->scen_lo); cudaFree(h->scen_hi); cudaFree(h->stats); cudaFree(h->restart);
     cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_reward); cudaFree(h->h_term); cudaFree(h->h_trunc); cudaFree(h->h_info);
     delete h;
     return TDE_OK;
@@ -667,7 +669,7 @@ static StepParams make_params(tde_handle* h) {
     p.cfg = h->cfg; p.E = h->E; p.A = h->A; p.num_scen = h->num_scen; p.seed = h->seed;
     p.maps = h->maps_dev; p.scens = h->scens_dev;
     p.state = h->state; p.attr = h->attr; p.infr = h->infr; p.vars = h->vars; p.ep_return = h->ep_return;
-    p.scen_lo = h->scen_lo; p.scen_hi = h->scen_hi; p.stats = h->stats;
+    p.scen_lo = h->scen_lo; p.scen_hi = h->scen_hi; p.stats = h->stats; p.restart = h->restart; p.n_stack = 1;
     for (int ch = 0; ch < 3; ++ch)
         for (int w = 0; w < 4; ++w) {
             uint32_t v = 0;
@@ -700,9 +702,10 @@ extern "C" int tde_reset(tde_handle* h, const uint8_t* env_mask_dev, uint64_t se
     return TDE_OK;
 }
 
-extern "C" int tde_step_phases(tde_handle* h, int32_t phases, const float* actions, uint8_t* obs, float* reward,
-                               uint8_t* terminated, uint8_t* truncated, float* info, void* stream) {
+static int step_impl(tde_handle* h, int32_t phases, const float* actions, uint8_t* obs, int32_t n_stack, float* reward,
+                     uint8_t* terminated, uint8_t* truncated, float* info, void* stream) {
     if (!h) return TDE_E_INVAL;
+    if (n_stack < 1 || n_stack > 8) return fail(h, TDE_E_INVAL, "n_stack must be in 1..8");
     if (!h->uploaded || !h->was_reset) return fail(h, TDE_E_STATE, "tde_step: upload scenarios and reset first");
     if ((phases & ~TDE_PH_ALL) || phases == 0) return fail(h, TDE_E_INVAL, "tde_step_phases: bad phase mask");
     if ((phases & TDE_PH_KINEMATICS) && !actions) return fail(h, TDE_E_INVAL, "tde_step: actions is null");
@@ -712,7 +715,7 @@ extern "C" int tde_step_phases(tde_handle* h, int32_t phases, const float* actio
     CUDA_TRY(h, cudaSetDevice(h->device));
     StepParams p = make_params(h);
     p.phases = phases; p.actions = actions; p.obs = obs; p.reward = reward; p.terminated = terminated;
-    p.truncated = truncated; p.info = info;
+    p.truncated = truncated; p.info = info; p.n_stack = n_stack;
     cudaStream_t st = (cudaStream_t)stream;
     const int threads = TDE_WARPS_PER_BLOCK * 32;
     if (phases & (TDE_PH_KINEMATICS | TDE_PH_INFRACTIONS | TDE_PH_REWARD)) {
@@ -722,12 +725,30 @@ extern "C" int tde_step_phases(tde_handle* h, int32_t phases, const float* actio
         h->launches++;
     }
     if ((phases & TDE_PH_RENDER) && obs) {
-        if (h->A <= 32) tde_render_kernel<1><<<h->grid_render, threads, h->smem_render, st>>>(p);
-        else tde_render_kernel<2><<<h->grid_render, threads, h->smem_render, st>>>(p);
+        if (n_stack > 1) {
+            if (h->A <= 32) tde_render_kernel<1, true><<<h->grid_render, threads, h->smem_render, st>>>(p);
+            else tde_render_kernel<2, true><<<h->grid_render, threads, h->smem_render, st>>>(p);
+        } else {
+            if (h->A <= 32) tde_render_kernel<1, false><<<h->grid_render, threads, h->smem_render, st>>>(p);
+            else tde_render_kernel<2, false><<<h->grid_render, threads, h->smem_render, st>>>(p);
+        }
         CUDA_TRY(h, cudaGetLastError());
         h->launches++;
     }
     return TDE_OK;
+}
+
+extern "C" int tde_step_phases(tde_handle* h, int32_t phases, const float* actions, uint8_t* obs, float* reward,
+                               uint8_t* terminated, uint8_t* truncated, float* info, void* stream) {
+    return step_impl(h, phases, actions, obs, 1, reward, terminated, truncated, info, stream);
+}
+extern "C" int tde_step_stacked(tde_handle* h, const float* actions, uint8_t* stack, int32_t n_stack, float* reward,
+                                uint8_t* terminated, uint8_t* truncated, float* info, void* stream) {
+    if (h && !stack) return fail(h, TDE_E_INVAL, "tde_step_stacked: stack is null");
+    return step_impl(h, TDE_PH_ALL, actions, stack, n_stack, reward, terminated, truncated, info, stream);
+}
+extern "C" int tde_render_stacked(tde_handle* h, uint8_t* stack, int32_t n_stack, void* stream) {
+    return step_impl(h, TDE_PH_RENDER, nullptr, stack, n_stack, nullptr, nullptr, nullptr, nullptr, stream);
 }
 
 extern "C" int tde_step(tde_handle* h, const float* actions, uint8_t* obs, float* reward, uint8_t* terminated,

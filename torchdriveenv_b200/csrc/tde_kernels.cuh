@@ -70,6 +70,8 @@ struct StepParams {
     float* info;
     double* stats;
     const uint8_t* reset_mask;
+    uint8_t* restart;    // [E] 1 = the env was reset since its last stacked frame
+    int n_stack;         // frames per env in obs (1 = plain observation)
     uint32_t pal[3][4];  // per channel: 16 class bytes
     float ppm, ppmy;
 };
@@ -386,7 +388,7 @@ __device__ __forceinline__ void reset_env_warp(const StepParams& p, int e, int l
     step = 0; target = 1; reached = 0;
     lphase = (int)((tde_rng(p.seed, genv, ep, 5) >> 32) % (unsigned long long)(P > 0 ? P : 1));
     episode = (int)((unsigned int)episode + 1u);
-    if (lane == 0) p.ep_return[e] = 0.0f;
+    if (lane == 0) { p.ep_return[e] = 0.0f; p.restart[e] = 1; }
 }
 
 __device__ __forceinline__ void store_vars(const StepParams& p, int e, int lane, int s, int step, int target,
@@ -642,7 +644,7 @@ __device__ __noinline__ int queue_static(const MapDev& M, Cam cam, float reach, 
 }
 
 // simulator.render_egocentric() (gym_env.py:122-124): one warp renders one env's 3x64x64 birdview.
-template <int AH>
+template <int AH, bool STACKED>
 __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, TDE_RENDER_BLOCKS_PER_SM) tde_render_kernel(const StepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -752,7 +754,27 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, TDE_RENDER_BLOCKS_PE
 
         // class-index planes -> palette lookup with byte permutes -> 128-bit stores
         const unsigned char* pl8 = reinterpret_cast<const unsigned char*>(ws->cover);
-        uint8_t* out = p.obs + (size_t)e * (TDE_OBS_C * TDE_OBS_H * TDE_OBS_W);
+        constexpr int FRAME = TDE_OBS_C * TDE_OBS_H * TDE_OBS_W;
+        if (STACKED) {
+            // fused VecFrameStack: frames 1..n-1 move one slot down (zeros after a restart); a warp-wide
+            // 128-bit access covers 512 contiguous bytes, eight are kept in flight per lane
+            uint4* const base = reinterpret_cast<uint4*>(p.obs + (size_t)e * p.n_stack * FRAME) + lane;
+            const int pieces = (p.n_stack - 1) * (FRAME / 512);
+            const bool fresh = p.restart[e] != 0;
+#pragma unroll 1
+            for (int i = 0; i < pieces; i += 8) {
+                uint4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    v[u] = make_uint4(0u, 0u, 0u, 0u);
+                    if (!fresh) v[u] = base[(size_t)(i + u) * 32 + FRAME / 16];
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) base[(size_t)(i + u) * 32] = v[u];
+            }
+        }
+        const int n_stack = STACKED ? p.n_stack : 1;
+        uint8_t* out = p.obs + ((size_t)e * n_stack + (n_stack - 1)) * FRAME;
 #pragma unroll 1
         for (int it = 0; it < TDE_OBS_H / 8; ++it) {
             int row = it * 8 + (lane >> 2), qd = lane & 3;
@@ -784,7 +806,7 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, TDE_RENDER_BLOCKS_PE
         // clear the coverage words for the next env
 #pragma unroll
         for (int i = 0; i < COVER_U4 / 32; ++i) cz[i * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
-        if (lane == 0) ws->used = 0u;
+        if (lane == 0) { ws->used = 0u; if (STACKED) p.restart[e] = 0; }
         __syncwarp();
     }
 }

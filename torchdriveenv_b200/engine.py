@@ -93,6 +93,25 @@ class Engine:
                                              _ptr(self.info), self._stream()), "tde_step")
         return (self.obs if render else None), self.reward, self.terminated, self.truncated, self.info
 
+    def _check_stack(self, stack: torch.Tensor, n_stack: int):
+        want = (self.E, 3 * n_stack, TDE_OBS_H, TDE_OBS_W)
+        if tuple(stack.shape) != want or stack.dtype != torch.uint8 or not stack.is_contiguous() or stack.device != self.obs.device:
+            raise ValueError(f"stack must be a contiguous uint8 tensor of shape {want} on {self.obs.device}")
+
+    def step_stacked(self, actions: torch.Tensor, stack: torch.Tensor, n_stack: int):
+        """tde_step with VecFrameStack fused into the observation store: `stack` [E, 3*n_stack, 64, 64]
+        is shifted by one frame and receives the new frame in its last three channels, in place."""
+        a = actions.to(device=self.device, dtype=torch.float32).contiguous().view(self.E, 2)
+        self._check_stack(stack, n_stack)
+        self._check(self.lib.tde_step_stacked(self.h, _ptr(a), _ptr(stack), int(n_stack), _ptr(self.reward), _ptr(self.terminated),
+                                              _ptr(self.truncated), _ptr(self.info), self._stream()), "tde_step_stacked")
+        return stack, self.reward, self.terminated, self.truncated, self.info
+
+    def render_stacked(self, stack: torch.Tensor, n_stack: int) -> torch.Tensor:
+        self._check_stack(stack, n_stack)
+        self._check(self.lib.tde_render_stacked(self.h, _ptr(stack), int(n_stack), self._stream()), "tde_render_stacked")
+        return stack
+
     def step_host(self, actions: np.ndarray, render: bool = True):
         """Reference-facing call with HOST buffers (tde_step_host): H2D, step, D2H, synchronise."""
         E = self.E

@@ -332,7 +332,8 @@ class TorchDriveVecEnv:
     (examples/rl_training.py:159-160: SubprocVecEnv + VecFrameStack(n_stack, channels_order="first")).
 
     ``reset() -> obs[E, 3*n_stack, 64, 64]``; ``step(actions[E, 2]) -> (obs, rewards[E], dones[E], infos)``;
-    finished envs are re-initialised inside the step kernel (auto-reset), their frame stack restarts.
+    finished envs are re-initialised inside the step kernel (auto-reset), their frame stack restarts;
+    the stack is shifted and filled by the render kernel itself (no separate roll / copy pass).
     Outputs stay on the GPU as torch tensors (``output="torch"``) or are copied to numpy (``"numpy"``).
     ``infos`` is a dict of per-env arrays (columns of get_info :419-437), not a list of dicts.
     """
@@ -353,23 +354,14 @@ class TorchDriveVecEnv:
         self._stack = torch.zeros((self.num_envs, 3 * self.n_stack, TDE_OBS_H, TDE_OBS_W), dtype=torch.uint8, device=self.device)
         self._actions = None
 
-    def _push(self, obs: torch.Tensor, restart: Optional[torch.Tensor]):
-        if self.n_stack == 1:
-            self._stack = obs
-            return
-        self._stack = torch.roll(self._stack, shifts=-3, dims=1)
-        if restart is not None and bool(restart.any()):
-            self._stack[restart] = 0   # VecFrameStack zeroes the stack of an env that just reset
-        self._stack[:, -3:] = obs
-
     def _out(self, t: torch.Tensor):
         return t.cpu().numpy() if self.output == "numpy" else t
 
     def reset(self):
         self.engine.reset(seed=self._seed)
-        obs = self.engine.render()
-        self._stack.zero_()
-        self._push(obs, None)
+        # the frame stack lives in one [E, 3*n_stack, 64, 64] tensor that the render kernel shifts and
+        # fills in place (tde_render_stacked / tde_step_stacked); a reset env restarts with zeros
+        self.engine.render_stacked(self._stack, self.n_stack)
         return self._out(self._stack)
 
     def step_async(self, actions):
@@ -377,9 +369,8 @@ class TorchDriveVecEnv:
 
     def step_wait(self):
         a = torch.as_tensor(self._actions, dtype=torch.float32)
-        obs, rew, term, trunc, info = self.engine.step(a)
+        _, rew, term, trunc, info = self.engine.step_stacked(a, self._stack, self.n_stack)
         dones = (term | trunc).bool()
-        self._push(obs, dones)
         infos = {k: self._out(info[:, i]) for k, i in INFO_COLUMNS.items()}
         infos["terminated"], infos["truncated"] = self._out(term.bool()), self._out(trunc.bool())
         return self._out(self._stack), self._out(rew), self._out(dones), infos
