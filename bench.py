@@ -34,6 +34,7 @@ WORKLOADS = {
     # name: (envs per GPU, agents, render)
     "c3": (16384, 32, True),
     "c2": (1024, 16, False),
+    "c4": (65536, 64, False),   # stateless collision + offroad micro-benchmark (tde_collision_boxes / tde_offroad_boxes)
 }
 
 
@@ -141,10 +142,124 @@ def cpu_oracle_throughput(workload: str, budget_s: float, seed: int = 0):
                        f"{threads} threads on {os.cpu_count()} visible cores")
 
 
+def c4_inputs(E: int, A: int, seed: int):
+    from torchdriveenv_b200 import scenarios as S
+    st, at = S.scatter_boxes(E, A, size=200.0, seed=seed)
+    patch = S.scatter_patch(200.0, 10.0)
+    return st, at, patch
+
+
+def cpu_oracle_c4(budget_s: float, seed: int = 0):
+    """CPU oracle on a bounded sample of config C4 (all-pairs SAT + brute-force corner-to-mesh distance)."""
+    from oracle import oracle as O
+    E, A = 512, 64
+    st, at, patch = c4_inputs(E, A, seed)
+    O.collision_boxes(st[:8], at[:8])
+    t0 = time.perf_counter(); n = 0
+    while True:
+        O.collision_boxes(st, at)
+        O.offroad_boxes(patch.road_tris, 0.5, st, at)
+        n += 1
+        if time.perf_counter() - t0 >= budget_s or n >= 10000:
+            break
+    dt = time.perf_counter() - t0
+    threads = O.num_threads()
+    return dict(value=E * n / dt, unit="envs/s", cores=threads, kind="port",
+                sample=f"{E} envs x 64 agents x {n} passes of collision + offroad ({dt:.1f} s), C oracle with OpenMP, "
+                       f"{threads} threads on {os.cpu_count()} visible cores")
+
+
+def run_c4(args, rank: int, local_rank: int, world: int):
+    """Config C4: 65,536 envs x 64 agents per GPU, all-pairs SAT + lane-mesh offroad, vs the HBM roofline."""
+    import torch
+    import torch.distributed as dist
+    from torchdriveenv_b200 import scenarios as S
+    from torchdriveenv_b200.engine import Engine
+    from torchdriveenv_b200.roofline import c4_bytes_per_env
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    E, A, _ = WORKLOADS["c4"]
+    st, at, patch = c4_inputs(E, A, seed=12 + rank)
+    eng = Engine(S.ScenarioSet([patch], [S.make_scenario(0, [[5, 5], [50, 5]], 0, 0, "p")]), 1, 1, device=str(dev))
+    st_d, at_d = torch.from_numpy(st).to(dev), torch.from_numpy(at).to(dev)
+    pin_s, pin_a = torch.from_numpy(st).pin_memory(), torch.from_numpy(at).pin_memory()
+    out_h = torch.zeros((2, E, A), dtype=torch.float32).pin_memory()
+    stream = torch.cuda.current_stream(dev)
+    K, W = args.steps, args.warmup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    for _ in range(W):
+        eng.collision_boxes(st_d, at_d); eng.offroad_boxes(0, st_d, at_d)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record(stream)
+    for _ in range(K):
+        eng.collision_boxes(st_d, at_d); eng.offroad_boxes(0, st_d, at_d)
+    e1.record(stream)
+    barrier()
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1) if sampler else None
+    tmax = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item()) / K
+    # end to end: boxes from pinned host memory, both results back to the host, every step
+    K2 = max(3, min(K, args.e2e_steps))
+    barrier()
+    e0.record(stream)
+    for _ in range(K2):
+        s2, a2 = pin_s.to(dev, non_blocking=True), pin_a.to(dev, non_blocking=True)
+        out_h[0].copy_(eng.collision_boxes(s2, a2), non_blocking=True)
+        out_h[1].copy_(eng.offroad_boxes(0, s2, a2), non_blocking=True)
+        torch.cuda.synchronize(dev)
+    e1.record(stream)
+    barrier()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        peak, peak_src = measured_peak_hbm()
+        bpe = c4_bytes_per_env(A)
+        achieved = bpe * E / (ms * 1e-3) / 1e9
+        cpu = cpu_oracle_c4(args.cpu_seconds) if world == 1 and not args.no_cpu_baseline else None
+        line = dict(metric="c4_collision_offroad_envs_per_sec", value=E * world / (ms * 1e-3), unit="envs/s", n_gpus=world, steps=K, warmup=W,
+                    ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                    config=dict(workload="C4: 65536 envs x 64 agents per GPU, all-pairs SAT + corner-to-lane-mesh offroad on scattered boxes "
+                                         "(200 m checkerboard patch)", envs_per_gpu=E, agents=A,
+                                l2="inputs 134 MB + outputs 34 MB per step exceed the 126 MB L2"),
+                    clocks=clocks, gpu_launches=2 * K,
+                    e2e=dict(value=E * world * K2 / (float(e2e_ms.item()) * 1e-3), unit="envs/s", h2d_bytes_per_step=2 * E * A * 16,
+                             d2h_bytes_per_step=2 * E * A * 4, steps=K2, api="tde_collision_boxes + tde_offroad_boxes on tensors copied from pinned host memory"),
+                    roofline=dict(bound="hbm", kernel="tde_collision_kernel + tde_offroad_kernel", achieved=achieved, peak=peak, unit="GB/s",
+                                  frac=achieved / peak, traffic=None, algorithmic_bytes_per_launch=bpe * E, bytes_per_env=bpe,
+                                  avg_launch_ms=ms, peak_source=peak_src,
+                                  note="issue-bound by design: ~2,016 pair tests and 256 point-to-mesh queries per env (SURVEY 8d)"),
+                    cpu_baseline=cpu)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
     workload = args.workload
+    if workload == "c4":
+        r = cpu_oracle_c4(max(2.0, min(20.0, 3.0 * (args.steps + args.warmup))))
+        print(json.dumps(dict(impl="reference", metric="c4_collision_offroad_envs_per_sec", value=r["value"], unit="envs/s", n_gpus=args.gpus,
+                              steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * 65536 / r["value"], higher_is_better=True, scaling="weak",
+                              vs_baseline=None, dtype="f32", data="synthetic", config=dict(workload="C4 (bounded 512-env sample per pass)"),
+                              cpu_baseline=r, e2e=dict(value=r["value"], unit="envs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))), flush=True)
+        return
     E, A, render = WORKLOADS[workload]
     _, desc = build_scenarios(workload)
     # each "step" = one bounded sample; K steps + W warm-up must finish within a few minutes
@@ -289,6 +404,9 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000), os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
+    if args.workload == "c4":
+        run_c4(args, rank, local_rank, world)
+        return
     run_cuda(args, rank, local_rank, world)
 
 

@@ -146,3 +146,44 @@ def test_engine_refuses_to_run_without_cuda():
     from torchdriveenv_b200.engine import Engine
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         Engine(S.three_way(0), 1)
+
+
+def test_background_traffic_loader_and_light_program(tmp_path):
+    """Background-traffic JSON schema of the reference (gym_env.py:200-233) and the light-controller
+    program compiler (gym_env.py:181-189, 290-291)."""
+    import json, os
+    from torchdriveenv_b200 import env_utils as U, scenarios as S
+    from torchdriveenv_b200.gym_env import EnvConfig, WaypointSuite, scenario_set_from_suite
+    agents = [dict(center=dict(x=10.0 * k, y=-5.0), orientation=0.1 * k, speed=3.0 + k) for k in range(30)]
+    attrs = [dict(length=4.5 + 0.01 * k, width=1.9, rear_axis_offset=1.2) for k in range(30)]
+    doc = dict(location="carla:Town03", agent_density=20, random_seed=7, agent_states=agents, agent_attributes=attrs,
+               recurrent_states=[dict(packed=[0.0] * 4)] * 30)
+    d = tmp_path / "background_traffic"; d.mkdir()
+    (d / "carla_Town03_20_7.json").write_text(json.dumps(doc))
+    doc2 = dict(doc, agent_density=90)                 # 30 + 90 >= 100: never chosen (:214)
+    (d / "carla_Town03_90_8.json").write_text(json.dumps(doc2))
+    (d / "carla_Town01_20_9.json").write_text(json.dumps(doc))
+    bt = U.pick_background_traffic(str(d), "Town03")
+    assert bt["agent_density"] == 20 and bt["states"].shape == (30, 4) and bt["attributes"].shape == (30, 3)
+    assert U.pick_background_traffic(str(d), "Town07") is None
+    st, at = U.background_agents_for_start(bt, (0.0, -5.0))
+    assert len(st) == 19 and (np.hypot(st[:, 0], st[:, 1] + 5.0) > 100).all()     # x = 110 .. 290
+    np.testing.assert_allclose(at[0], [4.5 + 0.11, 1.9, 1.2], rtol=1e-6)
+    suite = WaypointSuite(locations=["Town03"], waypoint_suite=[[[0, -5], [20, -5], [40, -5]]], car_sequence_suite=[None], scenarios=[None])
+    ss = scenario_set_from_suite(EnvConfig(), suite, background_traffic=bt)
+    assert ss.scenarios[0].agent_init.shape == (20, 4)                             # ego + 19 kept agents
+    np.testing.assert_allclose(ss.scenarios[0].agent_init[1], [110.0, -5.0, 1.1, 14.0], rtol=1e-6)
+    ref_dir = "/root/reference/torchdriveenv/resources/background_traffic"        # the real files, where the checkout exists
+    if os.path.isdir(ref_dir):
+        names = [n for n in os.listdir(ref_dir) if n.endswith(".json")]
+        assert names
+        for n in names:
+            b = U.load_background_traffic(os.path.join(ref_dir, n))
+            assert b["states"].shape[1] == 4 and b["states"].shape[0] == b["attributes"].shape[0] and np.isfinite(b["states"]).all()
+    # light program: 2 s green, 0.5 s yellow, 1.5 s red on light 0; light 1 opposite
+    sched = S.compile_light_program([(2.0, ["green", "red"]), (0.5, {0: "yellow"}), (1.5, {0: "red", 1: "green"})], 2, dt=0.1)
+    assert sched.shape == (40, 2) and sched.dtype == np.uint8
+    assert (sched[:20, 0] == S.LIGHT_GREEN).all() and (sched[20:25, 0] == S.LIGHT_YELLOW).all() and (sched[25:, 0] == S.LIGHT_RED).all()
+    assert (sched[:25, 1] == S.LIGHT_RED).all() and (sched[25:, 1] == S.LIGHT_GREEN).all()
+    with pytest.raises(ValueError):
+        S.compile_light_program([(1.0, ["green"])], 2)

@@ -96,3 +96,49 @@ def load_default_validation_data():
 
 def load_default_train_data():
     return _load_default_data("training_cases.yml")
+
+
+# ----------------------------------------------------------------------------- background traffic
+
+def load_background_traffic(json_path) -> dict:
+    """One background-traffic file of the reference (gym_env.py:200-214; files under
+    torchdriveenv/resources/background_traffic named ``carla_<Town>_<density>_<seed>.json``).  Schema:
+    ``location``, ``agent_density``, ``random_seed``, ``agent_states[{center{x,y}, orientation, speed}]``,
+    ``agent_attributes[{length, width, rear_axis_offset}]``, ``recurrent_states`` (IAI-internal, ignored).
+    Returns plain arrays: ``states`` (n, 4) x y psi v and ``attributes`` (n, 3) length width lr."""
+    import numpy as np
+    with open(json_path) as f:
+        d = json.load(f)
+    st = [[a["center"]["x"], a["center"]["y"], a["orientation"], a["speed"]] for a in d["agent_states"]]
+    at = [[a["length"], a["width"], a["rear_axis_offset"]] for a in d["agent_attributes"]]
+    if len(st) != len(at):
+        raise ValueError(f"{json_path}: {len(st)} agent_states but {len(at)} agent_attributes")
+    return dict(location=d.get("location"), agent_density=int(d.get("agent_density", 0)), random_seed=d.get("random_seed"),
+                states=np.asarray(st, np.float32).reshape(-1, 4), attributes=np.asarray(at, np.float32).reshape(-1, 3))
+
+
+def pick_background_traffic(directory, town: str, rng: Optional[random.Random] = None) -> Optional[dict]:
+    """The reference's file choice (gym_env.py:203-214): a random file of this town whose agent count
+    plus density stays under 100.  ``town`` is the part after ``carla_`` (e.g. ``Town03``)."""
+    rng = rng or random
+    names = sorted(n for n in os.listdir(directory) if n.endswith(".json") and len(n.split("_")) > 1 and n.split("_")[1] == town)
+    rng.shuffle(names)
+    for n in names:
+        bt = load_background_traffic(os.path.join(directory, n))
+        if len(bt["states"]) + bt["agent_density"] < 100:
+            return bt
+    return None
+
+
+def background_agents_for_start(bt: dict, ego_xy, min_distance: float = 100.0, max_agents: Optional[int] = None):
+    """The agents the reference keeps from a background-traffic file: those farther than 100 m from the
+    ego start (gym_env.py:229-233; nearer ones are re-sampled by the Inverted AI service, which is not
+    reachable offline).  Returns (states (k, 4), attributes (k, 3)); they are driven at constant
+    velocity by the step kernel (no replay)."""
+    import numpy as np
+    d = np.hypot(bt["states"][:, 0] - float(ego_xy[0]), bt["states"][:, 1] - float(ego_xy[1]))
+    keep = d > min_distance
+    st, at = bt["states"][keep], bt["attributes"][keep]
+    if max_agents is not None:
+        st, at = st[:max_agents], at[:max_agents]
+    return st, at

@@ -124,12 +124,14 @@ def engine_config(cfg: EnvConfig, **extra) -> Dict:
 
 
 def scenario_set_from_suite(cfg: EnvConfig, data: WaypointSuite, n_background: int = 0, seed: int = 0,
-                            map_builder=None) -> ScenarioSet:
+                            map_builder=None, background_traffic=None) -> ScenarioSet:
     """Scenario tables from a WaypointSuite, following build_simulator (gym_env.py:179-300): waypoints
     :252-257, predetermined agents :222-228, replay tensors from car sequences :275-283.  The CARLA map
     assets (find_map_config :312) are not available offline, so each entry gets a synthetic lane mesh
     extruded from its own waypoint polyline; the Inverted AI background agents (:236-238) are replaced
-    by ``n_background`` constant-speed replay NPCs."""
+    by ``n_background`` constant-speed replay NPCs.  ``background_traffic`` (a dict from
+    env_utils.load_background_traffic, or a list with one per suite entry) adds the file's agents that
+    are farther than 100 m from the start (:229-233) as constant-velocity NPCs."""
     maps: List[MapData] = []
     scen: List[ScenarioData] = []
     rng = np.random.default_rng(seed)
@@ -152,6 +154,12 @@ def scenario_set_from_suite(cfg: EnvConfig, data: WaypointSuite, n_background: i
         if not cfg.ego_only and n_background > 0:
             bg_states, bg_attrs, bg_rep, bg_mask = place_npcs(poly, n_background, rng)
             states += bg_states.tolist(); attrs += bg_attrs.tolist()
+        if not cfg.ego_only and cfg.use_background_traffic and background_traffic is not None:
+            from .env_utils import background_agents_for_start
+            bt = background_traffic[k] if isinstance(background_traffic, (list, tuple)) else background_traffic
+            if bt is not None:
+                bst, bat = background_agents_for_start(bt, poly[0], max_agents=max(0, 64 - len(states)))
+                states += bst.tolist(); attrs += bat.tolist()
         n = len(states)
         T = 0
         if seqs:

@@ -281,6 +281,40 @@ def subdivide_long_triangles(tris: np.ndarray, max_edge: float) -> np.ndarray:
     return np.asarray(out, np.float32).reshape(-1, width)
 
 
+# ----------------------------------------------------------------------------- traffic-light programs
+
+def compile_light_program(phases, num_stoplines: int, dt: float = 0.1) -> np.ndarray:
+    """Traffic-light controller program -> the periodic schedule table of ``tde_scenario_set``.
+
+    The reference ticks a finite-state controller once per step inside IAIWrapper (gym_env.py:181-189,
+    290-291): a cycle of phases, each holding every light in one state for a duration.  ``phases`` is a
+    sequence of ``(duration_seconds, states)`` with ``states`` either a list of ``num_stoplines`` states
+    or a dict ``{stopline_index: state}`` (missing lights stay as in the previous phase, initially red);
+    states are ``LIGHT_GREEN / LIGHT_YELLOW / LIGHT_RED`` or the strings ``"green" / "yellow" / "red"``.
+    Returns uint8 ``[period_steps][num_stoplines]``: row t is what the lights show ``t`` steps into the
+    cycle, which is all the step kernel needs (env time = (steps + phase offset) mod period)."""
+    names = {"green": LIGHT_GREEN, "yellow": LIGHT_YELLOW, "red": LIGHT_RED}
+    cur = np.full(num_stoplines, LIGHT_RED, np.uint8)
+    rows = []
+    for duration, states in phases:
+        if isinstance(states, dict):
+            for k, v in states.items():
+                cur[int(k)] = names[v] if isinstance(v, str) else int(v)
+        else:
+            vals = [names[v] if isinstance(v, str) else int(v) for v in states]
+            if len(vals) != num_stoplines:
+                raise ValueError(f"phase lists {len(vals)} lights, the map has {num_stoplines} stop lines")
+            cur = np.asarray(vals, np.uint8)
+        n = max(1, int(round(float(duration) / dt)))
+        rows += [cur.copy()] * n
+    if not rows:
+        return np.zeros((1, num_stoplines), np.uint8)
+    out = np.stack(rows).astype(np.uint8)
+    if out.max(initial=0) > LIGHT_RED:
+        raise ValueError("light states must be 0 (green), 1 (yellow) or 2 (red)")
+    return out
+
+
 # ----------------------------------------------------------------------------- path following (NPC replay)
 
 class _Path:
