@@ -359,7 +359,7 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
         peak, peak_src = measured_peak_hbm()
         bpe = bytes_per_env_step(A, render)
         achieved = bpe * E / (per_launch_ms * 1e-3) / 1e9
-        roof = dict(bound="hbm", kernel="tde_render_kernel (+ tde_physics_kernel, one launch each per step)", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
+        roof = dict(bound="hbm", kernel="tde_render_kernel (+ tde_physics_kernel, one launch each per step)" if render else "tde_physics_kernel (one launch per step)", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
                     traffic=ncu_traffic(workload), algorithmic_bytes_per_launch=bpe * E, bytes_per_env_step=bpe,
                     avg_launch_ms=per_launch_ms, peak_source=peak_src)
         cpu = cpu_oracle_throughput(workload, args.cpu_seconds) if world == 1 and not args.no_cpu_baseline else None
