@@ -25,6 +25,7 @@ struct tde_handle {
     int *scen_lo = nullptr, *scen_hi = nullptr;
     double* stats = nullptr;
     uint8_t* restart = nullptr;
+    unsigned int* tickets = nullptr;
     MapDev* maps_dev = nullptr;
     ScenDev* scens_dev = nullptr;
     std::vector<MapDev> maps_host;
@@ -492,7 +493,8 @@ extern "C" int tde_create(const tde_config* cfg, tde_handle** out) {
     if ((rc = dev_alloc(h, &h->state, EA)) || (rc = dev_alloc(h, &h->attr, EA)) || (rc = dev_alloc(h, &h->infr, EA)) ||
         (rc = dev_alloc(h, &h->vars, (size_t)h->E * 8)) || (rc = dev_alloc(h, &h->ep_return, (size_t)h->E)) ||
         (rc = dev_alloc(h, &h->scen_lo, (size_t)h->E)) || (rc = dev_alloc(h, &h->scen_hi, (size_t)h->E)) ||
-        (rc = dev_alloc(h, &h->stats, (size_t)TDE_NUM_STATS)) || (rc = dev_alloc(h, &h->restart, (size_t)h->E)))
+        (rc = dev_alloc(h, &h->stats, (size_t)TDE_NUM_STATS)) || (rc = dev_alloc(h, &h->restart, (size_t)h->E)) ||
+        (rc = dev_alloc(h, &h->tickets, (size_t)4)))
         return bail(rc);
     rc = h->A <= 32 ? configure_kernels<1>(h) : configure_kernels<2>(h);
     if (rc) return bail(rc);
@@ -505,7 +507,7 @@ extern "C" int tde_destroy(tde_handle* h) {
     cudaSetDevice(h->device);
     free_scenarios(h);
     cudaFree(h->state); cudaFree(h->attr); cudaFree(h->infr); cudaFree(h->vars); cudaFree(h->ep_return);
-    cudaFree(h->scen_lo); cudaFree(h->scen_hi); cudaFree(h->stats); cudaFree(h->restart);
+    cudaFree(h->scen_lo); cudaFree(h->scen_hi); cudaFree(h->stats); cudaFree(h->restart); cudaFree(h->tickets);
     cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_reward); cudaFree(h->h_term); cudaFree(h->h_trunc); cudaFree(h->h_info);
     delete h;
     return TDE_OK;
@@ -669,7 +671,7 @@ static StepParams make_params(tde_handle* h) {
     p.cfg = h->cfg; p.E = h->E; p.A = h->A; p.num_scen = h->num_scen; p.seed = h->seed;
     p.maps = h->maps_dev; p.scens = h->scens_dev;
     p.state = h->state; p.attr = h->attr; p.infr = h->infr; p.vars = h->vars; p.ep_return = h->ep_return;
-    p.scen_lo = h->scen_lo; p.scen_hi = h->scen_hi; p.stats = h->stats; p.restart = h->restart; p.n_stack = 1;
+    p.scen_lo = h->scen_lo; p.scen_hi = h->scen_hi; p.stats = h->stats; p.restart = h->restart; p.tickets = h->tickets; p.n_stack = 1;
     for (int ch = 0; ch < 3; ++ch)
         for (int w = 0; w < 4; ++w) {
             uint32_t v = 0;

@@ -70,6 +70,7 @@ struct StepParams {
     float* info;
     double* stats;
     const uint8_t* reset_mask;
+    unsigned int* tickets;   // render kernel: [2] next env, [3] finished warps ([0..1] spare)
     uint8_t* restart;    // [E] 1 = the env was reset since its last stacked frame
     int n_stack;         // frames per env in obs (1 = plain observation)
     uint32_t pal[3][4];  // per channel: 16 class bytes
@@ -77,6 +78,22 @@ struct StepParams {
 };
 
 struct Cam { float ex, ey, ce, se, ppm, ppmy; };
+
+// Envs are handed to warps one at a time from a device-side ticket counter: their costs differ (what
+// is in view, how many agents are off the road), so a fixed stride leaves most warps waiting for the
+// unluckiest one.  ctr[0] = next ticket, ctr[1] = warps that have run dry; the last of them re-arms
+// both for the next launch, so the kernels stay self-contained (and CUDA-graph replayable).
+__device__ __forceinline__ int next_env(unsigned int* ctr, int lane) {
+    unsigned int t = 0;
+    if (lane == 0) t = atomicAdd(&ctr[0], 1u);
+    return (int)__shfl_sync(FULL_MASK, t, 0);
+}
+__device__ __forceinline__ void envs_done(unsigned int* ctr, int lane, int warps_total) {
+    if (lane == 0) {
+        __threadfence();
+        if (atomicAdd(&ctr[1], 1u) == (unsigned)(warps_total - 1)) { ctr[0] = 0u; ctr[1] = 0u; }
+    }
+}
 
 #define TDE_PAIR_CAP 256
 struct SatScratch {  // per warp: staged boxes, candidate pairs and hit counters of the all-pairs SAT
@@ -664,7 +681,7 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, TDE_RENDER_BLOCKS_PE
     __syncwarp();
 
 #pragma unroll 1
-    for (int e = blockIdx.x * TDE_WARPS_PER_BLOCK + warp; e < p.E; e += warps_total) {
+    for (int e = next_env(p.tickets + 2, lane); e < p.E; e = next_env(p.tickets + 2, lane)) {
         int myvar = lane < 8 ? p.vars[(size_t)e * 8 + lane] : 0;
         const int s = __shfl_sync(FULL_MASK, myvar, 0), step = __shfl_sync(FULL_MASK, myvar, 1);
         const int target = __shfl_sync(FULL_MASK, myvar, 2), lphase = __shfl_sync(FULL_MASK, myvar, 4);
@@ -809,6 +826,7 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, TDE_RENDER_BLOCKS_PE
         if (lane == 0) { ws->used = 0u; if (STACKED) p.restart[e] = 0; }
         __syncwarp();
     }
+    envs_done(p.tickets + 2, lane, warps_total);
 }
 
 // ---------------------------------------------------------------- physics kernel
