@@ -308,8 +308,12 @@ __device__ __noinline__ MeshInfr mesh_infractions_warp(const MapDev& M, const Bo
     float best = INFINITY;
     if (rec[4].x >= 0) {
         const int i0 = rec[4].x, nover = rec[4].y & 0x7fff;
+        // the value is a minimum of non-negative terms: a containing triangle the agent follows (term 0) settles it
         for (int i = i0; i < i0 + nover; ++i)
-            if (tde_tri_contains(M.tri + 3 * (int)M.cell_items[i], b.x, b.y, dc, ds)) best = fminf(best, fmaxf(-(b.c * dc + b.s * ds), 0.0f));
+            if (tde_tri_contains(M.tri + 3 * (int)M.cell_items[i], b.x, b.y, dc, ds)) {
+                best = fminf(best, fmaxf(-(b.c * dc + b.s * ds), 0.0f));
+                if (best == 0.0f) break;
+            }
     } else {
         for (int t = 0; t < M.ntri; ++t)
             if (tde_tri_contains(M.tri + 3 * t, b.x, b.y, dc, ds)) best = fminf(best, fmaxf(-(b.c * dc + b.s * ds), 0.0f));
