@@ -109,6 +109,7 @@ struct RenderScratch {  // per warp, render kernel
     unsigned long long cover[(TDE_NUM_CLASSES - 1) * TDE_OBS_H];
     uint4 qv[64];          // ring of snapped primitives waiting for a full batch, 4 x (x | y << 16)
     unsigned char qc[64];  // their classes
+    unsigned char slot[64];  // agents near the viewport, compacted (agent index per rank)
     unsigned int used;     // classes that received coverage
     unsigned int pad[3];
 };
@@ -707,40 +708,72 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, TDE_RENDER_BLOCKS_PE
         float wx[4], wy[4];
         int qtot = 0;
         qtot = queue_static(M, cam, reach, ws, lane, qtot);                 // classes 1-2: road and lane markings
-        // classes 3-5: stop lines coloured by their light state
-        if (M.nstop > 0) {
-            bool valid = lane < M.nstop;
-            int ls = TDE_LIGHT_GREEN;
-            wx[0] = wx[1] = wx[2] = wx[3] = 0.f; wy[0] = wy[1] = wy[2] = wy[3] = 0.f;
-            if (valid) {
-                float4 u = M.stop[2 * lane], v = M.stop[2 * lane + 1];
-                Box b; b.x = u.x; b.y = u.y; b.hl = u.z; b.hw = u.w; b.c = v.x; b.s = v.y; b.present = 1.f; b.r = 0.f;
-                box_quad(b, wx, wy);
-                ls = light_state_at(M, step, lphase, lane);
-            }
-            Proj pr = project_quad(cam, wx, wy);
-            qtot = enqueue(ws, lane, pr.ok && valid, pr.v, TDE_CLS_TL_GREEN + ls, qtot);
-        }
-        // class 6: the current goal waypoint, a diamond of circumradius 2 m
-        if (target < S.W) {
-            float2 w = S.wp[target];
-            const float r = 2.0f;
-            Proj pr = project_quad(cam, w.x + r, w.y, w.x, w.y + r, w.x - r, w.y, w.x, w.y - r);
-            qtot = enqueue(ws, lane, pr.ok && lane == 0, pr.v, TDE_CLS_WAYPOINT, qtot);
-        }
-        // classes 7-8: vehicle rectangles and the highlighted ego; classes 9-10: their direction triangles
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
+        // classes 3-10: the dynamic items - stop lines coloured by their light state, the goal diamond
+        // (circumradius 2 m), and for every agent near the viewport its rectangle and direction triangle -
+        // are numbered consecutively and handled 32 per pass.  Each item is an oriented frame (centre,
+        // cos, sin) plus four vertex offsets, so one code path produces all of them.
+        int nv = 0;
 #pragma unroll
-            for (int h = 0; h < AH; ++h) {
-                int a = h * 32 + lane;
-                if (pass == 0) box_quad(mybox[h], wx, wy);
-                else { box_dirtri(mybox[h], wx, wy); wx[3] = wx[0]; wy[3] = wy[0]; }
-                Proj pr = project_quad(cam, wx, wy);
-                bool ok = pr.ok && a < p.A && mybox[h].present != 0.0f;
-                int cls = pass == 0 ? (a == 0 ? TDE_CLS_EGO : TDE_CLS_VEHICLE) : (a == 0 ? TDE_CLS_EGO_DIRECTION : TDE_CLS_DIRECTION);
-                qtot = enqueue(ws, lane, ok, pr.v, cls, qtot);
+        for (int h = 0; h < AH; ++h) {
+            const int a = h * 32 + lane;
+            const float rr = reach + mybox[h].r;
+            const bool near = a < p.A && mybox[h].present != 0.0f && fabsf(mybox[h].x - cam.ex) <= rr && fabsf(mybox[h].y - cam.ey) <= rr;
+            const unsigned nm = __ballot_sync(FULL_MASK, near);
+            if (near) ws->slot[nv + __popc(nm & ((1u << lane) - 1u))] = (unsigned char)a;
+            nv += __popc(nm);
+        }
+        __syncwarp();
+        const bool have_wp = target < S.W;
+        const int n_misc = M.nstop + (have_wp ? 1 : 0);
+        const int n_items = n_misc + 2 * nv;
+#pragma unroll 1
+        for (int base = 0; base < n_items; base += 32) {
+            const int i = base + lane;
+            const bool valid = i < n_items;
+            const int j = i - n_misc;                                   // >= 0: agent item (rank j >> 1, triangle if odd)
+            const int a = (valid && j >= 0) ? (int)ws->slot[j >> 1] : 0;
+            // the agent's frame comes from the lane that owns it
+            float bx, by, bc, bs, hl, hw;
+            {
+                const int src = a & 31;
+                bx = __shfl_sync(FULL_MASK, mybox[0].x, src); by = __shfl_sync(FULL_MASK, mybox[0].y, src);
+                bc = __shfl_sync(FULL_MASK, mybox[0].c, src); bs = __shfl_sync(FULL_MASK, mybox[0].s, src);
+                hl = __shfl_sync(FULL_MASK, mybox[0].hl, src); hw = __shfl_sync(FULL_MASK, mybox[0].hw, src);
+                if (AH > 1) {
+                    const float x1 = __shfl_sync(FULL_MASK, mybox[AH - 1].x, src), y1 = __shfl_sync(FULL_MASK, mybox[AH - 1].y, src);
+                    const float c1 = __shfl_sync(FULL_MASK, mybox[AH - 1].c, src), s1 = __shfl_sync(FULL_MASK, mybox[AH - 1].s, src);
+                    const float l1 = __shfl_sync(FULL_MASK, mybox[AH - 1].hl, src), w1 = __shfl_sync(FULL_MASK, mybox[AH - 1].hw, src);
+                    if (a >= 32) { bx = x1; by = y1; bc = c1; bs = s1; hl = l1; hw = w1; }
+                }
             }
+            int kind = (j & 1) ? 1 : 0;                                 // 0 rectangle, 1 direction triangle, 2 diamond
+            int cls = a == 0 ? (kind ? TDE_CLS_EGO_DIRECTION : TDE_CLS_EGO) : (kind ? TDE_CLS_DIRECTION : TDE_CLS_VEHICLE);
+            if (valid && j < 0) {
+                if (i < M.nstop) {
+                    const float4 u = M.stop[2 * i], v = M.stop[2 * i + 1];
+                    bx = u.x; by = u.y; hl = u.z; hw = u.w; bc = v.x; bs = v.y;
+                    kind = 0;
+                    cls = TDE_CLS_TL_GREEN + light_state_at(M, step, lphase, i);
+                } else {
+                    const float2 w = S.wp[target];
+                    bx = w.x; by = w.y; bc = 1.0f; bs = 0.0f; hl = 2.0f; hw = 2.0f;
+                    kind = 2;
+                    cls = TDE_CLS_WAYPOINT;
+                }
+            }
+            // vertex offsets in the item's frame (the same expressions as tde_box_corner / the oracle's
+            // direction triangle; the diamond is the frame (1, 0) with offsets on the axes)
+            const float hh = 0.5f * hl;
+            const float ox0 = kind == 0 ? hl : kind == 1 ? hl : hl, oy0 = kind == 0 ? hw : 0.0f;
+            const float ox1 = kind == 0 ? hl : kind == 1 ? hh : 0.0f, oy1 = kind == 0 ? -hw : hw;
+            const float ox2 = kind == 0 ? -hl : kind == 1 ? hh : -hl, oy2 = kind == 2 ? 0.0f : -hw;
+            const float ox3 = kind == 0 ? -hl : kind == 1 ? hl : 0.0f, oy3 = kind == 0 ? hw : kind == 1 ? 0.0f : -hw;
+            wx[0] = bx + (ox0 * bc - oy0 * bs); wy[0] = by + (ox0 * bs + oy0 * bc);
+            wx[1] = bx + (ox1 * bc - oy1 * bs); wy[1] = by + (ox1 * bs + oy1 * bc);
+            wx[2] = bx + (ox2 * bc - oy2 * bs); wy[2] = by + (ox2 * bs + oy2 * bc);
+            wx[3] = bx + (ox3 * bc - oy3 * bs); wy[3] = by + (ox3 * bs + oy3 * bc);
+            Proj pr = project_quad(cam, wx, wy);
+            qtot = enqueue(ws, lane, pr.ok && valid, pr.v, cls, qtot);
         }
         if (qtot & 31) raster_batch(ws, qtot & 32, qtot & 31, lane);
         __syncwarp();
