@@ -144,6 +144,22 @@ __device__ __forceinline__ void sat_counts(SatScratch* ws, const Box (&me)[AH], 
     for (int h = 0; h < AH; ++h)
 #pragma unroll
         for (int g = 0; g < AH; ++g) cm[h][g] = 0u;
+    if (AH == 1) {
+        // one slot per lane: rotate instead of broadcasting.  At step r lane a meets lane (a + r) mod 32, so
+        // r = 1..15 visits every unordered pair once and r = 16 twice (kept for a < 16): half the tests.
+        unsigned m = 0u;
+#pragma unroll 4
+        for (int r = 1; r <= 16; ++r) {
+            const int src = (lane + r) & 31;
+            const float ox = __shfl_sync(FULL_MASK, me[0].x, src), oy = __shfl_sync(FULL_MASK, me[0].y, src);
+            const float orr = __shfl_sync(FULL_MASK, rr[0], src);
+            float dx = ox - me[0].x, dy = oy - me[0].y;
+            float R = rr[0] + orr;
+            bool cand = (dx * dx + dy * dy <= R * R * 1.001f) && (r < 16 || lane < 16);  // NaN radius: never
+            if (cand) m |= 1u << src;
+        }
+        cm[0][0] = m;
+    } else
 #pragma unroll
     for (int g = 0; g < AH; ++g) {
         const int jn = min(A - g * 32, 32);
