@@ -124,3 +124,38 @@ def test_vec_env_frame_stack_and_auto_reset(oracle):
     stats = venv.episode_statistics()
     assert stats["episodes"] == n_done and stats["steps"] == 25 * E
     venv.close()
+
+
+def test_background_traffic_agents_drive_at_constant_velocity(oracle):
+    """Agents taken from a background-traffic file (gym_env.py:200-233 schema) have no replay: the step
+    kernel moves them with the bicycle model and zero action, exactly as the oracle does."""
+    from torchdriveenv_b200.gym_env import EnvConfig, TorchDriveVecEnv, WaypointSuite, scenario_set_from_suite
+    rng = np.random.default_rng(5)
+    poly = S.VALIDATION_POLYLINES["traffic_lights"]
+    n = 40
+    bt = dict(location="carla:Town01", agent_density=10, random_seed=1,
+              states=np.stack([rng.uniform(60, 220, n), rng.uniform(-20, 100, n), rng.uniform(-3, 3, n), rng.uniform(0, 8, n)], 1).astype(np.float32),
+              attributes=np.stack([rng.uniform(4.2, 5.2, n), rng.uniform(1.8, 2.1, n), rng.uniform(1.0, 1.6, n)], 1).astype(np.float32))
+    suite = WaypointSuite(locations=["Town01"], waypoint_suite=[poly], car_sequence_suite=[None], scenarios=[None])
+    cfg = EnvConfig(seed=5, device="cuda:0", max_environment_steps=30)
+    ss = scenario_set_from_suite(cfg, suite, background_traffic=bt)
+    far = np.hypot(bt["states"][:, 0] - poly[0][0], bt["states"][:, 1] - poly[0][1]) > 100
+    A = ss.max_agents()
+    assert A == 1 + int(far.sum()) and A > 4
+    E = 16
+    venv = TorchDriveVecEnv(cfg, ss, num_envs=E, n_stack=1)
+    obs = venv.reset()
+    orc = oracle.OracleEnvSet(default_config(num_envs=E, max_agents=A, auto_reset=1, max_environment_steps=30), venv.engine.packed)
+    orc.reset(seed=5)
+    assert np.array_equal(obs.cpu().numpy(), orc.render())
+    for k in range(12):
+        a = np.stack([rng.uniform(-1, 1, E), rng.uniform(-0.3, 0.3, E)], 1).astype(np.float32)
+        obs, rew, dones, infos = venv.step(a)
+        oobs, orr, ote, otr, oinfo = orc.step(a)
+        assert np.array_equal(obs.cpu().numpy(), oobs) and np.array_equal(rew.cpu().numpy(), orr)
+        assert np.array_equal(venv.engine.get_state().cpu().numpy(), orc.state)
+    st = venv.engine.get_state().cpu().numpy()
+    keep = ~(ote | otr).astype(bool)          # envs that were not just re-initialised
+    moved = np.hypot(st[keep][:, 1:, 0] - ss.scenarios[0].agent_init[1:, 0], st[keep][:, 1:, 1] - ss.scenarios[0].agent_init[1:, 1])
+    assert keep.any() and (moved[:, ss.scenarios[0].agent_init[1:, 3] > 0.5] > 0).all()
+    venv.close()
