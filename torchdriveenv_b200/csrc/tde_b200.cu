@@ -672,6 +672,7 @@ static StepParams make_params(tde_handle* h) {
     p.maps = h->maps_dev; p.scens = h->scens_dev;
     p.state = h->state; p.attr = h->attr; p.infr = h->infr; p.vars = h->vars; p.ep_return = h->ep_return;
     p.scen_lo = h->scen_lo; p.scen_hi = h->scen_hi; p.stats = h->stats; p.restart = h->restart; p.tickets = h->tickets; p.n_stack = 1;
+    p.e_begin = 0; p.e_end = h->E;
     for (int ch = 0; ch < 3; ++ch)
         for (int w = 0; w < 4; ++w) {
             uint32_t v = 0;
@@ -720,19 +721,24 @@ static int step_impl(tde_handle* h, int32_t phases, const float* actions, uint8_
     p.truncated = truncated; p.info = info; p.n_stack = n_stack;
     cudaStream_t st = (cudaStream_t)stream;
     const int threads = TDE_WARPS_PER_BLOCK * 32;
-    if (phases & (TDE_PH_KINEMATICS | TDE_PH_INFRACTIONS | TDE_PH_REWARD)) {
-        if (h->A <= 32) tde_physics_kernel<1><<<h->grid_phys, threads, 0, st>>>(p);
-        else tde_physics_kernel<2><<<h->grid_phys, threads, 0, st>>>(p);
+    const bool physics = phases & (TDE_PH_KINEMATICS | TDE_PH_INFRACTIONS | TDE_PH_REWARD);
+    const bool render = (phases & TDE_PH_RENDER) && obs;
+    const int want = (h->E + TDE_WARPS_PER_BLOCK - 1) / TDE_WARPS_PER_BLOCK;
+    if (physics) {
+        const int grid = std::min(h->grid_phys, want);
+        if (h->A <= 32) tde_physics_kernel<1><<<grid, threads, 0, st>>>(p);
+        else tde_physics_kernel<2><<<grid, threads, 0, st>>>(p);
         CUDA_TRY(h, cudaGetLastError());
         h->launches++;
     }
-    if ((phases & TDE_PH_RENDER) && obs) {
+    if (render) {
+        const int grid = std::min(h->grid_render, want);
         if (n_stack > 1) {
-            if (h->A <= 32) tde_render_kernel<1, true><<<h->grid_render, threads, h->smem_render, st>>>(p);
-            else tde_render_kernel<2, true><<<h->grid_render, threads, h->smem_render, st>>>(p);
+            if (h->A <= 32) tde_render_kernel<1, true><<<grid, threads, h->smem_render, st>>>(p);
+            else tde_render_kernel<2, true><<<grid, threads, h->smem_render, st>>>(p);
         } else {
-            if (h->A <= 32) tde_render_kernel<1, false><<<h->grid_render, threads, h->smem_render, st>>>(p);
-            else tde_render_kernel<2, false><<<h->grid_render, threads, h->smem_render, st>>>(p);
+            if (h->A <= 32) tde_render_kernel<1, false><<<grid, threads, h->smem_render, st>>>(p);
+            else tde_render_kernel<2, false><<<grid, threads, h->smem_render, st>>>(p);
         }
         CUDA_TRY(h, cudaGetLastError());
         h->launches++;
@@ -853,6 +859,12 @@ extern "C" int tde_offroad_boxes(tde_handle* h, int32_t map_id, const float* sta
     h->launches++;
     return TDE_OK;
 }
+
+#ifdef TDE_TRACE
+extern "C" int tde_debug_set_trace(unsigned long long* dev_ptr) {
+    return cudaMemcpyToSymbol(g_trace, &dev_ptr, sizeof(dev_ptr)) == cudaSuccess ? TDE_OK : TDE_E_CUDA;
+}
+#endif
 
 extern "C" int tde_clone(tde_handle* h, tde_handle** out) {
     if (!h || !out) return fail(h, TDE_E_INVAL, "tde_clone: null argument");

@@ -12,12 +12,16 @@
 #include "tde_device.cuh"
 #include "../../include/tde_b200.h"
 
-#define TDE_WARPS_PER_BLOCK 8
+// 32 warps per SM at 64 registers per thread; small blocks, so that the slots of a block are handed to
+// the next launch as soon as its few warps have run dry
+#ifndef TDE_WARPS_PER_BLOCK
+#define TDE_WARPS_PER_BLOCK 4
+#endif
 #ifndef TDE_RENDER_BLOCKS_PER_SM
-#define TDE_RENDER_BLOCKS_PER_SM 4
+#define TDE_RENDER_BLOCKS_PER_SM (32 / TDE_WARPS_PER_BLOCK)
 #endif
 #ifndef TDE_PHYS_BLOCKS_PER_SM
-#define TDE_PHYS_BLOCKS_PER_SM 4
+#define TDE_PHYS_BLOCKS_PER_SM (32 / TDE_WARPS_PER_BLOCK)
 #endif
 
 struct MapDev {
@@ -70,7 +74,8 @@ struct StepParams {
     float* info;
     double* stats;
     const uint8_t* reset_mask;
-    unsigned int* tickets;   // render kernel: [2] next env, [3] finished warps ([0..1] spare)
+    unsigned int* tickets;   // render kernel of this launch: [0] next ticket, [1] finished warps
+    int e_begin, e_end;      // envs [e_begin, e_end) of this launch
     uint8_t* restart;    // [E] 1 = the env was reset since its last stacked frame
     int n_stack;         // frames per env in obs (1 = plain observation)
     uint32_t pal[3][4];  // per channel: 16 class bytes
@@ -78,6 +83,14 @@ struct StepParams {
 };
 
 struct Cam { float ex, ey, ce, se, ppm, ppmy; };
+
+#ifdef TDE_TRACE   // debug builds only (tools/build_variant.sh trace -DTDE_TRACE): per-env start/end timestamps
+__device__ unsigned long long* g_trace = nullptr;   // [E][8]: render start, render end, physics start, physics end (ns), static queued, dynamic items, queued total
+__device__ __forceinline__ unsigned long long tde_now() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define TDE_TRACE_MARK(e, k) do { if (g_trace && lane == 0) g_trace[(size_t)(e) * 8 + (k)] = tde_now(); } while (0)
+#else
+#define TDE_TRACE_MARK(e, k) do { } while (0)
+#endif
 
 // Envs are handed to warps one at a time from a device-side ticket counter: their costs differ (what
 // is in view, how many agents are off the road), so a fixed stride leaves most warps waiting for the
@@ -681,28 +694,14 @@ __device__ __noinline__ int queue_static(const MapDev& M, Cam cam, float reach, 
     return qtot;
 }
 
-// simulator.render_egocentric() (gym_env.py:122-124): one warp renders one env's 3x64x64 birdview.
+// simulator.render_egocentric() (gym_env.py:122-124): one warp renders env e's 3x64x64 birdview.  The
+// coverage words of `ws` are zero on entry and zero again on return.
 template <int AH, bool STACKED>
-__global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, TDE_RENDER_BLOCKS_PER_SM) tde_render_kernel(const StepParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    RenderScratch* ws = reinterpret_cast<RenderScratch*>(smem_raw) + warp;
-    // spread table: byte of plane bits -> the same bits at the low bit of 8 nibbles
-    uint32_t* const spread_tab = reinterpret_cast<uint32_t*>(smem_raw + sizeof(RenderScratch) * TDE_WARPS_PER_BLOCK);
-    spread_tab[threadIdx.x] = spread8(threadIdx.x);
-    __syncthreads();
-    const int warps_total = gridDim.x * TDE_WARPS_PER_BLOCK;
-    // conservative world-space reach of the viewport around the ego (half diagonal + 2 px)
-    const float reach = (0.70710678f * (float)(TDE_OBS_W + TDE_OBS_H) * 0.5f + 2.0f) / p.ppm;
+__device__ __forceinline__ void render_env(const StepParams& p, const int e, const int lane, RenderScratch* ws,
+                                           const uint32_t* spread_tab, const float reach) {
     uint4* const cz = reinterpret_cast<uint4*>(ws->cover);
     constexpr int COVER_U4 = (TDE_NUM_CLASSES - 1) * TDE_OBS_H * 8 / 16;  // 320 = 10 per lane
-#pragma unroll
-    for (int i = 0; i < COVER_U4 / 32; ++i) cz[i * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
-    if (lane == 0) ws->used = 0u;
-    __syncwarp();
-
-#pragma unroll 1
-    for (int e = next_env(p.tickets + 2, lane); e < p.E; e = next_env(p.tickets + 2, lane)) {
+    {
         int myvar = lane < 8 ? p.vars[(size_t)e * 8 + lane] : 0;
         const int s = __shfl_sync(FULL_MASK, myvar, 0), step = __shfl_sync(FULL_MASK, myvar, 1);
         const int target = __shfl_sync(FULL_MASK, myvar, 2), lphase = __shfl_sync(FULL_MASK, myvar, 4);
@@ -724,6 +723,9 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, TDE_RENDER_BLOCKS_PE
         float wx[4], wy[4];
         int qtot = 0;
         qtot = queue_static(M, cam, reach, ws, lane, qtot);                 // classes 1-2: road and lane markings
+#ifdef TDE_TRACE
+        if (g_trace && lane == 0) g_trace[(size_t)e * 8 + 4] = qtot;
+#endif
         // classes 3-10: the dynamic items - stop lines coloured by their light state, the goal diamond
         // (circumradius 2 m), and for every agent near the viewport its rectangle and direction triangle -
         // are numbered consecutively and handled 32 per pass.  Each item is an oriented frame (centre,
@@ -792,6 +794,9 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, TDE_RENDER_BLOCKS_PE
             qtot = enqueue(ws, lane, pr.ok && valid, pr.v, cls, qtot);
         }
         if (qtot & 31) raster_batch(ws, qtot & 32, qtot & 31, lane);
+#ifdef TDE_TRACE
+        if (g_trace && lane == 0) { g_trace[(size_t)e * 8 + 5] = n_items; g_trace[(size_t)e * 8 + 6] = qtot; }
+#endif
         __syncwarp();
 
         // composite: lane owns rows lane and lane + 32; ascending classes overwrite the four bit-planes
@@ -879,7 +884,40 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, TDE_RENDER_BLOCKS_PE
         if (lane == 0) { ws->used = 0u; if (STACKED) p.restart[e] = 0; }
         __syncwarp();
     }
-    envs_done(p.tickets + 2, lane, warps_total);
+}
+
+// conservative world-space reach of the viewport around the ego (half diagonal + 2 px)
+__device__ __forceinline__ float viewport_reach(const StepParams& p) {
+    return (0.70710678f * (float)(TDE_OBS_W + TDE_OBS_H) * 0.5f + 2.0f) / p.ppm;
+}
+__device__ __forceinline__ void clear_cover(RenderScratch* ws, int lane) {
+    uint4* const cz = reinterpret_cast<uint4*>(ws->cover);
+    constexpr int COVER_U4 = (TDE_NUM_CLASSES - 1) * TDE_OBS_H * 8 / 16;
+#pragma unroll
+    for (int i = 0; i < COVER_U4 / 32; ++i) cz[i * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
+    if (lane == 0) ws->used = 0u;
+    __syncwarp();
+}
+
+template <int AH, bool STACKED>
+__global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, TDE_RENDER_BLOCKS_PER_SM) tde_render_kernel(const StepParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    RenderScratch* ws = reinterpret_cast<RenderScratch*>(smem_raw) + warp;
+    // spread table: byte of plane bits -> the same bits at the low bit of 8 nibbles
+    uint32_t* const spread_tab = reinterpret_cast<uint32_t*>(smem_raw + sizeof(RenderScratch) * TDE_WARPS_PER_BLOCK);
+    for (int i = threadIdx.x; i < 256; i += TDE_WARPS_PER_BLOCK * 32) spread_tab[i] = spread8(i);
+    __syncthreads();
+    const int warps_total = gridDim.x * TDE_WARPS_PER_BLOCK;
+    const float reach = viewport_reach(p);
+    clear_cover(ws, lane);
+#pragma unroll 1
+    for (int e = p.e_begin + next_env(p.tickets, lane); e < p.e_end; e = p.e_begin + next_env(p.tickets, lane)) {
+        TDE_TRACE_MARK(e, 0);
+        render_env<AH, STACKED>(p, e, lane, ws, spread_tab, reach);
+        TDE_TRACE_MARK(e, 1);
+    }
+    envs_done(p.tickets, lane, warps_total);
 }
 
 // ---------------------------------------------------------------- physics kernel
@@ -888,16 +926,9 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, TDE_RENDER_BLOCKS_PE
 // offroad / red-light / wrong-way against the lane mesh, reward, termination, truncation, info,
 // waypoint progress, episode statistics and (optionally) the in-kernel auto-reset.
 template <int AH>
-__global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, TDE_PHYS_BLOCKS_PER_SM) tde_physics_kernel(const StepParams p) {
-    __shared__ SatScratch scratch[TDE_WARPS_PER_BLOCK];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    SatScratch* ws = &scratch[warp];
-    const int warps_total = gridDim.x * TDE_WARPS_PER_BLOCK;
+__device__ __forceinline__ void physics_env(const StepParams& p, const int e, const int lane, SatScratch* ws, double& st_acc) {
     const tde_config& c = p.cfg;
-    double st_acc = 0.0;  // lane k accumulates statistic k
-
-#pragma unroll 1
-    for (int e = blockIdx.x * TDE_WARPS_PER_BLOCK + warp; e < p.E; e += warps_total) {
+    {
         int myvar = lane < 8 ? p.vars[(size_t)e * 8 + lane] : 0;
         int s = __shfl_sync(FULL_MASK, myvar, 0), step = __shfl_sync(FULL_MASK, myvar, 1);
         int target = __shfl_sync(FULL_MASK, myvar, 2), reached = __shfl_sync(FULL_MASK, myvar, 3);
@@ -1040,6 +1071,21 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, TDE_PHYS_BLOCKS_PER_
         }
         if (p.phases & (TDE_PH_KINEMATICS | TDE_PH_REWARD)) store_vars(p, e, lane, s, step, target, reached, lphase, episode, m);
         __syncwarp();
+    }
+}
+
+template <int AH>
+__global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, TDE_PHYS_BLOCKS_PER_SM) tde_physics_kernel(const StepParams p) {
+    __shared__ SatScratch scratch[TDE_WARPS_PER_BLOCK];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SatScratch* ws = &scratch[warp];
+    const int warps_total = gridDim.x * TDE_WARPS_PER_BLOCK;
+    double st_acc = 0.0;  // lane k accumulates statistic k
+#pragma unroll 1
+    for (int e = p.e_begin + blockIdx.x * TDE_WARPS_PER_BLOCK + warp; e < p.e_end; e += warps_total) {
+        TDE_TRACE_MARK(e, 2);
+        physics_env<AH>(p, e, lane, ws, st_acc);
+        TDE_TRACE_MARK(e, 3);
     }
     if ((p.phases & TDE_PH_REWARD) && lane < TDE_NUM_STATS && st_acc != 0.0) atomicAdd(&p.stats[lane], st_acc);
 }
