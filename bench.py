@@ -35,7 +35,9 @@ WORKLOADS = {
     "c3": (16384, 32, True),
     "c2": (1024, 16, False),
     "c4": (65536, 64, False),   # stateless collision + offroad micro-benchmark (tde_collision_boxes / tde_offroad_boxes)
+    "c5": (8192, 8, True),      # rollout collection: 65,536 envs over 8 GPUs, training-scenario mix, 3-frame stack into a GPU rollout buffer
 }
+C5_N_STACK, C5_N_STEPS = 3, 32
 
 
 def build_scenarios(workload: str):
@@ -44,6 +46,9 @@ def build_scenarios(workload: str):
         return S.traffic_lights(32), "C3: 16384 envs x 32 agents per GPU, Traffic Lights, birdview 3x64x64, auto-reset"
     if workload == "c2":
         return S.roundabout(16), "C2: 1024 envs x 16 agents, Roundabout, kinematics+collision+offroad+reward, no render"
+    if workload == "c5":
+        return S.training_mix(100, 8), ("C5: rollout collection, 8192 envs x 8 agents per GPU (65,536 over 8 GPUs), mix of 100 synthetic "
+                                        "training polylines, 3-frame stack written into a GPU-resident rollout buffer, uniform random policy")
     raise ValueError(workload)
 
 
@@ -249,6 +254,104 @@ def run_c4(args, rank: int, local_rank: int, world: int):
         dist.destroy_process_group()
 
 
+def run_c5(args, rank: int, local_rank: int, world: int):
+    """Config C5: on-policy rollout collection (examples/rl_training.py:159-160,178-181) on the training-scenario
+    mix, frame stack fused into the rollout-buffer store (tde_step_rollout), uniform random policy on the GPU."""
+    import torch
+    import torch.distributed as dist
+    from torchdriveenv_b200.distributed import reduce_episode_stats, summarize
+    from torchdriveenv_b200.engine import Engine
+    from torchdriveenv_b200.rollout import RolloutCollector, uniform_policy
+    from torchdriveenv_b200.roofline import rollout_bytes_per_env_step
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    E, A, _ = WORKLOADS["c5"]
+    ss, desc = build_scenarios("c5")
+    eng = Engine(ss, E, A, device=str(dev), auto_reset=1, env_index_offset=rank * E)
+    T = C5_N_STEPS
+    col = RolloutCollector(eng, T, n_stack=C5_N_STACK, seed=0)
+    policy = uniform_policy(seed=1000 + rank)
+    K = max(T, (args.steps // T) * T)          # whole rollouts
+    W = max(1, -(-args.warmup // T))
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    for _ in range(W):
+        col.collect(policy)
+    barrier()
+    launches0 = eng.num_kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record(stream)
+    for _ in range(K // T):
+        col.collect(policy)
+    e1.record(stream)
+    barrier()
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1) if sampler else None
+    gpu_launches = eng.num_kernel_launches() - launches0
+    tmax = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item()) / K
+    # end to end with a host-side policy: actions from pinned host memory every step, reward + flags back to the
+    # host every step; the observations stay in the GPU rollout buffer, where the learner reads them
+    K2 = max(3, min(K, args.e2e_steps))
+    pin_act = torch.from_numpy(make_actions(E, 8, seed=2000 + rank)).pin_memory()
+    host_rew, host_flags = torch.zeros(E, dtype=torch.float32).pin_memory(), torch.zeros((2, E), dtype=torch.uint8).pin_memory()
+    b = col.buffer
+
+    def host_policy_step(t, k):
+        a = pin_act[k % 8].to(dev, non_blocking=True)
+        eng.step_rollout(a, b.observations[t], b.observations[t + 1], C5_N_STACK, reward=b.rewards[t], terminated=b.terminated[t], truncated=b.truncated[t])
+        host_rew.copy_(b.rewards[t], non_blocking=True)
+        host_flags[0].copy_(b.terminated[t], non_blocking=True)
+        host_flags[1].copy_(b.truncated[t], non_blocking=True)
+        torch.cuda.synchronize(dev)
+
+    host_policy_step(0, 0)
+    barrier()
+    e0.record(stream)
+    for k in range(K2):
+        host_policy_step(k % T, k)
+    e1.record(stream)
+    barrier()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    stats = reduce_episode_stats(eng.episode_stats(), device=dev)
+    if rank == 0:
+        peak, peak_src = measured_peak_hbm()
+        bpe = rollout_bytes_per_env_step(A, C5_N_STACK)
+        achieved = bpe * E / (ms * 1e-3) / 1e9
+        cpu = cpu_oracle_throughput("c5", args.cpu_seconds) if world == 1 and not args.no_cpu_baseline else None
+        line = dict(metric=METRIC, value=E * world / (ms * 1e-3), unit=UNIT, n_gpus=world, steps=K, warmup=W * T, ms_per_step=ms,
+                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                    config=dict(workload=desc, envs_per_gpu=E, agents=A, render=True, global_envs=E * world, n_stack=C5_N_STACK,
+                                rollout_steps=T, rollout_buffer_bytes=b.nbytes(),
+                                parallelism=f"env-sharded x{world}, no collectives on the step path",
+                                l2="each step writes a fresh %.0f MB buffer slot: larger than the 126 MB L2" % (E * 9 * 4096 / 1e6)),
+                    clocks=clocks, gpu_launches=int(gpu_launches),
+                    e2e=dict(value=E * world * K2 / (float(e2e_ms.item()) * 1e-3), unit=UNIT, h2d_bytes_per_step=E * 8, d2h_bytes_per_step=E * 6,
+                             steps=K2, api="Engine.step_rollout with actions from pinned host memory and reward/terminated/truncated read back "
+                                           "every step (observations stay in the GPU rollout buffer)"),
+                    roofline=dict(bound="hbm", kernel="tde_render_kernel<stacked> (+ tde_physics_kernel, one launch each per step)", achieved=achieved,
+                                  peak=peak, unit="GB/s", frac=achieved / peak, traffic=None, algorithmic_bytes_per_launch=bpe * E,
+                                  bytes_per_env_step=bpe, avg_launch_ms=ms, peak_source=peak_src),
+                    cpu_baseline=cpu, episode_stats=summarize(stats))
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
@@ -406,6 +509,9 @@ def main():
         sys.exit(subprocess.call(cmd))
     if args.workload == "c4":
         run_c4(args, rank, local_rank, world)
+        return
+    if args.workload == "c5":
+        run_c5(args, rank, local_rank, world)
         return
     run_cuda(args, rank, local_rank, world)
 

@@ -15,6 +15,8 @@
  *   tde_render                   simulator.render_egocentric() :123,154
  *   tde_step_stacked,
  *   tde_render_stacked           the same with VecFrameStack (examples/rl_training.py:160) fused into the store
+ *   tde_step_rollout             the same, writing the next slot of a rollout buffer (collect_rollouts of the
+ *                                  trainer that drives the env, examples/rl_training.py:178-181,200)
  *   tde_get_state/tde_set_state  simulator.get_state() :127,371,392-393,397-399,420-423 / set_state :247
  *   tde_compute_infractions,
  *   tde_get_infractions          simulator.compute_offroad() :142,415,427; compute_collision() :143,415,428;
@@ -235,6 +237,15 @@ int tde_step_host(tde_handle* h, const float* actions_host, uint8_t* obs_host, f
 int tde_step_stacked(tde_handle* h, const float* actions_dev, uint8_t* stack_dev, int32_t n_stack, float* reward_dev,
                      uint8_t* terminated_dev, uint8_t* truncated_dev, float* info_dev, void* stream);
 int tde_render_stacked(tde_handle* h, uint8_t* stack_dev, int32_t n_stack, void* stream);
+/* Rollout collection (the on-policy loop that drives the env, examples/rl_training.py:159-160,178-181:
+   VecFrameStack output stored per step into the rollout buffer): the same step, but the older frames
+   are taken from stack_prev_dev (the observation slot of step t) while the shifted stack with the new
+   frame is written to stack_next_dev (slot t + 1), so the buffer is filled without a copy pass.  Both
+   are uint8[E][3*n_stack][64][64]; they must be the same buffer (= tde_step_stacked) or not overlap.
+   reward / terminated / truncated / info may point into the rollout buffer's own rows.  n_stack in 2..8. */
+int tde_step_rollout(tde_handle* h, const float* actions_dev, const uint8_t* stack_prev_dev, uint8_t* stack_next_dev,
+                     int32_t n_stack, float* reward_dev, uint8_t* terminated_dev, uint8_t* truncated_dev,
+                     float* info_dev, void* stream);
 
 int tde_kinematics(tde_handle* h, const float* actions_dev, void* stream);
 int tde_render(tde_handle* h, uint8_t* obs_dev, void* stream);

@@ -159,3 +159,82 @@ def test_background_traffic_agents_drive_at_constant_velocity(oracle):
     moved = np.hypot(st[keep][:, 1:, 0] - ss.scenarios[0].agent_init[1:, 0], st[keep][:, 1:, 1] - ss.scenarios[0].agent_init[1:, 1])
     assert keep.any() and (moved[:, ss.scenarios[0].agent_init[1:, 3] > 0.5] > 0).all()
     venv.close()
+
+
+def test_rollout_collector_fills_the_buffer_like_vec_frame_stack(oracle):
+    """Config C5 in small: RolloutCollector on the training-scenario mix.  Every slot of the GPU rollout buffer
+    must hold what SubprocVecEnv + VecFrameStack + RolloutBuffer.add would have stored (examples/rl_training.py
+    :159-160): oracle frames stacked oldest first, zeros before a restart, rewards / flags / episode starts."""
+    from torchdriveenv_b200.engine import Engine
+    from torchdriveenv_b200.rollout import RolloutCollector
+    E, A, T, NS = 40, 6, 9, 3
+    ss = S.training_mix(7, A, seed=3)
+    eng = Engine(ss, E, A, device="cuda:0", auto_reset=1, max_environment_steps=12)
+    orc = oracle.OracleEnvSet(default_config(num_envs=E, max_agents=A, auto_reset=1, max_environment_steps=12), eng.packed)
+    orc.reset(seed=11)
+    col = RolloutCollector(eng, T, n_stack=NS, seed=11, with_info=True)
+    rng = np.random.default_rng(11)
+    acts = np.stack([rng.uniform(-1, 1, (3 * T, E)), rng.uniform(-0.3, 0.3, (3 * T, E))], -1).astype(np.float32)
+    k = [0]
+
+    def policy(obs):
+        assert obs.shape == (E, 3 * NS, 64, 64) and obs.dtype == torch.uint8
+        a = torch.from_numpy(acts[k[0]]).to(obs.device)
+        k[0] += 1
+        return a, a[:, 0] * 2.0, a[:, 1] - 1.0         # (actions, values, log_probs)
+
+    frames = [orc.render()]
+    age = np.zeros(E, np.int64)
+
+    def want_stack():
+        w = np.zeros((E, 3 * NS, 64, 64), np.uint8)
+        for slot in range(NS):
+            back = NS - 1 - slot
+            if back < len(frames):
+                have = age >= back
+                w[have, 3 * slot:3 * slot + 3] = frames[-1 - back][have]
+        return w
+
+    n_done = 0
+    for r in range(3):
+        b = col.collect(policy)
+        torch.cuda.synchronize()
+        obs = b.observations.cpu().numpy()
+        assert np.array_equal(obs[0], want_stack()), f"rollout {r}: slot 0 carries the last observation over"
+        starts = b.episode_starts.cpu().numpy()
+        assert (starts[0] == (1 if r == 0 else d_last)).all()
+        for t in range(T):
+            a = acts[r * T + t]
+            oobs, orr, ote, otr, oinfo = orc.step(a)
+            d = (ote | otr).astype(bool)
+            frames.append(oobs)
+            age = np.where(d, 0, age + 1)
+            assert np.array_equal(obs[t + 1], want_stack()), f"rollout {r} step {t}: buffer slot"
+            assert np.array_equal(b.actions[t].cpu().numpy(), a)
+            assert np.array_equal(b.rewards[t].cpu().numpy(), orr)
+            assert np.array_equal(b.terminated[t].cpu().numpy(), ote) and np.array_equal(b.truncated[t].cpu().numpy(), otr)
+            assert np.array_equal(starts[t + 1].astype(bool), d)
+            assert np.array_equal(b.infos[t].cpu().numpy(), oinfo)
+            assert np.array_equal(b.values[t].cpu().numpy(), a[:, 0] * 2.0) and np.array_equal(b.log_probs[t].cpu().numpy(), a[:, 1] - 1.0)
+            n_done += int(d.sum())
+            d_last = d.astype(np.uint8)
+    assert n_done > 0 and col.num_timesteps == 3 * T * E
+    assert col.episode_statistics()["episodes"] == n_done
+    # GAE against a plain float64 loop
+    last_v = torch.linspace(-1, 1, E, device="cuda:0")
+    ret, adv = col.returns_and_advantages(last_v, gamma=0.99, gae_lambda=0.95)
+    rw, va, st = b.rewards.cpu().numpy().astype(np.float64), b.values.cpu().numpy().astype(np.float64), b.episode_starts.cpu().numpy()
+    want = np.zeros((T, E)); last = np.zeros(E); nxt = last_v.cpu().numpy().astype(np.float64)
+    for t in reversed(range(T)):
+        nt = 1.0 - st[t + 1]
+        delta = rw[t] + 0.99 * nxt * nt - va[t]
+        last = delta + 0.99 * 0.95 * nt * last
+        want[t] = last; nxt = va[t]
+    assert np.allclose(adv.cpu().numpy(), want, rtol=1e-4, atol=1e-3) and np.allclose(ret.cpu().numpy(), want + va, rtol=1e-4, atol=1e-3)
+    # overlapping but different slots are refused, n_stack = 1 is refused
+    from torchdriveenv_b200._capi import TdeError
+    flat = torch.zeros(E * 9 * 4096 + 4096, dtype=torch.uint8, device="cuda:0")
+    s0, s1 = flat[:E * 9 * 4096].view(E, 9, 64, 64), flat[4096:].view(E, 9, 64, 64)
+    with pytest.raises(TdeError, match="overlap"):
+        eng.step_rollout(torch.zeros(E, 2), s0, s1, 3)
+    eng.close()

@@ -187,3 +187,21 @@ def test_background_traffic_loader_and_light_program(tmp_path):
     assert (sched[:25, 1] == S.LIGHT_RED).all() and (sched[25:, 1] == S.LIGHT_GREEN).all()
     with pytest.raises(ValueError):
         S.compile_light_program([(1.0, ["green"])], 2)
+
+
+def test_training_mix_statistics_and_rollout_roofline():
+    """Config C5's synthetic scenario mix follows the statistics of the reference's training suite
+     and the rollout roofline formula adds the frame-stack traffic."""
+    from torchdriveenv_b200.roofline import rollout_bytes_per_env_step
+    ss = S.training_mix(12, 5, seed=2)
+    assert len(ss.maps) == 12 and len(ss.scenarios) == 12 and ss.max_agents() == 5
+    for sc in ss.scenarios:
+        w = np.asarray(sc.waypoints, np.float64)
+        assert 5 <= len(w) <= 20
+        seg = np.hypot(*np.diff(w, axis=0).T)
+        assert seg.min() > 12.8 and seg.max() < 15.1
+    packed = ss.pack(5)
+    assert packed["scen_map"].tolist() == list(range(12))
+    again = S.training_mix(12, 5, seed=2).pack(5)
+    assert all(np.array_equal(packed[k], again[k]) for k in packed)      # seeded and deterministic
+    assert rollout_bytes_per_env_step(8, 3) == bytes_per_env_step(8, False) + 5 * 12288 + 8

@@ -706,7 +706,7 @@ extern "C" int tde_reset(tde_handle* h, const uint8_t* env_mask_dev, uint64_t se
 }
 
 static int step_impl(tde_handle* h, int32_t phases, const float* actions, uint8_t* obs, int32_t n_stack, float* reward,
-                     uint8_t* terminated, uint8_t* truncated, float* info, void* stream) {
+                     uint8_t* terminated, uint8_t* truncated, float* info, void* stream, const uint8_t* obs_prev = nullptr) {
     if (!h) return TDE_E_INVAL;
     if (n_stack < 1 || n_stack > 8) return fail(h, TDE_E_INVAL, "n_stack must be in 1..8");
     if (!h->uploaded || !h->was_reset) return fail(h, TDE_E_STATE, "tde_step: upload scenarios and reset first");
@@ -719,6 +719,7 @@ static int step_impl(tde_handle* h, int32_t phases, const float* actions, uint8_
     StepParams p = make_params(h);
     p.phases = phases; p.actions = actions; p.obs = obs; p.reward = reward; p.terminated = terminated;
     p.truncated = truncated; p.info = info; p.n_stack = n_stack;
+    p.obs_prev = obs_prev ? obs_prev : obs;
     cudaStream_t st = (cudaStream_t)stream;
     const int threads = TDE_WARPS_PER_BLOCK * 32;
     const bool physics = phases & (TDE_PH_KINEMATICS | TDE_PH_INFRACTIONS | TDE_PH_REWARD);
@@ -757,6 +758,18 @@ extern "C" int tde_step_stacked(tde_handle* h, const float* actions, uint8_t* st
 }
 extern "C" int tde_render_stacked(tde_handle* h, uint8_t* stack, int32_t n_stack, void* stream) {
     return step_impl(h, TDE_PH_RENDER, nullptr, stack, n_stack, nullptr, nullptr, nullptr, nullptr, stream);
+}
+extern "C" int tde_step_rollout(tde_handle* h, const float* actions, const uint8_t* stack_prev, uint8_t* stack_next, int32_t n_stack,
+                                float* reward, uint8_t* terminated, uint8_t* truncated, float* info, void* stream) {
+    if (h && (!stack_prev || !stack_next)) return fail(h, TDE_E_INVAL, "tde_step_rollout: stack_prev / stack_next is null");
+    if (h && n_stack < 2) return fail(h, TDE_E_INVAL, "tde_step_rollout: n_stack must be in 2..8");
+    if (h && stack_prev != stack_next) {
+        // the two slots must not overlap unless they are the same buffer (then the shift is done in place)
+        const size_t bytes = (size_t)h->E * (size_t)n_stack * TDE_OBS_C * TDE_OBS_H * TDE_OBS_W;
+        const uint8_t *a = stack_prev, *b = stack_next;
+        if (a < b + bytes && b < a + bytes) return fail(h, TDE_E_INVAL, "tde_step_rollout: stack_prev and stack_next overlap");
+    }
+    return step_impl(h, TDE_PH_ALL, actions, stack_next, n_stack, reward, terminated, truncated, info, stream, stack_prev);
 }
 
 extern "C" int tde_step(tde_handle* h, const float* actions, uint8_t* obs, float* reward, uint8_t* terminated,

@@ -68,6 +68,7 @@ struct StepParams {
     const int* scen_hi;
     const float* actions;
     uint8_t* obs;
+    const uint8_t* obs_prev;  // stacked render: the stack the older frames are taken from (== obs: shifted in place)
     float* reward;
     uint8_t* terminated;
     uint8_t* truncated;
@@ -834,6 +835,7 @@ __device__ __forceinline__ void render_env(const StepParams& p, const int e, con
             // fused VecFrameStack: frames 1..n-1 move one slot down (zeros after a restart); a warp-wide
             // 128-bit access covers 512 contiguous bytes, eight are kept in flight per lane
             uint4* const base = reinterpret_cast<uint4*>(p.obs + (size_t)e * p.n_stack * FRAME) + lane;
+            const uint4* const prev = reinterpret_cast<const uint4*>(p.obs_prev + (size_t)e * p.n_stack * FRAME) + lane;
             const int pieces = (p.n_stack - 1) * (FRAME / 512);
             const bool fresh = p.restart[e] != 0;
 #pragma unroll 1
@@ -842,7 +844,7 @@ __device__ __forceinline__ void render_env(const StepParams& p, const int e, con
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     v[u] = make_uint4(0u, 0u, 0u, 0u);
-                    if (!fresh) v[u] = base[(size_t)(i + u) * 32 + FRAME / 16];
+                    if (!fresh) v[u] = prev[(size_t)(i + u) * 32 + FRAME / 16];
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) base[(size_t)(i + u) * 32] = v[u];

@@ -107,6 +107,27 @@ class Engine:
                                               _ptr(self.truncated), _ptr(self.info), self._stream()), "tde_step_stacked")
         return stack, self.reward, self.terminated, self.truncated, self.info
 
+    def step_rollout(self, actions: torch.Tensor, stack_prev: torch.Tensor, stack_next: torch.Tensor, n_stack: int,
+                     reward: Optional[torch.Tensor] = None, terminated: Optional[torch.Tensor] = None,
+                     truncated: Optional[torch.Tensor] = None, info: Optional[torch.Tensor] = None):
+        """tde_step_rollout: the stacked step out of place - older frames read from `stack_prev` (slot t of a
+        rollout buffer), shifted stack + new frame written to `stack_next` (slot t + 1).  The per-env results
+        go to the given rows (contiguous, on this device) or to the engine's own output tensors."""
+        a = actions.to(device=self.device, dtype=torch.float32).contiguous().view(self.E, 2)
+        self._check_stack(stack_prev, n_stack)
+        self._check_stack(stack_next, n_stack)
+        outs = []
+        for t, own, shape, dt in ((reward, self.reward, (self.E,), torch.float32), (terminated, self.terminated, (self.E,), torch.uint8),
+                                  (truncated, self.truncated, (self.E,), torch.uint8), (info, self.info, (self.E, TDE_INFO_STRIDE), torch.float32)):
+            if t is None:
+                t = own
+            elif tuple(t.shape) != shape or t.dtype != dt or not t.is_contiguous() or t.device != self.obs.device:
+                raise ValueError(f"step_rollout: output rows must be contiguous {dt} tensors of shape {shape} on {self.obs.device}")
+            outs.append(t)
+        self._check(self.lib.tde_step_rollout(self.h, _ptr(a), _ptr(stack_prev), _ptr(stack_next), int(n_stack), _ptr(outs[0]),
+                                              _ptr(outs[1]), _ptr(outs[2]), _ptr(outs[3]), self._stream()), "tde_step_rollout")
+        return stack_next, outs[0], outs[1], outs[2], outs[3]
+
     def render_stacked(self, stack: torch.Tensor, n_stack: int) -> torch.Tensor:
         self._check_stack(stack, n_stack)
         self._check(self.lib.tde_render_stacked(self.h, _ptr(stack), int(n_stack), self._stream()), "tde_render_stacked")

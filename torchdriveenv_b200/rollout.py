@@ -1,0 +1,140 @@
+"""GPU-resident on-policy rollout collection over the lockstep step (BASELINE config C5).
+
+The reference collects rollouts with stable-baselines3 (examples/rl_training.py:159-160,178-181,200:
+``SubprocVecEnv`` + ``VecFrameStack(n_stack, channels_order="first")`` feeding ``PPO.learn`` ->
+``collect_rollouts`` -> ``RolloutBuffer.add``): every step the stacked observation, action, reward and
+episode-start flag of every env are copied into the buffer on the host.  Here the buffer lives in HBM
+and the render kernel writes the shifted frame stack of step t + 1 straight into its slot
+(``tde_step_rollout``: older frames read from slot t), so filling the buffer costs no copy pass; reward
+and flags are written by the physics kernel into the buffer's own rows.
+
+Field names and shapes follow SB3's ``RolloutBuffer`` ([n_steps, n_envs, ...]); ``episode_starts[t]``
+is 1 where ``observations[t]`` is the first observation of an episode.  ``returns_and_advantages`` is
+GAE(lambda) as ``RolloutBuffer.compute_returns_and_advantage`` defines it.  stable-baselines3 itself
+is not needed (and not installed in the build image).
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Optional, Tuple
+
+import torch
+
+from ._capi import TDE_INFO_STRIDE, TDE_OBS_H, TDE_OBS_W
+from .engine import Engine
+
+
+class RolloutBuffer:
+    """[n_steps (+1 for observations / episode_starts), E, ...] tensors on the engine's GPU."""
+
+    def __init__(self, n_steps: int, num_envs: int, n_stack: int, device, with_info: bool = False):
+        T, E = int(n_steps), int(num_envs)
+        self.n_steps, self.num_envs, self.n_stack = T, E, int(n_stack)
+        z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=device)
+        self.observations = z((T + 1, E, 3 * self.n_stack, TDE_OBS_H, TDE_OBS_W), torch.uint8)
+        self.actions = z((T, E, 2), torch.float32)
+        self.rewards = z((T, E), torch.float32)
+        self.terminated = z((T, E), torch.uint8)
+        self.truncated = z((T, E), torch.uint8)
+        self.episode_starts = z((T + 1, E), torch.uint8)
+        self.values = z((T, E), torch.float32)
+        self.log_probs = z((T, E), torch.float32)
+        # info rows (get_info :419-437) per step are optional: 64 B per env-step
+        self.infos = z((T, E, TDE_INFO_STRIDE), torch.float32) if with_info else None
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in vars(self).values() if isinstance(t, torch.Tensor))
+
+
+Policy = Callable[[torch.Tensor], object]
+
+
+class RolloutCollector:
+    """``collect(policy)`` fills a RolloutBuffer with n_steps lockstep steps of all E envs.
+
+    ``policy(obs uint8[E, 3*n_stack, 64, 64]) -> actions[E, 2]`` or ``(actions, values[E], log_probs[E])``,
+    all on the engine's GPU.  Finished envs restart inside the step kernel (auto-reset) and their frame
+    stack restarts with zeros, as VecFrameStack does; the collector carries the last observation and
+    episode-start flags over to slot 0 of the next rollout.
+    """
+
+    def __init__(self, engine: Engine, n_steps: int, n_stack: int = 3, seed: int = 0, with_info: bool = False):
+        if n_stack < 2 or n_stack > 8:
+            raise ValueError("n_stack must be in 2..8 (use Engine.step for a plain observation)")
+        self.engine, self.n_steps, self.n_stack = engine, int(n_steps), int(n_stack)
+        self.buffer = RolloutBuffer(n_steps, engine.E, n_stack, engine.device, with_info=with_info)
+        self._info = None if with_info else torch.zeros((engine.E, TDE_INFO_STRIDE), dtype=torch.float32, device=engine.device)
+        self._seed = int(seed)
+        self._started = False
+        self.num_timesteps = 0
+
+    def reset(self) -> torch.Tensor:
+        b = self.buffer
+        self.engine.reset(seed=self._seed)
+        b.observations[0].zero_()
+        self.engine.render_stacked(b.observations[0], self.n_stack)
+        b.episode_starts[0].fill_(1)
+        self._started = True
+        return b.observations[0]
+
+    def collect(self, policy: Policy) -> RolloutBuffer:
+        b, eng, T = self.buffer, self.engine, self.n_steps
+        if not self._started:
+            self.reset()
+        elif self.num_timesteps:
+            b.observations[0].copy_(b.observations[T])      # one slot per rollout: 1/n_steps of the traffic
+            b.episode_starts[0].copy_(b.episode_starts[T])
+        for t in range(T):
+            out = policy(b.observations[t])
+            if isinstance(out, (tuple, list)):
+                act, val, logp = out
+                b.values[t].copy_(val.reshape(-1))
+                b.log_probs[t].copy_(logp.reshape(-1))
+            else:
+                act = out
+            b.actions[t].copy_(act.reshape(eng.E, 2))
+            eng.step_rollout(b.actions[t], b.observations[t], b.observations[t + 1], self.n_stack,
+                             reward=b.rewards[t], terminated=b.terminated[t], truncated=b.truncated[t],
+                             info=b.infos[t] if b.infos is not None else self._info)
+            torch.bitwise_or(b.terminated[t], b.truncated[t], out=b.episode_starts[t + 1])
+        self.num_timesteps += T * eng.E
+        return b
+
+    def last_observation(self) -> torch.Tensor:
+        return self.buffer.observations[self.n_steps]
+
+    def returns_and_advantages(self, last_values: torch.Tensor, gamma: float = 0.99, gae_lambda: float = 0.95) -> Tuple[torch.Tensor, torch.Tensor]:
+        """GAE(lambda) over the collected rollout (SB3 RolloutBuffer.compute_returns_and_advantage):
+        delta_t = r_t + gamma V_{t+1} (1 - start_{t+1}) - V_t;  A_t = delta_t + gamma lambda (1 - start_{t+1}) A_{t+1}."""
+        b, T = self.buffer, self.n_steps
+        adv = torch.zeros_like(b.rewards)
+        last = torch.zeros(b.num_envs, dtype=torch.float32, device=b.rewards.device)
+        nxt = last_values.reshape(-1).to(torch.float32)
+        for t in reversed(range(T)):
+            nonterminal = 1.0 - b.episode_starts[t + 1].to(torch.float32)
+            delta = b.rewards[t] + gamma * nxt * nonterminal - b.values[t]
+            last = delta + gamma * gae_lambda * nonterminal * last
+            adv[t] = last
+            nxt = b.values[t]
+        return adv + b.values, adv
+
+    def episode_statistics(self, reset: bool = False) -> Dict[str, float]:
+        from ._capi import STAT_NAMES
+        s = self.engine.episode_stats(reset=reset)
+        return {n: float(s[i]) for i, n in enumerate(STAT_NAMES)}
+
+
+def uniform_policy(action_low=(-1.0, -0.3), action_high=(1.0, 0.3), seed: int = 0) -> Policy:
+    """U(low, high) actions drawn on the GPU (the reference action space, gym_env.py:83-84): the stand-in
+    for the CnnPolicy of examples/rl_training.py when no trainer is attached."""
+    state: Dict[str, Optional[torch.Generator]] = {"gen": None}
+
+    def policy(obs: torch.Tensor) -> torch.Tensor:
+        if state["gen"] is None:
+            state["gen"] = torch.Generator(device=obs.device)
+            state["gen"].manual_seed(seed)
+            state["lo"] = torch.tensor(action_low, dtype=torch.float32, device=obs.device)
+            state["span"] = torch.tensor(action_high, dtype=torch.float32, device=obs.device) - state["lo"]
+        u = torch.rand((obs.shape[0], 2), generator=state["gen"], device=obs.device)
+        return state["lo"] + u * state["span"]
+
+    return policy

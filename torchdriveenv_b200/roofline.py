@@ -12,3 +12,11 @@ def bytes_per_env_step(num_agents: int, render: bool) -> int:
 def c4_bytes_per_env(num_agents: int) -> int:
     """collision/offroad micro-bench: read x,y,psi,length,width,present (21 B), write 2 floats (8 B)."""
     return 29 * num_agents
+
+
+def rollout_bytes_per_env_step(num_agents: int, n_stack: int) -> int:
+    """Rollout collection (config C5, tde_step_rollout): the step without its plain observation, plus the
+    frame stack written into the next buffer slot (n_stack frames) from the previous slot (n_stack - 1
+    frames read), plus the action row kept in the buffer (8 B)."""
+    frame = 3 * 64 * 64
+    return bytes_per_env_step(num_agents, False) + (2 * n_stack - 1) * frame + 8

@@ -486,6 +486,33 @@ def validation_mix(n_agents: int = 8, seed: int = 0) -> ScenarioSet:
     return ScenarioSet(maps, scen)
 
 
+def synthetic_training_polyline(rng: np.random.Generator) -> np.ndarray:
+    """One waypoint polyline with the statistics of the reference's training suite
+    (torchdriveenv/data/training_cases.yml:102-2980; SURVEY.md §8a row a10: 5-20 waypoints, mean 14.4,
+    spacing 12.9-15.0 m): a heading random walk with an occasional junction-sized turn."""
+    n = int(rng.integers(5, 21))
+    pts = [rng.uniform(-200.0, 200.0, 2)]
+    psi = float(rng.uniform(-math.pi, math.pi))
+    for _ in range(n - 1):
+        psi += float(rng.normal(0.0, 0.12)) + (float(rng.choice([-1.0, 1.0])) * float(rng.uniform(0.7, 1.4)) if rng.uniform() < 0.15 else 0.0)
+        step = float(rng.uniform(12.9, 15.0))
+        pts.append(pts[-1] + step * np.array([math.cos(psi), math.sin(psi)]))
+    return np.round(np.asarray(pts, np.float64), 3)
+
+
+def training_mix(n_scenarios: int = 100, n_agents: int = 8, seed: int = 0) -> ScenarioSet:
+    """BASELINE config C5's scenario mix: ``n_scenarios`` synthetic training polylines, one map each
+    (two-lane road, junction arms with stop lines + lights at sharp turns), ego + replay NPCs.  The
+    reference's own training_cases.yml loads through env_utils.load_waypoint_suite_data when present."""
+    rng = np.random.default_rng(seed)
+    maps, scen = [], []
+    for k in range(n_scenarios):
+        poly = synthetic_training_polyline(rng)
+        maps.append(build_polyline_map(poly, f"train_{k}", with_lights=True))
+        scen.append(make_scenario(k, poly, n_agents - 1, seed + 1000 + k, f"train_{k}"))
+    return ScenarioSet(maps, scen)
+
+
 def scatter_patch(size: float = 200.0, cell: float = 10.0) -> MapData:
     """Config C4's lane mesh: a checkerboard of road squares over a size x size patch, so that a
     uniformly scattered box is on/near/off the road with comparable probability."""
