@@ -15,6 +15,7 @@
  *   tde_render                   simulator.render_egocentric() :123,154
  *   tde_step_stacked,
  *   tde_render_stacked           the same with VecFrameStack (examples/rl_training.py:160) fused into the store
+ *   tde_step_terminal            the same, keeping info["terminal_observation"] of SB3's VecEnv (the caller's contract)
  *   tde_step_rollout             the same, writing the next slot of a rollout buffer (collect_rollouts of the
  *                                  trainer that drives the env, examples/rl_training.py:178-181,200)
  *   tde_get_state/tde_set_state  simulator.get_state() :127,371,392-393,397-399,420-423 / set_state :247
@@ -246,6 +247,16 @@ int tde_render_stacked(tde_handle* h, uint8_t* stack_dev, int32_t n_stack, void*
 int tde_step_rollout(tde_handle* h, const float* actions_dev, const uint8_t* stack_prev_dev, uint8_t* stack_next_dev,
                      int32_t n_stack, float* reward_dev, uint8_t* terminated_dev, uint8_t* truncated_dev,
                      float* info_dev, void* stream);
+
+/* The step with the terminal observation kept (SB3 VecEnv contract of the caller, examples/rl_training.py:159:
+   SubprocVecEnv stores the last observation of a finished episode in info["terminal_observation"] before it
+   resets the env; off-policy trainers use it as next_obs, PPO for the time-limit bootstrap).  obs_dev and
+   terminal_obs_dev are uint8[E][3*n_stack][64][64] (n_stack = 1: plain observations).  For an env that finished
+   in this step, terminal_obs_dev[e] receives the frame (stack) of its final state and obs_dev[e] the first
+   frame of the new episode (older stack slots zeroed); rows of the other envs in terminal_obs_dev are left
+   untouched.  Needs cfg.auto_reset.  Same results as tde_step / tde_step_stacked otherwise. */
+int tde_step_terminal(tde_handle* h, const float* actions_dev, uint8_t* obs_dev, int32_t n_stack, uint8_t* terminal_obs_dev,
+                      float* reward_dev, uint8_t* terminated_dev, uint8_t* truncated_dev, float* info_dev, void* stream);
 
 int tde_kinematics(tde_handle* h, const float* actions_dev, void* stream);
 int tde_render(tde_handle* h, uint8_t* obs_dev, void* stream);

@@ -40,6 +40,7 @@ def lib() -> C.CDLL:
         L.orc_destroy.argtypes = [vp]
         L.orc_set_env_scenario_range.argtypes = [vp, vp, vp]
         L.orc_set_palette.argtypes = [vp, vp]
+        L.orc_set_terminal_buffer.argtypes = [vp, vp]
         for name in ("orc_state", "orc_attr", "orc_infractions", "orc_vars", "orc_stats"):
             getattr(L, name).argtypes, getattr(L, name).restype = [vp], vp
         L.orc_reset.argtypes = [vp, vp, C.c_uint64]
@@ -127,6 +128,11 @@ class OracleEnvSet:
     def reset(self, mask: Optional[np.ndarray] = None, seed: int = 0):
         m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
         self.L.orc_reset(self.h, None if m is None else _p(m), C.c_uint64(seed))
+
+    def set_terminal_buffer(self, buf: Optional[np.ndarray]):
+        """uint8[E,3,64,64] that receives the frame of an env's final state before its auto-reset (or None)."""
+        self._terminal = buf
+        self.L.orc_set_terminal_buffer(self.h, None if buf is None else _p(buf))
 
     def step(self, actions, render: bool = True, phases: int = 15):
         a = _f32(actions).reshape(self.E, 2)

@@ -247,6 +247,8 @@ typedef struct orc_env_set {
     float* attr;    /* E*A*4 */
     float* infr;    /* E*A*4 */
     int32_t* vars;  /* E*8: scenario, step, target, reached, light_phase, episode, map, reserved */
+    uint8_t* terminal_obs; /* optional E*3*64*64: frame of the final state of an env, rendered before its auto-reset
+                              (what SB3's VecEnv puts in info["terminal_observation"]); not owned */
     float* ep_return; /* E */
     uint64_t seed;
     double stats[TDE_NUM_STATS];
@@ -325,6 +327,7 @@ void orc_set_env_scenario_range(orc_env_set* o, const int32_t* lo, const int32_t
     memcpy(o->scen_lo, lo, sizeof(int32_t) * o->E);
     memcpy(o->scen_hi, hi, sizeof(int32_t) * o->E);
 }
+void orc_set_terminal_buffer(orc_env_set* o, uint8_t* buf) { o->terminal_obs = buf; }
 void orc_set_palette(orc_env_set* o, const uint8_t* rgb) { memcpy(o->palette, rgb, TDE_NUM_CLASSES * 3); }
 float* orc_state(orc_env_set* o) { return o->state; }
 float* orc_attr(orc_env_set* o) { return o->attr; }
@@ -720,6 +723,8 @@ void orc_step_phases(orc_env_set* o, int phases, const float* actions, uint8_t* 
                     loc[TDE_STAT_SUCCESS] += trunc ? 1.0 : 0.0;
                     loc[TDE_STAT_REACHED_WAYPOINTS] += (double)v[3];
                     if (c->auto_reset) {
+                        if (o->terminal_obs && (phases & TDE_PH_RENDER) && obs)
+                            orc_render_env(o, e, o->terminal_obs + (size_t)e * 3 * TDE_OBS_H * TDE_OBS_W, NULL);
                         reset_env(o, e);
                         io[TDE_INFO_DID_RESET] = 1.0f;
                     }

@@ -238,3 +238,49 @@ def test_rollout_collector_fills_the_buffer_like_vec_frame_stack(oracle):
     with pytest.raises(TdeError, match="overlap"):
         eng.step_rollout(torch.zeros(E, 2), s0, s1, 3)
     eng.close()
+
+
+@pytest.mark.parametrize("n_stack", [1, 3])
+def test_vec_env_terminal_observation(oracle, n_stack):
+    """SB3 VecEnv contract (the caller, examples/rl_training.py:159): when an episode ends, infos carry the last
+    observation of that episode (`terminal_observation`) and `obs` is the first one of the next.  Everything
+    else must be what the in-kernel auto-reset path returns."""
+    from torchdriveenv_b200.gym_env import EnvConfig, TorchDriveVecEnv
+    E, A = 40, 8
+    cfg = EnvConfig(seed=4, device="cuda:0", max_environment_steps=14)
+    venv = TorchDriveVecEnv(cfg, S.traffic_lights(A), num_envs=E, n_stack=n_stack, terminal_observation=True)
+    twin = TorchDriveVecEnv(cfg, S.traffic_lights(A), num_envs=E, n_stack=n_stack)          # in-kernel auto-reset
+    orc = oracle.OracleEnvSet(default_config(num_envs=E, max_agents=A, auto_reset=1, max_environment_steps=14), venv.engine.packed)
+    term_buf = np.zeros((E, 3, 64, 64), np.uint8)
+    orc.set_terminal_buffer(term_buf)
+    orc.reset(seed=4)
+    obs = venv.reset(); obs2 = twin.reset()
+    assert torch.equal(obs, obs2)
+    rng = np.random.default_rng(4)
+    n_done = 0
+    prev_stack = obs.cpu().numpy().copy()
+    for k in range(30):
+        a = np.stack([rng.uniform(-1, 1, E), rng.uniform(-0.3, 0.3, E)], 1).astype(np.float32)
+        obs, rew, dones, infos = venv.step(a)
+        obs2, rew2, dones2, infos2 = twin.step(a)
+        oobs, orr, ote, otr, oinfo = orc.step(a)
+        d = (ote | otr).astype(bool)
+        assert torch.equal(obs, obs2) and torch.equal(rew, rew2) and torch.equal(dones, dones2)
+        assert torch.equal(venv.engine.get_state(), twin.engine.get_state())
+        assert torch.equal(venv.engine.get_env_vars(), twin.engine.get_env_vars())
+        for key in infos2:
+            assert torch.equal(infos[key], infos2[key]), key
+        assert np.array_equal(dones.cpu().numpy(), d) and np.array_equal(obs[:, -3:].cpu().numpy(), oobs)
+        tobs = infos["terminal_observation"].cpu().numpy()
+        assert tobs.shape == (E, 3 * n_stack, 64, 64)
+        if d.any():
+            assert np.array_equal(tobs[d][:, -3:], term_buf[d]), f"step {k}: terminal frame"
+            assert not np.array_equal(tobs[d][:, -3:], oobs[d])            # it is not the frame of the new episode
+            if n_stack > 1:   # the older slots of the terminal stack are the previous stack shifted by one frame
+                assert np.array_equal(tobs[d][:, :-3], prev_stack[d][:, 3:])
+                assert bool((obs[torch.from_numpy(d).cuda()][:, :-3] == 0).all())
+        n_done += int(d.sum())
+        prev_stack = obs.cpu().numpy().copy()
+    assert n_done > 5
+    assert venv.episode_statistics() == twin.episode_statistics()
+    venv.close(); twin.close()

@@ -8,6 +8,7 @@
 #include <tuple>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -26,6 +27,7 @@ struct tde_handle {
     double* stats = nullptr;
     uint8_t* restart = nullptr;
     unsigned int* tickets = nullptr;
+    uint8_t* done_mask = nullptr;   // [E] envs that finished in the current tde_step_terminal
     MapDev* maps_dev = nullptr;
     ScenDev* scens_dev = nullptr;
     std::vector<MapDev> maps_host;
@@ -456,11 +458,14 @@ static int configure_kernels(tde_handle* h) {
     int per_sm = 0;
     CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tde_render_kernel<AH, false>, TDE_WARPS_PER_BLOCK * 32, smem));
     if (per_sm < 1) per_sm = 1;
+    // tuning knobs for co-residency experiments (tools/coresident.py): cap the resident blocks per SM of either kernel
+    if (const char* v = std::getenv("TDE_RENDER_BLOCKS_CAP")) per_sm = std::max(1, std::min(per_sm, std::atoi(v)));
     h->smem_render = smem;
     int want = (h->E + TDE_WARPS_PER_BLOCK - 1) / TDE_WARPS_PER_BLOCK;
     h->grid_render = std::max(1, std::min(want, per_sm * h->sm_count));
     CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tde_physics_kernel<AH>, TDE_WARPS_PER_BLOCK * 32, 0));
     if (per_sm < 1) per_sm = 1;
+    if (const char* v = std::getenv("TDE_PHYS_BLOCKS_CAP")) per_sm = std::max(1, std::min(per_sm, std::atoi(v)));
     h->grid_phys = std::max(1, std::min(want, per_sm * h->sm_count));
     return TDE_OK;
 }
@@ -494,7 +499,7 @@ extern "C" int tde_create(const tde_config* cfg, tde_handle** out) {
         (rc = dev_alloc(h, &h->vars, (size_t)h->E * 8)) || (rc = dev_alloc(h, &h->ep_return, (size_t)h->E)) ||
         (rc = dev_alloc(h, &h->scen_lo, (size_t)h->E)) || (rc = dev_alloc(h, &h->scen_hi, (size_t)h->E)) ||
         (rc = dev_alloc(h, &h->stats, (size_t)TDE_NUM_STATS)) || (rc = dev_alloc(h, &h->restart, (size_t)h->E)) ||
-        (rc = dev_alloc(h, &h->tickets, (size_t)4)))
+        (rc = dev_alloc(h, &h->tickets, (size_t)4)) || (rc = dev_alloc(h, &h->done_mask, (size_t)h->E)))
         return bail(rc);
     rc = h->A <= 32 ? configure_kernels<1>(h) : configure_kernels<2>(h);
     if (rc) return bail(rc);
@@ -507,7 +512,7 @@ extern "C" int tde_destroy(tde_handle* h) {
     cudaSetDevice(h->device);
     free_scenarios(h);
     cudaFree(h->state); cudaFree(h->attr); cudaFree(h->infr); cudaFree(h->vars); cudaFree(h->ep_return);
-    cudaFree(h->scen_lo); cudaFree(h->scen_hi); cudaFree(h->stats); cudaFree(h->restart); cudaFree(h->tickets);
+    cudaFree(h->scen_lo); cudaFree(h->scen_hi); cudaFree(h->stats); cudaFree(h->restart); cudaFree(h->tickets); cudaFree(h->done_mask);
     cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_reward); cudaFree(h->h_term); cudaFree(h->h_trunc); cudaFree(h->h_info);
     delete h;
     return TDE_OK;
@@ -706,7 +711,8 @@ extern "C" int tde_reset(tde_handle* h, const uint8_t* env_mask_dev, uint64_t se
 }
 
 static int step_impl(tde_handle* h, int32_t phases, const float* actions, uint8_t* obs, int32_t n_stack, float* reward,
-                     uint8_t* terminated, uint8_t* truncated, float* info, void* stream, const uint8_t* obs_prev = nullptr) {
+                     uint8_t* terminated, uint8_t* truncated, float* info, void* stream, const uint8_t* obs_prev = nullptr,
+                     uint8_t* terminal_obs = nullptr) {
     if (!h) return TDE_E_INVAL;
     if (n_stack < 1 || n_stack > 8) return fail(h, TDE_E_INVAL, "n_stack must be in 1..8");
     if (!h->uploaded || !h->was_reset) return fail(h, TDE_E_STATE, "tde_step: upload scenarios and reset first");
@@ -725,6 +731,13 @@ static int step_impl(tde_handle* h, int32_t phases, const float* actions, uint8_
     const bool physics = phases & (TDE_PH_KINEMATICS | TDE_PH_INFRACTIONS | TDE_PH_REWARD);
     const bool render = (phases & TDE_PH_RENDER) && obs;
     const int want = (h->E + TDE_WARPS_PER_BLOCK - 1) / TDE_WARPS_PER_BLOCK;
+    // terminal observations: finished envs are only flagged by the physics kernel; after the frame of their last
+    // state is out it is copied to terminal_obs, the flagged envs are re-initialised and rendered again
+    const bool deferred = terminal_obs && physics && render && h->cfg.auto_reset;
+    if (deferred) {
+        CUDA_TRY(h, cudaMemsetAsync(h->done_mask, 0, (size_t)h->E, st));
+        p.done_mask = h->done_mask;
+    }
     if (physics) {
         const int grid = std::min(h->grid_phys, want);
         if (h->A <= 32) tde_physics_kernel<1><<<grid, threads, 0, st>>>(p);
@@ -744,7 +757,39 @@ static int step_impl(tde_handle* h, int32_t phases, const float* actions, uint8_
         CUDA_TRY(h, cudaGetLastError());
         h->launches++;
     }
+    if (deferred) {
+        const int u4_per_env = n_stack * (TDE_OBS_C * TDE_OBS_H * TDE_OBS_W / 16);
+        const int cgrid = std::max(1, std::min((h->E + 7) / 8, h->sm_count * 8));
+        tde_copy_rows_kernel<<<cgrid, 256, 0, st>>>(h->done_mask, (const uint4*)obs, (uint4*)terminal_obs, h->E, u4_per_env);
+        CUDA_TRY(h, cudaGetLastError());
+        StepParams q = p;
+        q.done_mask = nullptr;
+        q.reset_mask = h->done_mask;
+        const int rgrid = std::max(1, std::min(want, h->sm_count * 8));
+        if (h->A <= 32) tde_reset_kernel<1><<<rgrid, threads, 0, st>>>(q);
+        else tde_reset_kernel<2><<<rgrid, threads, 0, st>>>(q);
+        CUDA_TRY(h, cudaGetLastError());
+        q.render_mask = h->done_mask;
+        q.obs_prev = obs;   // the stack was shifted by the first pass; a re-initialised env only keeps zeros anyway
+        const int grid = std::min(h->grid_render, want);
+        if (n_stack > 1) {
+            if (h->A <= 32) tde_render_kernel<1, true><<<grid, threads, h->smem_render, st>>>(q);
+            else tde_render_kernel<2, true><<<grid, threads, h->smem_render, st>>>(q);
+        } else {
+            if (h->A <= 32) tde_render_kernel<1, false><<<grid, threads, h->smem_render, st>>>(q);
+            else tde_render_kernel<2, false><<<grid, threads, h->smem_render, st>>>(q);
+        }
+        CUDA_TRY(h, cudaGetLastError());
+        h->launches += 3;
+    }
     return TDE_OK;
+}
+
+extern "C" int tde_step_terminal(tde_handle* h, const float* actions, uint8_t* obs, int32_t n_stack, uint8_t* terminal_obs,
+                                 float* reward, uint8_t* terminated, uint8_t* truncated, float* info, void* stream) {
+    if (h && (!obs || !terminal_obs)) return fail(h, TDE_E_INVAL, "tde_step_terminal: obs / terminal_obs is null");
+    if (h && !h->cfg.auto_reset) return fail(h, TDE_E_STATE, "tde_step_terminal: needs auto_reset (without it nothing is re-initialised)");
+    return step_impl(h, TDE_PH_ALL, actions, obs, n_stack, reward, terminated, truncated, info, stream, nullptr, terminal_obs);
 }
 
 extern "C" int tde_step_phases(tde_handle* h, int32_t phases, const float* actions, uint8_t* obs, float* reward,

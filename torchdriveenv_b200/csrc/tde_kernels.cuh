@@ -77,6 +77,8 @@ struct StepParams {
     const uint8_t* reset_mask;
     unsigned int* tickets;   // render kernel of this launch: [0] next ticket, [1] finished warps
     int e_begin, e_end;      // envs [e_begin, e_end) of this launch
+    uint8_t* done_mask;  // non-null: the physics kernel flags finished envs here instead of re-initialising them (tde_step_terminal)
+    const uint8_t* render_mask;  // non-null: only envs with a non-zero byte are rendered (strided, no tickets)
     uint8_t* restart;    // [E] 1 = the env was reset since its last stacked frame
     int n_stack;         // frames per env in obs (1 = plain observation)
     uint32_t pal[3][4];  // per channel: 16 class bytes
@@ -913,13 +915,34 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, TDE_RENDER_BLOCKS_PE
     const int warps_total = gridDim.x * TDE_WARPS_PER_BLOCK;
     const float reach = viewport_reach(p);
     clear_cover(ws, lane);
+    // masked pass (re-render of the envs that were just re-initialised): plain stride, most envs are skipped
+    const bool masked = p.render_mask != nullptr;
+    int cursor = p.e_begin + blockIdx.x * TDE_WARPS_PER_BLOCK + warp;
 #pragma unroll 1
-    for (int e = p.e_begin + next_env(p.tickets, lane); e < p.e_end; e = p.e_begin + next_env(p.tickets, lane)) {
+    for (;;) {
+        int e;
+        if (masked) { e = cursor; cursor += warps_total; }
+        else e = p.e_begin + next_env(p.tickets, lane);
+        if (e >= p.e_end) break;
+        if (masked && p.render_mask[e] == 0) continue;
         TDE_TRACE_MARK(e, 0);
         render_env<AH, STACKED>(p, e, lane, ws, spread_tab, reach);
         TDE_TRACE_MARK(e, 1);
     }
-    envs_done(p.tickets, lane, warps_total);
+    if (!masked) envs_done(p.tickets, lane, warps_total);
+}
+
+// terminal observations: rows of the envs flagged in `mask` are copied out before those envs are re-initialised
+__global__ void __launch_bounds__(256) tde_copy_rows_kernel(const uint8_t* __restrict__ mask, const uint4* __restrict__ src,
+                                                            uint4* __restrict__ dst, int E, int u4_per_env) {
+    const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int warps_total = (gridDim.x * blockDim.x) >> 5;
+    for (int e = warp; e < E; e += warps_total) {
+        if (mask[e] == 0) continue;
+        const uint4* s = src + (size_t)e * u4_per_env;
+        uint4* d = dst + (size_t)e * u4_per_env;
+        for (int i = lane; i < u4_per_env; i += 32) d[i] = s[i];
+    }
 }
 
 // ---------------------------------------------------------------- physics kernel
@@ -1068,7 +1091,8 @@ __device__ __forceinline__ void physics_env(const StepParams& p, const int e, co
             st_acc += add;
             if (done && c.auto_reset) {
                 __syncwarp();
-                reset_env_warp<AH>(p, e, lane, s, step, target, reached, lphase, episode, m, st, at);
+                if (p.done_mask != nullptr) { if (lane == 0) p.done_mask[e] = 1; }   // reset deferred until the terminal frame is out
+                else reset_env_warp<AH>(p, e, lane, s, step, target, reached, lphase, episode, m, st, at);
             }
         }
         if (p.phases & (TDE_PH_KINEMATICS | TDE_PH_REWARD)) store_vars(p, e, lane, s, step, target, reached, lphase, episode, m);

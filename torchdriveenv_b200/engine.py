@@ -107,6 +107,17 @@ class Engine:
                                               _ptr(self.truncated), _ptr(self.info), self._stream()), "tde_step_stacked")
         return stack, self.reward, self.terminated, self.truncated, self.info
 
+    def step_terminal(self, actions: torch.Tensor, obs: torch.Tensor, terminal_obs: torch.Tensor, n_stack: int = 1):
+        """tde_step_terminal: the (stacked) step that keeps the terminal observation of finished envs in
+        `terminal_obs` (same shape as `obs`; only the rows of envs that finished in this step are written)."""
+        a = actions.to(device=self.device, dtype=torch.float32).contiguous().view(self.E, 2)
+        self._check_stack(obs, n_stack)
+        self._check_stack(terminal_obs, n_stack)
+        self._check(self.lib.tde_step_terminal(self.h, _ptr(a), _ptr(obs), int(n_stack), _ptr(terminal_obs), _ptr(self.reward),
+                                               _ptr(self.terminated), _ptr(self.truncated), _ptr(self.info), self._stream()),
+                    "tde_step_terminal")
+        return obs, self.reward, self.terminated, self.truncated, self.info
+
     def step_rollout(self, actions: torch.Tensor, stack_prev: torch.Tensor, stack_next: torch.Tensor, n_stack: int,
                      reward: Optional[torch.Tensor] = None, terminated: Optional[torch.Tensor] = None,
                      truncated: Optional[torch.Tensor] = None, info: Optional[torch.Tensor] = None):

@@ -347,7 +347,8 @@ class TorchDriveVecEnv:
     """
 
     def __init__(self, cfg: EnvConfig, data, num_envs: int, n_stack: Optional[int] = None, n_background: int = 0,
-                 device: Optional[str] = None, output: str = "torch", env_index_offset: int = 0, seed: Optional[int] = None):
+                 device: Optional[str] = None, output: str = "torch", env_index_offset: int = 0, seed: Optional[int] = None,
+                 terminal_observation: bool = False):
         self.config = cfg
         self.num_envs = int(num_envs)
         self.n_stack = int(n_stack if n_stack is not None else 1)
@@ -361,6 +362,9 @@ class TorchDriveVecEnv:
         self.observation_space = _Box(low=0, high=255, shape=(3 * self.n_stack, TDE_OBS_H, TDE_OBS_W), dtype=np.uint8)
         self._stack = torch.zeros((self.num_envs, 3 * self.n_stack, TDE_OBS_H, TDE_OBS_W), dtype=torch.uint8, device=self.device)
         self._actions = None
+        # SB3's VecEnv keeps the last observation of a finished episode in info["terminal_observation"]; here it is
+        # one [E, 3*n_stack, 64, 64] tensor whose rows are valid where `dones` is set (tde_step_terminal)
+        self._terminal = torch.zeros_like(self._stack) if terminal_observation else None
 
     def _out(self, t: torch.Tensor):
         return t.cpu().numpy() if self.output == "numpy" else t
@@ -377,9 +381,14 @@ class TorchDriveVecEnv:
 
     def step_wait(self):
         a = torch.as_tensor(self._actions, dtype=torch.float32)
-        _, rew, term, trunc, info = self.engine.step_stacked(a, self._stack, self.n_stack)
+        if self._terminal is not None:
+            _, rew, term, trunc, info = self.engine.step_terminal(a, self._stack, self._terminal, self.n_stack)
+        else:
+            _, rew, term, trunc, info = self.engine.step_stacked(a, self._stack, self.n_stack)
         dones = (term | trunc).bool()
         infos = {k: self._out(info[:, i]) for k, i in INFO_COLUMNS.items()}
+        if self._terminal is not None:
+            infos["terminal_observation"] = self._out(self._terminal)
         infos["terminated"], infos["truncated"] = self._out(term.bool()), self._out(trunc.bool())
         return self._out(self._stack), self._out(rew), self._out(dones), infos
 
