@@ -721,6 +721,10 @@ static int step_impl(tde_handle* h, int32_t phases, const float* actions, uint8_
     if ((phases & TDE_PH_REWARD) && (!reward || !terminated || !truncated || !info))
         return fail(h, TDE_E_INVAL, "tde_step: reward/terminated/truncated/info must be non-null");
     if (phases == TDE_PH_RENDER && !obs) return fail(h, TDE_E_INVAL, "tde_render: obs is null");
+    // the kernels move rows with 128-bit (obs, info) and 64-bit (actions) accesses
+    if (((uintptr_t)obs | (uintptr_t)obs_prev | (uintptr_t)terminal_obs | (uintptr_t)info) & 15)
+        return fail(h, TDE_E_INVAL, "tde_step: obs / terminal_obs / info must be 16-byte aligned");
+    if ((uintptr_t)actions & 7) return fail(h, TDE_E_INVAL, "tde_step: actions must be 8-byte aligned");
     CUDA_TRY(h, cudaSetDevice(h->device));
     StepParams p = make_params(h);
     p.phases = phases; p.actions = actions; p.obs = obs; p.reward = reward; p.terminated = terminated;

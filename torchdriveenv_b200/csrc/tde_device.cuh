@@ -109,7 +109,7 @@ __device__ __forceinline__ void tde_edge_terms(float ax, float ay, float bx, flo
 // Triangle record: 3 float4  [ax ay bx by] [cx cy il_ab il_bc] [il_ca dir_cos dir_sin 0]
 __device__ __forceinline__ float tde_point_tri_dist2(const float4* __restrict__ tri, float px, float py, bool& inside,
                                                      float& dc, float& ds) {
-    float4 t0 = tri[0], t1 = tri[1], t2 = tri[2];
+    float4 t0 = __ldg(tri), t1 = __ldg(tri + 1), t2 = __ldg(tri + 2);
     float d0, d1, d2, c0, c1, c2;
     tde_edge_terms(t0.x, t0.y, t0.z, t0.w, t1.z, px, py, d0, c0);
     tde_edge_terms(t0.z, t0.w, t1.x, t1.y, t1.w, px, py, d1, c1);
@@ -121,7 +121,7 @@ __device__ __forceinline__ float tde_point_tri_dist2(const float4* __restrict__ 
 
 // containment only (same edge functions, same operand order as tde_point_tri_dist2)
 __device__ __forceinline__ bool tde_tri_contains(const float4* __restrict__ tri, float px, float py, float& dc, float& ds) {
-    float4 t0 = tri[0], t1 = tri[1], t2 = tri[2];
+    float4 t0 = __ldg(tri), t1 = __ldg(tri + 1), t2 = __ldg(tri + 2);
     float c0 = (t0.z - t0.x) * (py - t0.y) - (t0.w - t0.y) * (px - t0.x);
     float c1 = (t1.x - t0.z) * (py - t0.w) - (t1.y - t0.w) * (px - t0.z);
     float c2 = (t0.x - t1.x) * (py - t1.y) - (t0.y - t1.y) * (px - t1.x);
@@ -130,7 +130,7 @@ __device__ __forceinline__ bool tde_tri_contains(const float4* __restrict__ tri,
 }
 // min squared distance to the three edges (what tde_point_tri_dist2 returns for a point outside)
 __device__ __forceinline__ float tde_tri_segdist2(const float4* __restrict__ tri, float px, float py) {
-    float4 t0 = tri[0], t1 = tri[1], t2 = tri[2];
+    float4 t0 = __ldg(tri), t1 = __ldg(tri + 1), t2 = __ldg(tri + 2);
     float d0, d1, d2, c;
     tde_edge_terms(t0.x, t0.y, t0.z, t0.w, t1.z, px, py, d0, c);
     tde_edge_terms(t0.z, t0.w, t1.x, t1.y, t1.w, px, py, d1, c);

@@ -275,7 +275,7 @@ __device__ __noinline__ MeshInfr mesh_infractions_warp(const MapDev& M, const Bo
         float fx = floorf((px - M.gx0) * M.inv_cell), fy = floorf((py - M.gy0) * M.inv_cell);
         bool in_grid = fx >= 0.0f && fy >= 0.0f && fx < (float)M.gnx && fy < (float)M.gny;
         rec[k] = make_int2(in_grid ? 0 : -1, in_grid ? TDE_CELL_SAFE : 0);
-        if (mine && in_grid) rec[k] = M.cell_rec[(int)fy * M.gnx + (int)fx];
+        if (mine && in_grid) rec[k] = __ldg(&M.cell_rec[(int)fy * M.gnx + (int)fx]);
         if (!mine) rec[k] = make_int2(0, TDE_CELL_SAFE);
     }
     float sum = 0.0f, dc, ds;
@@ -293,7 +293,7 @@ __device__ __noinline__ MeshInfr mesh_infractions_warp(const MapDev& M, const Bo
             const int nover = rc.y & 0x7fff;
             need = true;
             for (int i = i0; i < i0 + nover; ++i)
-                if (tde_tri_contains(M.tri + 3 * (int)M.cell_items[i], px, py, dc, ds)) { need = false; break; }
+                if (tde_tri_contains(M.tri + 3 * (int)__ldg(&M.cell_items[i]), px, py, dc, ds)) { need = false; break; }
         }
         unsigned nm = __ballot_sync(FULL_MASK, need);
         if (__popc(nm) > 4) {   // many lanes are off the road (scattered boxes): each walks its own candidates
@@ -306,7 +306,7 @@ __device__ __noinline__ MeshInfr mesh_infractions_warp(const MapDev& M, const Bo
                         best = fminf(best, tde_tri_segdist2(M.tri + 3 * t, px, py));
                     }
                 } else {
-                    for (int i = i0; i < i1; ++i) best = fminf(best, tde_tri_segdist2(M.tri + 3 * (int)M.cell_items[i], px, py));
+                    for (int i = i0; i < i1; ++i) best = fminf(best, tde_tri_segdist2(M.tri + 3 * (int)__ldg(&M.cell_items[i]), px, py));
                 }
                 d2 = inside ? 0.0f : best;
             }
@@ -326,7 +326,7 @@ __device__ __noinline__ MeshInfr mesh_infractions_warp(const MapDev& M, const Bo
                 }
                 inside = __any_sync(FULL_MASK, inside);
             } else {
-                for (int i = a0 + lane; i < a1; i += 32) best = fminf(best, tde_tri_segdist2(M.tri + 3 * (int)M.cell_items[i], qx, qy));
+                for (int i = a0 + lane; i < a1; i += 32) best = fminf(best, tde_tri_segdist2(M.tri + 3 * (int)__ldg(&M.cell_items[i]), qx, qy));
             }
             // non-negative binary32 values order like their bit patterns
             const unsigned ub = __reduce_min_sync(FULL_MASK, __float_as_uint(best));
@@ -343,7 +343,7 @@ __device__ __noinline__ MeshInfr mesh_infractions_warp(const MapDev& M, const Bo
         const int i0 = rec[4].x, nover = rec[4].y & 0x7fff;
         // the value is a minimum of non-negative terms: a containing triangle the agent follows (term 0) settles it
         for (int i = i0; i < i0 + nover; ++i)
-            if (tde_tri_contains(M.tri + 3 * (int)M.cell_items[i], b.x, b.y, dc, ds)) {
+            if (tde_tri_contains(M.tri + 3 * (int)__ldg(&M.cell_items[i]), b.x, b.y, dc, ds)) {
                 best = fminf(best, fmaxf(-(b.c * dc + b.s * ds), 0.0f));
                 if (best == 0.0f) break;
             }
@@ -358,7 +358,7 @@ __device__ __noinline__ MeshInfr mesh_infractions_warp(const MapDev& M, const Bo
 __device__ __forceinline__ int light_state_at(const MapDev& M, int step, int phase, int l) {
     if (M.period <= 0 || M.nstop <= 0) return TDE_LIGHT_GREEN;
     int t = (step + phase) % M.period;
-    return M.lights[t * M.nstop + l];
+    return __ldg(&M.lights[t * M.nstop + l]);
 }
 // bit l set = stop line l shows red at this env time (lane l looks its own light up)
 __device__ __forceinline__ unsigned red_lights_mask(const MapDev& M, int step, int phase, int lane) {
@@ -381,7 +381,7 @@ __device__ __noinline__ float tl_violation_warp(const MapDev& M, const Box& b, b
     while (red) {
         const int l = __ffs(red) - 1;
         red &= red - 1;
-        float4 u = M.stop[2 * l], v = M.stop[2 * l + 1];
+        float4 u = __ldg(&M.stop[2 * l]), v = __ldg(&M.stop[2 * l + 1]);
         float dx = u.x - rear.x, dy = u.y - rear.y, R = rr + v.z;
         bool cand = mine && dx * dx + dy * dy <= R * R * 1.001f;
         if (__any_sync(FULL_MASK, cand)) {
@@ -411,15 +411,15 @@ __device__ __forceinline__ void reset_env_warp(const StepParams& p, int e, int l
     float u_pos = tde_u01(tde_rng(p.seed, genv, ep, 1));
     float u_spd = tde_u01(tde_rng(p.seed, genv, ep, 2));
     float z = tde_normal8(tde_rng(p.seed, genv, ep, 3), tde_rng(p.seed, genv, ep, 4));
-    float2 p0 = S.wp[0];
-    float2 p1 = S.W > 1 ? S.wp[1] : p0;
+    float2 p0 = __ldg(&S.wp[0]);
+    float2 p1 = S.W > 1 ? __ldg(&S.wp[1]) : p0;
 #pragma unroll
     for (int h = 0; h < AH; ++h) {
         int a = h * 32 + lane;
         if (a < p.A) {
-            float4 init = S.init[a];
-            if (a >= 1 && S.rep_T > 0 && S.rep_mask[a]) init = S.rep_states[a];
-            float4 attr = S.attr[a];
+            float4 init = __ldg(&S.init[a]);
+            if (a >= 1 && S.rep_T > 0 && __ldg(&S.rep_mask[a])) init = __ldg(&S.rep_states[a]);
+            float4 attr = __ldg(&S.attr[a]);
             attr.w = a < S.nag ? 1.0f : 0.0f;
             if (a == 0) {
                 init.x = p0.x + u_pos * (p1.x - p0.x);
@@ -445,11 +445,33 @@ __device__ __forceinline__ void reset_env_warp(const StepParams& p, int e, int l
     if (lane == 0) { p.ep_return[e] = 0.0f; p.restart[e] = 1; }
 }
 
+// the eight env variables are warp-uniform: lane 0 writes the row as two 128-bit stores
+struct EnvVars { int s, step, target, reached, lphase, episode, m; };
+// BCAST: every lane loads the row itself (one broadcast transaction); otherwise lanes 0..7 load one variable each and
+// shuffle.  Measured (C3): the broadcast is faster in the physics kernel (54.0 vs 54.5 us), the shuffles in the render
+// kernel (135.4 vs 137.6 us).
+template <bool BCAST>
+__device__ __forceinline__ EnvVars load_vars(const StepParams& p, int e, int lane) {
+    EnvVars v;
+    if (BCAST) {
+        const int4* row = reinterpret_cast<const int4*>(p.vars) + (size_t)e * 2;
+        const int4 a = row[0], b = row[1];
+        v.s = a.x; v.step = a.y; v.target = a.z; v.reached = a.w; v.lphase = b.x; v.episode = b.y; v.m = b.z;
+    } else {
+        const int myvar = lane < 8 ? p.vars[(size_t)e * 8 + lane] : 0;
+        v.s = __shfl_sync(FULL_MASK, myvar, 0); v.step = __shfl_sync(FULL_MASK, myvar, 1); v.target = __shfl_sync(FULL_MASK, myvar, 2);
+        v.reached = __shfl_sync(FULL_MASK, myvar, 3); v.lphase = __shfl_sync(FULL_MASK, myvar, 4);
+        v.episode = __shfl_sync(FULL_MASK, myvar, 5); v.m = __shfl_sync(FULL_MASK, myvar, 6);
+    }
+    return v;
+}
 __device__ __forceinline__ void store_vars(const StepParams& p, int e, int lane, int s, int step, int target,
                                            int reached, int lphase, int episode, int m) {
-    int v = lane == 0 ? s : lane == 1 ? step : lane == 2 ? target : lane == 3 ? reached : lane == 4 ? lphase
-          : lane == 5 ? episode : lane == 6 ? m : 0;
-    if (lane < 8) p.vars[(size_t)e * 8 + lane] = v;
+    if (lane == 0) {
+        int4* row = reinterpret_cast<int4*>(p.vars) + (size_t)e * 2;
+        row[0] = make_int4(s, step, target, reached);
+        row[1] = make_int4(lphase, episode, m, 0);
+    }
 }
 
 // ---------------------------------------------------------------- birdview rasteriser
@@ -643,8 +665,8 @@ __device__ __noinline__ int queue_static(const MapDev& M, Cam cam, float reach, 
     int s = 0, n = 0;
     if (lane < nrows) {
         const int* ts = M.tile_start + (ty0 + lane) * M.tnx;
-        s = ts[tx0];
-        n = ts[tx1 + 1] - s;
+        s = __ldg(&ts[tx0]);
+        n = __ldg(&ts[tx1 + 1]) - s;
     }
     int incl = n;
 #pragma unroll
@@ -671,7 +693,7 @@ __device__ __noinline__ int queue_static(const MapDev& M, Cam cam, float reach, 
         const int t = g < M.n_big ? g : s_r + (g - e_r);
         float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
         int cls = TDE_CLS_ROAD;
-        if (valid) { p0 = M.rp[2 * t]; p1 = M.rp[2 * t + 1]; cls = M.rp_cls[t]; }
+                if (valid) { p0 = __ldg(&M.rp[2 * t]); p1 = __ldg(&M.rp[2 * t + 1]); cls = __ldg(&M.rp_cls[t]); }
         float lox = fminf(fminf(p0.x, p0.z), fminf(p1.x, p1.z)), hix = fmaxf(fmaxf(p0.x, p0.z), fmaxf(p1.x, p1.z));
         float loy = fminf(fminf(p0.y, p0.w), fminf(p1.y, p1.w)), hiy = fmaxf(fmaxf(p0.y, p0.w), fmaxf(p1.y, p1.w));
         valid = valid && hix >= cam.ex - reach && lox <= cam.ex + reach && hiy >= cam.ey - reach && loy <= cam.ey + reach;
@@ -705,10 +727,8 @@ __device__ __forceinline__ void render_env(const StepParams& p, const int e, con
     uint4* const cz = reinterpret_cast<uint4*>(ws->cover);
     constexpr int COVER_U4 = (TDE_NUM_CLASSES - 1) * TDE_OBS_H * 8 / 16;  // 320 = 10 per lane
     {
-        int myvar = lane < 8 ? p.vars[(size_t)e * 8 + lane] : 0;
-        const int s = __shfl_sync(FULL_MASK, myvar, 0), step = __shfl_sync(FULL_MASK, myvar, 1);
-        const int target = __shfl_sync(FULL_MASK, myvar, 2), lphase = __shfl_sync(FULL_MASK, myvar, 4);
-        const int m = __shfl_sync(FULL_MASK, myvar, 6);
+        const EnvVars ev = load_vars<false>(p, e, lane);
+        const int s = ev.s, step = ev.step, target = ev.target, lphase = ev.lphase, m = ev.m;
         const MapDev& M = p.maps[m];
         const ScenDev& S = p.scens[s];
         Box mybox[AH];
@@ -771,12 +791,12 @@ __device__ __forceinline__ void render_env(const StepParams& p, const int e, con
             int cls = a == 0 ? (kind ? TDE_CLS_EGO_DIRECTION : TDE_CLS_EGO) : (kind ? TDE_CLS_DIRECTION : TDE_CLS_VEHICLE);
             if (valid && j < 0) {
                 if (i < M.nstop) {
-                    const float4 u = M.stop[2 * i], v = M.stop[2 * i + 1];
+                    const float4 u = __ldg(&M.stop[2 * i]), v = __ldg(&M.stop[2 * i + 1]);
                     bx = u.x; by = u.y; hl = u.z; hw = u.w; bc = v.x; bs = v.y;
                     kind = 0;
                     cls = TDE_CLS_TL_GREEN + light_state_at(M, step, lphase, i);
                 } else {
-                    const float2 w = S.wp[target];
+                    const float2 w = __ldg(&S.wp[target]);
                     bx = w.x; by = w.y; bc = 1.0f; bs = 0.0f; hl = 2.0f; hw = 2.0f;
                     kind = 2;
                     cls = TDE_CLS_WAYPOINT;
@@ -951,14 +971,11 @@ __global__ void __launch_bounds__(256) tde_copy_rows_kernel(const uint8_t* __res
 // offroad / red-light / wrong-way against the lane mesh, reward, termination, truncation, info,
 // waypoint progress, episode statistics and (optionally) the in-kernel auto-reset.
 template <int AH>
-__device__ __forceinline__ void physics_env(const StepParams& p, const int e, const int lane, SatScratch* ws, double& st_acc) {
+__device__ __forceinline__ void physics_env(const StepParams& p, const int e, const int lane, SatScratch* ws, double& st_acc, int& n_steps) {
     const tde_config& c = p.cfg;
     {
-        int myvar = lane < 8 ? p.vars[(size_t)e * 8 + lane] : 0;
-        int s = __shfl_sync(FULL_MASK, myvar, 0), step = __shfl_sync(FULL_MASK, myvar, 1);
-        int target = __shfl_sync(FULL_MASK, myvar, 2), reached = __shfl_sync(FULL_MASK, myvar, 3);
-        int lphase = __shfl_sync(FULL_MASK, myvar, 4), episode = __shfl_sync(FULL_MASK, myvar, 5);
-        int m = __shfl_sync(FULL_MASK, myvar, 6);
+        const EnvVars ev = load_vars<true>(p, e, lane);
+        int s = ev.s, step = ev.step, target = ev.target, reached = ev.reached, lphase = ev.lphase, episode = ev.episode, m = ev.m;
         float4 st[AH], at[AH];
 #pragma unroll
         for (int h = 0; h < AH; ++h) {
@@ -973,14 +990,15 @@ __device__ __forceinline__ void physics_env(const StepParams& p, const int e, co
         if (p.phases & TDE_PH_KINEMATICS) {
             const ScenDev& S = p.scens[s];
             int t = step + 1;
-            float act_a = p.actions[2 * (size_t)e], act_b = p.actions[2 * (size_t)e + 1];
+            const float2 act = reinterpret_cast<const float2*>(p.actions)[e];
+            const float act_a = act.x, act_b = act.y;
 #pragma unroll
             for (int h = 0; h < AH; ++h) {
                 int a = h * 32 + lane;
                 if (a < p.A && at[h].w != 0.0f) {
-                    bool replay = a != 0 && t < S.rep_T && S.rep_mask[(size_t)t * p.A + a];
+                    bool replay = a != 0 && t < S.rep_T && __ldg(&S.rep_mask[(size_t)t * p.A + a]);
                     if (replay) {
-                        st[h] = S.rep_states[(size_t)t * p.A + a];
+                        st[h] = __ldg(&S.rep_states[(size_t)t * p.A + a]);
                     } else {
                         st[h] = tde_bicycle(st[h], a == 0 ? act_a : 0.0f, a == 0 ? act_b : 0.0f, at[h].z, c.dt);
                     }
@@ -1034,7 +1052,7 @@ __device__ __forceinline__ void physics_env(const StepParams& p, const int e, co
             float psi_reward = (1.0f - cd) * (-c.heading_penalty);                   // :403
             bool hit = false;
             if (target < S.W) {                                                      // :391-394
-                float2 w = S.wp[target];
+                float2 w = __ldg(&S.wp[target]);
                 float tx = x - w.x, ty = y - w.y;
                 hit = sqrtf(tx * tx + ty * ty) < c.reach_radius;
             }
@@ -1045,50 +1063,37 @@ __device__ __forceinline__ void physics_env(const StepParams& p, const int e, co
             bool trunc = step >= c.max_environment_steps;                            // :134-135
             float ep_ret = p.ep_return[e] + r;
             bool done = term || trunc;
-            // info row (get_info :419-437): lane k writes column k
-            float col = 0.0f;
-            switch (lane) {
-                case TDE_INFO_OFFROAD: col = i_off; break;
-                case TDE_INFO_COLLISION: col = i_col; break;
-                case TDE_INFO_TL_VIOLATION: col = i_tl; break;
-                case TDE_INFO_IS_SUCCESS: col = trunc ? 1.0f : 0.0f; break;
-                case TDE_INFO_REACHED_WAYPOINT_NUM: col = (float)reached; break;
-                case TDE_INFO_PSI_SMOOTHNESS: col = fabsf((lpsi - psi) / c.dt); break;
-                case TDE_INFO_PSI_REWARD: col = psi_reward; break;
-                case TDE_INFO_DIST_REWARD: col = dist_reward; break;
-                case TDE_INFO_SPEED_SMOOTHNESS: col = fabsf((lv - spd) / c.dt); break;
-                case TDE_INFO_WRONG_WAY: col = i_ww; break;
-                case TDE_INFO_EPISODE_RETURN: col = ep_ret; break;
-                case TDE_INFO_EPISODE_LENGTH: col = (float)step; break;
-                case TDE_INFO_SCENARIO: col = (float)s; break;
-                case TDE_INFO_DID_RESET: col = (done && c.auto_reset) ? 1.0f : 0.0f; break;
-                default: break;
-            }
-            if (lane < TDE_INFO_STRIDE) p.info[(size_t)e * TDE_INFO_STRIDE + lane] = col;
+            // info row (get_info :419-437): every value is warp-uniform, lane 0 writes the row as four 128-bit stores
+            const float did_reset = (done && c.auto_reset) ? 1.0f : 0.0f;
             if (lane == 0) {
+                float4* row = reinterpret_cast<float4*>(p.info + (size_t)e * TDE_INFO_STRIDE);
+                static_assert(TDE_INFO_OFFROAD == 0 && TDE_INFO_COLLISION == 1 && TDE_INFO_TL_VIOLATION == 2 && TDE_INFO_IS_SUCCESS == 3, "info layout");
+                static_assert(TDE_INFO_REACHED_WAYPOINT_NUM == 4 && TDE_INFO_PSI_SMOOTHNESS == 5 && TDE_INFO_PSI_REWARD == 6 && TDE_INFO_DIST_REWARD == 7, "info layout");
+                static_assert(TDE_INFO_SPEED_SMOOTHNESS == 8 && TDE_INFO_WRONG_WAY == 9 && TDE_INFO_EPISODE_RETURN == 10 && TDE_INFO_EPISODE_LENGTH == 11, "info layout");
+                static_assert(TDE_INFO_SCENARIO == 12 && TDE_INFO_DID_RESET == 13 && TDE_INFO_STRIDE == 16, "info layout");
+                row[0] = make_float4(i_off, i_col, i_tl, trunc ? 1.0f : 0.0f);
+                row[1] = make_float4((float)reached, fabsf((lpsi - psi) / c.dt), psi_reward, dist_reward);
+                row[2] = make_float4(fabsf((lv - spd) / c.dt), i_ww, ep_ret, (float)step);
+                row[3] = make_float4((float)s, did_reset, 0.0f, 0.0f);
                 p.reward[e] = r;
                 p.terminated[e] = term ? 1 : 0;
                 p.truncated[e] = trunc ? 1 : 0;
                 p.ep_return[e] = ep_ret;
             }
             if (hit) target += 1;                                                    // :378-383
-            // episode statistics: lane k owns statistic k
-            double add = 0.0;
-            if (lane == TDE_STAT_STEPS) add = 1.0;
+            // episode statistics: lane k owns statistic k; steps are counted as an integer and added at the end
+            n_steps += 1;
             if (done) {
-                switch (lane) {
-                    case TDE_STAT_EPISODES: add = 1.0; break;
-                    case TDE_STAT_RETURN_SUM: add = (double)ep_ret; break;
-                    case TDE_STAT_LENGTH_SUM: add = (double)step; break;
-                    case TDE_STAT_OFFROAD: add = i_off > 0.0f ? 1.0 : 0.0; break;
-                    case TDE_STAT_COLLISION: add = i_col > 0.0f ? 1.0 : 0.0; break;
-                    case TDE_STAT_TL_VIOLATION: add = i_tl > 0.0f ? 1.0 : 0.0; break;
-                    case TDE_STAT_SUCCESS: add = trunc ? 1.0 : 0.0; break;
-                    case TDE_STAT_REACHED_WAYPOINTS: add = (double)reached; break;
-                    default: break;
-                }
+                const double add = lane == TDE_STAT_EPISODES ? 1.0
+                                 : lane == TDE_STAT_RETURN_SUM ? (double)ep_ret
+                                 : lane == TDE_STAT_LENGTH_SUM ? (double)step
+                                 : lane == TDE_STAT_OFFROAD ? (i_off > 0.0f ? 1.0 : 0.0)
+                                 : lane == TDE_STAT_COLLISION ? (i_col > 0.0f ? 1.0 : 0.0)
+                                 : lane == TDE_STAT_TL_VIOLATION ? (i_tl > 0.0f ? 1.0 : 0.0)
+                                 : lane == TDE_STAT_SUCCESS ? (trunc ? 1.0 : 0.0)
+                                 : lane == TDE_STAT_REACHED_WAYPOINTS ? (double)reached : 0.0;
+                st_acc += add;
             }
-            st_acc += add;
             if (done && c.auto_reset) {
                 __syncwarp();
                 if (p.done_mask != nullptr) { if (lane == 0) p.done_mask[e] = 1; }   // reset deferred until the terminal frame is out
@@ -1107,12 +1112,14 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, TDE_PHYS_BLOCKS_PER_
     SatScratch* ws = &scratch[warp];
     const int warps_total = gridDim.x * TDE_WARPS_PER_BLOCK;
     double st_acc = 0.0;  // lane k accumulates statistic k
+    int n_steps = 0;      // env steps taken by this warp
 #pragma unroll 1
     for (int e = p.e_begin + blockIdx.x * TDE_WARPS_PER_BLOCK + warp; e < p.e_end; e += warps_total) {
         TDE_TRACE_MARK(e, 2);
-        physics_env<AH>(p, e, lane, ws, st_acc);
+        physics_env<AH>(p, e, lane, ws, st_acc, n_steps);
         TDE_TRACE_MARK(e, 3);
     }
+    if (lane == TDE_STAT_STEPS) st_acc += (double)n_steps;
     if ((p.phases & TDE_PH_REWARD) && lane < TDE_NUM_STATS && st_acc != 0.0) atomicAdd(&p.stats[lane], st_acc);
 }
 
@@ -1122,9 +1129,8 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32) tde_reset_kernel(con
     const int warps_total = gridDim.x * TDE_WARPS_PER_BLOCK;
     for (int e = blockIdx.x * TDE_WARPS_PER_BLOCK + warp; e < p.E; e += warps_total) {
         if (p.reset_mask != nullptr && p.reset_mask[e] == 0) continue;
-        int myvar = lane < 8 ? p.vars[(size_t)e * 8 + lane] : 0;
         int s, step, target, reached, lphase, m;
-        int episode = __shfl_sync(FULL_MASK, myvar, 5);
+        int episode = load_vars<true>(p, e, lane).episode;
         float4 st[AH], at[AH];
         reset_env_warp<AH>(p, e, lane, s, step, target, reached, lphase, episode, m, st, at);
         store_vars(p, e, lane, s, step, target, reached, lphase, episode, m);
