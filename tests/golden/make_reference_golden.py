@@ -1,0 +1,281 @@
+"""Golden vectors produced by the REFERENCE'S OWN CODE for the rows of the hot path whose arithmetic lives
+in the reference checkout itself: step ordering, reward, waypoint progress,
+termination, truncation, info, spaces and the SingleAgentWrapper output conventions.
+
+How: `/root/reference/torchdriveenv/gym_env.py` is imported UNMODIFIED.  Its third-party imports that are
+absent offline (gymnasium, invertedai, torchdrivesim) are satisfied by name-only stand-ins, and the one
+function that glues the env to torchdrivesim (`build_simulator`, gym_env.py:179-300) is replaced by a
+factory that returns an object with the SimulatorInterface-level call surface (step,
+get_state, compute_offroad, compute_collision, compute_traffic_lights_violations, render_egocentric,
+to, copy) whose state comes from this repo's CPU oracle.  Everything above that surface is the real
+reference: `WaypointSuiteEnv.__init__/reset/set_start_pos/step/check_reach_target/get_reward/
+is_terminated/is_truncated/get_info`, `GymEnv.step/get_obs`, `SingleAgentWrapper.step/transform_out`.
+
+What it pins: given the same simulator states and infraction values, the reference's Python decides the
+reward, flags, info and waypoint progress; the fixtures freeze those decisions, and tests compare the
+oracle's (CPU) and the CUDA path's (GPU) own outputs for the same episode against them.  What it does
+NOT pin: kinematics, collision, offroad, lights and the birdview themselves (torchdrivesim, absent).
+
+Needs `/root/reference` (this container only; the fixtures travel).  Run from the repo root:
+    python tests/golden/make_reference_golden.py
+"""
+import importlib
+import json
+import math
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+REFERENCE = os.environ.get("TDE_REFERENCE", "/root/reference")
+
+INFO_KEYS = ["offroad", "collision", "traffic_light_violation", "is_success", "reached_waypoint_num",
+             "psi_smoothness", "psi_reward", "dist_reward", "speed_smoothness"]
+
+
+# ----------------------------------------------------------------------------- name-only stand-ins
+def _install_stand_ins():
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    class Anything:
+        """Accepts any constructor arguments; attribute access yields another Anything."""
+        def __init__(self, *a, **k):
+            self.__dict__.update(k)
+
+        def __getattr__(self, name):
+            if name.startswith("__"):
+                raise AttributeError(name)
+            return Anything()
+
+        def __call__(self, *a, **k):
+            return Anything()
+
+    def cls(name):
+        return type(name, (Anything,), {})
+
+    # gymnasium: the three things gym_env.py touches
+    class Env:
+        metadata = {}
+
+    class Wrapper(Env):
+        def __init__(self, env):
+            self.env = env
+
+        def __getattr__(self, name):
+            if name == "env":
+                raise AttributeError(name)
+            return getattr(self.env, name)
+
+        def reset(self, **kwargs):
+            return self.env.reset(**kwargs)
+
+        def step(self, action):
+            return self.env.step(action)
+
+    class Box:
+        def __init__(self, low, high, shape=None, dtype=np.float32):
+            self.low, self.high, self.dtype = low, high, np.dtype(dtype)
+            self.shape = tuple(shape) if shape is not None else np.shape(low)
+
+    registry = {}
+    gym = mod("gymnasium", Env=Env, Wrapper=Wrapper, register=lambda id, entry_point=None, **k: registry.__setitem__(id, entry_point),
+              registry=registry)
+    gym.spaces = mod("gymnasium.spaces", Box=Box)
+
+    mod("invertedai")
+    mod("invertedai.common", AgentState=cls("AgentState"), Point=cls("Point"), AgentAttributes=cls("AgentAttributes"),
+        RecurrentState=cls("RecurrentState"))
+    mod("torchdrivesim")
+    mod("torchdrivesim.behavior")
+    mod("torchdrivesim.behavior.iai", IAIWrapper=cls("IAIWrapper"))
+    mod("torchdrivesim.goals", WaypointGoal=cls("WaypointGoal"))
+    mod("torchdrivesim.kinematic", KinematicBicycle=cls("KinematicBicycle"))
+    mod("torchdrivesim.rendering", renderer_from_config=Anything())
+    mod("torchdrivesim.rendering.base", RendererConfig=cls("RendererConfig"))
+    mod("torchdrivesim.utils", Resolution=cls("Resolution"))
+    mod("torchdrivesim.lanelet2", find_lanelet_directions=None)
+    mod("torchdrivesim.map", find_map_config=None, traffic_controls_from_map_config=None)
+    mod("torchdrivesim.traffic_lights", current_light_state_tensor_from_controller=None)
+    mod("torchdrivesim.simulator", TorchDriveConfig=cls("TorchDriveConfig"), SimulatorInterface=cls("SimulatorInterface"),
+        BirdviewRecordingWrapper=cls("BirdviewRecordingWrapper"), Simulator=cls("Simulator"),
+        HomogeneousWrapper=cls("HomogeneousWrapper"), CollisionMetric=type("CollisionMetric", (), {"nograd": "nograd"}))
+
+
+def import_reference():
+    """Imports the reference's gym_env.py; the stand-ins only live in sys.modules while it is being imported
+    (the module keeps the names it bound), so nothing else in the process ever sees them."""
+    before = set(sys.modules)
+    _install_stand_ins()
+    sys.path.insert(0, REFERENCE)
+    try:
+        ref = importlib.import_module("torchdriveenv.gym_env")
+    finally:
+        sys.path.remove(REFERENCE)
+        for name in set(sys.modules) - before:
+            if name.split(".")[0] in ("gymnasium", "invertedai", "torchdrivesim"):
+                del sys.modules[name]
+    return ref
+
+
+# ----------------------------------------------------------------------------- the simulator surface
+class OracleSimulator:
+    """SimulatorInterface-level surface over one env of the CPU oracle, B = A = 1 at the
+    interface (NPCs hidden, as IAIWrapper hides them, gym_env.py:269-271)."""
+
+    def __init__(self, orc):
+        self.orc = orc
+        self.outputs = None      # the oracle's own (reward, terminated, truncated, info row) of the last step
+
+    def step(self, action):
+        a = np.asarray(action.detach().cpu().numpy(), np.float32).reshape(-1)[:2]
+        obs, rew, term, trunc, info = self.orc.step(a[None])
+        self.outputs = (obs[0].copy(), float(rew[0]), bool(term[0]), bool(trunc[0]), info[0].copy())
+
+    def get_state(self):
+        return torch.from_numpy(self.orc.state[0:1, 0:1].copy())                      # 1 x 1 x 4
+
+    def _infr(self, k):
+        return torch.from_numpy(self.orc.infractions[0:1, 0, k].copy()).reshape(1, 1)  # 1 x 1
+
+    def compute_collision(self): return self._infr(0)
+    def compute_offroad(self): return self._infr(1)
+    def compute_traffic_lights_violations(self): return self._infr(2)
+    def compute_wrong_way(self): return self._infr(3)
+
+    def render_egocentric(self):
+        return torch.from_numpy(self.orc.render()[None].astype(np.float32))            # 1 x 1 x 3 x 64 x 64
+
+    def to(self, device): return self
+    def copy(self): return self
+
+
+# ----------------------------------------------------------------------------- cases
+def scenario_sets():
+    from torchdriveenv_b200 import scenarios as S
+    return {
+        "three_way": (lambda: S.three_way(6), 9),
+        "traffic_lights": (lambda: S.traffic_lights(12), 12),
+        "roundabout": (lambda: S.roundabout(8), 8),
+        "validation_mix": (lambda: S.validation_mix(8), 10),
+    }
+
+
+CASES = {
+    # name: (scenario set, env-config overrides, steps, policy, numpy seed)
+    "ref_three_way_default": ("three_way", dict(), 60, "pursuit", 11),
+    "ref_three_way_no_termination": ("three_way", dict(terminated_at_infraction=False, distance_cutoff=0.25), 206, "pursuit", 12),
+    "ref_traffic_lights_pursuit": ("traffic_lights", dict(terminated_at_infraction=False, distance_cutoff=0.25), 206, "pursuit", 13),
+    "ref_roundabout_random": ("roundabout", dict(), 40, "random", 14),
+    "ref_mix_custom_rewards": ("validation_mix", dict(terminated_at_infraction=False, waypoint_bonus=10.0, heading_penalty=5.0,
+                                                      distance_bonus=0.5, distance_cutoff=0.1, max_environment_steps=50), 60, "pursuit", 15),
+    "ref_mix_slow_start": ("validation_mix", dict(terminated_at_infraction=True, distance_cutoff=0.5), 80, "crawl", 16),
+    "ref_three_way_swerve_offroad": ("three_way", dict(), 50, "swerve", 17),
+    "ref_traffic_lights_swerve": ("traffic_lights", dict(distance_cutoff=0.25), 70, "swerve", 18),
+    "ref_traffic_lights_red_run": ("traffic_lights", dict(terminated_at_infraction=True, distance_cutoff=0.25), 206, "pursuit", 19),
+    "ref_three_way_oncoming": ("three_way", dict(), 120, "oncoming", 20),
+}
+
+
+def oracle_config(ref_cfg, A):
+    """EnvConfig (the reference's dataclass instance) -> tde_config, through the product's own mapping."""
+    from torchdriveenv_b200 import gym_env as G
+    from torchdriveenv_b200._capi import default_config
+    mine = G.EnvConfig(**{k: getattr(ref_cfg, k) for k in ("max_environment_steps", "waypoint_bonus", "heading_penalty", "distance_bonus",
+                                                          "distance_cutoff", "terminated_at_infraction")})
+    return default_config(num_envs=1, max_agents=A, **G.engine_config(mine, auto_reset=0))
+
+
+def run_case(ref, name):
+    from oracle import oracle as O
+    set_name, overrides, steps, policy, seed = CASES[name]
+    builder, A = scenario_sets()[set_name]
+    ss = builder()
+    packed = ss.pack(A)
+    cfg = ref.EnvConfig(seed=seed, **overrides)
+    data = ref.WaypointSuite(locations=[f"Town{k:02d}" for k in range(len(ss.scenarios))],
+                             waypoint_suite=[np.asarray(s.waypoints, np.float64).tolist() for s in ss.scenarios],
+                             car_sequence_suite=[None] * len(ss.scenarios), scenarios=[None] * len(ss.scenarios))
+    made = {}
+
+    # the glue to torchdrivesim, replaced (see the module docstring)
+    ref.find_map_config = lambda map_name: types.SimpleNamespace(name=map_name, lanelet_map=int(map_name[-2:]))
+    ref.find_lanelet_directions = lambda lanelet_map, x, y: [float(ss.scenarios[lanelet_map].start_heading)]
+
+    def build_simulator(cfg, map_cfg, device, ego_state, scenario=None, car_sequences=None, waypointseq=None):
+        k = map_cfg.lanelet_map
+        orc = O.OracleEnvSet(oracle_config(cfg, A), packed)
+        orc.set_env_scenario_range([k], [k + 1])
+        orc.reset(seed=seed)
+        start = np.asarray(ego_state, np.float32)
+        orc.state[0, 0, :] = start
+        made.update(orc=orc, scenario=k, start=start.copy(), waypointseq=waypointseq)
+        return OracleSimulator(orc)
+    ref.build_simulator = build_simulator
+
+    env = ref.SingleAgentWrapper(ref.WaypointSuiteEnv(cfg=cfg, data=data))
+    obs, _ = env.reset()
+    assert obs.shape == (3, 64, 64) and obs.dtype == np.uint8
+    assert env.action_space.shape == (2,) and env.observation_space.shape == (3, 64, 64)
+    rng = np.random.default_rng(seed)
+    out = dict(actions=[], reward=[], terminated=[], truncated=[], info=[], states=[], target_idx=[], orc_reward=[], orc_flags=[], orc_info=[])
+    types_seen = {}
+    for t in range(steps):
+        sim = env.env.simulator
+        x, y, psi, v = sim.orc.state[0, 0]
+        tgt = env.env.current_target
+        if policy == "random" or tgt is None:
+            a = np.array([rng.uniform(-1, 1), rng.uniform(-0.3, 0.3)], np.float32)
+        elif policy == "swerve":     # straight for a second, then a constant turn: leaves the road
+            a = np.array([1.0, 0.0 if t < 10 else (0.12 if seed % 2 else -0.12)], np.float32)
+        elif policy == "oncoming":   # drift into the oncoming lane (left-handed map: towards the lane beside the ego's)
+            a = np.array([0.5, 0.0 if (t < 5 or t > 16) else (0.1 if t < 11 else -0.1)], np.float32)
+        else:
+            err = math.atan2(tgt[1] - y, tgt[0] - x) - psi
+            err = (err + math.pi) % (2 * math.pi) - math.pi
+            v_want = 0.6 if policy == "crawl" else 8.0
+            a = np.array([np.clip(0.8 * (v_want - v), -1, 1), np.clip(0.35 * err + rng.normal(0, 0.02), -0.3, 0.3)], np.float32)
+        obs, reward, terminated, truncated, info = env.step(a)
+        o_obs, o_rew, o_term, o_trunc, o_info = sim.outputs
+        assert np.array_equal(obs, o_obs)
+        types_seen = dict(obs=[str(obs.dtype), list(obs.shape)], reward=type(reward).__name__, terminated=type(terminated).__name__,
+                          truncated=type(truncated).__name__,
+                          info={k: (type(val).__name__ if not torch.is_tensor(val) else f"tensor{list(val.shape)}") for k, val in info.items()})
+        out["actions"].append(a)
+        out["reward"].append(reward); out["terminated"].append(terminated); out["truncated"].append(truncated)
+        out["info"].append([float(info[k]) for k in INFO_KEYS])
+        out["states"].append(sim.orc.state[0, 0].copy())
+        out["target_idx"].append(env.env.current_target_idx)
+        out["orc_reward"].append(o_rew); out["orc_flags"].append([o_term, o_trunc]); out["orc_info"].append(o_info)
+    res = dict(actions=np.asarray(out["actions"], np.float32), reward=np.asarray(out["reward"], np.float64),
+               terminated=np.asarray(out["terminated"], np.uint8), truncated=np.asarray(out["truncated"], np.uint8),
+               info=np.asarray(out["info"], np.float64), states=np.asarray(out["states"], np.float32),
+               target_idx=np.asarray(out["target_idx"], np.int32), start_state=made["start"], scenario=np.int32(made["scenario"]),
+               seed=np.int64(seed), max_agents=np.int32(A), scenario_set=np.str_(set_name),
+               env_config=np.str_(json.dumps(overrides)), info_keys=np.str_(json.dumps(INFO_KEYS)), types=np.str_(json.dumps(types_seen)))
+    # the comparison itself (also what tests/test_reference_golden.py repeats from the frozen vectors)
+    orc_info = np.asarray(out["orc_info"], np.float64)
+    report = dict(reward_max_abs=float(np.max(np.abs(res["reward"] - np.asarray(out["orc_reward"])))),
+                  flags_equal=bool(np.array_equal(np.stack([res["terminated"], res["truncated"]], 1), np.asarray(out["orc_flags"], np.uint8))),
+                  info_max_abs=float(np.max(np.abs(res["info"] - orc_info[:, :len(INFO_KEYS)]))),
+                  waypoints_reached=int(res["info"][-1, 4]), terminated_steps=int(res["terminated"].sum()),
+                  offroad_steps=int((res["info"][:, 0] > 0).sum()), collision_steps=int((res["info"][:, 1] > 0).sum()),
+                  red_light_steps=int((res["info"][:, 2] > 0).sum()),
+                  truncated_steps=int(res["truncated"].sum()))
+    return res, report
+
+
+if __name__ == "__main__":
+    ref = import_reference()
+    here = os.path.dirname(os.path.abspath(__file__))
+    for name in CASES:
+        res, report = run_case(ref, name)
+        np.savez_compressed(os.path.join(here, name + ".npz"), **res)
+        print(name, report)
