@@ -624,6 +624,136 @@ void orc_render_env(orc_env_set* o, int e, uint8_t* obs /* 3*64*64 */, uint8_t* 
     if (cls_out) memcpy(cls_out, cls_img, sizeof(cls_img));
 }
 
+/* ------------------------------------------------------------------ recording view
+
+   BirdviewRecordingWrapper(simulator, res=Resolution(video_res, video_res), fov=video_fov) gym_env.py:52-53,
+   :295-297 [EXT-RECALLED]: a W x H frame of ONE env from a free camera (centre, heading, field of view in
+   metres across the width).  Same primitives, classes and fill rule as the observation (raw triangles, no
+   quad merging), but the snapped coordinates are kept in a wider range (+-2^20 sixteenths of a pixel, 64-bit
+   edge functions), so any resolution up to 4096 and any zoom can be drawn. */
+#define VIEW_SNAP_MAX 1048575.0f
+typedef struct { float ex, ey, ce, se, ppm, ppmy; int W, H; } view_cam;
+
+static int view_make_prim(const view_cam* cam, const float* wx, const float* wy, int n, int cls, orc_prim* p) {
+    float minx = INFINITY, maxx = -INFINITY, miny = INFINITY, maxy = -INFINITY;
+    float fx[4], fy[4];
+    for (int k = 0; k < n; ++k) {
+        float dx = wx[k] - cam->ex, dy = wy[k] - cam->ey;
+        float cx = dx * cam->ce + dy * cam->se;
+        float cy = dy * cam->ce - dx * cam->se;
+        fx[k] = cx * cam->ppm + 0.5f * (float)cam->W;
+        fy[k] = cy * cam->ppmy + 0.5f * (float)cam->H;
+        minx = fminf(minx, fx[k]); maxx = fmaxf(maxx, fx[k]);
+        miny = fminf(miny, fy[k]); maxy = fmaxf(maxy, fy[k]);
+    }
+    if (!(maxx >= -1.0f && minx <= (float)cam->W + 1.0f && maxy >= -1.0f && miny <= (float)cam->H + 1.0f)) return 0;
+    for (int k = 0; k < n; ++k) {
+        float rx = rintf(fx[k] * 16.0f), ry = rintf(fy[k] * 16.0f);
+        rx = fminf(fmaxf(rx, -VIEW_SNAP_MAX), VIEW_SNAP_MAX);
+        ry = fminf(fmaxf(ry, -VIEW_SNAP_MAX), VIEW_SNAP_MAX);
+        p->x[k] = (int32_t)rx; p->y[k] = (int32_t)ry;
+    }
+    p->n = n; p->cls = cls;
+    return 1;
+}
+
+static void view_paint_prim(const orc_prim* p, uint8_t* cls_img, int W, int H) {
+    int n = p->n;
+    int64_t area2 = 0;
+    for (int k = 0; k < n; ++k) {
+        int k1 = (k + 1) % n;
+        area2 += (int64_t)p->x[k] * p->y[k1] - (int64_t)p->x[k1] * p->y[k];
+    }
+    if (area2 == 0) return;
+    int64_t X[4], Y[4];
+    for (int k = 0; k < n; ++k) {
+        int src = area2 > 0 ? k : (n - 1 - k);
+        X[k] = p->x[src]; Y[k] = p->y[src];
+    }
+    int64_t xmin = X[0], xmax = X[0], ymin = Y[0], ymax = Y[0];
+    for (int k = 1; k < n; ++k) {
+        if (X[k] < xmin) xmin = X[k];
+        if (X[k] > xmax) xmax = X[k];
+        if (Y[k] < ymin) ymin = Y[k];
+        if (Y[k] > ymax) ymax = Y[k];
+    }
+    int64_t i0 = (xmin - 8) >= 0 ? (xmin - 8 + 15) / 16 : 0, i1 = (xmax - 8) >= 0 ? (xmax - 8) / 16 : -1;
+    int64_t j0 = (ymin - 8) >= 0 ? (ymin - 8 + 15) / 16 : 0, j1 = (ymax - 8) >= 0 ? (ymax - 8) / 16 : -1;
+    if (i1 > W - 1) i1 = W - 1;
+    if (j1 > H - 1) j1 = H - 1;
+    for (int64_t j = j0; j <= j1; ++j)
+        for (int64_t i = i0; i <= i1; ++i) {
+            int64_t px = 16 * i + 8, py = 16 * j + 8;
+            int in = 1;
+            for (int k = 0; k < n && in; ++k) {
+                int k1 = (k + 1) % n;
+                int64_t dx = X[k1] - X[k], dy = Y[k1] - Y[k];
+                if (dx == 0 && dy == 0) continue;
+                int64_t E = dx * (py - Y[k]) - dy * (px - X[k]);
+                int incl = (dy < 0) || (dy == 0 && dx > 0);
+                if (E < 0 || (E == 0 && !incl)) in = 0;
+            }
+            if (in && p->cls > cls_img[j * W + i]) cls_img[j * W + i] = (uint8_t)p->cls;
+        }
+}
+
+/* out: 3*H*W uint8 (planar RGB).  Returns 0, or -1 for a bad argument. */
+int orc_render_view(orc_env_set* o, int e, float cam_x, float cam_y, float cam_psi, float fov, int W, int H, uint8_t* out) {
+    if (e < 0 || e >= o->E || W < 1 || H < 1 || W > 4096 || H > 4096 || !(fov > 0.0f) || !out) return -1;
+    int A = o->A;
+    const int32_t* v = o->vars + 8 * e;
+    int s = v[0], m = v[6];
+    const float* st = o->state + (size_t)e * A * 4;
+    const float* at = o->attr + (size_t)e * A * 4;
+    uint8_t* cls_img = (uint8_t*)calloc((size_t)W * H, 1);
+    view_cam cam;
+    cam.ex = cam_x; cam.ey = cam_y; cam.W = W; cam.H = H;
+    orc_sincosf(cam_psi, &cam.se, &cam.ce);
+    cam.ppm = (float)W / fov;
+    cam.ppmy = o->cfg.left_handed_coordinates ? cam.ppm : -cam.ppm;
+    orc_prim p;
+    float wx[4], wy[4];
+    for (int t = o->tri_off[m]; t < o->tri_off[m + 1]; ++t) {
+        const float* tr = o->road_tris + 8 * (size_t)t;
+        wx[0] = tr[0]; wy[0] = tr[1]; wx[1] = tr[2]; wy[1] = tr[3]; wx[2] = tr[4]; wy[2] = tr[5];
+        if (view_make_prim(&cam, wx, wy, 3, TDE_CLS_ROAD, &p)) view_paint_prim(&p, cls_img, W, H);
+    }
+    for (int t = o->mark_off[m]; t < o->mark_off[m + 1]; ++t) {
+        const float* tr = o->mark_tris + 6 * (size_t)t;
+        wx[0] = tr[0]; wy[0] = tr[1]; wx[1] = tr[2]; wy[1] = tr[3]; wx[2] = tr[4]; wy[2] = tr[5];
+        if (view_make_prim(&cam, wx, wy, 3, TDE_CLS_LANE_MARKING, &p)) view_paint_prim(&p, cls_img, W, H);
+    }
+    int L = o->stop_off[m + 1] - o->stop_off[m];
+    for (int l = 0; l < L; ++l) {
+        const float* sl = o->stoplines + 5 * ((size_t)o->stop_off[m] + l);
+        orc_box sb = make_box(sl[0], sl[1], sl[4], sl[2], sl[3]);
+        box_world_quad(&sb, wx, wy);
+        int ls = light_state(o, m, v[1], v[4], l);
+        int cls = ls == TDE_LIGHT_RED ? TDE_CLS_TL_RED : (ls == TDE_LIGHT_YELLOW ? TDE_CLS_TL_YELLOW : TDE_CLS_TL_GREEN);
+        if (view_make_prim(&cam, wx, wy, 4, cls, &p)) view_paint_prim(&p, cls_img, W, H);
+    }
+    int NW = o->wp_off[s + 1] - o->wp_off[s];
+    if (v[2] < NW) {
+        const float* wp = o->waypoints + 2 * ((size_t)o->wp_off[s] + v[2]);
+        float r = 2.0f;
+        wx[0] = wp[0] + r; wy[0] = wp[1]; wx[1] = wp[0]; wy[1] = wp[1] + r;
+        wx[2] = wp[0] - r; wy[2] = wp[1]; wx[3] = wp[0]; wy[3] = wp[1] - r;
+        if (view_make_prim(&cam, wx, wy, 4, TDE_CLS_WAYPOINT, &p)) view_paint_prim(&p, cls_img, W, H);
+    }
+    for (int a = 0; a < A; ++a) {
+        if (at[4 * a + 3] == 0.0f) continue;
+        orc_box b = make_box(st[4 * a], st[4 * a + 1], st[4 * a + 2], at[4 * a], at[4 * a + 1]);
+        box_world_quad(&b, wx, wy);
+        if (view_make_prim(&cam, wx, wy, 4, a == 0 ? TDE_CLS_EGO : TDE_CLS_VEHICLE, &p)) view_paint_prim(&p, cls_img, W, H);
+        box_world_dirtri(&b, wx, wy);
+        if (view_make_prim(&cam, wx, wy, 3, a == 0 ? TDE_CLS_EGO_DIRECTION : TDE_CLS_DIRECTION, &p)) view_paint_prim(&p, cls_img, W, H);
+    }
+    for (int ch = 0; ch < 3; ++ch)
+        for (size_t k = 0; k < (size_t)W * H; ++k) out[(size_t)ch * W * H + k] = o->palette[3 * cls_img[k] + ch];
+    free(cls_img);
+    return 0;
+}
+
 void orc_render(orc_env_set* o, uint8_t* obs) {
 #pragma omp parallel for schedule(dynamic, 8)
     for (int e = 0; e < o->E; ++e) orc_render_env(o, e, obs + (size_t)e * 3 * TDE_OBS_H * TDE_OBS_W, NULL);

@@ -298,6 +298,25 @@ def test_host_buffer_entry_point(oracle):
         assert np.array_equal(obs, oobs) and np.array_equal(r, orr) and np.array_equal(te, ote) and np.array_equal(info, oinfo)
 
 
+def test_host_buffer_entry_point_chunked_pipeline():
+    """From 4,096 envs on tde_step_host steps the envs in chunks and sends each chunk's frames back while the
+    next chunk is computed: same results as the one-launch device-resident step, statistics included."""
+    E, A = 4100, 8          # not a multiple of the chunk count
+    ss = S.traffic_lights(A)
+    eng = _engine(ss, E, A, auto_reset=1)
+    ref = _engine(ss, E, A, auto_reset=1)
+    eng.reset(seed=21); ref.reset(seed=21)
+    rng = np.random.default_rng(21)
+    for _ in range(5):
+        a = np.stack([rng.uniform(-1, 1, E), rng.uniform(-0.3, 0.3, E)], 1).astype(np.float32)
+        obs, r, te, tr, info = eng.step_host(a)
+        robs, rr, rte, rtr, rinfo = ref.step(torch.from_numpy(a).cuda())
+        assert np.array_equal(obs, robs.cpu().numpy()) and np.array_equal(r, rr.cpu().numpy())
+        assert np.array_equal(te, rte.cpu().numpy()) and np.array_equal(tr, rtr.cpu().numpy()) and np.array_equal(info, rinfo.cpu().numpy())
+        assert torch.equal(eng.get_state(), ref.get_state()) and torch.equal(eng.get_env_vars(), ref.get_env_vars())
+    np.testing.assert_allclose(eng.episode_stats(), ref.episode_stats(), rtol=1e-12)
+
+
 def test_cuda_graph_capture_of_the_step():
     """tde_step only enqueues on the caller's stream, so a step can be captured and replayed."""
     E, A = 256, 16

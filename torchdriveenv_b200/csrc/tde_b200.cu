@@ -44,6 +44,8 @@ struct tde_handle {
     // device staging for tde_step_host
     float* h_actions = nullptr; uint8_t* h_obs = nullptr; float* h_reward = nullptr;
     uint8_t *h_term = nullptr, *h_trunc = nullptr; float* h_info = nullptr;
+    cudaStream_t copy_stream = nullptr;          // tde_step_host: observation chunks go back while later chunks are computed
+    cudaEvent_t chunk_done[8] = {}, copies_done = nullptr;
     std::string err;
 };
 
@@ -513,6 +515,9 @@ extern "C" int tde_destroy(tde_handle* h) {
     free_scenarios(h);
     cudaFree(h->state); cudaFree(h->attr); cudaFree(h->infr); cudaFree(h->vars); cudaFree(h->ep_return);
     cudaFree(h->scen_lo); cudaFree(h->scen_hi); cudaFree(h->stats); cudaFree(h->restart); cudaFree(h->tickets); cudaFree(h->done_mask);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (cudaEvent_t ev : h->chunk_done) if (ev) cudaEventDestroy(ev);
+    if (h->copies_done) cudaEventDestroy(h->copies_done);
     cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_reward); cudaFree(h->h_term); cudaFree(h->h_trunc); cudaFree(h->h_info);
     delete h;
     return TDE_OK;
@@ -712,7 +717,7 @@ extern "C" int tde_reset(tde_handle* h, const uint8_t* env_mask_dev, uint64_t se
 
 static int step_impl(tde_handle* h, int32_t phases, const float* actions, uint8_t* obs, int32_t n_stack, float* reward,
                      uint8_t* terminated, uint8_t* truncated, float* info, void* stream, const uint8_t* obs_prev = nullptr,
-                     uint8_t* terminal_obs = nullptr) {
+                     uint8_t* terminal_obs = nullptr, int e_begin = 0, int e_end = -1) {
     if (!h) return TDE_E_INVAL;
     if (n_stack < 1 || n_stack > 8) return fail(h, TDE_E_INVAL, "n_stack must be in 1..8");
     if (!h->uploaded || !h->was_reset) return fail(h, TDE_E_STATE, "tde_step: upload scenarios and reset first");
@@ -730,11 +735,12 @@ static int step_impl(tde_handle* h, int32_t phases, const float* actions, uint8_
     p.phases = phases; p.actions = actions; p.obs = obs; p.reward = reward; p.terminated = terminated;
     p.truncated = truncated; p.info = info; p.n_stack = n_stack;
     p.obs_prev = obs_prev ? obs_prev : obs;
+    if (e_end >= 0) { p.e_begin = e_begin; p.e_end = e_end; }   // a slice of the envs (tde_step_host's chunks)
     cudaStream_t st = (cudaStream_t)stream;
     const int threads = TDE_WARPS_PER_BLOCK * 32;
     const bool physics = phases & (TDE_PH_KINEMATICS | TDE_PH_INFRACTIONS | TDE_PH_REWARD);
     const bool render = (phases & TDE_PH_RENDER) && obs;
-    const int want = (h->E + TDE_WARPS_PER_BLOCK - 1) / TDE_WARPS_PER_BLOCK;
+    const int want = (p.e_end - p.e_begin + TDE_WARPS_PER_BLOCK - 1) / TDE_WARPS_PER_BLOCK;
     // terminal observations: finished envs are only flagged by the physics kernel; after the frame of their last
     // state is out it is copied to terminal_obs, the flagged envs are re-initialised and rendered again
     const bool deferred = terminal_obs && physics && render && h->cfg.auto_reset;
@@ -853,9 +859,31 @@ extern "C" int tde_step_host(tde_handle* h, const float* actions, uint8_t* obs, 
     }
     if (obs && !h->h_obs) CUDA_TRY(h, cudaMalloc((void**)&h->h_obs, obs_bytes));
     CUDA_TRY(h, cudaMemcpyAsync(h->h_actions, actions, E * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
-    int rc = tde_step(h, h->h_actions, obs ? h->h_obs : nullptr, h->h_reward, h->h_term, h->h_trunc, h->h_info, stream);
-    if (rc) return rc;
-    if (obs) CUDA_TRY(h, cudaMemcpyAsync(obs, h->h_obs, obs_bytes, cudaMemcpyDeviceToHost, st));
+    // With observations the step is bound by the 12 KB per env that cross PCIe: the envs are stepped in
+    // chunks, and the frames of a finished chunk travel on a second stream while the next chunk is computed.
+    const int chunks = (obs && h->E >= 4096) ? 8 : 1;
+    if (chunks == 1) {
+        int rc = tde_step(h, h->h_actions, obs ? h->h_obs : nullptr, h->h_reward, h->h_term, h->h_trunc, h->h_info, stream);
+        if (rc) return rc;
+        if (obs) CUDA_TRY(h, cudaMemcpyAsync(obs, h->h_obs, obs_bytes, cudaMemcpyDeviceToHost, st));
+    } else {
+        if (!h->copy_stream) {
+            CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+            for (cudaEvent_t& ev : h->chunk_done) CUDA_TRY(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            CUDA_TRY(h, cudaEventCreateWithFlags(&h->copies_done, cudaEventDisableTiming));
+        }
+        const size_t frame = (size_t)TDE_OBS_C * TDE_OBS_H * TDE_OBS_W;
+        for (int c = 0; c < chunks; ++c) {
+            const int e0 = (int)((long long)h->E * c / chunks), e1 = (int)((long long)h->E * (c + 1) / chunks);
+            int rc = step_impl(h, TDE_PH_ALL, h->h_actions, h->h_obs, 1, h->h_reward, h->h_term, h->h_trunc, h->h_info, stream, nullptr, nullptr, e0, e1);
+            if (rc) return rc;
+            CUDA_TRY(h, cudaEventRecord(h->chunk_done[c], st));
+            CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->chunk_done[c], 0));
+            CUDA_TRY(h, cudaMemcpyAsync(obs + e0 * frame, h->h_obs + e0 * frame, (size_t)(e1 - e0) * frame, cudaMemcpyDeviceToHost, h->copy_stream));
+        }
+        CUDA_TRY(h, cudaEventRecord(h->copies_done, h->copy_stream));
+        CUDA_TRY(h, cudaStreamWaitEvent(st, h->copies_done, 0));
+    }
     CUDA_TRY(h, cudaMemcpyAsync(reward, h->h_reward, E * sizeof(float), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(h, cudaMemcpyAsync(terminated, h->h_term, E, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(h, cudaMemcpyAsync(truncated, h->h_trunc, E, cudaMemcpyDeviceToHost, st));

@@ -519,23 +519,39 @@ __device__ __forceinline__ Proj project_quad(const Cam& cam, const float (&wx)[4
 template <int NE>
 __device__ __forceinline__ void cover_rows(int j, int jend, int (&V)[4], const int (&dV)[4], int (&rem)[4], const int (&rS)[4],
                                            const int (&D)[4], const int (&cstep)[4], const int (&cap)[4], unsigned int* cov) {
+#ifdef TDE_COVER_PRED
+    bool left[4];   // a slanted edge bounds the span on one side only (cap = INT_MAX: left, also an unused slot with V = INT_MIN)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) left[k] = cap[k] == INT_MAX;
+#endif
 #pragma unroll 1
     for (; j <= jend; ++j) {
         int xl = 0, xr = TDE_OBS_W;
 #pragma unroll
         for (int k = 0; k < NE; ++k) {
+#ifdef TDE_COVER_PRED
+            if (left[k]) xl = max(xl, V[k]); else xr = min(xr, V[k]);
+#else
             xl = max(xl, min(V[k], cap[k]));
             xr = min(xr, max(V[k], cap[k]));
+#endif
             V[k] += dV[k];
             rem[k] += rS[k];
             if (rem[k] >= D[k]) { rem[k] -= D[k]; V[k] += cstep[k]; }
         }
+#ifdef TDE_COVER_MASK32
+        // the two 32-bit halves of the span [xl, xr), each a run of w = 1..32 bits: (~0u >> (32 - w)) << l
+        const int l0 = min(xl, 32), r0 = min(xr, 32), l1 = max(xl, 32) - 32, r1 = max(xr, 32) - 32;
+        if (l0 < r0) atomicOr(cov + 2 * j, (0xffffffffu >> (32 - r0 + l0)) << l0);
+        if (l1 < r1) atomicOr(cov + 2 * j + 1, (0xffffffffu >> (32 - r1 + l1)) << l1);
+#else
         if (xl < xr) {
             unsigned long long m = (~0ull >> (64 - xr)) & (~0ull << xl);
             unsigned int lo = (unsigned int)m, hi = (unsigned int)(m >> 32);
             if (lo) atomicOr(cov + 2 * j, lo);
             if (hi) atomicOr(cov + 2 * j + 1, hi);
         }
+#endif
     }
 }
 
