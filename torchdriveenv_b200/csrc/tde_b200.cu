@@ -455,6 +455,7 @@ static void free_scenarios(tde_handle* h) {
 template <int AH>
 static int configure_kernels(tde_handle* h) {
     size_t smem = sizeof(RenderScratch) * TDE_WARPS_PER_BLOCK + 256 * sizeof(uint32_t);  // + the spread table
+    smem += (TDE_OBS_W + 1) * sizeof(unsigned long long);                               // + the span-mask table
     CUDA_TRY(h, cudaFuncSetAttribute(tde_render_kernel<AH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_TRY(h, cudaFuncSetAttribute(tde_render_kernel<AH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;

@@ -513,45 +513,34 @@ __device__ __forceinline__ Proj project_quad(const Cam& cam, const float (&wx)[4
     return project_quad(cam, wx[0], wy[0], wx[1], wy[1], wx[2], wy[2], wx[3], wy[3]);
 }
 
-// Row loop of raster_batch for primitives with at most NE slanted edges: step the edges down the
-// rows (an exact integer DDA on floor(K/D) per edge) and OR each row's span into the coverage word of
-// the primitive's class.  Lanes own different primitives, so the ORs are shared-memory atomics.
+// floor(r * 2^32 / d) to within +-1 for 0 <= r < d < 2^18: float estimate, exact 32-bit residual, one correction
+__device__ __forceinline__ unsigned tde_frac32(int r, int d, float inv_d) {
+    const unsigned b1 = __float2uint_rz((float)r * (inv_d * 4294967296.0f));
+    const int res = -(int)(b1 * (unsigned)d);             // r * 2^32 - b1 * d: |.| < 2^30, so its low 32 bits are the value
+    return b1 + (unsigned)__float2int_rn((float)res * inv_d);
+}
+// Row loop on 32.32 fixed-point edge positions: acc[k] >> 32 is the bound of edge k on the current row, exactly
+// floor((K + S j) / d) - the fraction is biased by 2^13 units and the per-row increment is within one unit of
+// S / d, so after <= 63 steps the accumulated error stays inside the gap of 2^32 / d >= 2^14 units between
+// representable quotients (d = 16 |dy| < 2^18).  Per edge and row: one 64-bit add (IADD3 + IMAD.X) and one min or max.
 template <int NE>
-__device__ __forceinline__ void cover_rows(int j, int jend, int (&V)[4], const int (&dV)[4], int (&rem)[4], const int (&rS)[4],
-                                           const int (&D)[4], const int (&cstep)[4], const int (&cap)[4], unsigned int* cov) {
-#ifdef TDE_COVER_PRED
-    bool left[4];   // a slanted edge bounds the span on one side only (cap = INT_MAX: left, also an unused slot with V = INT_MIN)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) left[k] = cap[k] == INT_MAX;
-#endif
+__device__ __forceinline__ void cover_rows64(int j, int jend, unsigned long long (&acc)[4], const unsigned long long (&inc)[4],
+                                             const bool (&left)[4], unsigned int* cov, const unsigned long long* below) {
 #pragma unroll 1
     for (; j <= jend; ++j) {
         int xl = 0, xr = TDE_OBS_W;
 #pragma unroll
         for (int k = 0; k < NE; ++k) {
-#ifdef TDE_COVER_PRED
-            if (left[k]) xl = max(xl, V[k]); else xr = min(xr, V[k]);
-#else
-            xl = max(xl, min(V[k], cap[k]));
-            xr = min(xr, max(V[k], cap[k]));
-#endif
-            V[k] += dV[k];
-            rem[k] += rS[k];
-            if (rem[k] >= D[k]) { rem[k] -= D[k]; V[k] += cstep[k]; }
+            const int v = (int)(acc[k] >> 32);
+            if (left[k]) xl = max(xl, v); else xr = min(xr, v);
+            acc[k] += inc[k];
         }
-#ifdef TDE_COVER_MASK32
-        // the two 32-bit halves of the span [xl, xr), each a run of w = 1..32 bits: (~0u >> (32 - w)) << l
-        const int l0 = min(xl, 32), r0 = min(xr, 32), l1 = max(xl, 32) - 32, r1 = max(xr, 32) - 32;
-        if (l0 < r0) atomicOr(cov + 2 * j, (0xffffffffu >> (32 - r0 + l0)) << l0);
-        if (l1 < r1) atomicOr(cov + 2 * j + 1, (0xffffffffu >> (32 - r1 + l1)) << l1);
-#else
         if (xl < xr) {
-            unsigned long long m = (~0ull >> (64 - xr)) & (~0ull << xl);
-            unsigned int lo = (unsigned int)m, hi = (unsigned int)(m >> 32);
+            const uint2 br = reinterpret_cast<const uint2*>(below)[xr], bl = reinterpret_cast<const uint2*>(below)[xl];
+            const unsigned int lo = br.x & ~bl.x, hi = br.y & ~bl.y;
             if (lo) atomicOr(cov + 2 * j, lo);
             if (hi) atomicOr(cov + 2 * j + 1, hi);
         }
-#endif
     }
 }
 
@@ -559,7 +548,9 @@ __device__ __forceinline__ void cover_rows(int j, int jend, int (&V)[4], const i
 // per-class coverage bitmaps.  The final pixel is the highest class covering it, so neither the order
 // of the primitives nor their grouping matters.  Pixel-centre sampling on the 1/16-px grid with the
 // top-left rule: the same pixel set as the oracle's per-pixel edge-function test.
-__device__ __noinline__ void raster_batch(RenderScratch* ws, int base, int count, int lane) {
+#define TDE_RB_PARAMS , const unsigned long long* below
+#define TDE_RB_ARGS , below
+__device__ __noinline__ void raster_batch(RenderScratch* ws, int base, int count, int lane TDE_RB_PARAMS) {
     const bool have = lane < count;
     const uint4 q = ws->qv[base + lane];
     const int cls = have ? (int)ws->qc[base + lane] : 1;
@@ -593,33 +584,35 @@ __device__ __noinline__ void raster_batch(RenderScratch* ws, int base, int count
     const unsigned touched = __reduce_or_sync(FULL_MASK, active ? (1u << cls) : 0u);
     if (lane == 0) ws->used |= touched;
 
-    // slanted edges: V = current bound (left: first covered column, right: one past the last), stepped per row
-    int V[4], dV[4], rem[4], rS[4], D[4], cstep[4], cap[4];
+    // slanted edges: bound = floor((K + S j) / d) for every edge (a left edge's -floor(K/d) = floor((d - 1 - K) / d),
+    // a right edge's floor(K/d) + 1 = floor((K + d) / d)), kept as a 32.32 fixed-point accumulator per edge
+    unsigned long long acc[4], inc[4]; bool left[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         int k1 = (k + 1) & 3;
         int ax = X[k], ay = Y[k];
         int dx = X[k1] - ax, dy = Y[k1] - ay;
-        V[k] = INT_MIN; dV[k] = 0; rem[k] = 0; rS[k] = 0; D[k] = 0x40000000; cstep[k] = 0; cap[k] = INT_MAX;
+        acc[k] = (unsigned long long)0x80000000u << 32; inc[k] = 0ull; left[k] = true;   // unused slot: bound INT_MIN on the left
         if (active && dy != 0) {
             int bias = dy < 0 ? 0 : -1;
             int C0 = dx * (8 - ay) - dy * (8 - ax) + bias;
             int S = 16 * dx;
             int K = C0 + S * j0;
             int d = dy > 0 ? 16 * dy : -16 * dy;
+            if (dy > 0) { K = K + d; left[k] = false; }
+            else { K = (d - 1) - K; S = -S; }
             float inv_d = __fdividef(1.0f, (float)d);
-            int F = tde_floordiv(K, d, inv_d, rem[k]);
-            int qs = tde_floordiv(S, d, inv_d, rS[k]);
-            D[k] = d;
-            if (dy > 0) { V[k] = F + 1; dV[k] = qs; cstep[k] = 1; cap[k] = INT_MIN; }
-            else { V[k] = -F; dV[k] = -qs; cstep[k] = -1; cap[k] = INT_MAX; }
+            int r0, rS;
+            int F = tde_floordiv(K, d, inv_d, r0);
+            int qs = tde_floordiv(S, d, inv_d, rS);
+            inc[k] = ((unsigned long long)(unsigned)qs << 32) + (unsigned long long)tde_frac32(rS, d, inv_d);
+            acc[k] = ((unsigned long long)(unsigned)F << 32) + (unsigned long long)(tde_frac32(r0, d, inv_d) + 8192u);
         }
     }
     if (active) {
         unsigned int* cov = reinterpret_cast<unsigned int*>(ws->cover + (cls - 1) * TDE_OBS_H);
-        // a triangle's fourth slot is the degenerate edge 3 -> 0: skip it when the whole batch is triangles
-        if (__any_sync(bm, n == 4)) cover_rows<4>(j0, j1, V, dV, rem, rS, D, cstep, cap, cov);
-        else cover_rows<3>(j0, j1, V, dV, rem, rS, D, cstep, cap, cov);
+        if (__any_sync(bm, n == 4)) cover_rows64<4>(j0, j1, acc, inc, left, cov, below);
+        else cover_rows64<3>(j0, j1, acc, inc, left, cov, below);
     }
     __syncwarp();
 }
@@ -627,7 +620,7 @@ __device__ __noinline__ void raster_batch(RenderScratch* ws, int base, int count
 // Append the primitives of the lanes with `valid` (each with its own class) to the ring by ballot/popc
 // compaction; a batch is rasterised as soon as 32 are pending.  `qtot` counts everything queued so
 // far for this env (warp-uniform); the new count is returned.
-__device__ __noinline__ int enqueue(RenderScratch* ws, int lane, bool valid, uint4 v, int cls, int qtot) {
+__device__ __noinline__ int enqueue(RenderScratch* ws, int lane, bool valid, uint4 v, int cls, int qtot TDE_RB_PARAMS) {
     int y0 = unpack_y(v.x), y1 = unpack_y(v.y), y2 = unpack_y(v.z), y3 = unpack_y(v.w);
     int x0 = unpack_x(v.x), x1 = unpack_x(v.y), x2 = unpack_x(v.z), x3 = unpack_x(v.w);
     int ymin = min(min(y0, y1), min(y2, y3)), ymax = max(max(y0, y1), max(y2, y3));
@@ -640,7 +633,7 @@ __device__ __noinline__ int enqueue(RenderScratch* ws, int lane, bool valid, uin
     if (valid) { ws->qv[pos] = v; ws->qc[pos] = (unsigned char)cls; }
     const int qnew = qtot + __popc(m);
     __syncwarp();
-    if ((qnew ^ qtot) & ~31) raster_batch(ws, qtot & 32, 32, lane);  // crossed a multiple of 32: that half of the ring is full
+    if ((qnew ^ qtot) & ~31) raster_batch(ws, qtot & 32, 32, lane TDE_RB_ARGS);  // crossed a multiple of 32: that half of the ring is full
     return qnew;
 }
 
@@ -672,7 +665,7 @@ __device__ __forceinline__ uint32_t spread8(uint32_t b) {
 // so the candidates of a viewport are one contiguous run per tile row: lanes fetch the runs of the
 // rows in reach, a scan numbers the candidates, and they are projected and queued 32 at a time with
 // every lane busy.  Oversized primitives (kept out of the tiles) are always candidates.
-__device__ __noinline__ int queue_static(const MapDev& M, Cam cam, float reach, RenderScratch* ws, int lane, int qtot) {
+__device__ __noinline__ int queue_static(const MapDev& M, Cam cam, float reach, RenderScratch* ws, int lane, int qtot TDE_RB_PARAMS) {
     if (M.n_rp <= 0) return qtot;
     const float lo_reach = reach + M.maxext;
     const int tx0 = max(0, (int)floorf((cam.ex - lo_reach - M.tgx0) * M.tinv)), tx1 = min(M.tnx - 1, (int)floorf((cam.ex + reach - M.tgx0) * M.tinv));
@@ -725,11 +718,11 @@ __device__ __noinline__ int queue_static(const MapDev& M, Cam cam, float reach, 
         int c2 = (x3 - x2) * (y0 - y3) - (y3 - y2) * (x0 - x3), c3 = (x0 - x3) * (y1 - y0) - (y0 - y3) * (x1 - x0);
         bool convex = (c0 > 0 && c1 > 0 && c2 > 0 && c3 > 0) || (c0 < 0 && c1 < 0 && c2 < 0 && c3 < 0);
         bool is_tri = pv.w == pv.x;
-        qtot = enqueue(ws, lane, ok && (is_tri || convex), pv, cls, qtot);
+        qtot = enqueue(ws, lane, ok && (is_tri || convex), pv, cls, qtot TDE_RB_ARGS);
         bool split = ok && !is_tri && !convex;
         if (__any_sync(FULL_MASK, split)) {
-            qtot = enqueue(ws, lane, split, make_uint4(pv.x, pv.y, pv.w, pv.x), cls, qtot);
-            qtot = enqueue(ws, lane, split, make_uint4(pv.y, pv.z, pv.w, pv.y), cls, qtot);
+            qtot = enqueue(ws, lane, split, make_uint4(pv.x, pv.y, pv.w, pv.x), cls, qtot TDE_RB_ARGS);
+            qtot = enqueue(ws, lane, split, make_uint4(pv.y, pv.z, pv.w, pv.y), cls, qtot TDE_RB_ARGS);
         }
     }
     return qtot;
@@ -739,7 +732,7 @@ __device__ __noinline__ int queue_static(const MapDev& M, Cam cam, float reach, 
 // coverage words of `ws` are zero on entry and zero again on return.
 template <int AH, bool STACKED>
 __device__ __forceinline__ void render_env(const StepParams& p, const int e, const int lane, RenderScratch* ws,
-                                           const uint32_t* spread_tab, const float reach) {
+                                           const uint32_t* spread_tab, const float reach TDE_RB_PARAMS) {
     uint4* const cz = reinterpret_cast<uint4*>(ws->cover);
     constexpr int COVER_U4 = (TDE_NUM_CLASSES - 1) * TDE_OBS_H * 8 / 16;  // 320 = 10 per lane
     {
@@ -761,7 +754,7 @@ __device__ __forceinline__ void render_env(const StepParams& p, const int e, con
         cam.ppm = p.ppm; cam.ppmy = p.ppmy;
         float wx[4], wy[4];
         int qtot = 0;
-        qtot = queue_static(M, cam, reach, ws, lane, qtot);                 // classes 1-2: road and lane markings
+        qtot = queue_static(M, cam, reach, ws, lane, qtot TDE_RB_ARGS);                 // classes 1-2: road and lane markings
 #ifdef TDE_TRACE
         if (g_trace && lane == 0) g_trace[(size_t)e * 8 + 4] = qtot;
 #endif
@@ -830,9 +823,9 @@ __device__ __forceinline__ void render_env(const StepParams& p, const int e, con
             wx[2] = bx + (ox2 * bc - oy2 * bs); wy[2] = by + (ox2 * bs + oy2 * bc);
             wx[3] = bx + (ox3 * bc - oy3 * bs); wy[3] = by + (ox3 * bs + oy3 * bc);
             Proj pr = project_quad(cam, wx, wy);
-            qtot = enqueue(ws, lane, pr.ok && valid, pr.v, cls, qtot);
+            qtot = enqueue(ws, lane, pr.ok && valid, pr.v, cls, qtot TDE_RB_ARGS);
         }
-        if (qtot & 31) raster_batch(ws, qtot & 32, qtot & 31, lane);
+        if (qtot & 31) raster_batch(ws, qtot & 32, qtot & 31, lane TDE_RB_ARGS);
 #ifdef TDE_TRACE
         if (g_trace && lane == 0) { g_trace[(size_t)e * 8 + 5] = n_items; g_trace[(size_t)e * 8 + 6] = qtot; }
 #endif
@@ -947,6 +940,9 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, TDE_RENDER_BLOCKS_PE
     // spread table: byte of plane bits -> the same bits at the low bit of 8 nibbles
     uint32_t* const spread_tab = reinterpret_cast<uint32_t*>(smem_raw + sizeof(RenderScratch) * TDE_WARPS_PER_BLOCK);
     for (int i = threadIdx.x; i < 256; i += TDE_WARPS_PER_BLOCK * 32) spread_tab[i] = spread8(i);
+    // below[x] = the x low bits set (x = 0..64): a span [xl, xr) is below[xr] & ~below[xl], two LDS instead of shifts
+    unsigned long long* const below = reinterpret_cast<unsigned long long*>(spread_tab + 256);
+    for (int i = threadIdx.x; i <= TDE_OBS_W; i += TDE_WARPS_PER_BLOCK * 32) below[i] = i >= 64 ? ~0ull : ((1ull << i) - 1ull);
     __syncthreads();
     const int warps_total = gridDim.x * TDE_WARPS_PER_BLOCK;
     const float reach = viewport_reach(p);
@@ -962,7 +958,7 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, TDE_RENDER_BLOCKS_PE
         if (e >= p.e_end) break;
         if (masked && p.render_mask[e] == 0) continue;
         TDE_TRACE_MARK(e, 0);
-        render_env<AH, STACKED>(p, e, lane, ws, spread_tab, reach);
+        render_env<AH, STACKED>(p, e, lane, ws, spread_tab, reach TDE_RB_ARGS);
         TDE_TRACE_MARK(e, 1);
     }
     if (!masked) envs_done(p.tickets, lane, warps_total);
