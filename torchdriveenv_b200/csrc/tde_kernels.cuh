@@ -898,16 +898,28 @@ __device__ __forceinline__ void render_env(const StepParams& p, const int e, con
                 sel7[g] = sel & 0x7777u;
                 himask[g] = __byte_perm(0x0000ff00u, 0u, (sel >> 3) & 0x1111u);
             }
+            // classes 8..15 (the ego and the direction triangles) are rare: eight rows without one take the short path
+            const bool any_hi = __any_sync(FULL_MASK, ((idx[0] | idx[1]) & 0x88888888u) != 0u);
+            if (any_hi) {
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-                uint32_t w[4];
+                for (int ch = 0; ch < 3; ++ch) {
+                    uint32_t w[4];
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    uint32_t lo = __byte_perm(p.pal[ch][0], p.pal[ch][1], sel7[g]);
-                    uint32_t hi = __byte_perm(p.pal[ch][2], p.pal[ch][3], sel7[g]);
-                    w[g] = (lo & ~himask[g]) | (hi & himask[g]);
+                    for (int g = 0; g < 4; ++g) {
+                        uint32_t lo = __byte_perm(p.pal[ch][0], p.pal[ch][1], sel7[g]);
+                        uint32_t hi = __byte_perm(p.pal[ch][2], p.pal[ch][3], sel7[g]);
+                        w[g] = (lo & ~himask[g]) | (hi & himask[g]);
+                    }
+                    *reinterpret_cast<uint4*>(out + ch * (TDE_OBS_H * TDE_OBS_W) + row * TDE_OBS_W + qd * 16) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
-                *reinterpret_cast<uint4*>(out + ch * (TDE_OBS_H * TDE_OBS_W) + row * TDE_OBS_W + qd * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+            } else {
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) w[g] = __byte_perm(p.pal[ch][0], p.pal[ch][1], sel7[g]);
+                    *reinterpret_cast<uint4*>(out + ch * (TDE_OBS_H * TDE_OBS_W) + row * TDE_OBS_W + qd * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
             }
         }
         __syncwarp();
