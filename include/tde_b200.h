@@ -280,6 +280,15 @@ int tde_collision_boxes(const float* state_dev, const float* attr_dev, int32_t n
 int tde_offroad_boxes(tde_handle* h, int32_t map_id, const float* state_dev, const float* attr_dev,
                       int32_t num_envs, int32_t num_agents, float* out_offroad_dev, void* stream);
 
+/* Recording view: BirdviewRecordingWrapper(simulator, res=Resolution(video_res, video_res), fov=video_fov)
+   gym_env.py:52-53,295-297 + simulator.get_birdviews() :174.  Draws ONE env as a width x height RGB frame
+   (out_dev uint8[3][height][width], planar) from a free camera: centre (cam_x, cam_y) in world metres, heading
+   cam_psi (the camera's +x axis points right in the image), `fov` metres across the width.  Same primitives,
+   painter's levels, palette and fill rule as the observation; coordinates are kept in a wider fixed-point
+   range so any resolution up to 4096 works.  Not part of the per-step path (two small launches per frame). */
+int tde_render_view(tde_handle* h, int32_t env, float cam_x, float cam_y, float cam_psi, float fov,
+                    int32_t width, int32_t height, uint8_t* out_dev, void* stream);
+
 int tde_clone(tde_handle* h, tde_handle** out);
 
 /* double[TDE_NUM_STATS]; synchronises `stream`. reset_after != 0 zeroes the accumulators. */

@@ -50,6 +50,7 @@ def lib() -> C.CDLL:
         L.orc_compute_infractions.argtypes = [vp]
         L.orc_render.argtypes = [vp, vp]
         L.orc_render_classes.argtypes = [vp, vp]
+        L.orc_render_view.argtypes, L.orc_render_view.restype = [vp, i, f, f, f, f, i, i, vp], i
         L.orc_collision_boxes.argtypes = [vp, vp, i, i, vp]
         L.orc_collision_margins.argtypes = [vp, vp, i, i, vp]
         L.orc_offroad_boxes.argtypes = [vp, i, f, vp, vp, i, i, vp]
@@ -157,6 +158,15 @@ class OracleEnvSet:
         obs = np.zeros((self.E, 3, TDE_OBS_H, TDE_OBS_W), np.uint8)
         self.L.orc_render(self.h, _p(obs))
         return obs
+
+    def render_view(self, env: int, cam_x: float, cam_y: float, cam_psi: float, fov: float, width: int, height: int) -> np.ndarray:
+        """uint8[3, height, width]: the recording view of one env (twin of tde_render_view)."""
+        out = np.zeros((3, int(height), int(width)), np.uint8)
+        rc = self.L.orc_render_view(self.h, int(env), C.c_float(cam_x), C.c_float(cam_y), C.c_float(cam_psi), C.c_float(fov),
+                                    int(width), int(height), _p(out))
+        if rc != 0:
+            raise ValueError("orc_render_view: bad argument")
+        return out
 
     def render_classes(self) -> np.ndarray:
         cls = np.zeros((self.E, TDE_OBS_H, TDE_OBS_W), np.uint8)

@@ -284,3 +284,56 @@ def test_vec_env_terminal_observation(oracle, n_stack):
     assert n_done > 5
     assert venv.episode_statistics() == twin.episode_statistics()
     venv.close(); twin.close()
+
+
+def test_recording_view_matches_the_oracle(oracle):
+    """tde_render_view (BirdviewRecordingWrapper's frame, gym_env.py:52-53,295-297) against orc_render_view: exact,
+    at several resolutions, cameras and zooms, on a multi-map set (maps smaller than the scratch's largest)."""
+    from torchdriveenv_b200.engine import Engine
+    from torchdriveenv_b200._capi import default_config
+    ss = S.validation_mix(8); A = 10; E = 10
+    eng = Engine(ss, E, A, device="cuda:0", auto_reset=1)
+    orc = oracle.OracleEnvSet(default_config(num_envs=E, max_agents=A, auto_reset=1), eng.packed)
+    eng.reset(seed=9); orc.reset(seed=9)
+    rng = np.random.default_rng(9)
+    for _ in range(4):
+        a = np.stack([rng.uniform(-1, 1, E), rng.uniform(-0.3, 0.3, E)], 1).astype(np.float32)
+        eng.step(torch.from_numpy(a).cuda()); orc.step(a)
+    st = orc.state
+    cases = [(0, float(st[0, 0, 0]), float(st[0, 0, 1]), float(st[0, 0, 2]), 35.0, 64, 64),
+             (3, float(st[3, 0, 0]), float(st[3, 0, 1]), 0.0, 120.0, 256, 192),
+             (5, float(st[5, 0, 0]) + 7.5, float(st[5, 0, 1]) - 3.25, 1.1, 60.0, 333, 127),
+             (7, 0.0, 0.0, -0.4, 500.0, 1024, 1024),
+             (9, float(st[9, 0, 0]), float(st[9, 0, 1]), 2.0, 8.0, 512, 512)]
+    for (e, cx, cy, psi, fov, W, H) in cases:
+        got = eng.render_view(e, (cx, cy), psi, fov, (W, H)).cpu().numpy()
+        want = orc.render_view(e, cx, cy, psi, fov, W, H)
+        assert got.shape == (3, H, W)
+        assert np.array_equal(got, want), f"case env {e} {W}x{H}: {(got != want).mean()}"
+    # the observation settings reproduce the observation
+    assert np.array_equal(eng.render_view(0, (cases[0][1], cases[0][2]), cases[0][3], 35.0, (64, 64)).cpu().numpy(), eng.render()[0].cpu().numpy())
+    with pytest.raises(Exception, match="TDE_E_INVAL"):
+        eng.render_view(E, (0.0, 0.0), 0.0, 35.0, (64, 64))
+    with pytest.raises(Exception, match="TDE_E_INVAL"):
+        eng.render_view(0, (0.0, 0.0), 0.0, 35.0, (5000, 64))
+    eng.close()
+
+
+def test_video_render_mode_records_and_saves(tmp_path):
+    """render_mode='video' (gym_env.py:295-297,170-177): one video_res x video_res frame after reset and after every
+    step, written as mp4 by close()."""
+    from torchdriveenv_b200 import gym_env as G
+    fn = str(tmp_path / "episode.mp4")
+    cfg = G.EnvConfig(seed=4, device="cuda:0", render_mode="video", video_filename=fn, video_res=256, video_fov=300)
+    env = G.SingleAgentWrapper(G.WaypointSuiteEnv(cfg, S.three_way(6)))
+    env.reset()
+    for _ in range(5):
+        env.step(np.array([0.5, 0.0], np.float32))
+    bvs = env.env.simulator.get_birdviews()
+    assert len(bvs) == 6 and tuple(bvs[0].shape) == (1, 3, 256, 256) and bvs[0].dtype == torch.uint8 and not bvs[0].is_cuda
+    assert not torch.equal(bvs[0], bvs[-1])
+    with pytest.raises(NotImplementedError):
+        env.render()                      # the reference's render() only serves 'rgb_array' (gym_env.py:152-157)
+    env.close()
+    import os
+    assert os.path.getsize(fn) > 1000

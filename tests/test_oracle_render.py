@@ -88,3 +88,42 @@ def test_render_fill_rule_shared_edges(oracle):
     cls = env.render_classes()[0]
     ys, xs = np.nonzero(cls >= 1)
     assert xs.min() == 22 and xs.max() == 41 and ys.min() == 22 and ys.max() == 41
+
+
+def test_recording_view_at_observation_settings_is_the_observation(oracle):
+    """orc_render_view (twin of tde_render_view, the BirdviewRecordingWrapper frame) with the camera on the ego,
+    64 x 64 px over the observation's fov draws from the raw triangles through the wide-range fixed-point path:
+    it must give the observation itself, for both handednesses."""
+    from torchdriveenv_b200 import scenarios as S
+    from torchdriveenv_b200._capi import default_config
+    for lh in (1, 0):
+        ss = S.validation_mix(8); A = 10
+        orc = oracle.OracleEnvSet(default_config(num_envs=10, max_agents=A, left_handed_coordinates=lh), ss.pack(A))
+        orc.reset(seed=5)
+        rng = np.random.default_rng(5)
+        for _ in range(3):
+            orc.step(np.stack([rng.uniform(-1, 1, 10), rng.uniform(-0.3, 0.3, 10)], 1).astype(np.float32))
+        obs = orc.render()
+        for e in range(10):
+            x, y, psi = (float(v) for v in orc.state[e, 0, :3])
+            assert np.array_equal(orc.render_view(e, x, y, psi, 35.0, 64, 64), obs[e]), (lh, e)
+
+
+def test_recording_view_whole_map(oracle):
+    """A whole-map frame: every class that exists in the scene shows up, the image is mostly background, and a
+    2x zoom on the same centre keeps the centre pixel's class."""
+    from torchdriveenv_b200 import scenarios as S
+    from torchdriveenv_b200._capi import default_config
+    ss = S.traffic_lights(12); A = 12
+    orc = oracle.OracleEnvSet(default_config(num_envs=1, max_agents=A), ss.pack(A))
+    orc.reset(seed=2)
+    x, y = (float(v) for v in orc.state[0, 0, :2])
+    far = orc.render_view(0, x, y, 0.0, 400.0, 512, 384)
+    near = orc.render_view(0, x, y, 0.0, 200.0, 512, 384)
+    assert far.shape == (3, 384, 512)
+    colours = {tuple(c) for c in far.reshape(3, -1).T}
+    assert (128, 128, 128) in colours and (255, 255, 255) in colours and (250, 120, 0) in colours   # road, markings, ego
+    assert (far.sum(0) == 0).mean() > 0.8
+    assert np.array_equal(far[:, 192, 256], near[:, 192, 256])
+    with pytest.raises(ValueError):
+        orc.render_view(0, x, y, 0.0, 0.0, 64, 64)

@@ -127,7 +127,7 @@ EXPORTS = [
     "tde_compute_infractions",
     "tde_get_state", "tde_set_state", "tde_get_attributes", "tde_set_attributes", "tde_get_infractions",
     "tde_get_env_vars", "tde_set_env_vars", "tde_collision_boxes", "tde_offroad_boxes", "tde_clone",
-    "tde_get_episode_stats", "tde_num_kernel_launches", "tde_device_sm_count", "tde_get_map_info",
+    "tde_get_episode_stats", "tde_num_kernel_launches", "tde_device_sm_count", "tde_get_map_info", "tde_render_view",
 ]
 
 
@@ -180,6 +180,7 @@ def load_library() -> C.CDLL:
         "tde_num_kernel_launches": ([vp, C.POINTER(i64)], C.c_int),
         "tde_device_sm_count": ([vp, C.POINTER(i32)], C.c_int),
         "tde_get_map_info": ([vp, i32, C.POINTER(i32)], C.c_int),
+        "tde_render_view": ([vp, i32, C.c_float, C.c_float, C.c_float, C.c_float, i32, i32, vp, vp], C.c_int),
     }
     for name, (args, res) in sig.items():
         fn = getattr(lib, name)  # AttributeError here = the library does not match the header

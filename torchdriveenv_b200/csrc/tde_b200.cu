@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "tde_kernels.cuh"
+#include "tde_view.cuh"
 
 static thread_local std::string g_create_error;
 
@@ -44,6 +45,7 @@ struct tde_handle {
     // device staging for tde_step_host
     float* h_actions = nullptr; uint8_t* h_obs = nullptr; float* h_reward = nullptr;
     uint8_t *h_term = nullptr, *h_trunc = nullptr; float* h_info = nullptr;
+    ViewPrim* view_prims = nullptr; int view_cap = 0;   // tde_render_view scratch
     cudaStream_t copy_stream = nullptr;          // tde_step_host: observation chunks go back while later chunks are computed
     cudaEvent_t chunk_done[8] = {}, copies_done = nullptr;
     std::string err;
@@ -516,6 +518,7 @@ extern "C" int tde_destroy(tde_handle* h) {
     free_scenarios(h);
     cudaFree(h->state); cudaFree(h->attr); cudaFree(h->infr); cudaFree(h->vars); cudaFree(h->ep_return);
     cudaFree(h->scen_lo); cudaFree(h->scen_hi); cudaFree(h->stats); cudaFree(h->restart); cudaFree(h->tickets); cudaFree(h->done_mask);
+    cudaFree(h->view_prims);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (cudaEvent_t ev : h->chunk_done) if (ev) cudaEventDestroy(ev);
     if (h->copies_done) cudaEventDestroy(h->copies_done);
@@ -575,6 +578,9 @@ extern "C" int tde_upload_scenarios(tde_handle* h, const tde_scenario_set* s) {
         if (nt) prep_tris_kernel<<<(nt + 127) / 128, 128>>>(raw, nt, rec);
         M.tri = rec; M.ntri = nt;
         M.nmark = nk;
+        float* mraw = nullptr;
+        if ((rc = dev_upload(h, &mraw, s->mark_tris + 6 * (size_t)k0, (size_t)nk * 6))) return rc;
+        M.mark_raw = mraw;
         // render-only static primitives: merged quads / leftover triangles of both layers, indexed by tile
         {
             std::vector<float> rp_road = merge_into_quads(s->road_tris + 8 * (size_t)t0, nt, 8);
@@ -890,6 +896,42 @@ extern "C" int tde_step_host(tde_handle* h, const float* actions, uint8_t* obs, 
     CUDA_TRY(h, cudaMemcpyAsync(truncated, h->h_trunc, E, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(h, cudaMemcpyAsync(info, h->h_info, E * TDE_INFO_STRIDE * sizeof(float), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(h, cudaStreamSynchronize(st));
+    return TDE_OK;
+}
+
+extern "C" int tde_render_view(tde_handle* h, int32_t env, float cam_x, float cam_y, float cam_psi, float fov, int32_t width,
+                               int32_t height, uint8_t* out, void* stream) {
+    if (!h) return TDE_E_INVAL;
+    if (!out) return fail(h, TDE_E_INVAL, "tde_render_view: out is null");
+    if (!h->uploaded || !h->was_reset) return fail(h, TDE_E_STATE, "tde_render_view: upload scenarios and reset first");
+    if (env < 0 || env >= h->E) return fail(h, TDE_E_INVAL, "tde_render_view: env out of range");
+    if (width < 1 || height < 1 || width > TDE_VIEW_MAX_RES || height > TDE_VIEW_MAX_RES) return fail(h, TDE_E_INVAL, "tde_render_view: resolution must be in 1..4096");
+    if (!(fov > 0.0f)) return fail(h, TDE_E_INVAL, "tde_render_view: fov must be positive");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int nmax = 0;   // the env's map is only known on the device: size the scratch for the largest map
+    for (const MapDev& M : h->maps_host) nmax = std::max(nmax, M.ntri + M.nmark + M.nstop);
+    nmax += 1 + 2 * h->A;
+    if (nmax > h->view_cap) {
+        CUDA_TRY(h, cudaStreamSynchronize(st));
+        cudaFree(h->view_prims); h->view_prims = nullptr; h->view_cap = 0;
+        CUDA_TRY(h, cudaMalloc((void**)&h->view_prims, sizeof(ViewPrim) * (size_t)nmax));
+        h->view_cap = nmax;
+    }
+    StepParams p = make_params(h);
+    ViewParams v;
+    v.env = env; v.W = width; v.H = height; v.ex = cam_x; v.ey = cam_y;
+    v.psi = cam_psi; v.ce = 1.0f; v.se = 0.0f;   // sin / cos are taken on the device (tde_sincosf, as the oracle's twin does)
+    v.ppm = (float)width / fov;
+    v.ppmy = h->cfg.left_handed_coordinates ? v.ppm : -v.ppm;
+    std::memcpy(v.pal, h->palette, sizeof(v.pal));
+    // slots beyond the env's own map (a smaller map than the largest) are emitted as rejected primitives
+    tde_view_prims_kernel<<<(nmax + 127) / 128, 128, 0, st>>>(p, v, h->view_prims, nmax);
+    CUDA_TRY(h, cudaGetLastError());
+    dim3 grid((width + TDE_VIEW_TX - 1) / TDE_VIEW_TX, (height + TDE_VIEW_TY - 1) / TDE_VIEW_TY), block(TDE_VIEW_TX, TDE_VIEW_TY);
+    tde_view_raster_kernel<<<grid, block, 0, st>>>(h->view_prims, nmax, v, out);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 2;
     return TDE_OK;
 }
 

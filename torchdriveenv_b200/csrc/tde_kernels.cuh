@@ -40,6 +40,7 @@ struct MapDev {
     int gnx, gny;
     float tgx0, tgy0, tinv, maxext;  // tile grid of the render primitives; maxext = largest bbox extent of a tiled primitive
     int tnx, tny;
+    const float* mark_raw;      // [nmark][6] lane-marking triangles as uploaded (recording view, tde_view.cuh)
 };
 
 struct ScenDev {

@@ -15,7 +15,7 @@
 
 struct ViewParams {
     int env, W, H;
-    float ex, ey, ce, se, ppm, ppmy;
+    float ex, ey, psi, ce, se, ppm, ppmy;
     uint8_t pal[TDE_NUM_CLASSES * 3];
 };
 
@@ -83,9 +83,10 @@ __device__ __forceinline__ void view_emit(const ViewParams& v, const float (&wx)
 
 // primitive i of env v.env: [0, ntri) road triangles, [.., +nmark) marking triangles, [.., +nstop) stop lines,
 // one goal waypoint slot, then (rectangle, direction triangle) per agent slot
-__global__ void __launch_bounds__(128) tde_view_prims_kernel(const StepParams p, const ViewParams v, ViewPrim* __restrict__ out, int n_total) {
+__global__ void __launch_bounds__(128) tde_view_prims_kernel(const StepParams p, ViewParams v, ViewPrim* __restrict__ out, int n_total) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_total) return;
+    tde_sincosf(v.psi, v.se, v.ce);
     const int* vars = p.vars + (size_t)v.env * 8;
     const int s = vars[0], step = vars[1], target = vars[2], lphase = vars[4], m = vars[6];
     const MapDev& M = p.maps[m];
@@ -117,7 +118,8 @@ __global__ void __launch_bounds__(128) tde_view_prims_kernel(const StepParams p,
     } else {
         k -= 1;
         const int a = k >> 1;
-        const float4 st = p.state[(size_t)v.env * p.A + a], at = p.attr[(size_t)v.env * p.A + a];
+        float4 st = make_float4(0.f, 0.f, 0.f, 0.f), at = st;
+        if (a < p.A) { st = p.state[(size_t)v.env * p.A + a]; at = p.attr[(size_t)v.env * p.A + a]; }   // the scratch is sized for the largest map
         if (at.w != 0.0f) {
             const Box b = tde_make_box(st.x, st.y, st.z, at.x, at.y, at.w);
             if (k & 1) {

@@ -171,6 +171,23 @@ class Engine:
         self._check(self.lib.tde_render(self.h, _ptr(out), self._stream()), "tde_render")
         return out
 
+    def render_view(self, env: int = 0, camera_xy=None, camera_psi: float = 0.0, fov: float = 500.0, res=(1024, 1024),
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Recording view (tde_render_view): env `env` as a uint8[3, H, W] frame from a free camera.  camera_xy = None
+        centres the camera on the road mesh of the env's map (what a fixed whole-map recording camera shows)."""
+        W, H = int(res[0]), int(res[1])
+        if camera_xy is None:
+            m = int(self.get_env_vars()[int(env), 6])
+            tris = np.asarray(self.scenarios.maps[m].road_tris, np.float32)[:, :6].reshape(-1, 2)
+            camera_xy = (0.5 * (float(tris[:, 0].min()) + float(tris[:, 0].max())), 0.5 * (float(tris[:, 1].min()) + float(tris[:, 1].max())))
+        if out is None:
+            out = torch.empty((3, H, W), dtype=torch.uint8, device=self.device)
+        if out.shape != (3, H, W) or out.dtype != torch.uint8 or not out.is_contiguous() or out.device != self.device:
+            raise ValueError("render_view: out must be a contiguous uint8[3, H, W] tensor on the engine's device")
+        self._check(self.lib.tde_render_view(self.h, int(env), float(camera_xy[0]), float(camera_xy[1]), float(camera_psi),
+                                             float(fov), W, H, _ptr(out), self._stream()), "tde_render_view")
+        return out
+
     def compute_infractions(self) -> torch.Tensor:
         self._check(self.lib.tde_compute_infractions(self.h, self._stream()), "tde_compute_infractions")
         return self.get_infractions()

@@ -22,7 +22,8 @@ import torch
 from ._capi import INFO_COLUMNS, TDE_OBS_H, TDE_OBS_W
 from .engine import Engine
 from .scenarios import (MapData, ScenarioData, ScenarioSet, build_polyline_map, place_npcs)
-from .simulator import BatchedSimulator
+from .helpers import save_video
+from .simulator import BatchedSimulator, BirdviewRecordingWrapper
 
 logger = logging.getLogger(__name__)
 
@@ -235,6 +236,10 @@ class GymEnv(_Env):
 
     def close(self):
         sim = getattr(self, "simulator", None)
+        if isinstance(sim, BirdviewRecordingWrapper):    # gym_env.py:170-177
+            bvs = sim.get_birdviews()
+            if len(bvs) > 1:
+                save_video(bvs, self.config.video_filename)
         if sim is not None and hasattr(sim, "engine"):
             sim.engine.close()
 
@@ -243,7 +248,10 @@ def build_simulator(cfg: EnvConfig, scenarios: ScenarioSet, device, num_envs: in
                     **extra) -> BatchedSimulator:
     """Counterpart of build_simulator (gym_env.py:179-300): the scenario tables play the role of the
     map config + agent tensors, the returned object exposes the SimulatorInterface call surface."""
-    return BatchedSimulator(scenarios, num_envs=num_envs, device=device, seed=seed, **engine_config(cfg, **extra))
+    simulator = BatchedSimulator(scenarios, num_envs=num_envs, device=device, seed=seed, **engine_config(cfg, **extra))
+    if cfg.render_mode == "video":   # gym_env.py:295-297
+        simulator = BirdviewRecordingWrapper(simulator, res=(int(cfg.video_res), int(cfg.video_res)), fov=float(cfg.video_fov), to_cpu=True)
+    return simulator
 
 
 class WaypointSuiteEnv(GymEnv):
@@ -273,6 +281,9 @@ class WaypointSuiteEnv(GymEnv):
         self.environment_steps = 0
         self.reached_waypoint_num = 0
         self.last_obs = self.last_reward = self.last_info = None
+        if isinstance(self.simulator, BirdviewRecordingWrapper):   # the reference builds a fresh recorder per episode
+            self.simulator.birdviews = []
+            self.simulator._record()
         v = self.engine.get_env_vars()[0].cpu().numpy()
         self.current_waypoint_suite_idx = int(v[0])
         self.current_target_idx = int(v[2])
@@ -285,6 +296,8 @@ class WaypointSuiteEnv(GymEnv):
         a = torch.as_tensor(np.asarray(action.cpu() if torch.is_tensor(action) else action, dtype=np.float32)).reshape(-1)[:2]
         obs, rew, term, trunc, info = self.engine.step(a.view(1, 2))
         self.simulator._infractions_valid = True
+        if isinstance(self.simulator, BirdviewRecordingWrapper):
+            self.simulator._record()
         self.environment_steps += 1
         obs_np = obs.unsqueeze(1).cpu().numpy()
         row = info[0].cpu().numpy()

@@ -113,3 +113,44 @@ class BatchedSimulator:
         self.engine.set_attributes(src.engine.get_attributes().to(self.device))
         self.engine.set_env_vars(src.engine.get_env_vars().to(self.device))
         self._infractions_valid = False
+
+
+class BirdviewRecordingWrapper:
+    """Records a large top-down frame of env 0 after construction and after every step, as the reference's
+    ``BirdviewRecordingWrapper(simulator, res=Resolution(video_res, video_res), fov=video_fov, to_cpu=True)``
+    does (gym_env.py:52-53, :295-297); ``get_birdviews()`` (:174) hands the frames to ``save_video``.
+    Everything else is forwarded to the wrapped simulator.  The frames come from ``tde_render_view``
+    (camera fixed on the centre of the map's road mesh unless ``camera_xy`` is given)."""
+
+    def __init__(self, simulator: BatchedSimulator, res=(1024, 1024), fov: float = 500.0, camera_xy=None,
+                 camera_psi: float = 0.0, to_cpu: bool = True, env: int = 0):
+        self.simulator = simulator
+        self.res = (int(res[0]), int(res[1])) if not isinstance(res, int) else (int(res), int(res))
+        self.fov, self.camera_xy, self.camera_psi, self.to_cpu, self.env = float(fov), camera_xy, float(camera_psi), bool(to_cpu), int(env)
+        self.birdviews = []
+        self._record()
+
+    def _record(self):
+        frame = self.simulator.engine.render_view(self.env, self.camera_xy, self.camera_psi, self.fov, self.res).unsqueeze(0)
+        self.birdviews.append(frame.cpu() if self.to_cpu else frame.clone())
+
+    def step(self, action):
+        self.simulator.step(action)
+        self._record()
+
+    def get_birdviews(self):
+        return self.birdviews
+
+    def copy(self):
+        other = BirdviewRecordingWrapper.__new__(BirdviewRecordingWrapper)
+        other.__dict__.update(self.__dict__)
+        other.simulator = self.simulator.copy()
+        other.birdviews = list(self.birdviews)
+        return other
+
+    def to(self, device):
+        self.simulator = self.simulator.to(device)
+        return self
+
+    def __getattr__(self, name):
+        return getattr(self.simulator, name)
