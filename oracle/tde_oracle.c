@@ -5,18 +5,23 @@
  * this file; it is used by tests/, by __graft_entry__.smoke() and by bench.py's cpu_baseline /
  * --impl reference legs as the checker and as the timed CPU baseline.
  *
- * PARITY UNPINNED: the arithmetic of this path lives in the third-party package torchdrivesim
+ * PARITY: partly pinned.  The arithmetic of rows a2-a8 lives in the third-party package torchdrivesim
  * (pinned >=0.2.1, pyproject.toml:30; git 6c7957c780404980d9f69a00b40cb98eab0a87d5,
  * requirements.txt:74) which is neither vendored under /root/reference nor installable offline,
  * and the reference ships no tests or golden vectors.  What is restated here:
  *   - exactly, from the reference's own source: step ordering, reward, termination, truncation,
  *     info, waypoint progress, reset sampling and replay conventions (torchdriveenv/gym_env.py,
- *     cited per function below);
+ *     cited per function below).  PINNED: the reference's own gym_env.py, imported unmodified and
+ *     run over a SimulatorInterface-level surface backed by this oracle, produced the golden
+ *     vectors tests/golden/ref_*.npz (tests/golden/make_reference_golden.py); the oracle and the
+ *     CUDA path are compared with them in tests/test_reference_golden.py and
+ *     tests/test_gpu_reference_golden.py;
  *   - from the published torchdrivesim algorithms as recalled in SURVEY.md §8a (a2-a8), with every
  *     open decision fixed in DESIGN.md §SPEC: kinematic bicycle, oriented-box overlap, corner-to-
  *     mesh offroad distance, wrong-way, red-light stop-line overlap, egocentric birdview.
- * The oracle is pinned instead by independent property tests (tests/test_oracle_*.py: float64
- * closed forms, cv2.rotatedRectangleIntersection, cv2.fillPoly, brute-force float64 distances).
+ *     PARITY UNPINNED for these rows; they are pinned instead by independent property tests
+ *     (tests/test_oracle_*.py: float64 closed forms, cv2.rotatedRectangleIntersection,
+ *     cv2.fillPoly, brute-force float64 distances).
  *
  * Arithmetic contract (what makes CPU/GPU comparisons bit-exact): IEEE binary32, one rounding per
  * written operation, no contraction (-ffp-contract=off here, -fmad=false in nvcc) except where
