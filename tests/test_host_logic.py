@@ -205,3 +205,22 @@ def test_training_mix_statistics_and_rollout_roofline():
     again = S.training_mix(12, 5, seed=2).pack(5)
     assert all(np.array_equal(packed[k], again[k]) for k in packed)      # seeded and deterministic
     assert rollout_bytes_per_env_step(8, 3) == bytes_per_env_step(8, False) + 5 * 12288 + 8
+
+
+def test_save_video_writes_the_frames(tmp_path):
+    """helpers.save_video (reference helpers.py:7-36): list of B x 3 x H x W uint8 frames -> mp4v file at 10 fps."""
+    import torch
+    from torchdriveenv_b200.helpers import save_video, set_seeds
+    frames = []
+    for k in range(8):
+        f = torch.zeros((1, 3, 64, 96), dtype=torch.uint8)
+        f[0, 0, :, : 12 * (k + 1)] = 255
+        frames.append(f)
+    fn = str(tmp_path / "v.mp4")
+    save_video(frames, fn)
+    assert os.path.getsize(fn) > 200
+    import cv2
+    cap = cv2.VideoCapture(fn)
+    assert int(cap.get(cv2.CAP_PROP_FRAME_WIDTH)) == 96 and int(cap.get(cv2.CAP_PROP_FRAME_HEIGHT)) == 64
+    assert int(round(cap.get(cv2.CAP_PROP_FPS))) == 10
+    assert set_seeds(123) == 123
