@@ -469,6 +469,16 @@ static int configure_kernels(tde_handle* h) {
     int want = (h->E + TDE_WARPS_PER_BLOCK - 1) / TDE_WARPS_PER_BLOCK;
     h->grid_render = std::max(1, std::min(want, per_sm * h->sm_count));
     CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tde_physics_kernel<AH>, TDE_WARPS_PER_BLOCK * 32, 0));
+    {   // The physics kernel lives on L1 hits of the map tables (grid cells, triangle records): ask for no more shared
+        // memory than its resident blocks need, the rest of the SM's 228 KB stays L1 (C3: 54.3 -> 52.5 us at 30 %,
+        // 57.7 us at 60 %, 73.3 us at 100 %; tools/carve_sweep.sh).  TDE_PHYS_CARVEOUT overrides the percentage.
+        cudaFuncAttributes fa;
+        CUDA_TRY(h, cudaFuncGetAttributes(&fa, tde_physics_kernel<AH>));
+        const size_t need = (size_t)std::max(per_sm, 1) * (fa.sharedSizeBytes + 1024);
+        int pct = (int)((need * 100 + 233471) / 233472) + 3;
+        if (const char* v = std::getenv("TDE_PHYS_CARVEOUT")) pct = std::atoi(v);
+        CUDA_TRY(h, cudaFuncSetAttribute(tde_physics_kernel<AH>, cudaFuncAttributePreferredSharedMemoryCarveout, std::max(0, std::min(pct, 100))));
+    }
     if (per_sm < 1) per_sm = 1;
     if (const char* v = std::getenv("TDE_PHYS_BLOCKS_CAP")) per_sm = std::max(1, std::min(per_sm, std::atoi(v)));
     h->grid_phys = std::max(1, std::min(want, per_sm * h->sm_count));
@@ -722,6 +732,24 @@ extern "C" int tde_reset(tde_handle* h, const uint8_t* env_mask_dev, uint64_t se
     return TDE_OK;
 }
 
+// Experiment switch (-DTDE_PDL): launch the step kernels with programmatic stream serialization; see DESIGN.md §5
+// ("tried and measured but not kept") for why the default build does not.
+template <typename Kernel>
+static cudaError_t launch_step(Kernel k, int grid, int threads, size_t smem, cudaStream_t st, const StepParams& p) {
+#ifdef TDE_PDL
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k, p);
+#else
+    k<<<grid, threads, smem, st>>>(p);
+    return cudaGetLastError();
+#endif
+}
+
 static int step_impl(tde_handle* h, int32_t phases, const float* actions, uint8_t* obs, int32_t n_stack, float* reward,
                      uint8_t* terminated, uint8_t* truncated, float* info, void* stream, const uint8_t* obs_prev = nullptr,
                      uint8_t* terminal_obs = nullptr, int e_begin = 0, int e_end = -1) {
@@ -757,21 +785,19 @@ static int step_impl(tde_handle* h, int32_t phases, const float* actions, uint8_
     }
     if (physics) {
         const int grid = std::min(h->grid_phys, want);
-        if (h->A <= 32) tde_physics_kernel<1><<<grid, threads, 0, st>>>(p);
-        else tde_physics_kernel<2><<<grid, threads, 0, st>>>(p);
-        CUDA_TRY(h, cudaGetLastError());
+        if (h->A <= 32) CUDA_TRY(h, launch_step(tde_physics_kernel<1>, grid, threads, 0, st, p));
+        else CUDA_TRY(h, launch_step(tde_physics_kernel<2>, grid, threads, 0, st, p));
         h->launches++;
     }
     if (render) {
         const int grid = std::min(h->grid_render, want);
         if (n_stack > 1) {
-            if (h->A <= 32) tde_render_kernel<1, true><<<grid, threads, h->smem_render, st>>>(p);
-            else tde_render_kernel<2, true><<<grid, threads, h->smem_render, st>>>(p);
+            if (h->A <= 32) CUDA_TRY(h, launch_step(tde_render_kernel<1, true>, grid, threads, h->smem_render, st, p));
+            else CUDA_TRY(h, launch_step(tde_render_kernel<2, true>, grid, threads, h->smem_render, st, p));
         } else {
-            if (h->A <= 32) tde_render_kernel<1, false><<<grid, threads, h->smem_render, st>>>(p);
-            else tde_render_kernel<2, false><<<grid, threads, h->smem_render, st>>>(p);
+            if (h->A <= 32) CUDA_TRY(h, launch_step(tde_render_kernel<1, false>, grid, threads, h->smem_render, st, p));
+            else CUDA_TRY(h, launch_step(tde_render_kernel<2, false>, grid, threads, h->smem_render, st, p));
         }
-        CUDA_TRY(h, cudaGetLastError());
         h->launches++;
     }
     if (deferred) {

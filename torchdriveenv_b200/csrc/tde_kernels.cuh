@@ -96,6 +96,17 @@ __device__ __forceinline__ unsigned long long tde_now() { unsigned long long t; 
 #define TDE_TRACE_MARK(e, k) do { } while (0)
 #endif
 
+// Programmatic dependent launch (experiment, -DTDE_PDL): a step kernel lets the next kernel on the stream be
+// scheduled once all its warps have run dry, and itself waits for the previous kernel's completion and memory
+// flush before it reads anything that kernel may have written.  No-ops without the launch attribute.
+#ifdef TDE_PDL
+__device__ __forceinline__ void tde_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void tde_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#else
+__device__ __forceinline__ void tde_pdl_launch_dependents() {}
+__device__ __forceinline__ void tde_pdl_wait() {}
+#endif
+
 // Envs are handed to warps one at a time from a device-side ticket counter: their costs differ (what
 // is in view, how many agents are off the road), so a fixed stride leaves most warps waiting for the
 // unluckiest one.  ctr[0] = next ticket, ctr[1] = warps that have run dry; the last of them re-arms
@@ -113,10 +124,11 @@ __device__ __forceinline__ void envs_done(unsigned int* ctr, int lane, int warps
 }
 
 #define TDE_PAIR_CAP 256
+template <int AH>   // sized for 32 * AH agents: the physics kernel lives on L1 hits, every KB not carved out for shared memory counts
 struct SatScratch {  // per warp: staged boxes, candidate pairs and hit counters of the all-pairs SAT
-    float4 pos[TDE_MAX_AGENTS];            // x y rr -   (rr = circumradius bound + 5 mm, NaN for an absent agent)
-    float4 ext[TDE_MAX_AGENTS];            // c s hl hw
-    int cnt[TDE_MAX_AGENTS];               // overlaps found per agent
+    float4 pos[32 * AH];                   // x y rr -   (rr = circumradius bound + 5 mm, NaN for an absent agent)
+    float4 ext[32 * AH];                   // c s hl hw
+    int cnt[32 * AH];                      // overlaps found per agent
     unsigned short pairs[TDE_PAIR_CAP];    // a | j << 8, a < j: pairs that survived the broad phase
 };
 
@@ -131,7 +143,8 @@ struct RenderScratch {  // per warp, render kernel
     unsigned int pad[3];
 };
 
-__device__ __forceinline__ Box sat_ld(const SatScratch* ws, int a) {
+template <int AH>
+__device__ __forceinline__ Box sat_ld(const SatScratch<AH>* ws, int a) {
     float4 u = ws->pos[a], v = ws->ext[a];
     Box b; b.x = u.x; b.y = u.y; b.hl = v.z; b.hw = v.w; b.c = v.x; b.s = v.y; b.present = 1.0f; b.r = u.z;
     return b;
@@ -143,7 +156,7 @@ __device__ __forceinline__ Box sat_ld(const SatScratch* ws, int a) {
 // surviving pairs are compacted into a list and the exact 4-axis SAT (bitwise symmetric in its
 // arguments) runs once per pair with all lanes busy; a hit counts for both agents.
 template <int AH>
-__device__ __forceinline__ void sat_counts(SatScratch* ws, const Box (&me)[AH], int A, int lane, float (&cnt_out)[AH]) {
+__device__ __forceinline__ void sat_counts(SatScratch<AH>* ws, const Box (&me)[AH], int A, int lane, float (&cnt_out)[AH]) {
     float rr[AH];
 #pragma unroll
     for (int h = 0; h < AH; ++h) {
@@ -960,6 +973,7 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, TDE_RENDER_BLOCKS_PE
     const int warps_total = gridDim.x * TDE_WARPS_PER_BLOCK;
     const float reach = viewport_reach(p);
     clear_cover(ws, lane);
+    tde_pdl_wait();
     // masked pass (re-render of the envs that were just re-initialised): plain stride, most envs are skipped
     const bool masked = p.render_mask != nullptr;
     int cursor = p.e_begin + blockIdx.x * TDE_WARPS_PER_BLOCK + warp;
@@ -974,6 +988,7 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, TDE_RENDER_BLOCKS_PE
         render_env<AH, STACKED>(p, e, lane, ws, spread_tab, reach TDE_RB_ARGS);
         TDE_TRACE_MARK(e, 1);
     }
+    tde_pdl_launch_dependents();
     if (!masked) envs_done(p.tickets, lane, warps_total);
 }
 
@@ -996,7 +1011,7 @@ __global__ void __launch_bounds__(256) tde_copy_rows_kernel(const uint8_t* __res
 // offroad / red-light / wrong-way against the lane mesh, reward, termination, truncation, info,
 // waypoint progress, episode statistics and (optionally) the in-kernel auto-reset.
 template <int AH>
-__device__ __forceinline__ void physics_env(const StepParams& p, const int e, const int lane, SatScratch* ws, double& st_acc, int& n_steps) {
+__device__ __forceinline__ void physics_env(const StepParams& p, const int e, const int lane, SatScratch<AH>* ws, double& st_acc, int& n_steps) {
     const tde_config& c = p.cfg;
     {
         const EnvVars ev = load_vars<true>(p, e, lane);
@@ -1132,10 +1147,11 @@ __device__ __forceinline__ void physics_env(const StepParams& p, const int e, co
 
 template <int AH>
 __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, TDE_PHYS_BLOCKS_PER_SM) tde_physics_kernel(const StepParams p) {
-    __shared__ SatScratch scratch[TDE_WARPS_PER_BLOCK];
+    __shared__ SatScratch<AH> scratch[TDE_WARPS_PER_BLOCK];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    SatScratch* ws = &scratch[warp];
+    SatScratch<AH>* ws = &scratch[warp];
     const int warps_total = gridDim.x * TDE_WARPS_PER_BLOCK;
+    tde_pdl_wait();
     double st_acc = 0.0;  // lane k accumulates statistic k
     int n_steps = 0;      // env steps taken by this warp
 #pragma unroll 1
@@ -1144,6 +1160,7 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, TDE_PHYS_BLOCKS_PER_
         physics_env<AH>(p, e, lane, ws, st_acc, n_steps);
         TDE_TRACE_MARK(e, 3);
     }
+    tde_pdl_launch_dependents();
     if (lane == TDE_STAT_STEPS) st_acc += (double)n_steps;
     if ((p.phases & TDE_PH_REWARD) && lane < TDE_NUM_STATS && st_acc != 0.0) atomicAdd(&p.stats[lane], st_acc);
 }
@@ -1170,10 +1187,10 @@ template <int AH>
 __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32) tde_collision_kernel(const float4* __restrict__ state,
                                                                                   const float4* __restrict__ attr, int E, int A,
                                                                                   float* __restrict__ out) {
-    __shared__ SatScratch scratch[TDE_WARPS_PER_BLOCK];
+    __shared__ SatScratch<AH> scratch[TDE_WARPS_PER_BLOCK];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int warps_total = gridDim.x * TDE_WARPS_PER_BLOCK;
-    SatScratch* ws = &scratch[warp];
+    SatScratch<AH>* ws = &scratch[warp];
     for (int e = blockIdx.x * TDE_WARPS_PER_BLOCK + warp; e < E; e += warps_total) {
         Box me[AH];
         float cnt[AH];
