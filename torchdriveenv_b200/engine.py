@@ -178,8 +178,11 @@ class Engine:
         W, H = int(res[0]), int(res[1])
         if camera_xy is None:
             m = int(self.get_env_vars()[int(env), 6])
-            tris = np.asarray(self.scenarios.maps[m].road_tris, np.float32)[:, :6].reshape(-1, 2)
-            camera_xy = (0.5 * (float(tris[:, 0].min()) + float(tris[:, 0].max())), 0.5 * (float(tris[:, 1].min()) + float(tris[:, 1].max())))
+            tris = np.asarray(self.scenarios.maps[m].road_tris, np.float32).reshape(-1, 8)[:, :6].reshape(-1, 2)
+            if tris.shape[0] == 0:      # a map without a road mesh: look at the ego
+                camera_xy = tuple(float(v) for v in self.get_state()[int(env), 0, :2])
+            else:
+                camera_xy = (0.5 * (float(tris[:, 0].min()) + float(tris[:, 0].max())), 0.5 * (float(tris[:, 1].min()) + float(tris[:, 1].max())))
         if out is None:
             out = torch.empty((3, H, W), dtype=torch.uint8, device=self.device)
         if out.shape != (3, H, W) or out.dtype != torch.uint8 or not out.is_contiguous() or out.device != self.device:
