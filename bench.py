@@ -59,12 +59,28 @@ def make_actions(E: int, n: int, seed: int) -> np.ndarray:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock, power and throttle reasons sampled DURING the timed region: NVML in a thread every 2 ms (a C3 run of
+    100 steps lasts 18 ms, too short for `nvidia-smi -lms`), `nvidia-smi` as the fallback when NVML is not importable."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
-        self.rows, self.proc, self.thread = [], None, None
+        self.rows, self.proc, self.thread, self.nvml, self.alive = [], None, None, None, True
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it lists plain indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [int(x) for x in vis.split(",")] if vis and all(x.strip().isdigit() for x in vis.split(",")) else None
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(ids[index] if ids and index < len(ids) else index)
+            self.nvml = pynvml
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -73,33 +89,57 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll_nvml(self):
+        n = self.nvml
+        bits = [(getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8), "hw_slowdown"),
+                (getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40), "hw_thermal_slowdown"),
+                (getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), "sw_thermal_slowdown"),
+                (getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4), "sw_power_cap")]
+        while self.alive:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                pw = float(n.nvmlDeviceGetPowerUsage(self.handle)) / 1e3
+                try:
+                    mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                flags = ["Active" if mask & b else "Not Active" for b, _ in bits]
+                self.rows.append((time.time(), ", ".join([f"{sm}", f"{self.max_sm}", f"{pw}"] + flags)))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
     def stop(self, t0: float, t1: float):
-        if self.proc is None:
+        if self.proc is None and self.nvml is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
-        time.sleep(0.12)
-        self.proc.terminate()
-        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.1]
+        if self.nvml is not None:
+            self.alive = False
+            self.thread.join(timeout=1.0)
+        else:
+            time.sleep(0.12)
+            self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1]
         window = "timed region"
         if len(rows) < 3:   # short timed region: fall back to every sample taken while the GPU was busy (warm-up .. end)
-            rows, window = [r for (_, r) in self.rows], "warm-up + timed region"
+            rows, window = [r for (t, r) in self.rows if t <= t1 + 0.1], "warm-up + timed region"
         self.window = window
         sm, mx, reasons, pw = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in rows:
             f = [x.strip() for x in r.split(",")]
             try:
                 sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
             except Exception:
                 continue
-            for n, v in zip(names, f[3:7]):
+            for n, v in zip(self.NAMES, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=float(max(mx)) if mx else None,
-                    power_w_max=float(max(pw)) if pw else None, reasons=sorted(reasons), samples=len(sm), window=self.window)
+                    power_w_max=float(max(pw)) if pw else None, reasons=sorted(reasons), samples=len(sm), window=self.window,
+                    source="nvml" if self.nvml is not None else "nvidia-smi")
 
 
 def measured_peak_hbm():

@@ -351,10 +351,11 @@ def test_host_buffer_entry_point(oracle):
         assert np.array_equal(obs, oobs) and np.array_equal(r, orr) and np.array_equal(te, ote) and np.array_equal(info, oinfo)
 
 
-def test_host_buffer_entry_point_chunked_pipeline():
+@pytest.mark.parametrize("E", [4100, 8200])    # 8 and 16 chunks; neither is a multiple of its chunk count
+def test_host_buffer_entry_point_chunked_pipeline(E):
     """From 4,096 envs on tde_step_host steps the envs in chunks and sends each chunk's frames back while the
     next chunk is computed: same results as the one-launch device-resident step, statistics included."""
-    E, A = 4100, 8          # not a multiple of the chunk count
+    A = 8
     ss = S.traffic_lights(A)
     eng = _engine(ss, E, A, auto_reset=1)
     ref = _engine(ss, E, A, auto_reset=1)

@@ -47,7 +47,7 @@ struct tde_handle {
     uint8_t *h_term = nullptr, *h_trunc = nullptr; float* h_info = nullptr;
     ViewPrim* view_prims = nullptr; int view_cap = 0;   // tde_render_view scratch
     cudaStream_t copy_stream = nullptr;          // tde_step_host: observation chunks go back while later chunks are computed
-    cudaEvent_t chunk_done[8] = {}, copies_done = nullptr;
+    cudaEvent_t chunk_done[16] = {}, copies_done = nullptr;
     std::string err;
 };
 
@@ -894,7 +894,7 @@ extern "C" int tde_step_host(tde_handle* h, const float* actions, uint8_t* obs, 
     CUDA_TRY(h, cudaMemcpyAsync(h->h_actions, actions, E * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
     // With observations the step is bound by the 12 KB per env that cross PCIe: the envs are stepped in
     // chunks, and the frames of a finished chunk travel on a second stream while the next chunk is computed.
-    const int chunks = (obs && h->E >= 4096) ? 8 : 1;
+    const int chunks = !obs || h->E < 4096 ? 1 : h->E < 8192 ? 8 : 16;   // only the first chunk's compute is not hidden behind the copies
     if (chunks == 1) {
         int rc = tde_step(h, h->h_actions, obs ? h->h_obs : nullptr, h->h_reward, h->h_term, h->h_trunc, h->h_info, stream);
         if (rc) return rc;
