@@ -905,16 +905,17 @@ __device__ __forceinline__ void render_env(const StepParams& p, const int e, con
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf)
                 idx[hf] = spread_tab[pb[hf]] + 2u * spread_tab[pb[8 + hf]] + 4u * spread_tab[pb[16 + hf]] + 8u * spread_tab[pb[24 + hf]];
-            uint32_t sel7[4], himask[4];
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                uint32_t sel = (idx[g >> 1] >> (16 * (g & 1))) & 0xffffu;
-                sel7[g] = sel & 0x7777u;
-                himask[g] = __byte_perm(0x0000ff00u, 0u, (sel >> 3) & 0x1111u);
-            }
-            // classes 8..15 (the ego and the direction triangles) are rare: eight rows without one take the short path
+            // classes 8..15 (the ego and the direction triangles) are rare: eight rows without one take the short path,
+            // where the nibbles of idx are PRMT selectors as they stand (values 0..7; PRMT reads selector bits 0..15 only)
             const bool any_hi = __any_sync(FULL_MASK, ((idx[0] | idx[1]) & 0x88888888u) != 0u);
+            const uint32_t sel[4] = {idx[0], idx[0] >> 16, idx[1], idx[1] >> 16};
             if (any_hi) {
+                uint32_t sel7[4], himask[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    sel7[g] = sel[g] & 0x7777u;
+                    himask[g] = __byte_perm(0x0000ff00u, 0u, (sel[g] >> 3) & 0x1111u);
+                }
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) {
                     uint32_t w[4];
@@ -931,7 +932,7 @@ __device__ __forceinline__ void render_env(const StepParams& p, const int e, con
                 for (int ch = 0; ch < 3; ++ch) {
                     uint32_t w[4];
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) w[g] = __byte_perm(p.pal[ch][0], p.pal[ch][1], sel7[g]);
+                    for (int g = 0; g < 4; ++g) w[g] = __byte_perm(p.pal[ch][0], p.pal[ch][1], sel[g]);
                     *reinterpret_cast<uint4*>(out + ch * (TDE_OBS_H * TDE_OBS_W) + row * TDE_OBS_W + qd * 16) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
             }
