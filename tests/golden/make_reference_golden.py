@@ -193,24 +193,22 @@ def oracle_config(ref_cfg, A):
     return default_config(num_envs=1, max_agents=A, **G.engine_config(mine, auto_reset=0))
 
 
-def run_case(ref, name):
+def drive_episode(ref, cfg, data, ss, A, steps, policy, seed, check_build=None):
+    """Runs the reference's SingleAgentWrapper(WaypointSuiteEnv(cfg, data)) for `steps` steps over an OracleSimulator on
+    the scenario set `ss`; returns the recorded episode and the agreement report."""
     from oracle import oracle as O
-    set_name, overrides, steps, policy, seed = CASES[name]
-    builder, A = scenario_sets()[set_name]
-    ss = builder()
     packed = ss.pack(A)
-    cfg = ref.EnvConfig(seed=seed, **overrides)
-    data = ref.WaypointSuite(locations=[f"Town{k:02d}" for k in range(len(ss.scenarios))],
-                             waypoint_suite=[np.asarray(s.waypoints, np.float64).tolist() for s in ss.scenarios],
-                             car_sequence_suite=[None] * len(ss.scenarios), scenarios=[None] * len(ss.scenarios))
     made = {}
 
     # the glue to torchdrivesim, replaced (see the module docstring)
-    ref.find_map_config = lambda map_name: types.SimpleNamespace(name=map_name, lanelet_map=int(map_name[-2:]))
+    locations = list(data.locations)      # find_map_config(f"carla_{location}") :312 -> the suite entry of that name
+    ref.find_map_config = lambda map_name: types.SimpleNamespace(name=map_name, lanelet_map=locations.index(map_name[len("carla_"):]))
     ref.find_lanelet_directions = lambda lanelet_map, x, y: [float(ss.scenarios[lanelet_map].start_heading)]
 
     def build_simulator(cfg, map_cfg, device, ego_state, scenario=None, car_sequences=None, waypointseq=None):
         k = map_cfg.lanelet_map
+        if check_build is not None:
+            check_build(k, scenario, car_sequences, waypointseq, packed)
         orc = O.OracleEnvSet(oracle_config(cfg, A), packed)
         orc.set_env_scenario_range([k], [k + 1])
         orc.reset(seed=seed)
@@ -258,8 +256,7 @@ def run_case(ref, name):
                terminated=np.asarray(out["terminated"], np.uint8), truncated=np.asarray(out["truncated"], np.uint8),
                info=np.asarray(out["info"], np.float64), states=np.asarray(out["states"], np.float32),
                target_idx=np.asarray(out["target_idx"], np.int32), start_state=made["start"], scenario=np.int32(made["scenario"]),
-               seed=np.int64(seed), max_agents=np.int32(A), scenario_set=np.str_(set_name),
-               env_config=np.str_(json.dumps(overrides)), info_keys=np.str_(json.dumps(INFO_KEYS)), types=np.str_(json.dumps(types_seen)))
+               seed=np.int64(seed), max_agents=np.int32(A), info_keys=np.str_(json.dumps(INFO_KEYS)), types=np.str_(json.dumps(types_seen)))
     # the comparison itself (also what tests/test_reference_golden.py repeats from the frozen vectors)
     orc_info = np.asarray(out["orc_info"], np.float64)
     report = dict(reward_max_abs=float(np.max(np.abs(res["reward"] - np.asarray(out["orc_reward"])))),
@@ -272,10 +269,122 @@ def run_case(ref, name):
     return res, report
 
 
+def run_case(ref, name):
+    set_name, overrides, steps, policy, seed = CASES[name]
+    builder, A = scenario_sets()[set_name]
+    ss = builder()
+    cfg = ref.EnvConfig(seed=seed, **overrides)
+    data = ref.WaypointSuite(locations=[f"Town{k:02d}" for k in range(len(ss.scenarios))],
+                             waypoint_suite=[np.asarray(s.waypoints, np.float64).tolist() for s in ss.scenarios],
+                             car_sequence_suite=[None] * len(ss.scenarios), scenarios=[None] * len(ss.scenarios))
+    res, report = drive_episode(ref, cfg, data, ss, A, steps, policy, seed)
+    res.update(scenario_set=np.str_(set_name), env_config=np.str_(json.dumps(overrides)))
+    return res, report
+
+
+# ----------------------------------------------------------------------------- the reference's own validation suite
+VALIDATION_YML = os.path.join(REFERENCE, "torchdriveenv", "data", "validation_cases.yml")
+SUITE_CASES = {   # name: (entry of validation_cases.yml, env-config overrides, steps, policy, seed)
+    "refsuite_case0_three_way": (0, dict(terminated_at_infraction=False), 150, "pursuit", 31),
+    "refsuite_case1_parked_car": (1, dict(terminated_at_infraction=False), 150, "pursuit", 32),
+    "refsuite_case2_chicken": (2, dict(), 100, "pursuit", 33),
+    "refsuite_case3_roundabout": (3, dict(terminated_at_infraction=False, distance_cutoff=0.25), 206, "pursuit", 34),
+    "refsuite_case4_traffic_lights": (4, dict(terminated_at_infraction=False, distance_cutoff=0.25), 206, "pursuit", 35),
+}
+
+
+def import_reference_env_utils():
+    """The reference's torchdriveenv/env_utils.py, unmodified; OmegaConf (absent) is stood in for by PyYAML."""
+    import yaml
+    before = set(sys.modules)
+    _install_stand_ins()
+    om = types.ModuleType("omegaconf")
+    om.OmegaConf = type("OmegaConf", (), {"load": staticmethod(lambda path: yaml.load(open(path), Loader=getattr(yaml, "CSafeLoader", yaml.SafeLoader))),
+                                          "to_object": staticmethod(lambda x: x)})
+    sys.modules["omegaconf"] = om
+    sys.path.insert(0, REFERENCE)
+    try:
+        mod = importlib.import_module("torchdriveenv.env_utils")
+    finally:
+        sys.path.remove(REFERENCE)
+        for name in set(sys.modules) - before:
+            if name.split(".")[0] in ("gymnasium", "invertedai", "torchdrivesim", "omegaconf"):
+                del sys.modules[name]
+    return mod
+
+
+def suite_entry(data, k):
+    """Entry k of a WaypointSuite as plain arrays (what the fixture stores and the tests rebuild the scenario from)."""
+    sc = data.scenarios[k]
+    seqs = data.car_sequence_suite[k] or {}
+    keys = sorted(int(q) for q in seqs)
+    return dict(suite_location=np.str_(data.locations[k]), suite_waypoints=np.asarray(data.waypoint_suite[k], np.float64),
+                suite_agent_states=np.asarray(sc.agent_states if sc is not None else [], np.float64).reshape(-1, 4),
+                suite_agent_attributes=np.asarray(sc.agent_attributes if sc is not None else [], np.float64).reshape(-1, 3),
+                suite_car_seq_keys=np.asarray(keys, np.int32),
+                suite_car_seqs=(np.asarray([seqs[q] if q in seqs else seqs[str(q)] for q in keys], np.float64).reshape(len(keys), -1, 4)
+                                if keys else np.zeros((0, 0, 4), np.float64)))
+
+
+def suite_from_entry(d, G):
+    """The inverse of suite_entry: a one-entry WaypointSuite of the product's dataclasses."""
+    sc = None
+    if len(d["suite_agent_states"]):
+        sc = G.Scenario(agent_states=d["suite_agent_states"].tolist(), agent_attributes=d["suite_agent_attributes"].tolist(),
+                        recurrent_states=[[0.0]] * len(d["suite_agent_states"]))
+    seqs = {int(q): d["suite_car_seqs"][i].tolist() for i, q in enumerate(d["suite_car_seq_keys"])}
+    return G.WaypointSuite(locations=[str(d["suite_location"])], waypoint_suite=[d["suite_waypoints"].tolist()],
+                           car_sequence_suite=[seqs], scenarios=[sc])
+
+
+def run_suite_case(ref, ref_utils, name):
+    """One entry of the reference's validation_cases.yml, loaded by the REFERENCE'S loader, driven through the reference's
+    env; the scenario tables come from the product's loader + scenario_set_from_suite on the same file, and the
+    arguments the reference hands to build_simulator are checked against those tables."""
+    from torchdriveenv_b200 import env_utils as U, gym_env as G
+    k, overrides, steps, policy, seed = SUITE_CASES[name]
+    data_ref = ref_utils.load_waypoint_suite_data(VALIDATION_YML)
+    data_mine = U.load_waypoint_suite_data(VALIDATION_YML)
+    for field in ("locations", "waypoint_suite", "car_sequence_suite"):
+        assert getattr(data_ref, field) == getattr(data_mine, field), field
+    for a, b in zip(data_ref.scenarios, data_mine.scenarios):
+        assert (a is None) == (b is None) and (a is None or (a.agent_states == b.agent_states and a.agent_attributes == b.agent_attributes))
+    entry = suite_entry(data_mine, k)
+    one_mine = suite_from_entry(entry, G)
+    one_ref = ref.WaypointSuite(locations=[data_ref.locations[k]], waypoint_suite=[data_ref.waypoint_suite[k]],
+                                car_sequence_suite=[data_ref.car_sequence_suite[k]], scenarios=[data_ref.scenarios[k]])
+    cfg = ref.EnvConfig(seed=seed, **overrides)
+    ss = G.scenario_set_from_suite(G.EnvConfig(**overrides), one_mine, n_background=0, seed=0)
+    A = ss.max_agents()
+
+    def check_build(idx, scenario, car_sequences, waypointseq, packed):
+        # what the reference passes down (gym_env.py:339-345) against the tables the product built from the same file
+        assert idx == 0
+        assert np.allclose(packed["waypoints"], np.asarray(waypointseq, np.float32))
+        n_pre = 0 if scenario is None else len(scenario.agent_states)
+        if n_pre:
+            assert np.allclose(packed["agent_init"][0, 1:1 + n_pre], np.asarray(scenario.agent_states, np.float32))
+            assert np.allclose(packed["agent_attr"][0, 1:1 + n_pre], np.asarray(scenario.agent_attributes, np.float32))
+        assert int(packed["scen_num_agents"][0]) == 1 + n_pre
+        for key, seq in (car_sequences or {}).items():      # dict key = agent slot (gym_env.py:279)
+            seq = np.asarray(seq, np.float32)
+            rs = packed["replay_states"].reshape(-1, A, 4)
+            assert np.allclose(rs[: len(seq), int(key)], seq) and packed["replay_mask"][: len(seq), int(key)].all()
+    res, report = drive_episode(ref, cfg, one_ref, ss, A, steps, policy, seed, check_build)
+    res.update(entry)
+    res.update(env_config=np.str_(json.dumps(overrides)), suite_index=np.int32(k))
+    return res, report
+
+
 if __name__ == "__main__":
     ref = import_reference()
     here = os.path.dirname(os.path.abspath(__file__))
     for name in CASES:
         res, report = run_case(ref, name)
+        np.savez_compressed(os.path.join(here, name + ".npz"), **res)
+        print(name, report)
+    ref_utils = import_reference_env_utils()
+    for name in SUITE_CASES:
+        res, report = run_suite_case(ref, ref_utils, name)
         np.savez_compressed(os.path.join(here, name + ".npz"), **res)
         print(name, report)

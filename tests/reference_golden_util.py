@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-NAMES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(HERE, "golden", "ref_*.npz")))
+NAMES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(HERE, "golden", "ref_*.npz")) + glob.glob(os.path.join(HERE, "golden", "refsuite_*.npz")))
 
 # the reference evaluates reward and info in float64 (math.dist / math.cos on fp32 tensors, gym_env.py:401-403,
 # :430-435); the path computes them in binary32 (DESIGN D12): north-star tolerance 1e-5 relative
@@ -24,6 +24,19 @@ def load(name):
 
 def scenario_set(d):
     from torchdriveenv_b200 import scenarios as S
+    if "suite_waypoints" in d:
+        # an entry of the reference's validation_cases.yml (frozen in the fixture): WaypointSuite -> scenario tables through
+        # the product's own scenario_set_from_suite, as WaypointSuiteEnv does
+        from torchdriveenv_b200 import gym_env as G
+        sc = None
+        if len(d["suite_agent_states"]):
+            sc = G.Scenario(agent_states=d["suite_agent_states"].tolist(), agent_attributes=d["suite_agent_attributes"].tolist(),
+                            recurrent_states=[[0.0]] * len(d["suite_agent_states"]))
+        seqs = {int(q): d["suite_car_seqs"][i].tolist() for i, q in enumerate(d["suite_car_seq_keys"])}
+        suite = G.WaypointSuite(locations=[str(d["suite_location"])], waypoint_suite=[d["suite_waypoints"].tolist()],
+                                car_sequence_suite=[seqs], scenarios=[sc])
+        ss = G.scenario_set_from_suite(G.EnvConfig(**d["env_config"]), suite, n_background=0, seed=0)
+        return ss, ss.max_agents()
     builders = {"three_way": lambda: S.three_way(6), "traffic_lights": lambda: S.traffic_lights(12),
                 "roundabout": lambda: S.roundabout(8), "validation_mix": lambda: S.validation_mix(8)}
     return builders[str(d["scenario_set"])](), int(d["max_agents"])

@@ -13,7 +13,7 @@ import reference_golden_util as R
 
 
 def test_fixtures_exist_and_cover_the_decisions():
-    assert len(R.NAMES) >= 8
+    assert len(R.NAMES) >= 15 and sum(n.startswith("refsuite_") for n in R.NAMES) == 5
     seen = dict(terminated=0, truncated=0, reached=0, offroad=0, collision=0, red=0)
     for n in R.NAMES:
         d = R.load(n)
@@ -63,5 +63,14 @@ def test_fixtures_regenerate_from_the_reference(oracle):
         res, report = m.run_case(ref, name)
         d = R.load(name)
         for key in ("actions", "reward", "terminated", "truncated", "info", "states", "target_idx", "start_state"):
+            assert np.array_equal(res[key], d[key]), f"{name}:{key}"
+        assert report["flags_equal"] and report["reward_max_abs"] < 1e-5 and report["info_max_abs"] < 1e-5
+    # the reference's own validation suite, loaded by the reference's loader (and by the product's: same content), with the
+    # arguments the reference hands to build_simulator checked against the product's scenario tables
+    ref_utils = m.import_reference_env_utils()
+    for name in ("refsuite_case1_parked_car", "refsuite_case2_chicken"):
+        res, report = m.run_suite_case(ref, ref_utils, name)
+        d = R.load(name)
+        for key in ("actions", "reward", "terminated", "truncated", "info", "states", "target_idx", "start_state", "suite_waypoints", "suite_car_seqs"):
             assert np.array_equal(res[key], d[key]), f"{name}:{key}"
         assert report["flags_equal"] and report["reward_max_abs"] < 1e-5 and report["info_max_abs"] < 1e-5
