@@ -376,6 +376,86 @@ def run_suite_case(ref, ref_utils, name):
     return res, report
 
 
+# ----------------------------------------------------------------------------- the reference's episode metrics
+def import_reference_eval_callback():
+    """examples/rl_training.py, unmodified, for its EvalNTimestepsCallback._calc_metrics (:39-67): the per-episode
+    aggregates the episode-statistics vector of the C ABI (TDE_STAT_*) stands for.  stable-baselines3 and wandb
+    (absent) are name-only stand-ins; the callback's metric code does not touch them."""
+    import yaml
+    before = set(sys.modules)
+    _install_stand_ins()
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name); m.__dict__.update(attrs); sys.modules[name] = m
+        return m
+    blank = lambda n: type(n, (), {"__init__": lambda self, *a, **k: None})
+    mod("omegaconf", OmegaConf=type("OmegaConf", (), {"load": staticmethod(lambda path: yaml.load(open(path), Loader=getattr(yaml, "CSafeLoader", yaml.SafeLoader))),
+                                                      "to_object": staticmethod(lambda x: x)}))
+    mod("wandb"); mod("wandb.integration"); mod("wandb.integration.sb3", WandbCallback=blank("WandbCallback"))
+    mod("stable_baselines3", SAC=blank("SAC"), PPO=blank("PPO"), A2C=blank("A2C"), TD3=blank("TD3"))
+    mod("stable_baselines3.common")
+    mod("stable_baselines3.common.monitor", Monitor=blank("Monitor"))
+    mod("stable_baselines3.common.vec_env", VecVideoRecorder=blank("VecVideoRecorder"), VecFrameStack=blank("VecFrameStack"), SubprocVecEnv=blank("SubprocVecEnv"))
+    mod("stable_baselines3.common.callbacks", BaseCallback=blank("BaseCallback"))
+    mod("stable_baselines3.common.evaluation", evaluate_policy=None)
+    ex = os.path.join(REFERENCE, "examples")
+    sys.path.insert(0, REFERENCE); sys.path.insert(0, ex)
+    try:
+        rl = importlib.import_module("rl_training")
+    finally:
+        sys.path.remove(ex); sys.path.remove(REFERENCE)
+        for name in set(sys.modules) - before:
+            if name.split(".")[0] in ("gymnasium", "invertedai", "torchdrivesim", "omegaconf", "wandb", "stable_baselines3", "common", "rl_training"):
+                del sys.modules[name]
+    return rl
+
+
+def reference_episode_metrics(rl, infos_per_episode):
+    """Feeds per-step info dicts (one list per episode) through the reference's EvalNTimestepsCallback._calc_metrics,
+    the way _evaluate does (:83-95), and returns its counters."""
+    cb = rl.EvalNTimestepsCallback(eval_env=None, n_steps=1, eval_n_episodes=len(infos_per_episode))
+    cb.episode_num = cb.offroad_num = cb.collision_num = cb.traffic_light_violation_num = cb.success_num = 0
+    cb.reached_waypoint_nums, cb.psi_smoothness, cb.speed_smoothness = [], [], []
+    for infos in infos_per_episode:
+        cb.psi_smoothness_for_single_episode, cb.speed_smoothness_for_single_episode = [], []
+        for info in infos:
+            cb._calc_metrics({"info": info}, {})
+    return dict(episodes=cb.episode_num, offroad=cb.offroad_num, collision=cb.collision_num,
+                traffic_light_violation=cb.traffic_light_violation_num, success=cb.success_num,
+                reached_waypoints=float(sum(cb.reached_waypoint_nums)))
+
+
+def run_metrics_case(rl, E=48, steps=260, seed=41):
+    """E oracle envs with auto-reset, random actions: every finished episode's per-step infos go through the reference's
+    metric code; its counters must equal the oracle's episode-statistics vector."""
+    from oracle import oracle as O
+    from torchdriveenv_b200 import scenarios as S
+    from torchdriveenv_b200._capi import INFO_COLUMNS as IC, STAT_NAMES, default_config
+    ss = S.validation_mix(8)
+    A = ss.max_agents()
+    orc = O.OracleEnvSet(default_config(num_envs=E, max_agents=A, auto_reset=1, max_environment_steps=60), ss.pack(A))
+    orc.reset(seed=seed)
+    rng = np.random.default_rng(seed)
+    open_eps = [[] for _ in range(E)]
+    done_eps = []
+    acts = []
+    for t in range(steps):
+        a = np.stack([rng.uniform(-0.2, 1, E), rng.uniform(-0.1, 0.1, E)], 1).astype(np.float32)
+        acts.append(a)
+        _, rew, term, trunc, info = orc.step(a)
+        for e in range(E):
+            row = info[e]
+            open_eps[e].append(dict(offroad=row[IC["offroad"]], collision=row[IC["collision"]], traffic_light_violation=row[IC["traffic_light_violation"]],
+                                    is_success=bool(row[IC["is_success"]] != 0), reached_waypoint_num=int(row[IC["reached_waypoint_num"]]),
+                                    psi_smoothness=float(row[IC["psi_smoothness"]]), speed_smoothness=float(row[IC["speed_smoothness"]])))
+            if term[e] or trunc[e]:
+                done_eps.append(open_eps[e]); open_eps[e] = []
+    want = reference_episode_metrics(rl, done_eps)
+    stats = {n: float(orc.stats[i]) for i, n in enumerate(STAT_NAMES)}
+    return dict(actions=np.asarray(acts, np.float32), seed=np.int64(seed), num_envs=np.int32(E), max_agents=np.int32(A),
+                ref_metrics=np.str_(json.dumps(want))), want, stats
+
+
 if __name__ == "__main__":
     ref = import_reference()
     here = os.path.dirname(os.path.abspath(__file__))
@@ -383,6 +463,11 @@ if __name__ == "__main__":
         res, report = run_case(ref, name)
         np.savez_compressed(os.path.join(here, name + ".npz"), **res)
         print(name, report)
+    rl = import_reference_eval_callback()
+    res, want, stats = run_metrics_case(rl)
+    print("refmetrics_validation_mix", want, {k: stats[k] for k in want})
+    assert all(float(want[k]) == stats[k] for k in want)
+    np.savez_compressed(os.path.join(here, "refmetrics_validation_mix.npz"), **res)
     ref_utils = import_reference_env_utils()
     for name in SUITE_CASES:
         res, report = run_suite_case(ref, ref_utils, name)

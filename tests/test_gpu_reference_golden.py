@@ -52,3 +52,24 @@ def test_product_api_returns_what_the_reference_returns():
         else:
             assert got == kind, f"info[{key}]: {got} vs the reference's {kind}"
     env.close()
+
+
+def test_cuda_episode_statistics_match_the_reference_callback():
+    """tde_get_episode_stats against the counters of the reference's EvalNTimestepsCallback._calc_metrics
+    (examples/rl_training.py:39-67) for the 366 episodes of the frozen run."""
+    import json
+    import os
+    from torchdriveenv_b200 import scenarios as S
+    from torchdriveenv_b200._capi import STAT_NAMES
+    from torchdriveenv_b200.engine import Engine
+    d = dict(np.load(os.path.join(R.HERE, "golden", "refmetrics_validation_mix.npz")))
+    want = json.loads(str(d["ref_metrics"]))
+    E, A = int(d["num_envs"]), int(d["max_agents"])
+    eng = Engine(S.validation_mix(8), E, A, device="cuda:0", auto_reset=1, max_environment_steps=60)
+    eng.reset(seed=int(d["seed"]))
+    for a in d["actions"]:
+        eng.step(torch.from_numpy(a).cuda(), render=False)
+    got = {n: float(v) for n, v in zip(STAT_NAMES, eng.episode_stats())}
+    for k, v in want.items():
+        assert got[k] == float(v), k
+    eng.close()

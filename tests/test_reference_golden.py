@@ -74,3 +74,38 @@ def test_fixtures_regenerate_from_the_reference(oracle):
         for key in ("actions", "reward", "terminated", "truncated", "info", "states", "target_idx", "start_state", "suite_waypoints", "suite_car_seqs"):
             assert np.array_equal(res[key], d[key]), f"{name}:{key}"
         assert report["flags_equal"] and report["reward_max_abs"] < 1e-5 and report["info_max_abs"] < 1e-5
+
+
+def _metrics_fixture():
+    d = dict(np.load(os.path.join(R.HERE, "golden", "refmetrics_validation_mix.npz")))
+    return d, json.loads(str(d["ref_metrics"]))
+
+
+def test_episode_statistics_match_the_reference_callback(oracle):
+    """The episode-statistics vector (TDE_STAT_*, what the N GPUs all-reduce) against the counters of the reference's
+    own EvalNTimestepsCallback._calc_metrics (examples/rl_training.py:39-67), which were fed every finished episode
+    of this run when the fixture was made (tests/golden/make_reference_golden.py::run_metrics_case)."""
+    from torchdriveenv_b200 import scenarios as S
+    from torchdriveenv_b200._capi import STAT_NAMES, default_config
+    d, want = _metrics_fixture()
+    E, A = int(d["num_envs"]), int(d["max_agents"])
+    orc = oracle.OracleEnvSet(default_config(num_envs=E, max_agents=A, auto_reset=1, max_environment_steps=60), S.validation_mix(8).pack(A))
+    orc.reset(seed=int(d["seed"]))
+    for a in d["actions"]:
+        orc.step(a)
+    got = {n: float(orc.stats[i]) for i, n in enumerate(STAT_NAMES)}
+    assert want["episodes"] > 300
+    for k, v in want.items():
+        assert got[k] == float(v), k
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/examples/rl_training.py"), reason="reference checkout not present")
+def test_metrics_fixture_regenerates_from_the_reference(oracle):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_reference_golden", os.path.join(R.HERE, "golden", "make_reference_golden.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    rl = m.import_reference_eval_callback()
+    res, want, stats = m.run_metrics_case(rl)
+    d, frozen = _metrics_fixture()
+    assert want == frozen and np.array_equal(res["actions"], d["actions"])
+    assert all(float(want[k]) == stats[k] for k in want)
