@@ -456,6 +456,52 @@ def run_metrics_case(rl, E=48, steps=260, seed=41):
                 ref_metrics=np.str_(json.dumps(want))), want, stats
 
 
+# ----------------------------------------------------------------------------- scenario-builder JSON (row f2)
+LABELED_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "labeled_json")
+
+
+def write_labeled_inputs():
+    """Three small scenario-builder files with the schema the reference reads (env_utils.py:31-105): a plain route, a
+    route with a parked car (max_speed 0 -> 200-step replay) and a moving one (5 states -> replay), and a route with a
+    single-state agent (random initial speed 5..10: the only random draw, so the file order does not matter)."""
+    os.makedirs(LABELED_DIR, exist_ok=True)
+    st = lambda x, y, o=0.0: dict(center=dict(x=x, y=y), orientation=o, speed=0.0)
+    route = lambda pts: {"0": dict(states=[st(x, y) for x, y in pts])}
+    attrs = lambda l, w, r, **k: dict(length=l, width=w, rear_axis_offset=r, **k)
+    files = {
+        "carla_Town01_plain.json": dict(individual_suggestions=route([(0, 0), (12, 0), (24, 3), (36, 9)]), predetermined_agents=None),
+        "carla_Town03_replay.json": dict(individual_suggestions=route([(5, 5), (5, 20), (5, 35)]),
+                                         predetermined_agents={"1": dict(states={"0": st(5.0, 30.0, 1.57)}, static_attributes=attrs(4.9, 2.0, 1.4, max_speed=0)),
+                                                               "2": dict(states={str(i): st(9.0, 10.0 + 2.0 * i, 1.57) for i in range(5)},
+                                                                         static_attributes=attrs(5.2, 2.1, 1.5))}),
+        "carla_Town07_single.json": dict(individual_suggestions=route([(-3, 1), (-15, 1), (-27, 4)]),
+                                         predetermined_agents={"1": dict(states={"0": st(-20.0, 4.5, 3.14)}, static_attributes=attrs(4.5, 1.9, 1.3))}),
+    }
+    for name, content in files.items():
+        with open(os.path.join(LABELED_DIR, name), "w") as f:
+            json.dump(content, f, indent=1)
+
+
+def suite_as_plain(suite):
+    """WaypointSuite (either package's dataclass) -> JSON-able entries sorted by location."""
+    rows = []
+    for k, loc in enumerate(suite.locations):
+        sc = suite.scenarios[k]
+        seqs = suite.car_sequence_suite[k]
+        rows.append(dict(location=loc, waypoints=suite.waypoint_suite[k],
+                         agent_states=None if sc is None else sc.agent_states, agent_attributes=None if sc is None else sc.agent_attributes,
+                         n_recurrent=None if sc is None else [len(r) for r in sc.recurrent_states],
+                         car_sequences=None if seqs is None else {str(q): v for q, v in sorted(seqs.items())}))
+    return sorted(rows, key=lambda r: r["location"])
+
+
+def run_labeled_case(ref_utils):
+    import random
+    write_labeled_inputs()
+    random.seed(7)
+    return suite_as_plain(ref_utils.load_labeled_data(LABELED_DIR))
+
+
 if __name__ == "__main__":
     ref = import_reference()
     here = os.path.dirname(os.path.abspath(__file__))
@@ -469,6 +515,10 @@ if __name__ == "__main__":
     assert all(float(want[k]) == stats[k] for k in want)
     np.savez_compressed(os.path.join(here, "refmetrics_validation_mix.npz"), **res)
     ref_utils = import_reference_env_utils()
+    labeled = run_labeled_case(ref_utils)
+    with open(os.path.join(here, "ref_labeled_suite.json"), "w") as f:
+        json.dump(labeled, f, indent=1)
+    print("ref_labeled_suite", [(r["location"], None if r["agent_states"] is None else len(r["agent_states"])) for r in labeled])
     for name in SUITE_CASES:
         res, report = run_suite_case(ref, ref_utils, name)
         np.savez_compressed(os.path.join(here, name + ".npz"), **res)

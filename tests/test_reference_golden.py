@@ -109,3 +109,24 @@ def test_metrics_fixture_regenerates_from_the_reference(oracle):
     d, frozen = _metrics_fixture()
     assert want == frozen and np.array_equal(res["actions"], d["actions"])
     assert all(float(want[k]) == stats[k] for k in want)
+
+
+def test_labeled_data_loader_matches_the_reference():
+    """env_utils.load_labeled_data (scenario-builder JSON, reference env_utils.py:31-105): tests/golden/ref_labeled_suite.json
+    is what the reference's own loader returned for tests/golden/labeled_json/*.json with random.seed(7)."""
+    import random
+    from torchdriveenv_b200 import env_utils as U
+    want = json.load(open(os.path.join(R.HERE, "golden", "ref_labeled_suite.json")))
+    random.seed(7)
+    suite = U.load_labeled_data(os.path.join(R.HERE, "golden", "labeled_json"))
+    rows = []
+    for k, loc in enumerate(suite.locations):
+        sc, seqs = suite.scenarios[k], suite.car_sequence_suite[k]
+        rows.append(dict(location=loc, waypoints=suite.waypoint_suite[k],
+                         agent_states=None if sc is None else sc.agent_states, agent_attributes=None if sc is None else sc.agent_attributes,
+                         n_recurrent=None if sc is None else [len(r) for r in sc.recurrent_states],
+                         car_sequences=None if seqs is None else {str(q): v for q, v in sorted(seqs.items())}))
+    got = json.loads(json.dumps(sorted(rows, key=lambda r: r["location"])))
+    assert got == want
+    assert want[1]["car_sequences"].keys() == {"1", "2"} and len(want[1]["car_sequences"]["1"]) == 200 and len(want[1]["car_sequences"]["2"]) == 5
+    assert 5 <= want[2]["agent_states"][0][3] <= 10
