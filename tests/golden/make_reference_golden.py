@@ -515,6 +515,17 @@ if __name__ == "__main__":
     assert all(float(want[k]) == stats[k] for k in want)
     np.savez_compressed(os.path.join(here, "refmetrics_validation_mix.npz"), **res)
     ref_utils = import_reference_env_utils()
+    # EnvConfig as the reference constructs it from the `env:` section of its shipped training configs (env_utils.py:10-12)
+    import glob
+    import yaml
+    env_cfgs = {}
+    for path in sorted(glob.glob(os.path.join(REFERENCE, "examples", "env_configs", "*", "*.yml"))):
+        raw = yaml.safe_load(open(path))["env"]
+        c = ref_utils.construct_env_config(raw)
+        env_cfgs["/".join(path.split(os.sep)[-2:])] = dict(raw=raw, fields={k: getattr(c, k) for k in c.__dataclass_fields__ if k != "simulator"})
+    with open(os.path.join(here, "ref_env_configs.json"), "w") as f:
+        json.dump(env_cfgs, f, indent=1)
+    print("ref_env_configs", len(env_cfgs))
     labeled = run_labeled_case(ref_utils)
     with open(os.path.join(here, "ref_labeled_suite.json"), "w") as f:
         json.dump(labeled, f, indent=1)

@@ -130,3 +130,15 @@ def test_labeled_data_loader_matches_the_reference():
     assert got == want
     assert want[1]["car_sequences"].keys() == {"1", "2"} and len(want[1]["car_sequences"]["1"]) == 200 and len(want[1]["car_sequences"]["2"]) == 5
     assert 5 <= want[2]["agent_states"][0][3] <= 10
+
+
+def test_env_config_construction_matches_the_reference():
+    """construct_env_config (reference env_utils.py:10-12) on the `env:` sections of the reference's eight shipped training
+    configs: tests/golden/ref_env_configs.json holds the raw sections and every EnvConfig field the reference ended up with."""
+    from torchdriveenv_b200 import env_utils as U
+    frozen = json.load(open(os.path.join(R.HERE, "golden", "ref_env_configs.json")))
+    assert len(frozen) == 8
+    for name, entry in frozen.items():
+        cfg = U.construct_env_config(entry["raw"])
+        for k, v in entry["fields"].items():
+            assert getattr(cfg, k) == v, f"{name}: {k}"
