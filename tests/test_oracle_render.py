@@ -127,3 +127,39 @@ def test_recording_view_whole_map(oracle):
     assert np.array_equal(far[:, 192, 256], near[:, 192, 256])
     with pytest.raises(ValueError):
         orc.render_view(0, x, y, 0.0, 0.0, 64, 64)
+
+
+def test_oracle_render_triangle_soup_vs_fixed_point_restatement(oracle):
+    """The adversarial input of tests/test_gpu_parity.py::test_render_random_triangle_soup (overlapping random triangles
+    from slivers to 60 m, random cameras) through the oracle and through the independent numpy restatement of the
+    fixed-point rule: every pixel equal.  Pins the checker the CUDA rasteriser is compared with on that input."""
+    rng = np.random.default_rng(3)
+
+    def soup(n, scales, width):
+        c = rng.uniform(-60, 60, (n, 1, 2)); sc = rng.choice(scales, (n, 1, 1))
+        out = np.zeros((n, width), np.float32)
+        out[:, :6] = (c + rng.normal(0, 1, (n, 3, 2)) * sc).reshape(n, 6)
+        if width == 8:
+            out[:, 6] = 1.0
+        return out
+    road = S.subdivide_long_triangles(soup(160, [0.05, 0.5, 3.0, 20.0], 8), 200.0)
+    mark = S.subdivide_long_triangles(soup(120, [0.05, 0.3, 2.0, 10.0], 6), 200.0)
+    m = S.MapData(road_tris=road, mark_tris=mark)
+    A, E = 4, 10
+    init = np.column_stack([rng.uniform(-50, 50, (A, 2)), rng.uniform(-3, 3, A), rng.uniform(0, 8, A)]).astype(np.float32)
+    attr = np.column_stack([rng.uniform(3, 9, A), rng.uniform(1.5, 2.6, A), rng.uniform(0.8, 2.0, A)]).astype(np.float32)
+    sc = S.ScenarioData(0, rng.uniform(-40, 40, (4, 2)).astype(np.float32), 0.3, init, attr)
+    ss = S.ScenarioSet([m], [sc])
+    for lh in (1, 0):
+        cfg = default_config(num_envs=E, max_agents=A, left_handed_coordinates=lh)
+        packed = ss.pack(A)
+        env = oracle.OracleEnvSet(cfg, packed)
+        env.reset(seed=2)
+        env.state[:, 0, 0:2] = rng.uniform(-65, 65, (E, 2)); env.state[:, 0, 2] = rng.uniform(-np.pi, np.pi, E)
+        env.state[:2, 0, 2] = [0.0, np.pi / 2]          # axis-aligned cameras
+        cls = env.render_classes()
+        for e in range(E):
+            prims = world_primitives(packed, cfg, env.state[e], env.attr[e], env.env_vars[e], oracle.sincos)
+            ref = raster_fixed(prims, camera(cfg, env.state[e, 0], oracle.sincos))
+            assert np.array_equal(ref, cls[e]), f"lh {lh} env {e}: {(ref != cls[e]).sum()} pixels differ"
+        assert (cls > 0).mean() > 0.2
