@@ -76,6 +76,7 @@ class ClockSampler:
             self.handle = pynvml.nvmlDeviceGetHandleByIndex(ids[index] if ids and index < len(ids) else index)
             self.nvml = pynvml
             self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            sys.setswitchinterval(5e-4)   # the launching loop keeps the GIL busy: let the 2 ms poller in more often than every 5 ms
             self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
             self.thread.start()
             return
