@@ -224,3 +224,23 @@ def test_save_video_writes_the_frames(tmp_path):
     assert int(cap.get(cv2.CAP_PROP_FRAME_WIDTH)) == 96 and int(cap.get(cv2.CAP_PROP_FRAME_HEIGHT)) == 64
     assert int(round(cap.get(cv2.CAP_PROP_FPS))) == 10
     assert set_seeds(123) == 123
+
+
+def test_vec_env_sb3_surface_without_an_engine():
+    """The attribute / method part of SB3's VecEnv surface is plain host logic: exercised on an instance whose engine is
+    never created (no GPU here)."""
+    import torch
+    from torchdriveenv_b200.gym_env import TorchDriveVecEnv
+    v = object.__new__(TorchDriveVecEnv)
+    v.num_envs, v.n_stack, v._seed = 5, 3, 11
+    v._stack = torch.arange(5 * 9 * 64 * 64, dtype=torch.int64).remainder(251).to(torch.uint8).reshape(5, 9, 64, 64)
+    assert v.get_attr("num_envs") == [5] * 5 and v.get_attr("n_stack", indices=[1, 3]) == [3, 3]
+    v.set_attr("tag", "x")
+    assert v.get_attr("tag", indices=2) == ["x"]
+    assert v.env_is_wrapped(object) == [False] * 5
+    assert v.seed(40) == [40, 41, 42, 43, 44] and v._seed == 40
+    assert v.env_method("seed", indices=[0, 1]) == [[40, 41, 42, 43, 44]] * 2
+    img = v.render()
+    assert img.shape == (64, 64, 3) and np.array_equal(img[:, :, 0], v._stack[0, 6].numpy())
+    assert len(v.get_images()) == 5 and v.get_images()[4].shape == (64, 64, 3)
+    assert v.unwrapped is v and v.render_mode == "rgb_array"

@@ -409,6 +409,48 @@ class TorchDriveVecEnv:
         self.step_async(actions)
         return self.step_wait()
 
+    # -- the rest of SB3's VecEnv surface (stable_baselines3.common.vec_env.base_vec_env.VecEnv): the E envs are one object
+    #    here, so attribute and method calls address that object and answer once per selected env
+    metadata = {"render_modes": ["rgb_array"], "render_fps": 10}
+    render_mode = "rgb_array"
+
+    def _indices(self, indices):
+        if indices is None:
+            return list(range(self.num_envs))
+        return [int(indices)] if isinstance(indices, (int, np.integer)) else [int(i) for i in indices]
+
+    def get_attr(self, attr_name: str, indices=None):
+        return [getattr(self, attr_name) for _ in self._indices(indices)]
+
+    def set_attr(self, attr_name: str, value, indices=None) -> None:
+        setattr(self, attr_name, value)
+
+    def env_method(self, method_name: str, *method_args, indices=None, **method_kwargs):
+        n = len(self._indices(indices))
+        return [getattr(self, method_name)(*method_args, **method_kwargs)] * n
+
+    def env_is_wrapped(self, wrapper_class, indices=None):
+        return [False for _ in self._indices(indices)]
+
+    def seed(self, seed: Optional[int] = None):
+        """SB3 semantics: env i gets seed + i; here the reset RNG is keyed by (seed, global env index), so one value does it."""
+        if seed is not None:
+            self._seed = int(seed)
+        return [self._seed + i for i in range(self.num_envs)]
+
+    def get_images(self):
+        """Last frame of every env as HWC arrays (VecEnv.get_images)."""
+        frames = self._stack[:, -3:].permute(0, 2, 3, 1).cpu().numpy()
+        return [f for f in frames]
+
+    def render(self, mode: Optional[str] = None):
+        """The newest birdview of env 0, H x W x 3 (rgb_array)."""
+        return self._stack[0, -3:].permute(1, 2, 0).cpu().numpy()
+
+    @property
+    def unwrapped(self):
+        return self
+
     def episode_statistics(self, reset: bool = False) -> Dict[str, float]:
         from ._capi import STAT_NAMES
         s = self.engine.episode_stats(reset=reset)
