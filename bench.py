@@ -405,22 +405,39 @@ def run_reference(args, rank: int, world: int):
                               cpu_baseline=r, e2e=dict(value=r["value"], unit="envs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))), flush=True)
         return
     E, A, render = WORKLOADS[workload]
-    _, desc = build_scenarios(workload)
-    # each "step" = one bounded sample; K steps + W warm-up must finish within a few minutes
-    per_step_budget = max(0.5, min(5.0, 150.0 / max(1, args.steps + args.warmup)))
-    vals = []
+    ss, desc = build_scenarios(workload)
+    # each "step" = one bounded sample of the workload: a 1024-env slice stepped for the step's share of ~150 s (at least
+    # one oracle step), so that any --steps K --warmup W ends within a few minutes; the oracle env is built once
+    from oracle import oracle as O
+    from torchdriveenv_b200._capi import default_config
+    ES = 1024
+    env = O.OracleEnvSet(default_config(num_envs=ES, max_agents=A, auto_reset=1), ss.pack(A))
+    env.reset(seed=0)
+    acts = make_actions(ES, 64, 0)
+    env.step(acts[0], render=render)
+    per_step_budget = min(5.0, 150.0 / max(1, args.steps + args.warmup))
+    n_total, t_total, k_act = 0, 0.0, 0
     t_all = time.perf_counter()
     for k in range(args.warmup + args.steps):
-        r = cpu_oracle_throughput(workload, per_step_budget, seed=k)
+        t0 = time.perf_counter()
+        n = 0
+        while True:
+            env.step(acts[k_act % 64], render=render)
+            k_act += 1; n += 1
+            if time.perf_counter() - t0 >= per_step_budget:
+                break
         if k >= args.warmup:
-            vals.append(r)
-    value = float(np.mean([v["value"] for v in vals]))
-    cb = dict(vals[-1]); cb["value"] = value
+            n_total += n; t_total += time.perf_counter() - t0
+    value = ES * n_total / t_total
+    threads = O.num_threads()
+    cb = dict(value=value, unit=UNIT, cores=threads, kind="port",
+              sample=f"{ES} envs x {n_total} oracle steps over {args.steps} bench steps ({t_total:.1f} s), C oracle with OpenMP over envs, "
+                     f"{threads} threads on {os.cpu_count()} visible cores")
     line = dict(impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1e3 * E / value, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic", config=dict(workload=desc, envs_per_gpu=E, agents=A, render=render,
                                               note="reference arm = CPU oracle port (the reference itself needs torchdrivesim, absent offline); "
-                                                   "each step is a bounded 1024-env sample of the workload"),
+                                                   "each step is a bounded 1024-env sample of the workload (its share of ~150 s, >= 1 oracle step)"),
                 cpu_baseline=cb, e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 wall_s=time.perf_counter() - t_all)
     print(json.dumps(line), flush=True)
