@@ -1,0 +1,121 @@
+"""Kernel LOGIC checks without a GPU: the product's CUDA sources, compiled for the host-side lockstep emulator
+(tests/emu/cuda_emu.h -> tests/emu/libtde_emu.so), against the CPU oracle, bit for bit.
+
+Test infrastructure only.  The emulator runs the same kernel source (warp shuffles, ballots, shared-memory atomics,
+named barriers; bulk-async copies as immediate copies) with the threads of a block as fibers on one OS thread; it says
+nothing about speed, data races or PTX semantics - the `-m gpu` tests are the parity tests proper.  What it buys: a
+logic error in a kernel shows up here, in the CPU suite, before a GPU lease is spent on it."""
+import numpy as np
+import pytest
+
+from torchdriveenv_b200 import scenarios as S
+from torchdriveenv_b200._capi import default_config
+
+from emu_engine import EmuEngine
+
+
+def rollout_compare(oracle, ss, E, A, steps, seed, **cfg):
+    eng = EmuEngine(ss, E, A, **cfg)
+    orc = oracle.OracleEnvSet(default_config(num_envs=E, max_agents=A, **cfg), eng.packed)
+    eng.reset(seed=seed); orc.reset(seed=seed)
+    assert np.array_equal(eng.get_state(), orc.state)
+    assert np.array_equal(eng.get_env_vars(), orc.env_vars)
+    assert np.array_equal(eng.render(), orc.render()), "reset observation"
+    rng = np.random.default_rng(seed)
+    for k in range(steps):
+        a = np.stack([rng.uniform(-1, 1, E), rng.uniform(-0.3, 0.3, E)], 1).astype(np.float32)
+        obs, r, te, tr, info = eng.step(a)
+        oobs, orr, ote, otr, oinfo = orc.step(a)
+        assert np.array_equal(eng.get_state(), orc.state), f"step {k}: state"
+        assert np.array_equal(eng.get_infractions(), orc.infractions), f"step {k}: infractions"
+        assert np.array_equal(info, oinfo), f"step {k}: info"
+        assert np.array_equal(eng.get_env_vars(), orc.env_vars), f"step {k}: env vars"
+        assert np.array_equal(te, ote) and np.array_equal(tr, otr), f"step {k}: flags"
+        assert np.array_equal(r, orr), f"step {k}: reward"
+        assert np.array_equal(obs, oobs), f"step {k}: observation ({float((obs == oobs).mean())} identical)"
+    np.testing.assert_allclose(eng.episode_stats(), orc.stats, rtol=1e-9)
+    return eng, orc
+
+
+def test_emu_c3_traffic_lights(oracle):
+    rollout_compare(oracle, S.traffic_lights(32), 96, 32, steps=25, seed=2, auto_reset=1)
+
+
+def test_emu_c2_roundabout(oracle):
+    rollout_compare(oracle, S.roundabout(16), 64, 16, steps=20, seed=1, auto_reset=1)
+
+
+def test_emu_c1_three_way(oracle):
+    rollout_compare(oracle, S.three_way(6), 1, 9, steps=120, seed=0)
+
+
+@pytest.mark.parametrize("E,A,n_agents,cfg", [
+    (1, 1, 1, dict()),
+    (13, 5, 3, dict(auto_reset=1)),
+    (11, 64, 64, dict(auto_reset=1, randomize_ego_attributes=1)),
+    (9, 33, 33, dict(auto_reset=1, left_handed_coordinates=0)),
+    (21, 8, 8, dict(auto_reset=1, terminated_at_infraction=0, max_environment_steps=7)),
+    (16, 8, 8, dict(auto_reset=0, offroad_threshold=0.0, tl_rear_factor=1.0, fov=50.0)),
+])
+def test_emu_edge_configurations(oracle, E, A, n_agents, cfg):
+    rollout_compare(oracle, S.traffic_lights(n_agents), E, A, steps=15, seed=E + A, **cfg)
+
+
+def test_emu_scenario_mix(oracle):
+    rollout_compare(oracle, S.validation_mix(12), 60, 16, steps=15, seed=3, auto_reset=1)
+
+
+def test_emu_stacked_and_terminal(oracle):
+    E, A, n = 24, 8, 3
+    ss = S.traffic_lights(A)
+    eng = EmuEngine(ss, E, A, auto_reset=1)
+    orc = oracle.OracleEnvSet(default_config(num_envs=E, max_agents=A, auto_reset=1), eng.packed)
+    eng.reset(seed=5); orc.reset(seed=5)
+    stack, term_obs = eng.new_stack(n), eng.new_stack(n)
+    eng.render_stacked(stack, n)
+    want = np.zeros_like(stack)
+    want[:, 6:] = orc.render()
+    assert np.array_equal(stack, want)
+    tbuf = np.zeros((E, 3, 64, 64), np.uint8)
+    orc.set_terminal_buffer(tbuf)
+    rng = np.random.default_rng(5)
+    finished = 0
+    for k in range(30):
+        a = np.stack([rng.uniform(-1, 1, E), rng.uniform(-0.3, 0.3, E)], 1).astype(np.float32)
+        eng.step_terminal(a, stack, term_obs, n)
+        oobs, orr, ote, otr, oinfo = orc.step(a)
+        done = (ote | otr).astype(bool)
+        prev = want.copy()
+        want[:, :6] = prev[:, 3:]
+        want[:, 6:] = oobs
+        for e in np.nonzero(done)[0]:
+            tstack = np.concatenate([prev[e, 3:], tbuf[e]], 0)
+            assert np.array_equal(term_obs[e], tstack), f"step {k} env {e}: terminal stack"
+            want[e, :6] = 0
+            finished += 1
+        assert np.array_equal(stack, want), f"step {k}: stack"
+        assert np.array_equal(eng.terminated, ote) and np.array_equal(eng.truncated, otr)
+    assert finished > 0
+
+
+def test_emu_collision_and_offroad_boxes(oracle):
+    st, at = S.scatter_boxes(24, 64, size=60.0, seed=3)
+    patch = S.scatter_patch(60.0, 10.0)
+    eng = EmuEngine(S.ScenarioSet([patch], [S.make_scenario(0, [[5, 5], [50, 5]], 0, 0, "p")]), 1, 1)
+    assert np.array_equal(eng.collision_boxes(st, at), oracle.collision_boxes(st, at))
+    assert np.array_equal(eng.offroad_boxes(0, st, at), oracle.offroad_boxes(patch.road_tris, 0.5, st, at))
+    # a pile-up: more candidate pairs than the compacted pair list holds
+    st2, at2 = S.scatter_boxes(6, 64, size=15.0, seed=4)
+    got, want = eng.collision_boxes(st2, at2), oracle.collision_boxes(st2, at2)
+    assert want.max() > 8
+    assert np.array_equal(got, want)
+
+
+def test_emu_recording_view(oracle):
+    E, A = 3, 8
+    eng = EmuEngine(S.traffic_lights(A), E, A)
+    orc = oracle.OracleEnvSet(default_config(num_envs=E, max_agents=A), eng.packed)
+    eng.reset(seed=9); orc.reset(seed=9)
+    x, y = [float(v) for v in orc.state[1, 0, :2]]
+    got = eng.render_view(1, x, y, 0.3, 120.0, 96, 80)
+    assert np.array_equal(got, orc.render_view(1, x, y, 0.3, 120.0, 96, 80))

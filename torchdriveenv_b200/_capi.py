@@ -145,6 +145,13 @@ def load_library() -> C.CDLL:
             f"{_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a). torchdriveenv_b200 has no CPU fallback.")
     lib = C.CDLL(_LIB_PATH, mode=C.RTLD_GLOBAL)
+    bind_signatures(lib)
+    _LIB = lib
+    return lib
+
+
+def bind_signatures(lib: C.CDLL) -> C.CDLL:
+    """Attach the argument / result types of include/tde_b200.h to a loaded library."""
     vp, i32, i64, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
     sig = {
         "tde_version": ([], C.c_int),
@@ -185,7 +192,6 @@ def load_library() -> C.CDLL:
     for name, (args, res) in sig.items():
         fn = getattr(lib, name)  # AttributeError here = the library does not match the header
         fn.argtypes, fn.restype = args, res
-    _LIB = lib
     return lib
 
 

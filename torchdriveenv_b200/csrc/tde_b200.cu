@@ -1,6 +1,8 @@
 // tde_b200.cu — host side of libtde_b200.so: handle, scenario upload (incl. the nearest-candidate
 // grid over the lane mesh), launches.  C ABI declared in include/tde_b200.h.
+#ifndef TDE_HOST_EMU
 #include <cuda_runtime.h>
+#endif
 
 #include <algorithm>
 #include <array>
@@ -585,7 +587,7 @@ extern "C" int tde_upload_scenarios(tde_handle* h, const tde_scenario_set* s) {
         if ((rc = dev_upload(h, &raw, road_sorted.data(), (size_t)nt * 8))) return rc;
         if ((rc = dev_alloc(h, &rec, (size_t)nt * 3))) return rc;
         h->scenario_allocs.push_back(rec);
-        if (nt) prep_tris_kernel<<<(nt + 127) / 128, 128>>>(raw, nt, rec);
+        if (nt) TDE_LAUNCH((nt + 127) / 128, 128, 0, 0, prep_tris_kernel)(raw, nt, rec);
         M.tri = rec; M.ntri = nt;
         M.nmark = nk;
         float* mraw = nullptr;
@@ -609,7 +611,7 @@ extern "C" int tde_upload_scenarios(tde_handle* h, const tde_scenario_set* s) {
         if ((rc = dev_upload(h, &sraw, s->stoplines + 5 * (size_t)l0, (size_t)nl * 5))) return rc;
         if ((rc = dev_alloc(h, &srec, (size_t)nl * 2))) return rc;
         h->scenario_allocs.push_back(srec);
-        if (nl) prep_stops_kernel<<<1, 64>>>(sraw, nl, srec);
+        if (nl) TDE_LAUNCH(1, 64, 0, 0, prep_stops_kernel)(sraw, nl, srec);
         M.stop = srec; M.nstop = nl;
         int P = s->map_light_period[m];
         int lo = s->map_light_offset[m], ln = s->map_light_offset[m + 1] - lo;
@@ -724,8 +726,8 @@ extern "C" int tde_reset(tde_handle* h, const uint8_t* env_mask_dev, uint64_t se
     p.reset_mask = env_mask_dev;
     cudaStream_t st = (cudaStream_t)stream;
     int grid = std::max(1, std::min((h->E + TDE_WARPS_PER_BLOCK - 1) / TDE_WARPS_PER_BLOCK, h->sm_count * 8));
-    if (h->A <= 32) tde_reset_kernel<1><<<grid, TDE_WARPS_PER_BLOCK * 32, 0, st>>>(p);
-    else tde_reset_kernel<2><<<grid, TDE_WARPS_PER_BLOCK * 32, 0, st>>>(p);
+    if (h->A <= 32) TDE_LAUNCH(grid, TDE_WARPS_PER_BLOCK * 32, 0, st, tde_reset_kernel<1>)(p);
+    else TDE_LAUNCH(grid, TDE_WARPS_PER_BLOCK * 32, 0, st, tde_reset_kernel<2>)(p);
     CUDA_TRY(h, cudaGetLastError());
     h->launches++;
     h->was_reset = true;
@@ -745,7 +747,7 @@ static cudaError_t launch_step(Kernel k, int grid, int threads, size_t smem, cud
     cfg.attrs = attr; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, k, p);
 #else
-    k<<<grid, threads, smem, st>>>(p);
+    TDE_LAUNCH(grid, threads, smem, st, k)(p);
     return cudaGetLastError();
 #endif
 }
@@ -803,24 +805,24 @@ static int step_impl(tde_handle* h, int32_t phases, const float* actions, uint8_
     if (deferred) {
         const int u4_per_env = n_stack * (TDE_OBS_C * TDE_OBS_H * TDE_OBS_W / 16);
         const int cgrid = std::max(1, std::min((h->E + 7) / 8, h->sm_count * 8));
-        tde_copy_rows_kernel<<<cgrid, 256, 0, st>>>(h->done_mask, (const uint4*)obs, (uint4*)terminal_obs, h->E, u4_per_env);
+        TDE_LAUNCH(cgrid, 256, 0, st, tde_copy_rows_kernel)(h->done_mask, (const uint4*)obs, (uint4*)terminal_obs, h->E, u4_per_env);
         CUDA_TRY(h, cudaGetLastError());
         StepParams q = p;
         q.done_mask = nullptr;
         q.reset_mask = h->done_mask;
         const int rgrid = std::max(1, std::min(want, h->sm_count * 8));
-        if (h->A <= 32) tde_reset_kernel<1><<<rgrid, threads, 0, st>>>(q);
-        else tde_reset_kernel<2><<<rgrid, threads, 0, st>>>(q);
+        if (h->A <= 32) TDE_LAUNCH(rgrid, threads, 0, st, tde_reset_kernel<1>)(q);
+        else TDE_LAUNCH(rgrid, threads, 0, st, tde_reset_kernel<2>)(q);
         CUDA_TRY(h, cudaGetLastError());
         q.render_mask = h->done_mask;
         q.obs_prev = obs;   // the stack was shifted by the first pass; a re-initialised env only keeps zeros anyway
         const int grid = std::min(h->grid_render, want);
         if (n_stack > 1) {
-            if (h->A <= 32) tde_render_kernel<1, true><<<grid, threads, h->smem_render, st>>>(q);
-            else tde_render_kernel<2, true><<<grid, threads, h->smem_render, st>>>(q);
+            if (h->A <= 32) TDE_LAUNCH(grid, threads, h->smem_render, st, tde_render_kernel<1, true>)(q);
+            else TDE_LAUNCH(grid, threads, h->smem_render, st, tde_render_kernel<2, true>)(q);
         } else {
-            if (h->A <= 32) tde_render_kernel<1, false><<<grid, threads, h->smem_render, st>>>(q);
-            else tde_render_kernel<2, false><<<grid, threads, h->smem_render, st>>>(q);
+            if (h->A <= 32) TDE_LAUNCH(grid, threads, h->smem_render, st, tde_render_kernel<1, false>)(q);
+            else TDE_LAUNCH(grid, threads, h->smem_render, st, tde_render_kernel<2, false>)(q);
         }
         CUDA_TRY(h, cudaGetLastError());
         h->launches += 3;
@@ -952,10 +954,10 @@ extern "C" int tde_render_view(tde_handle* h, int32_t env, float cam_x, float ca
     v.ppmy = h->cfg.left_handed_coordinates ? v.ppm : -v.ppm;
     std::memcpy(v.pal, h->palette, sizeof(v.pal));
     // slots beyond the env's own map (a smaller map than the largest) are emitted as rejected primitives
-    tde_view_prims_kernel<<<(nmax + 127) / 128, 128, 0, st>>>(p, v, h->view_prims, nmax);
+    TDE_LAUNCH((nmax + 127) / 128, 128, 0, st, tde_view_prims_kernel)(p, v, h->view_prims, nmax);
     CUDA_TRY(h, cudaGetLastError());
     dim3 grid((width + TDE_VIEW_TX - 1) / TDE_VIEW_TX, (height + TDE_VIEW_TY - 1) / TDE_VIEW_TY), block(TDE_VIEW_TX, TDE_VIEW_TY);
-    tde_view_raster_kernel<<<grid, block, 0, st>>>(h->view_prims, nmax, v, out);
+    TDE_LAUNCH(grid, block, 0, st, tde_view_raster_kernel)(h->view_prims, nmax, v, out);
     CUDA_TRY(h, cudaGetLastError());
     h->launches += 2;
     return TDE_OK;
@@ -997,8 +999,8 @@ extern "C" int tde_collision_boxes(const float* state, const float* attr, int32_
         return fail(nullptr, TDE_E_CUDA, "tde_collision_boxes: no CUDA device");
     int grid = std::max(1, std::min((E + TDE_WARPS_PER_BLOCK - 1) / TDE_WARPS_PER_BLOCK, sms * 8));
     cudaStream_t st = (cudaStream_t)stream;
-    if (A <= 32) tde_collision_kernel<1><<<grid, TDE_WARPS_PER_BLOCK * 32, 0, st>>>((const float4*)state, (const float4*)attr, E, A, out);
-    else tde_collision_kernel<2><<<grid, TDE_WARPS_PER_BLOCK * 32, 0, st>>>((const float4*)state, (const float4*)attr, E, A, out);
+    if (A <= 32) TDE_LAUNCH(grid, TDE_WARPS_PER_BLOCK * 32, 0, st, tde_collision_kernel<1>)((const float4*)state, (const float4*)attr, E, A, out);
+    else TDE_LAUNCH(grid, TDE_WARPS_PER_BLOCK * 32, 0, st, tde_collision_kernel<2>)((const float4*)state, (const float4*)attr, E, A, out);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(nullptr, TDE_E_CUDA, std::string("tde_collision_boxes: ") + cudaGetErrorString(e));
     return TDE_OK;
@@ -1012,7 +1014,7 @@ extern "C" int tde_offroad_boxes(tde_handle* h, int32_t map_id, const float* sta
     CUDA_TRY(h, cudaSetDevice(h->device));
     int n = E * A;
     int grid = std::max(1, std::min((n + 255) / 256, h->sm_count * 8));
-    tde_offroad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h->maps_dev, map_id, h->cfg.offroad_threshold, (const float4*)state,
+    TDE_LAUNCH(grid, 256, 0, (cudaStream_t)stream, tde_offroad_kernel)(h->maps_dev, map_id, h->cfg.offroad_threshold, (const float4*)state,
                                                                (const float4*)attr, n, out);
     CUDA_TRY(h, cudaGetLastError());
     h->launches++;

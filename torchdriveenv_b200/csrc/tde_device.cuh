@@ -4,7 +4,13 @@
 // compiled with -fmad=false), FMA only where __fmaf_rn is written.  This is what lets the CPU oracle
 // be compared bit for bit; see DESIGN.md §SPEC.
 #pragma once
+#ifdef TDE_HOST_EMU
+#include "cuda_emu.h"   // tests/emu: the same source compiled for the host-side lockstep emulator (test infrastructure only)
+#else
 #include <cuda_runtime.h>
+#define TDE_LAUNCH(g, b, s, st, ...) __VA_ARGS__<<<g, b, s, st>>>
+#endif
+#include <math.h>
 #include <stdint.h>
 
 #define TDE_PI_F 3.14159274101257324219f

@@ -12,6 +12,12 @@
 #include "tde_device.cuh"
 #include "../../include/tde_b200.h"
 
+#ifdef TDE_HOST_EMU
+#define TDE_DYN_SMEM(name) unsigned char* const name = emu::dyn_smem()
+#else
+#define TDE_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
 // 32 warps per SM at 64 registers per thread; small blocks, so that the slots of a block are handed to
 // the next launch as soon as its few warps have run dry
 #ifndef TDE_WARPS_PER_BLOCK
@@ -961,7 +967,7 @@ __device__ __forceinline__ void clear_cover(RenderScratch* ws, int lane) {
 
 template <int AH, bool STACKED>
 __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, TDE_RENDER_BLOCKS_PER_SM) tde_render_kernel(const StepParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TDE_DYN_SMEM(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     RenderScratch* ws = reinterpret_cast<RenderScratch*>(smem_raw) + warp;
     // spread table: byte of plane bits -> the same bits at the low bit of 8 nibbles
@@ -1102,7 +1108,8 @@ __device__ __forceinline__ void physics_env(const StepParams& p, const int e, co
             float r = (reach_reward + dist_reward) + psi_reward;                     // :410
             bool term = c.terminated_at_infraction && (i_off > 0.0f || i_col > 0.0f || i_tl > 0.0f);  // :413-417
             bool trunc = step >= c.max_environment_steps;                            // :134-135
-            float ep_ret = p.ep_return[e] + r;
+            // lane 0 owns the env's return accumulator (it also writes it back below): the other lanes get the value by shuffle
+            const float ep_ret = __shfl_sync(FULL_MASK, lane == 0 ? p.ep_return[e] + r : 0.0f, 0);
             bool done = term || trunc;
             // info row (get_info :419-437): every value is warp-uniform, lane 0 writes the row as four 128-bit stores
             const float did_reset = (done && c.auto_reset) ? 1.0f : 0.0f;
@@ -1174,6 +1181,7 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32) tde_reset_kernel(con
         if (p.reset_mask != nullptr && p.reset_mask[e] == 0) continue;
         int s, step, target, reached, lphase, m;
         int episode = load_vars<true>(p, e, lane).episode;
+        __syncwarp();   // every lane has read the row before lane 0 rewrites it below
         float4 st[AH], at[AH];
         reset_env_warp<AH>(p, e, lane, s, step, target, reached, lphase, episode, m, st, at);
         store_vars(p, e, lane, s, step, target, reached, lphase, episode, m);
