@@ -5,5 +5,5 @@ set -e
 here=$(cd "$(dirname "$0")" && pwd)
 root=$(cd "$here/../.." && pwd)
 g++ -x c++ -std=c++17 -O2 -g -fPIC -shared -DTDE_HOST_EMU -ffp-contract=off -fno-fast-math -mfma \
-    -Wno-unknown-pragmas -Wno-attributes -I"$here" "$@" -o "$here/libtde_emu.so" "$root/torchdriveenv_b200/csrc/tde_b200.cu"
+    -Wl,-Bsymbolic -Wno-unknown-pragmas -Wno-attributes -I"$here" "$@" -o "$here/libtde_emu.so" "$root/torchdriveenv_b200/csrc/tde_b200.cu"
 echo "built $here/libtde_emu.so"

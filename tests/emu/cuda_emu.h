@@ -361,6 +361,7 @@ static inline float __fdividef(float a, float b) { return a / b; }
 static inline float __frcp_rn(float a) { return 1.0f / a; }
 static inline int __float2int_rd(float f) { return (int)std::floor(f); }
 static inline int __float2int_rn(float f) { return (int)std::nearbyint(f); }
+static inline int __float2int_ru(float f) { return (int)std::ceil(f); }
 static inline int __float2int_rz(float f) { return (int)f; }
 static inline unsigned __float2uint_rz(float f) { return f <= 0.0f ? 0u : (f >= 4294967296.0f ? 0xffffffffu : (unsigned)f); }
 static inline long long __double2ll_rd(double d) { return (long long)std::floor(d); }

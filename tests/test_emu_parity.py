@@ -119,3 +119,54 @@ def test_emu_recording_view(oracle):
     x, y = [float(v) for v in orc.state[1, 0, :2]]
     got = eng.render_view(1, x, y, 0.3, 120.0, 96, 80)
     assert np.array_equal(got, orc.render_view(1, x, y, 0.3, 120.0, 96, 80))
+
+
+def _triangle_soup(rng, n, scales, extent, width):
+    c = rng.uniform(-extent, extent, (n, 1, 2))
+    sc = rng.choice(scales, (n, 1, 1))
+    v = c + rng.normal(0, 1, (n, 3, 2)) * sc
+    out = np.zeros((n, width), np.float32)
+    out[:, :6] = v.reshape(n, 6)
+    if width == 8:
+        ang = rng.uniform(-np.pi, np.pi, n)
+        out[:, 6], out[:, 7] = np.cos(ang), np.sin(ang)
+    return out
+
+
+@pytest.mark.parametrize("fov,lh", [(35.0, 1), (12.0, 0), (140.0, 1)])
+def test_emu_render_random_triangle_soup(oracle, fov, lh):
+    """The GPU suite's adversarial rasteriser input (slivers of 0.05 m to triangles of 150 m, overlapping, random and
+    axis-aligned cameras, three zoom levels) at a smaller batch: every pixel must equal the oracle's per-pixel test."""
+    rng = np.random.default_rng(int(fov) + lh)
+    max_edge = min(200.0, 400.0 * fov / 64.0)
+    road = S.subdivide_long_triangles(_triangle_soup(rng, 500, [0.05, 0.5, 3.0, 20.0, 60.0], 120.0, 8), max_edge)
+    mark = S.subdivide_long_triangles(_triangle_soup(rng, 400, [0.05, 0.3, 2.0, 15.0], 120.0, 6), max_edge)
+    stop = np.column_stack([rng.uniform(-100, 100, (8, 2)), rng.uniform(0.3, 3, 8), rng.uniform(1, 6, 8), rng.uniform(-3, 3, 8)]).astype(np.float32)
+    lights = rng.integers(0, 3, (17, 8)).astype(np.uint8)
+    m = S.MapData(road_tris=road.astype(np.float32), mark_tris=mark, stoplines=stop, light_states=lights)
+    A = 12
+    init = np.column_stack([rng.uniform(-100, 100, (A, 2)), rng.uniform(-3, 3, A), rng.uniform(0, 8, A)]).astype(np.float32)
+    attr = np.column_stack([rng.uniform(3, 9, A), rng.uniform(1.5, 2.6, A), rng.uniform(0.8, 2.0, A)]).astype(np.float32)
+    sc = S.ScenarioData(0, rng.uniform(-80, 80, (6, 2)).astype(np.float32), 0.3, init, attr)
+    E = 96
+    cfg = dict(fov=fov, left_handed_coordinates=lh, auto_reset=0)
+    eng = EmuEngine(S.ScenarioSet([m], [sc]), E, A, **cfg)
+    orc = oracle.OracleEnvSet(default_config(num_envs=E, max_agents=A, **cfg), eng.packed)
+    eng.reset(seed=1); orc.reset(seed=1)
+    st = orc.state.copy()
+    st[:, 0, 0:2] = rng.uniform(-125, 125, (E, 2)); st[:, 0, 2] = rng.uniform(-np.pi, np.pi, E)
+    st[:, 1:, 0:2] += rng.normal(0, 15, (E, A - 1, 2)); st[:, 1:, 2] = rng.uniform(-np.pi, np.pi, (E, A - 1))
+    st[: E // 8, 0, 2] = np.round(st[: E // 8, 0, 2] / (np.pi / 2)) * (np.pi / 2)
+    orc.state[...] = st
+    eng.set_state(st)
+    got, want = eng.render(), orc.render()
+    bad = (got != want).reshape(E, -1).any(1)
+    assert not bad.any(), f"{int(bad.sum())} envs differ, first {int(np.argmax(bad))}: {(got != want).mean():.2e} of the bytes"
+    assert (want.reshape(E, -1).max(1) > 0).mean() > 0.9
+    for k in range(2):
+        a = np.stack([rng.uniform(-1, 1, E), rng.uniform(-0.3, 0.3, E)], 1).astype(np.float32)
+        obs, r, te, tr, info = eng.step(a)
+        oobs, orr, ote, otr, oinfo = orc.step(a)
+        assert np.array_equal(eng.get_state(), orc.state), f"step {k}: state"
+        assert np.array_equal(eng.get_infractions(), orc.infractions), f"step {k}: infractions"
+        assert np.array_equal(info, oinfo) and np.array_equal(obs, oobs), f"step {k}"

@@ -281,7 +281,7 @@ uint32_t morton_key(double x, double y, double lox, double loy, double inv) {
 // Render-only primitives: pairs of triangles that share an edge and form a strictly convex
 // quadrilateral are merged (the fixed-point fill rule is watertight, so a quad covers exactly the
 // union of its two triangles); the rest stay triangles (fourth vertex = first).  8 floats each.
-std::vector<float> merge_into_quads(const float* tris, int n, int stride) {
+std::vector<float> merge_into_quads(const float* tris, int n, int stride, double max_extent) {
     struct Key { float ax, ay, bx, by; bool operator<(const Key& o) const { return std::tie(ax, ay, bx, by) < std::tie(o.ax, o.ay, o.bx, o.by); } };
     auto mk = [](float ax, float ay, float bx, float by) { return std::tie(ax, ay) < std::tie(bx, by) ? Key{ax, ay, bx, by} : Key{bx, by, ax, ay}; };
     std::map<Key, std::vector<int>> edges;  // undirected edge -> triangle*3 + edge index
@@ -319,6 +319,9 @@ std::vector<float> merge_into_quads(const float* tris, int n, int stride) {
                 // quad: t's opposite vertex, shared a, u's opposite vertex, shared b
                 double q[4][2] = {{r[2 * k2], r[2 * k2 + 1]}, {r[2 * k], r[2 * k + 1]}, {w[2 * uo], w[2 * uo + 1]}, {r[2 * k1], r[2 * k1 + 1]}};
                 if (!convex(q)) continue;
+                // the far diagonal of a merged pair is not an edge of either triangle: keep the quad within the extent the
+                // rasteriser's fixed-point range is sized for (the device skips the oracle's coordinate clamp on that basis)
+                if (std::hypot(q[0][0] - q[2][0], q[0][1] - q[2][1]) > max_extent) continue;
                 for (int v = 0; v < 4; ++v) { out.push_back((float)q[v][0]); out.push_back((float)q[v][1]); }
                 used[t] = used[u] = 1; merged = true;
                 break;
@@ -458,8 +461,7 @@ static void free_scenarios(tde_handle* h) {
 // persistent grids: a multiple of the SM count (resident blocks per SM from the occupancy calculator)
 template <int AH>
 static int configure_kernels(tde_handle* h) {
-    size_t smem = sizeof(RenderScratch) * TDE_WARPS_PER_BLOCK + 256 * sizeof(uint32_t);  // + the spread table
-    smem += (TDE_OBS_W + 1) * sizeof(unsigned long long);                               // + the span-mask table
+    size_t smem = TDE_RENDER_SMEM_BYTES;   // groups + warps + the spread and span-mask tables
     CUDA_TRY(h, cudaFuncSetAttribute(tde_render_kernel<AH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_TRY(h, cudaFuncSetAttribute(tde_render_kernel<AH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -469,7 +471,7 @@ static int configure_kernels(tde_handle* h) {
     if (const char* v = std::getenv("TDE_RENDER_BLOCKS_CAP")) per_sm = std::max(1, std::min(per_sm, std::atoi(v)));
     h->smem_render = smem;
     int want = (h->E + TDE_WARPS_PER_BLOCK - 1) / TDE_WARPS_PER_BLOCK;
-    h->grid_render = std::max(1, std::min(want, per_sm * h->sm_count));
+    h->grid_render = std::max(1, std::min((h->E + TDE_RENDER_GROUPS - 1) / TDE_RENDER_GROUPS, per_sm * h->sm_count));
     CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tde_physics_kernel<AH>, TDE_WARPS_PER_BLOCK * 32, 0));
     {   // The physics kernel lives on L1 hits of the map tables (grid cells, triangle records): ask for no more shared
         // memory than its resident blocks need, the rest of the SM's 228 KB stays L1 (C3: 54.3 -> 52.5 us at 30 %,
@@ -595,8 +597,8 @@ extern "C" int tde_upload_scenarios(tde_handle* h, const tde_scenario_set* s) {
         M.mark_raw = mraw;
         // render-only static primitives: merged quads / leftover triangles of both layers, indexed by tile
         {
-            std::vector<float> rp_road = merge_into_quads(s->road_tris + 8 * (size_t)t0, nt, 8);
-            std::vector<float> rp_mark = merge_into_quads(s->mark_tris + 6 * (size_t)k0, nk, 6);
+            std::vector<float> rp_road = merge_into_quads(s->road_tris + 8 * (size_t)t0, nt, 8, max_edge_m);
+            std::vector<float> rp_mark = merge_into_quads(s->mark_tris + 6 * (size_t)k0, nk, 6, max_edge_m);
             const float reach = (0.70710678f * (float)(TDE_OBS_W + TDE_OBS_H) * 0.5f + 2.0f) / ppm;  // as in tde_render_kernel
             StaticIndex si = build_static_index(rp_road, rp_mark, reach);
             float* rpd = nullptr; uint8_t* clsd = nullptr; int* tsd = nullptr;
@@ -606,6 +608,11 @@ extern "C" int tde_upload_scenarios(tde_handle* h, const tde_scenario_set* s) {
             M.rp = (const float4*)rpd; M.rp_cls = clsd; M.tile_start = tsd;
             M.n_rp = (int)si.cls.size(); M.n_big = si.n_big;
             M.tgx0 = si.gx0; M.tgy0 = si.gy0; M.tinv = si.inv; M.maxext = si.maxext; M.tnx = si.nx; M.tny = si.ny;
+        }
+        for (int l = 0; l < nl; ++l) {
+            const float* sl = s->stoplines + 5 * (size_t)(l0 + l);
+            if (!(std::hypot((double)sl[2], (double)sl[3]) <= max_edge_m))
+                return fail(h, TDE_E_SHAPE, "tde_upload_scenarios: stop line larger than the rasteriser's fixed-point range (430 px)");
         }
         float* sraw = nullptr; float4* srec = nullptr;
         if ((rc = dev_upload(h, &sraw, s->stoplines + 5 * (size_t)l0, (size_t)nl * 5))) return rc;
@@ -778,6 +785,7 @@ static int step_impl(tde_handle* h, int32_t phases, const float* actions, uint8_
     const bool physics = phases & (TDE_PH_KINEMATICS | TDE_PH_INFRACTIONS | TDE_PH_REWARD);
     const bool render = (phases & TDE_PH_RENDER) && obs;
     const int want = (p.e_end - p.e_begin + TDE_WARPS_PER_BLOCK - 1) / TDE_WARPS_PER_BLOCK;
+    const int want_render = (p.e_end - p.e_begin + TDE_RENDER_GROUPS - 1) / TDE_RENDER_GROUPS;   // one env per warp group
     // terminal observations: finished envs are only flagged by the physics kernel; after the frame of their last
     // state is out it is copied to terminal_obs, the flagged envs are re-initialised and rendered again
     const bool deferred = terminal_obs && physics && render && h->cfg.auto_reset;
@@ -792,7 +800,7 @@ static int step_impl(tde_handle* h, int32_t phases, const float* actions, uint8_
         h->launches++;
     }
     if (render) {
-        const int grid = std::min(h->grid_render, want);
+        const int grid = std::min(h->grid_render, want_render);
         if (n_stack > 1) {
             if (h->A <= 32) CUDA_TRY(h, launch_step(tde_render_kernel<1, true>, grid, threads, h->smem_render, st, p));
             else CUDA_TRY(h, launch_step(tde_render_kernel<2, true>, grid, threads, h->smem_render, st, p));
@@ -816,7 +824,7 @@ static int step_impl(tde_handle* h, int32_t phases, const float* actions, uint8_
         CUDA_TRY(h, cudaGetLastError());
         q.render_mask = h->done_mask;
         q.obs_prev = obs;   // the stack was shifted by the first pass; a re-initialised env only keeps zeros anyway
-        const int grid = std::min(h->grid_render, want);
+        const int grid = std::min(h->grid_render, want_render);
         if (n_stack > 1) {
             if (h->A <= 32) TDE_LAUNCH(grid, threads, h->smem_render, st, tde_render_kernel<1, true>)(q);
             else TDE_LAUNCH(grid, threads, h->smem_render, st, tde_render_kernel<2, true>)(q);

@@ -138,17 +138,6 @@ struct SatScratch {  // per warp: staged boxes, candidate pairs and hit counters
     unsigned short pairs[TDE_PAIR_CAP];    // a | j << 8, a < j: pairs that survived the broad phase
 };
 
-struct RenderScratch {  // per warp, render kernel
-    // classes 1..10: one 64-bit coverage word per image row (bit x = pixel x); once every primitive is
-    // in, the first 2 KB are reused for the four bit-planes of the class-index image ([row][plane])
-    unsigned long long cover[(TDE_NUM_CLASSES - 1) * TDE_OBS_H];
-    uint4 qv[64];          // ring of snapped primitives waiting for a full batch, 4 x (x | y << 16)
-    unsigned char qc[64];  // their classes
-    unsigned char slot[64];  // agents near the viewport, compacted (agent index per rank)
-    unsigned int used;     // classes that received coverage
-    unsigned int pad[3];
-};
-
 template <int AH>
 __device__ __forceinline__ Box sat_ld(const SatScratch<AH>* ws, int a) {
     float4 u = ws->pos[a], v = ws->ext[a];
@@ -494,510 +483,7 @@ __device__ __forceinline__ void store_vars(const StepParams& p, int e, int lane,
     }
 }
 
-// ---------------------------------------------------------------- birdview rasteriser
-
-__device__ __forceinline__ int snap16(float f) {
-    float r = rintf(f * 16.0f);
-    r = fminf(fmaxf(r, -8191.0f), 8191.0f);
-    return (int)r;
-}
-__device__ __forceinline__ unsigned pack_xy(int x, int y) { return ((unsigned)x & 0xffffu) | ((unsigned)y << 16); }
-__device__ __forceinline__ int unpack_x(unsigned w) { return (int)(w << 16) >> 16; }
-__device__ __forceinline__ int unpack_y(unsigned w) { return (int)w >> 16; }
-
-// world -> pixel (translate to ego, rotate by -psi, scale), viewport test, snap to the 1/16-px grid.
-// ok = false when the primitive's float bounding box misses the viewport grown by one pixel.
-// Triangles are passed with their first vertex repeated as the fourth.
-struct Proj { uint4 v; bool ok; };
-__device__ __noinline__ Proj project_quad(Cam cam, float x0, float y0, float x1, float y1, float x2, float y2, float x3, float y3) {
-    const float wx[4] = {x0, x1, x2, x3}, wy[4] = {y0, y1, y2, y3};
-    float minx = INFINITY, maxx = -INFINITY, miny = INFINITY, maxy = -INFINITY;
-    unsigned v[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        float dx = wx[k] - cam.ex, dy = wy[k] - cam.ey;
-        float cx = dx * cam.ce + dy * cam.se;
-        float cy = dy * cam.ce - dx * cam.se;
-        float fx = cx * cam.ppm + 0.5f * (float)TDE_OBS_W;
-        float fy = cy * cam.ppmy + 0.5f * (float)TDE_OBS_H;
-        minx = fminf(minx, fx); maxx = fmaxf(maxx, fx);
-        miny = fminf(miny, fy); maxy = fmaxf(maxy, fy);
-        v[k] = pack_xy(snap16(fx), snap16(fy));
-    }
-    Proj r;
-    r.v = make_uint4(v[0], v[1], v[2], v[3]);
-    r.ok = maxx >= -1.0f && minx <= (float)TDE_OBS_W + 1.0f && maxy >= -1.0f && miny <= (float)TDE_OBS_H + 1.0f;
-    return r;
-}
-__device__ __forceinline__ Proj project_quad(const Cam& cam, const float (&wx)[4], const float (&wy)[4]) {
-    return project_quad(cam, wx[0], wy[0], wx[1], wy[1], wx[2], wy[2], wx[3], wy[3]);
-}
-
-// floor(r * 2^32 / d) to within +-1 for 0 <= r < d < 2^18: float estimate, exact 32-bit residual, one correction
-__device__ __forceinline__ unsigned tde_frac32(int r, int d, float inv_d) {
-    const unsigned b1 = __float2uint_rz((float)r * (inv_d * 4294967296.0f));
-    const int res = -(int)(b1 * (unsigned)d);             // r * 2^32 - b1 * d: |.| < 2^30, so its low 32 bits are the value
-    return b1 + (unsigned)__float2int_rn((float)res * inv_d);
-}
-// Row loop on 32.32 fixed-point edge positions: acc[k] >> 32 is the bound of edge k on the current row, exactly
-// floor((K + S j) / d) - the fraction is biased by 2^13 units and the per-row increment is within one unit of
-// S / d, so after <= 63 steps the accumulated error stays inside the gap of 2^32 / d >= 2^14 units between
-// representable quotients (d = 16 |dy| < 2^18).  Per edge and row: one 64-bit add (IADD3 + IMAD.X) and one min or max.
-template <int NE>
-__device__ __forceinline__ void cover_rows64(int j, int jend, unsigned long long (&acc)[4], const unsigned long long (&inc)[4],
-                                             const bool (&left)[4], unsigned int* cov, const unsigned long long* below) {
-#pragma unroll 1
-    for (; j <= jend; ++j) {
-        int xl = 0, xr = TDE_OBS_W;
-#pragma unroll
-        for (int k = 0; k < NE; ++k) {
-            const int v = (int)(acc[k] >> 32);
-            if (left[k]) xl = max(xl, v); else xr = min(xr, v);
-            acc[k] += inc[k];
-        }
-        if (xl < xr) {
-            const uint2 br = reinterpret_cast<const uint2*>(below)[xr], bl = reinterpret_cast<const uint2*>(below)[xl];
-            const unsigned int lo = br.x & ~bl.x, hi = br.y & ~bl.y;
-            if (lo) atomicOr(cov + 2 * j, lo);
-            if (hi) atomicOr(cov + 2 * j + 1, hi);
-        }
-    }
-}
-
-// Rasterise `count` (<= 32) queued primitives starting at ring slot `base`, one per lane, into the
-// per-class coverage bitmaps.  The final pixel is the highest class covering it, so neither the order
-// of the primitives nor their grouping matters.  Pixel-centre sampling on the 1/16-px grid with the
-// top-left rule: the same pixel set as the oracle's per-pixel edge-function test.
-#define TDE_RB_PARAMS , const unsigned long long* below
-#define TDE_RB_ARGS , below
-__device__ __noinline__ void raster_batch(RenderScratch* ws, int base, int count, int lane TDE_RB_PARAMS) {
-    const bool have = lane < count;
-    const uint4 q = ws->qv[base + lane];
-    const int cls = have ? (int)ws->qc[base + lane] : 1;
-    int n = have ? 4 : 0;
-    if (q.w == q.x) n = min(n, 3);  // a triangle travels as a quad whose last vertex repeats the first
-    int X[4] = {unpack_x(q.x), unpack_x(q.y), unpack_x(q.z), unpack_x(q.w)};
-    int Y[4] = {unpack_y(q.x), unpack_y(q.y), unpack_y(q.z), unpack_y(q.w)};
-    // orientation: make the signed area positive (x right, y down) by swapping vertices 1 and n-1
-    int area2 = (X[0] * Y[1] - X[1] * Y[0]) + (X[1] * Y[2] - X[2] * Y[1]) + (X[2] * Y[3] - X[3] * Y[2]) + (X[3] * Y[0] - X[0] * Y[3]);
-    if (area2 == 0) n = 0;
-    if (area2 < 0) {
-        if (n == 4) { int t = X[1]; X[1] = X[3]; X[3] = t; t = Y[1]; Y[1] = Y[3]; Y[3] = t; }
-        else { int t = X[1]; X[1] = X[2]; X[2] = t; t = Y[1]; Y[1] = Y[2]; Y[2] = t; }
-    }
-    int ymin = min(min(Y[0], Y[1]), min(Y[2], Y[3])), ymax = max(max(Y[0], Y[1]), max(Y[2], Y[3]));
-    int j0 = max(0, (ymin - 8 + 15) >> 4);              // ceil((ymin - 8) / 16)
-    int j1 = min(TDE_OBS_H - 1, (ymax - 8) >> 4);       // floor((ymax - 8) / 16)
-    // horizontal edges only restrict the row range (top edges are inclusive, bottom edges exclusive)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        int k1 = (k + 1) & 3;
-        int dx = X[k1] - X[k], dy = Y[k1] - Y[k];
-        if (dy == 0 && dx != 0) {
-            int c = (Y[k] - 8 + 15) >> 4;
-            if (dx > 0) j0 = max(j0, c); else j1 = min(j1, c - 1);
-        }
-    }
-    const bool active = n >= 3 && j0 <= j1;
-    const unsigned bm = __ballot_sync(FULL_MASK, active);
-    if (bm == 0) return;
-    const unsigned touched = __reduce_or_sync(FULL_MASK, active ? (1u << cls) : 0u);
-    if (lane == 0) ws->used |= touched;
-
-    // slanted edges: bound = floor((K + S j) / d) for every edge (a left edge's -floor(K/d) = floor((d - 1 - K) / d),
-    // a right edge's floor(K/d) + 1 = floor((K + d) / d)), kept as a 32.32 fixed-point accumulator per edge
-    unsigned long long acc[4], inc[4]; bool left[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        int k1 = (k + 1) & 3;
-        int ax = X[k], ay = Y[k];
-        int dx = X[k1] - ax, dy = Y[k1] - ay;
-        acc[k] = (unsigned long long)0x80000000u << 32; inc[k] = 0ull; left[k] = true;   // unused slot: bound INT_MIN on the left
-        if (active && dy != 0) {
-            int bias = dy < 0 ? 0 : -1;
-            int C0 = dx * (8 - ay) - dy * (8 - ax) + bias;
-            int S = 16 * dx;
-            int K = C0 + S * j0;
-            int d = dy > 0 ? 16 * dy : -16 * dy;
-            if (dy > 0) { K = K + d; left[k] = false; }
-            else { K = (d - 1) - K; S = -S; }
-            float inv_d = __fdividef(1.0f, (float)d);
-            int r0, rS;
-            int F = tde_floordiv(K, d, inv_d, r0);
-            int qs = tde_floordiv(S, d, inv_d, rS);
-            inc[k] = ((unsigned long long)(unsigned)qs << 32) + (unsigned long long)tde_frac32(rS, d, inv_d);
-            acc[k] = ((unsigned long long)(unsigned)F << 32) + (unsigned long long)(tde_frac32(r0, d, inv_d) + 8192u);
-        }
-    }
-    if (active) {
-        unsigned int* cov = reinterpret_cast<unsigned int*>(ws->cover + (cls - 1) * TDE_OBS_H);
-        if (__any_sync(bm, n == 4)) cover_rows64<4>(j0, j1, acc, inc, left, cov, below);
-        else cover_rows64<3>(j0, j1, acc, inc, left, cov, below);
-    }
-    __syncwarp();
-}
-
-// Append the primitives of the lanes with `valid` (each with its own class) to the ring by ballot/popc
-// compaction; a batch is rasterised as soon as 32 are pending.  `qtot` counts everything queued so
-// far for this env (warp-uniform); the new count is returned.
-__device__ __noinline__ int enqueue(RenderScratch* ws, int lane, bool valid, uint4 v, int cls, int qtot TDE_RB_PARAMS) {
-    int y0 = unpack_y(v.x), y1 = unpack_y(v.y), y2 = unpack_y(v.z), y3 = unpack_y(v.w);
-    int x0 = unpack_x(v.x), x1 = unpack_x(v.y), x2 = unpack_x(v.z), x3 = unpack_x(v.w);
-    int ymin = min(min(y0, y1), min(y2, y3)), ymax = max(max(y0, y1), max(y2, y3));
-    int xmin = min(min(x0, x1), min(x2, x3)), xmax = max(max(x0, x1), max(x2, x3));
-    int j0 = max(0, (ymin - 8 + 15) >> 4), j1 = min(TDE_OBS_H - 1, (ymax - 8) >> 4);
-    valid = valid && j0 <= j1 && xmax >= 8 && xmin <= 16 * (TDE_OBS_W - 1) + 8;  // bbox holds at least one pixel centre
-    const unsigned m = __ballot_sync(FULL_MASK, valid);
-    if (m == 0) return qtot;
-    const int pos = (qtot + __popc(m & ((1u << lane) - 1u))) & 63;
-    if (valid) { ws->qv[pos] = v; ws->qc[pos] = (unsigned char)cls; }
-    const int qnew = qtot + __popc(m);
-    __syncwarp();
-    if ((qnew ^ qtot) & ~31) raster_batch(ws, qtot & 32, 32, lane TDE_RB_ARGS);  // crossed a multiple of 32: that half of the ring is full
-    return qnew;
-}
-
-__device__ __forceinline__ void box_quad(const Box& b, float (&wx)[4], float (&wy)[4]) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) tde_box_corner(b, k, wx[k], wy[k]);
-}
-__device__ __forceinline__ void box_dirtri(const Box& b, float (&wx)[4], float (&wy)[4]) {
-    float ox[3] = {b.hl, 0.5f * b.hl, 0.5f * b.hl};
-    float oy[3] = {0.0f, b.hw, -b.hw};
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        wx[k] = b.x + (ox[k] * b.c - oy[k] * b.s);
-        wy[k] = b.y + (ox[k] * b.s + oy[k] * b.c);
-    }
-    wx[3] = 0.f; wy[3] = 0.f;
-}
-
-// spread the 8 bits of b to the low bit of 8 nibbles
-__device__ __forceinline__ uint32_t spread8(uint32_t b) {
-    uint32_t x = b & 0xffu;
-    x = (x | (x << 12)) & 0x000f000fu;
-    x = (x | (x << 6)) & 0x03030303u;
-    x = (x | (x << 3)) & 0x11111111u;
-    return x;
-}
-
-// static layers (road, lane markings).  The primitives are sorted by the tile of their bbox min corner,
-// so the candidates of a viewport are one contiguous run per tile row: lanes fetch the runs of the
-// rows in reach, a scan numbers the candidates, and they are projected and queued 32 at a time with
-// every lane busy.  Oversized primitives (kept out of the tiles) are always candidates.
-__device__ __noinline__ int queue_static(const MapDev& M, Cam cam, float reach, RenderScratch* ws, int lane, int qtot TDE_RB_PARAMS) {
-    if (M.n_rp <= 0) return qtot;
-    const float lo_reach = reach + M.maxext;
-    const int tx0 = max(0, (int)floorf((cam.ex - lo_reach - M.tgx0) * M.tinv)), tx1 = min(M.tnx - 1, (int)floorf((cam.ex + reach - M.tgx0) * M.tinv));
-    const int ty0 = max(0, (int)floorf((cam.ey - lo_reach - M.tgy0) * M.tinv)), ty1 = min(M.tny - 1, (int)floorf((cam.ey + reach - M.tgy0) * M.tinv));
-    const int nrows = (tx0 <= tx1 && ty0 <= ty1) ? min(ty1 - ty0 + 1, 32) : 0;   // the upload sizes the tiles for <= 24 rows
-    int s = 0, n = 0;
-    if (lane < nrows) {
-        const int* ts = M.tile_start + (ty0 + lane) * M.tnx;
-        s = __ldg(&ts[tx0]);
-        n = __ldg(&ts[tx1 + 1]) - s;
-    }
-    int incl = n;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        int t = __shfl_up_sync(FULL_MASK, incl, d);
-        if (lane >= d) incl += t;
-    }
-    incl += M.n_big;                                   // candidates are numbered: oversized first, then row by row
-    const int total = __shfl_sync(FULL_MASK, incl, 31);
-    const int excl = incl - n;
-#pragma unroll 1
-    for (int base = 0; base < total; base += 32) {
-        const int g = base + lane;
-        int r = 0;   // number of rows that end at or before g (binary search over the lanes' running totals)
-#pragma unroll
-        for (int st = 16; st >= 1; st >>= 1) {
-            const int probe = r + st - 1;
-            const int v = __shfl_sync(FULL_MASK, incl, probe);
-            if (probe < nrows && g >= v) r += st;
-        }
-        r = min(r, 31);
-        const int s_r = __shfl_sync(FULL_MASK, s, r), e_r = __shfl_sync(FULL_MASK, excl, r);
-        bool valid = g < total;
-        const int t = g < M.n_big ? g : s_r + (g - e_r);
-        float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
-        int cls = TDE_CLS_ROAD;
-                if (valid) { p0 = __ldg(&M.rp[2 * t]); p1 = __ldg(&M.rp[2 * t + 1]); cls = __ldg(&M.rp_cls[t]); }
-        float lox = fminf(fminf(p0.x, p0.z), fminf(p1.x, p1.z)), hix = fmaxf(fmaxf(p0.x, p0.z), fmaxf(p1.x, p1.z));
-        float loy = fminf(fminf(p0.y, p0.w), fminf(p1.y, p1.w)), hiy = fmaxf(fmaxf(p0.y, p0.w), fmaxf(p1.y, p1.w));
-        valid = valid && hix >= cam.ex - reach && lox <= cam.ex + reach && hiy >= cam.ey - reach && loy <= cam.ey + reach;
-        if (!__any_sync(FULL_MASK, valid)) continue;
-        Proj pr = project_quad(cam, p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w);
-        const uint4 pv = pr.v;
-        bool ok = pr.ok && valid;
-        // a merged quad is drawn as one primitive only if it is still strictly convex after
-        // snapping (then it covers exactly its two triangles); otherwise fall back to the pair
-        int x0 = unpack_x(pv.x), y0 = unpack_y(pv.x), x1 = unpack_x(pv.y), y1 = unpack_y(pv.y);
-        int x2 = unpack_x(pv.z), y2 = unpack_y(pv.z), x3 = unpack_x(pv.w), y3 = unpack_y(pv.w);
-        int c0 = (x1 - x0) * (y2 - y1) - (y1 - y0) * (x2 - x1), c1 = (x2 - x1) * (y3 - y2) - (y2 - y1) * (x3 - x2);
-        int c2 = (x3 - x2) * (y0 - y3) - (y3 - y2) * (x0 - x3), c3 = (x0 - x3) * (y1 - y0) - (y0 - y3) * (x1 - x0);
-        bool convex = (c0 > 0 && c1 > 0 && c2 > 0 && c3 > 0) || (c0 < 0 && c1 < 0 && c2 < 0 && c3 < 0);
-        bool is_tri = pv.w == pv.x;
-        qtot = enqueue(ws, lane, ok && (is_tri || convex), pv, cls, qtot TDE_RB_ARGS);
-        bool split = ok && !is_tri && !convex;
-        if (__any_sync(FULL_MASK, split)) {
-            qtot = enqueue(ws, lane, split, make_uint4(pv.x, pv.y, pv.w, pv.x), cls, qtot TDE_RB_ARGS);
-            qtot = enqueue(ws, lane, split, make_uint4(pv.y, pv.z, pv.w, pv.y), cls, qtot TDE_RB_ARGS);
-        }
-    }
-    return qtot;
-}
-
-// simulator.render_egocentric() (gym_env.py:122-124): one warp renders env e's 3x64x64 birdview.  The
-// coverage words of `ws` are zero on entry and zero again on return.
-template <int AH, bool STACKED>
-__device__ __forceinline__ void render_env(const StepParams& p, const int e, const int lane, RenderScratch* ws,
-                                           const uint32_t* spread_tab, const float reach TDE_RB_PARAMS) {
-    uint4* const cz = reinterpret_cast<uint4*>(ws->cover);
-    constexpr int COVER_U4 = (TDE_NUM_CLASSES - 1) * TDE_OBS_H * 8 / 16;  // 320 = 10 per lane
-    {
-        const EnvVars ev = load_vars<false>(p, e, lane);
-        const int s = ev.s, step = ev.step, target = ev.target, lphase = ev.lphase, m = ev.m;
-        const MapDev& M = p.maps[m];
-        const ScenDev& S = p.scens[s];
-        Box mybox[AH];
-#pragma unroll
-        for (int h = 0; h < AH; ++h) {
-            int a = h * 32 + lane;
-            float4 st = make_float4(0.f, 0.f, 0.f, 0.f), at = make_float4(1.f, 1.f, 1.f, 0.f);
-            if (a < p.A) { st = p.state[(size_t)e * p.A + a]; at = p.attr[(size_t)e * p.A + a]; }
-            mybox[h] = tde_make_box(st.x, st.y, st.z, at.x, at.y, at.w);
-        }
-        Cam cam;
-        cam.ex = __shfl_sync(FULL_MASK, mybox[0].x, 0); cam.ey = __shfl_sync(FULL_MASK, mybox[0].y, 0);
-        cam.ce = __shfl_sync(FULL_MASK, mybox[0].c, 0); cam.se = __shfl_sync(FULL_MASK, mybox[0].s, 0);
-        cam.ppm = p.ppm; cam.ppmy = p.ppmy;
-        float wx[4], wy[4];
-        int qtot = 0;
-        qtot = queue_static(M, cam, reach, ws, lane, qtot TDE_RB_ARGS);                 // classes 1-2: road and lane markings
-#ifdef TDE_TRACE
-        if (g_trace && lane == 0) g_trace[(size_t)e * 8 + 4] = qtot;
-#endif
-        // classes 3-10: the dynamic items - stop lines coloured by their light state, the goal diamond
-        // (circumradius 2 m), and for every agent near the viewport its rectangle and direction triangle -
-        // are numbered consecutively and handled 32 per pass.  Each item is an oriented frame (centre,
-        // cos, sin) plus four vertex offsets, so one code path produces all of them.
-        int nv = 0;
-#pragma unroll
-        for (int h = 0; h < AH; ++h) {
-            const int a = h * 32 + lane;
-            const float rr = reach + mybox[h].r;
-            const bool near = a < p.A && mybox[h].present != 0.0f && fabsf(mybox[h].x - cam.ex) <= rr && fabsf(mybox[h].y - cam.ey) <= rr;
-            const unsigned nm = __ballot_sync(FULL_MASK, near);
-            if (near) ws->slot[nv + __popc(nm & ((1u << lane) - 1u))] = (unsigned char)a;
-            nv += __popc(nm);
-        }
-        __syncwarp();
-        const bool have_wp = target < S.W;
-        const int n_misc = M.nstop + (have_wp ? 1 : 0);
-        const int n_items = n_misc + 2 * nv;
-#pragma unroll 1
-        for (int base = 0; base < n_items; base += 32) {
-            const int i = base + lane;
-            const bool valid = i < n_items;
-            const int j = i - n_misc;                                   // >= 0: agent item (rank j >> 1, triangle if odd)
-            const int a = (valid && j >= 0) ? (int)ws->slot[j >> 1] : 0;
-            // the agent's frame comes from the lane that owns it
-            float bx, by, bc, bs, hl, hw;
-            {
-                const int src = a & 31;
-                bx = __shfl_sync(FULL_MASK, mybox[0].x, src); by = __shfl_sync(FULL_MASK, mybox[0].y, src);
-                bc = __shfl_sync(FULL_MASK, mybox[0].c, src); bs = __shfl_sync(FULL_MASK, mybox[0].s, src);
-                hl = __shfl_sync(FULL_MASK, mybox[0].hl, src); hw = __shfl_sync(FULL_MASK, mybox[0].hw, src);
-                if (AH > 1) {
-                    const float x1 = __shfl_sync(FULL_MASK, mybox[AH - 1].x, src), y1 = __shfl_sync(FULL_MASK, mybox[AH - 1].y, src);
-                    const float c1 = __shfl_sync(FULL_MASK, mybox[AH - 1].c, src), s1 = __shfl_sync(FULL_MASK, mybox[AH - 1].s, src);
-                    const float l1 = __shfl_sync(FULL_MASK, mybox[AH - 1].hl, src), w1 = __shfl_sync(FULL_MASK, mybox[AH - 1].hw, src);
-                    if (a >= 32) { bx = x1; by = y1; bc = c1; bs = s1; hl = l1; hw = w1; }
-                }
-            }
-            int kind = (j & 1) ? 1 : 0;                                 // 0 rectangle, 1 direction triangle, 2 diamond
-            int cls = a == 0 ? (kind ? TDE_CLS_EGO_DIRECTION : TDE_CLS_EGO) : (kind ? TDE_CLS_DIRECTION : TDE_CLS_VEHICLE);
-            if (valid && j < 0) {
-                if (i < M.nstop) {
-                    const float4 u = __ldg(&M.stop[2 * i]), v = __ldg(&M.stop[2 * i + 1]);
-                    bx = u.x; by = u.y; hl = u.z; hw = u.w; bc = v.x; bs = v.y;
-                    kind = 0;
-                    cls = TDE_CLS_TL_GREEN + light_state_at(M, step, lphase, i);
-                } else {
-                    const float2 w = __ldg(&S.wp[target]);
-                    bx = w.x; by = w.y; bc = 1.0f; bs = 0.0f; hl = 2.0f; hw = 2.0f;
-                    kind = 2;
-                    cls = TDE_CLS_WAYPOINT;
-                }
-            }
-            // vertex offsets in the item's frame (the same expressions as tde_box_corner / the oracle's
-            // direction triangle; the diamond is the frame (1, 0) with offsets on the axes)
-            const float hh = 0.5f * hl;
-            const float ox0 = kind == 0 ? hl : kind == 1 ? hl : hl, oy0 = kind == 0 ? hw : 0.0f;
-            const float ox1 = kind == 0 ? hl : kind == 1 ? hh : 0.0f, oy1 = kind == 0 ? -hw : hw;
-            const float ox2 = kind == 0 ? -hl : kind == 1 ? hh : -hl, oy2 = kind == 2 ? 0.0f : -hw;
-            const float ox3 = kind == 0 ? -hl : kind == 1 ? hl : 0.0f, oy3 = kind == 0 ? hw : kind == 1 ? 0.0f : -hw;
-            wx[0] = bx + (ox0 * bc - oy0 * bs); wy[0] = by + (ox0 * bs + oy0 * bc);
-            wx[1] = bx + (ox1 * bc - oy1 * bs); wy[1] = by + (ox1 * bs + oy1 * bc);
-            wx[2] = bx + (ox2 * bc - oy2 * bs); wy[2] = by + (ox2 * bs + oy2 * bc);
-            wx[3] = bx + (ox3 * bc - oy3 * bs); wy[3] = by + (ox3 * bs + oy3 * bc);
-            Proj pr = project_quad(cam, wx, wy);
-            qtot = enqueue(ws, lane, pr.ok && valid, pr.v, cls, qtot TDE_RB_ARGS);
-        }
-        if (qtot & 31) raster_batch(ws, qtot & 32, qtot & 31, lane TDE_RB_ARGS);
-#ifdef TDE_TRACE
-        if (g_trace && lane == 0) { g_trace[(size_t)e * 8 + 5] = n_items; g_trace[(size_t)e * 8 + 6] = qtot; }
-#endif
-        __syncwarp();
-
-        // composite: lane owns rows lane and lane + 32; ascending classes overwrite the four bit-planes
-        // of the class index, so the highest class covering a pixel wins
-        const unsigned used = ws->used;
-        unsigned long long P[2][4];
-#pragma unroll
-        for (int r = 0; r < 2; ++r)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) P[r][b] = 0ull;
-#pragma unroll
-        for (int c = 1; c < TDE_NUM_CLASSES; ++c) {
-            if (used & (1u << c)) {
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    unsigned long long mk = ws->cover[(c - 1) * TDE_OBS_H + r * 32 + lane];
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) P[r][b] = (c >> b) & 1 ? (P[r][b] | mk) : (P[r][b] & ~mk);
-                }
-            }
-        }
-        __syncwarp();   // every lane has read its coverage words: the planes may now overwrite them
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            ulonglong2* pp = reinterpret_cast<ulonglong2*>(&ws->cover[(r * 32 + lane) * 4]);
-            pp[0] = make_ulonglong2(P[r][0], P[r][1]);
-            pp[1] = make_ulonglong2(P[r][2], P[r][3]);
-        }
-        __syncwarp();
-
-        // class-index planes -> palette lookup with byte permutes -> 128-bit stores
-        const unsigned char* pl8 = reinterpret_cast<const unsigned char*>(ws->cover);
-        constexpr int FRAME = TDE_OBS_C * TDE_OBS_H * TDE_OBS_W;
-        if (STACKED) {
-            // fused VecFrameStack: frames 1..n-1 move one slot down (zeros after a restart); a warp-wide
-            // 128-bit access covers 512 contiguous bytes, eight are kept in flight per lane
-            uint4* const base = reinterpret_cast<uint4*>(p.obs + (size_t)e * p.n_stack * FRAME) + lane;
-            const uint4* const prev = reinterpret_cast<const uint4*>(p.obs_prev + (size_t)e * p.n_stack * FRAME) + lane;
-            const int pieces = (p.n_stack - 1) * (FRAME / 512);
-            const bool fresh = p.restart[e] != 0;
-#pragma unroll 1
-            for (int i = 0; i < pieces; i += 8) {
-                uint4 v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    v[u] = make_uint4(0u, 0u, 0u, 0u);
-                    if (!fresh) v[u] = prev[(size_t)(i + u) * 32 + FRAME / 16];
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) base[(size_t)(i + u) * 32] = v[u];
-            }
-        }
-        const int n_stack = STACKED ? p.n_stack : 1;
-        uint8_t* out = p.obs + ((size_t)e * n_stack + (n_stack - 1)) * FRAME;
-#pragma unroll 1
-        for (int it = 0; it < TDE_OBS_H / 8; ++it) {
-            int row = it * 8 + (lane >> 2), qd = lane & 3;
-            const unsigned char* pb = pl8 + row * 32 + qd * 2;   // plane b of this row at +8b, pixels 16qd.. at +2qd
-            uint32_t idx[2];
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf)
-                idx[hf] = spread_tab[pb[hf]] + 2u * spread_tab[pb[8 + hf]] + 4u * spread_tab[pb[16 + hf]] + 8u * spread_tab[pb[24 + hf]];
-            // classes 8..15 (the ego and the direction triangles) are rare: eight rows without one take the short path,
-            // where the nibbles of idx are PRMT selectors as they stand (values 0..7; PRMT reads selector bits 0..15 only)
-            const bool any_hi = __any_sync(FULL_MASK, ((idx[0] | idx[1]) & 0x88888888u) != 0u);
-            const uint32_t sel[4] = {idx[0], idx[0] >> 16, idx[1], idx[1] >> 16};
-            if (any_hi) {
-                uint32_t sel7[4], himask[4];
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    sel7[g] = sel[g] & 0x7777u;
-                    himask[g] = __byte_perm(0x0000ff00u, 0u, (sel[g] >> 3) & 0x1111u);
-                }
-#pragma unroll
-                for (int ch = 0; ch < 3; ++ch) {
-                    uint32_t w[4];
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        uint32_t lo = __byte_perm(p.pal[ch][0], p.pal[ch][1], sel7[g]);
-                        uint32_t hi = __byte_perm(p.pal[ch][2], p.pal[ch][3], sel7[g]);
-                        w[g] = (lo & ~himask[g]) | (hi & himask[g]);
-                    }
-                    *reinterpret_cast<uint4*>(out + ch * (TDE_OBS_H * TDE_OBS_W) + row * TDE_OBS_W + qd * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-                }
-            } else {
-#pragma unroll
-                for (int ch = 0; ch < 3; ++ch) {
-                    uint32_t w[4];
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) w[g] = __byte_perm(p.pal[ch][0], p.pal[ch][1], sel[g]);
-                    *reinterpret_cast<uint4*>(out + ch * (TDE_OBS_H * TDE_OBS_W) + row * TDE_OBS_W + qd * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-                }
-            }
-        }
-        __syncwarp();
-        // clear the coverage words for the next env
-#pragma unroll
-        for (int i = 0; i < COVER_U4 / 32; ++i) cz[i * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
-        if (lane == 0) { ws->used = 0u; if (STACKED) p.restart[e] = 0; }
-        __syncwarp();
-    }
-}
-
-// conservative world-space reach of the viewport around the ego (half diagonal + 2 px)
-__device__ __forceinline__ float viewport_reach(const StepParams& p) {
-    return (0.70710678f * (float)(TDE_OBS_W + TDE_OBS_H) * 0.5f + 2.0f) / p.ppm;
-}
-__device__ __forceinline__ void clear_cover(RenderScratch* ws, int lane) {
-    uint4* const cz = reinterpret_cast<uint4*>(ws->cover);
-    constexpr int COVER_U4 = (TDE_NUM_CLASSES - 1) * TDE_OBS_H * 8 / 16;
-#pragma unroll
-    for (int i = 0; i < COVER_U4 / 32; ++i) cz[i * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
-    if (lane == 0) ws->used = 0u;
-    __syncwarp();
-}
-
-template <int AH, bool STACKED>
-__global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, TDE_RENDER_BLOCKS_PER_SM) tde_render_kernel(const StepParams p) {
-    TDE_DYN_SMEM(smem_raw);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    RenderScratch* ws = reinterpret_cast<RenderScratch*>(smem_raw) + warp;
-    // spread table: byte of plane bits -> the same bits at the low bit of 8 nibbles
-    uint32_t* const spread_tab = reinterpret_cast<uint32_t*>(smem_raw + sizeof(RenderScratch) * TDE_WARPS_PER_BLOCK);
-    for (int i = threadIdx.x; i < 256; i += TDE_WARPS_PER_BLOCK * 32) spread_tab[i] = spread8(i);
-    // below[x] = the x low bits set (x = 0..64): a span [xl, xr) is below[xr] & ~below[xl], two LDS instead of shifts
-    unsigned long long* const below = reinterpret_cast<unsigned long long*>(spread_tab + 256);
-    for (int i = threadIdx.x; i <= TDE_OBS_W; i += TDE_WARPS_PER_BLOCK * 32) below[i] = i >= 64 ? ~0ull : ((1ull << i) - 1ull);
-    __syncthreads();
-    const int warps_total = gridDim.x * TDE_WARPS_PER_BLOCK;
-    const float reach = viewport_reach(p);
-    clear_cover(ws, lane);
-    tde_pdl_wait();
-    // masked pass (re-render of the envs that were just re-initialised): plain stride, most envs are skipped
-    const bool masked = p.render_mask != nullptr;
-    int cursor = p.e_begin + blockIdx.x * TDE_WARPS_PER_BLOCK + warp;
-#pragma unroll 1
-    for (;;) {
-        int e;
-        if (masked) { e = cursor; cursor += warps_total; }
-        else e = p.e_begin + next_env(p.tickets, lane);
-        if (e >= p.e_end) break;
-        if (masked && p.render_mask[e] == 0) continue;
-        TDE_TRACE_MARK(e, 0);
-        render_env<AH, STACKED>(p, e, lane, ws, spread_tab, reach TDE_RB_ARGS);
-        TDE_TRACE_MARK(e, 1);
-    }
-    tde_pdl_launch_dependents();
-    if (!masked) envs_done(p.tickets, lane, warps_total);
-}
+#include "tde_render.cuh"
 
 // terminal observations: rows of the envs flagged in `mask` are copied out before those envs are re-initialised
 __global__ void __launch_bounds__(256) tde_copy_rows_kernel(const uint8_t* __restrict__ mask, const uint4* __restrict__ src,
