@@ -90,7 +90,9 @@ struct Fiber {
     bool done = true;
     uint3 tid;
     // what the fiber is waiting for (checked by the scheduler, so that a blocked fiber costs no context switch)
-    int wkind = 0;            // 0 runnable, 1 cell no longer draining, 2 cell ready for this lane, 3 block barrier
+    int wkind = 0;            // 0 runnable, 1 cell no longer draining, 2 cell ready for this lane, 3 block barrier, 4 memory word
+    const volatile unsigned long long* wword = nullptr;   // kind 4: runnable once (*wword >> 32 & 1) != wparity
+    unsigned wparity = 0;
     Cell* wcell = nullptr;
     unsigned wbit = 0;
     BlockBarrier* wbar = nullptr;
@@ -129,6 +131,7 @@ inline bool runnable(Runtime& r, Fiber& f) {
         case 1: return !f.wcell->drain;
         case 2: return f.wcell->drain && (f.wcell->toread & f.wbit);
         case 3: return f.wbar->generation != f.wgen || f.wbar->arrived >= (f.wid < 0 ? r.alive : f.wcount);
+        case 4: return (((unsigned)(*f.wword >> 32)) & 1u) != f.wparity;
         default: return true;
     }
 }
@@ -174,17 +177,29 @@ inline void run_block(dim3 bid, dim3 bdim, dim3 gdim) {
     r.alive = n;
     blockIdx = uint3{bid.x, bid.y, bid.z};
     blockDim = bdim; gridDim = gdim;
+    // Scheduling policy (TDE_EMU_SCHED): 0 = round robin over all threads; 1 = the lowest-numbered warp that can make
+    // progress always runs first; 2 = the highest-numbered one.  1 and 2 let one warp run as far ahead of the others as the
+    // barriers allow, which exposes inter-warp ordering assumptions (a warp reading what another has already overwritten).
+    static const int policy = std::getenv("TDE_EMU_SCHED") ? std::atoi(std::getenv("TDE_EMU_SCHED")) : 0;
+    const int nw = (n + 31) / 32;
     while (r.alive > 0) {
-        const unsigned long long before = r.progress;
-        for (int t = 0; t < n; ++t) {
-            Fiber& f = r.fibers[t];
-            if (f.done || !runnable(r, f)) continue;
-            f.wkind = 0;
-            r.current = t;
-            threadIdx = f.tid;
-            emu_switch(&r.sched_sp, f.sp);
+        bool ran_any = false;   // every wait names its condition (Fiber::wkind), so a thread that is resumed does make progress
+        for (int wi = 0; wi < nw; ++wi) {
+            const int w = policy == 2 ? nw - 1 - wi : wi;
+            bool ran = false;
+            for (int t = w * 32; t < std::min(n, w * 32 + 32); ++t) {
+                Fiber& f = r.fibers[t];
+                if (f.done || !runnable(r, f)) continue;
+                f.wkind = 0;
+                r.current = t;
+                threadIdx = f.tid;
+                emu_switch(&r.sched_sp, f.sp);
+                ran = true;
+            }
+            ran_any = ran_any || ran;
+            if (ran && policy != 0) break;   // start over from the preferred end
         }
-        if (r.alive > 0 && r.progress == before) die("deadlock: no thread of the block can make progress (divergent collective or barrier?)");
+        if (r.alive > 0 && !ran_any) die("deadlock: no thread of the block can make progress (divergent collective or barrier?)");
     }
     r.current = -1;
 }
@@ -236,6 +251,15 @@ inline void release(Cell& c) {
     c.toread &= ~bit;
     rt().progress++;
     if (c.toread == 0) { c.arrived = 0; c.drain = false; }
+}
+// block until the phase bit (bit 32) of an emulated mbarrier word differs from `parity`
+inline void wait_phase(const unsigned long long* word, unsigned parity) {
+    Runtime& r = rt();
+    Fiber& f = r.fibers[r.current];
+    while ((((unsigned)(*(const volatile unsigned long long*)word >> 32)) & 1u) == parity) {
+        f.wkind = 4; f.wword = word; f.wparity = parity;
+        yield();
+    }
 }
 inline void block_barrier(int id, int count) {
     Runtime& r = rt();

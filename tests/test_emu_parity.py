@@ -170,3 +170,24 @@ def test_emu_render_random_triangle_soup(oracle, fov, lh):
         assert np.array_equal(eng.get_state(), orc.state), f"step {k}: state"
         assert np.array_equal(eng.get_infractions(), orc.infractions), f"step {k}: infractions"
         assert np.array_equal(info, oinfo) and np.array_equal(obs, oobs), f"step {k}"
+
+
+def test_emu_physics_global_path_when_staging_is_off(oracle, monkeypatch):
+    """TDE_PHYS_STAGE=0: the physics kernel reads the map tables from global memory (the path taken when they do not
+    fit in shared memory); same results as the staged launch."""
+    monkeypatch.setenv("TDE_PHYS_STAGE", "0")
+    rollout_compare(oracle, S.traffic_lights(16), 40, 16, steps=12, seed=11, auto_reset=1)
+
+
+@pytest.mark.parametrize("policy", ["1", "2"])
+def test_emu_is_independent_of_warp_scheduling(policy):
+    """The emulator's adversarial schedules (one end of the block always runs first, so a warp gets as far ahead of the
+    others as the barriers allow): results must not depend on which warp of a group or CTA runs first."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, TDE_EMU_SCHED=policy)
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", os.path.join(here, "test_emu_parity.py"), "-k",
+                        "c3_traffic or stacked or scenario_mix or edge_configurations"], env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -3,6 +3,8 @@ sections are inferred from the enclosing function names found by scanning the so
 import csv, subprocess, sys, collections, re, os
 rep = sys.argv[1]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# optional third argument: the csrc directory the profiled library was built from (default: the working tree)
+CSRC = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "torchdriveenv_b200", "csrc")
 def func_map(path):
     """line -> name of the enclosing top-level function/kernel (crude: last line matching a definition)."""
     m = {}; cur = "?"
@@ -11,7 +13,7 @@ def func_map(path):
         if g and not line.startswith(" "): cur = g.group(1)
         m[i] = cur
     return m
-maps = {f: func_map(os.path.join(ROOT, "torchdriveenv_b200", "csrc", f)) for f in ("tde_kernels.cuh", "tde_device.cuh")}
+maps = {f: func_map(os.path.join(CSRC, f)) for f in ("tde_kernels.cuh", "tde_device.cuh", "tde_render.cuh") if os.path.exists(os.path.join(CSRC, f))}
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 def num(x):
     try: return float(x)

@@ -44,6 +44,12 @@ struct tde_handle {
     long long launches = 0;
     int grid_phys = 0, grid_render = 0;
     size_t smem_render = 0;
+    // physics launch: warps per CTA, CTAs per SM, dynamic shared memory; the staged blob of map tables (nullptr: the
+    // tables do not fit beside the SAT scratch, or staging is switched off -> the kernel reads them from global memory)
+    int phys_wpb = TDE_WARPS_PER_BLOCK, phys_per_sm = 1;
+    size_t smem_phys = 0;
+    unsigned char* stage_blob = nullptr;
+    unsigned int stage_bytes = 0, stage_maps_off = 0;
     // device staging for tde_step_host
     float* h_actions = nullptr; uint8_t* h_obs = nullptr; float* h_reward = nullptr;
     uint8_t *h_term = nullptr, *h_trunc = nullptr; float* h_info = nullptr;
@@ -453,14 +459,15 @@ static void free_scenarios(tde_handle* h) {
     h->scenario_allocs.clear();
     if (h->maps_dev) cudaFree(h->maps_dev);
     if (h->scens_dev) cudaFree(h->scens_dev);
-    h->maps_dev = nullptr; h->scens_dev = nullptr;
+    if (h->stage_blob) cudaFree(h->stage_blob);
+    h->maps_dev = nullptr; h->scens_dev = nullptr; h->stage_blob = nullptr; h->stage_bytes = 0;
     h->maps_host.clear(); h->scens_host.clear(); h->map_info.clear();
     h->uploaded = false;
 }
 
 // persistent grids: a multiple of the SM count (resident blocks per SM from the occupancy calculator)
 template <int AH>
-static int configure_kernels(tde_handle* h) {
+static int configure_render(tde_handle* h) {
     size_t smem = TDE_RENDER_SMEM_BYTES;   // groups + warps + the spread and span-mask tables
     CUDA_TRY(h, cudaFuncSetAttribute(tde_render_kernel<AH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_TRY(h, cudaFuncSetAttribute(tde_render_kernel<AH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -470,22 +477,51 @@ static int configure_kernels(tde_handle* h) {
     // tuning knobs for co-residency experiments (tools/coresident.py): cap the resident blocks per SM of either kernel
     if (const char* v = std::getenv("TDE_RENDER_BLOCKS_CAP")) per_sm = std::max(1, std::min(per_sm, std::atoi(v)));
     h->smem_render = smem;
-    int want = (h->E + TDE_WARPS_PER_BLOCK - 1) / TDE_WARPS_PER_BLOCK;
     h->grid_render = std::max(1, std::min((h->E + TDE_RENDER_GROUPS - 1) / TDE_RENDER_GROUPS, per_sm * h->sm_count));
-    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tde_physics_kernel<AH>, TDE_WARPS_PER_BLOCK * 32, 0));
-    {   // The physics kernel lives on L1 hits of the map tables (grid cells, triangle records): ask for no more shared
-        // memory than its resident blocks need, the rest of the SM's 228 KB stays L1 (C3: 54.3 -> 52.5 us at 30 %,
-        // 57.7 us at 60 %, 73.3 us at 100 %; tools/carve_sweep.sh).  TDE_PHYS_CARVEOUT overrides the percentage.
-        cudaFuncAttributes fa;
-        CUDA_TRY(h, cudaFuncGetAttributes(&fa, tde_physics_kernel<AH>));
-        const size_t need = (size_t)std::max(per_sm, 1) * (fa.sharedSizeBytes + 1024);
+    return TDE_OK;
+}
+
+// The physics launch, chosen once the scenario tables are known (end of tde_upload_scenarios).
+//  * STAGED: the map tables fit beside the SAT scratch -> every CTA copies them into shared memory with bulk-async copies
+//    (north-star item 3).  Fat CTAs (up to 32 warps, one per SM) so the copy is made once per SM; fewer warps per CTA for
+//    small batches so that every SM still gets a CTA.
+//  * otherwise 4-warp CTAs that read the tables through L1: ask for no more shared memory than the resident blocks need,
+//    the rest of the SM's 228 KB stays L1 (round 1: 54.3 -> 52.5 us at 30 %, 57.7 us at 60 %, 73.3 us at 100 %).
+template <int AH>
+static int configure_physics(tde_handle* h) {
+    const size_t scratch = sizeof(SatScratch<AH>);
+    const size_t smem_max = 227 * 1024;
+    if (h->stage_blob) {
+        int wpb = 32;
+        while (wpb > 4 && (h->E + wpb - 1) / wpb < h->sm_count) wpb >>= 1;
+        if (const char* v = std::getenv("TDE_PHYS_WARPS")) wpb = std::max(1, std::min(32, std::atoi(v)));
+        const size_t smem = (size_t)h->stage_bytes + 16 + (size_t)wpb * scratch;
+        if (smem <= smem_max) {
+            CUDA_TRY(h, cudaFuncSetAttribute(tde_physics_kernel<AH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int per_sm = 0;
+            CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tde_physics_kernel<AH, true>, wpb * 32, smem));
+            if (per_sm >= 1) {
+                h->phys_wpb = wpb; h->phys_per_sm = per_sm; h->smem_phys = smem;
+                h->grid_phys = std::max(1, std::min((h->E + wpb - 1) / wpb, per_sm * h->sm_count));
+                return TDE_OK;
+            }
+        }
+        cudaFree(h->stage_blob); h->stage_blob = nullptr; h->stage_bytes = 0;   // does not fit: global path
+    }
+    const int wpb = TDE_WARPS_PER_BLOCK;
+    const size_t smem = 16 + (size_t)wpb * scratch;
+    int per_sm = 0;
+    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tde_physics_kernel<AH, false>, wpb * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    {
+        const size_t need = (size_t)per_sm * (smem + 1024);
         int pct = (int)((need * 100 + 233471) / 233472) + 3;
         if (const char* v = std::getenv("TDE_PHYS_CARVEOUT")) pct = std::atoi(v);
-        CUDA_TRY(h, cudaFuncSetAttribute(tde_physics_kernel<AH>, cudaFuncAttributePreferredSharedMemoryCarveout, std::max(0, std::min(pct, 100))));
+        CUDA_TRY(h, cudaFuncSetAttribute(tde_physics_kernel<AH, false>, cudaFuncAttributePreferredSharedMemoryCarveout, std::max(0, std::min(pct, 100))));
     }
-    if (per_sm < 1) per_sm = 1;
     if (const char* v = std::getenv("TDE_PHYS_BLOCKS_CAP")) per_sm = std::max(1, std::min(per_sm, std::atoi(v)));
-    h->grid_phys = std::max(1, std::min(want, per_sm * h->sm_count));
+    h->phys_wpb = wpb; h->phys_per_sm = per_sm; h->smem_phys = smem;
+    h->grid_phys = std::max(1, std::min((h->E + wpb - 1) / wpb, per_sm * h->sm_count));
     return TDE_OK;
 }
 
@@ -520,7 +556,7 @@ extern "C" int tde_create(const tde_config* cfg, tde_handle** out) {
         (rc = dev_alloc(h, &h->stats, (size_t)TDE_NUM_STATS)) || (rc = dev_alloc(h, &h->restart, (size_t)h->E)) ||
         (rc = dev_alloc(h, &h->tickets, (size_t)4)) || (rc = dev_alloc(h, &h->done_mask, (size_t)h->E)))
         return bail(rc);
-    rc = h->A <= 32 ? configure_kernels<1>(h) : configure_kernels<2>(h);
+    rc = h->A <= 32 ? configure_render<1>(h) : configure_render<2>(h);
     if (rc) return bail(rc);
     *out = h;
     return TDE_OK;
@@ -556,6 +592,11 @@ extern "C" int tde_upload_scenarios(tde_handle* h, const tde_scenario_set* s) {
     const float ppm = (float)TDE_OBS_W / h->cfg.fov;
     const double max_edge_m = 430.0 / (double)ppm;  // keeps snapped vertices of drawn primitives inside +-511 px
     h->maps_host.resize(s->num_maps);
+    // pieces of the staged blob (physics kernel): per map the device triangle / stop-line records, the light schedule and
+    // the per-cell summary (u16: SAFE flag | the overlapping triangle covering most of the cell)
+    struct StagePiece { const float4* tri; int ntri; const float4* stop; int nstop; const uint8_t* lights; size_t nlights; std::vector<uint16_t> cells; };
+    std::vector<StagePiece> pieces((size_t)s->num_maps);
+    bool stage_ok = true;
     for (int m = 0; m < s->num_maps; ++m) {
         MapDev& M = h->maps_host[m];
         std::memset(&M, 0, sizeof(M));
@@ -643,6 +684,18 @@ extern "C" int tde_upload_scenarios(tde_handle* h, const tde_scenario_set* s) {
             h->map_info.push_back({nt, nk, nl, g.nx, g.ny, (int)g.items.size(), (int)safe, M.n_rp});
         }
         M.gx0 = g.gx0; M.gy0 = g.gy0; M.inv_cell = g.inv_cell; M.gnx = g.nx; M.gny = g.ny;
+        {
+            StagePiece& sp = pieces[(size_t)m];
+            sp.tri = rec; sp.ntri = nt; sp.stop = srec; sp.nstop = nl;
+            sp.lights = s->light_states + lo; sp.nlights = (size_t)std::max(ln, 0);
+            sp.cells.resize(g.meta.size());
+            if (nt >= TDE_CELL16_NONE) stage_ok = false;   // triangle ids must fit 15 bits
+            for (size_t c = 0; c < g.meta.size(); ++c) {
+                const int nover = g.meta[c] & 0x7fff;
+                const uint16_t first = nover > 0 ? g.items[(size_t)g.cell_start[c]] : (uint16_t)TDE_CELL16_NONE;
+                sp.cells[c] = (uint16_t)((g.meta[c] & TDE_CELL_SAFE) | (first & 0x7fff));
+            }
+        }
     }
     h->scens_host.resize(s->num_scenarios);
     for (int k = 0; k < s->num_scenarios; ++k) {
@@ -685,6 +738,40 @@ extern "C" int tde_upload_scenarios(tde_handle* h, const tde_scenario_set* s) {
     std::vector<int> lo((size_t)h->E, 0), hi((size_t)h->E, h->num_scen);
     CUDA_TRY(h, cudaMemcpy(h->scen_lo, lo.data(), sizeof(int) * h->E, cudaMemcpyHostToDevice));
     CUDA_TRY(h, cudaMemcpy(h->scen_hi, hi.data(), sizeof(int) * h->E, cudaMemcpyHostToDevice));
+    // the staged blob: [16 B header per map] [MapDev per map] [per map: triangle records, stop lines, lights, cell summary]
+    if (const char* v = std::getenv("TDE_PHYS_STAGE")) stage_ok = stage_ok && std::atoi(v) != 0;
+    if (stage_ok) {
+        auto al16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+        std::vector<uint32_t> hdr((size_t)h->num_maps * 4);
+        const size_t maps_off = al16((size_t)h->num_maps * 16);
+        size_t cur = al16(maps_off + sizeof(MapDev) * h->num_maps);
+        for (int m = 0; m < h->num_maps; ++m) {
+            const StagePiece& sp = pieces[(size_t)m];
+            hdr[4 * m + 0] = (uint32_t)cur; cur = al16(cur + (size_t)sp.ntri * 48);
+            hdr[4 * m + 1] = (uint32_t)cur; cur = al16(cur + (size_t)sp.nstop * 32);
+            hdr[4 * m + 2] = (uint32_t)cur; cur = al16(cur + sp.nlights);
+            hdr[4 * m + 3] = (uint32_t)cur; cur = al16(cur + sp.cells.size() * 2);
+        }
+        const size_t scratch_min = 16 + 4 * sizeof(SatScratch<1>);
+        if (cur + scratch_min <= 227 * 1024) {
+            CUDA_TRY(h, cudaMalloc((void**)&h->stage_blob, cur));
+            CUDA_TRY(h, cudaMemset(h->stage_blob, 0, cur));
+            CUDA_TRY(h, cudaMemcpy(h->stage_blob, hdr.data(), hdr.size() * 4, cudaMemcpyHostToDevice));
+            CUDA_TRY(h, cudaMemcpy(h->stage_blob + maps_off, h->maps_host.data(), sizeof(MapDev) * h->num_maps, cudaMemcpyHostToDevice));
+            for (int m = 0; m < h->num_maps; ++m) {
+                const StagePiece& sp = pieces[(size_t)m];
+                if (sp.ntri) CUDA_TRY(h, cudaMemcpy(h->stage_blob + hdr[4 * m + 0], sp.tri, (size_t)sp.ntri * 48, cudaMemcpyDeviceToDevice));
+                if (sp.nstop) CUDA_TRY(h, cudaMemcpy(h->stage_blob + hdr[4 * m + 1], sp.stop, (size_t)sp.nstop * 32, cudaMemcpyDeviceToDevice));
+                if (sp.nlights) CUDA_TRY(h, cudaMemcpy(h->stage_blob + hdr[4 * m + 2], sp.lights, sp.nlights, cudaMemcpyHostToDevice));
+                if (!sp.cells.empty()) CUDA_TRY(h, cudaMemcpy(h->stage_blob + hdr[4 * m + 3], sp.cells.data(), sp.cells.size() * 2, cudaMemcpyHostToDevice));
+            }
+            h->stage_bytes = (unsigned int)cur; h->stage_maps_off = (unsigned int)maps_off;
+        }
+    }
+    {
+        int rc = h->A <= 32 ? configure_physics<1>(h) : configure_physics<2>(h);
+        if (rc) return rc;
+    }
     CUDA_TRY(h, cudaDeviceSynchronize());
     h->uploaded = true; h->was_reset = false;
     return TDE_OK;
@@ -709,6 +796,7 @@ static StepParams make_params(tde_handle* h) {
     p.state = h->state; p.attr = h->attr; p.infr = h->infr; p.vars = h->vars; p.ep_return = h->ep_return;
     p.scen_lo = h->scen_lo; p.scen_hi = h->scen_hi; p.stats = h->stats; p.restart = h->restart; p.tickets = h->tickets; p.n_stack = 1;
     p.e_begin = 0; p.e_end = h->E;
+    p.stage_blob = h->stage_blob; p.stage_bytes = h->stage_bytes; p.stage_maps_off = h->stage_maps_off;
     for (int ch = 0; ch < 3; ++ch)
         for (int w = 0; w < 4; ++w) {
             uint32_t v = 0;
@@ -794,9 +882,15 @@ static int step_impl(tde_handle* h, int32_t phases, const float* actions, uint8_
         p.done_mask = h->done_mask;
     }
     if (physics) {
-        const int grid = std::min(h->grid_phys, want);
-        if (h->A <= 32) CUDA_TRY(h, launch_step(tde_physics_kernel<1>, grid, threads, 0, st, p));
-        else CUDA_TRY(h, launch_step(tde_physics_kernel<2>, grid, threads, 0, st, p));
+        const int wpb = h->phys_wpb, pthreads = wpb * 32;
+        const int grid = std::min(h->grid_phys, (p.e_end - p.e_begin + wpb - 1) / wpb);
+        if (h->stage_blob) {
+            if (h->A <= 32) CUDA_TRY(h, launch_step(tde_physics_kernel<1, true>, grid, pthreads, h->smem_phys, st, p));
+            else CUDA_TRY(h, launch_step(tde_physics_kernel<2, true>, grid, pthreads, h->smem_phys, st, p));
+        } else {
+            if (h->A <= 32) CUDA_TRY(h, launch_step(tde_physics_kernel<1, false>, grid, pthreads, h->smem_phys, st, p));
+            else CUDA_TRY(h, launch_step(tde_physics_kernel<2, false>, grid, pthreads, h->smem_phys, st, p));
+        }
         h->launches++;
     }
     if (render) {

@@ -13,6 +13,74 @@
 #include <math.h>
 #include <stdint.h>
 
+// ---------------------------------------------------------------- bulk-async staging into shared memory (TMA engine)
+//
+// cp.async.bulk global -> shared::cta, completion signalled on an mbarrier (SASS: UBLKCP + SYNCS).  One thread arms the
+// barrier with the byte count and issues the copies; every thread that reads the staged tables waits on the barrier's
+// phase first.  Sizes and addresses are multiples of 16 bytes.  Shared-memory data is then read through explicit
+// ld.shared wrappers taking 32-bit shared-window addresses (the helpers that use them are not inlined, so a C++ pointer
+// would degrade to generic loads).  The emulator build copies immediately and reads through the block's buffer.
+#ifdef TDE_HOST_EMU
+__device__ __forceinline__ uint32_t tde_smem_addr(const void* p) { return (uint32_t)((const unsigned char*)p - emu::dyn_smem()); }
+// emulated mbarrier word: low half = bytes still expected, high half = completed phases (one arrival per phase)
+__device__ __forceinline__ void tde_mbar_init(unsigned long long* bar, int) { *bar = 0ull; }
+__device__ __forceinline__ void tde_mbar_expect_tx(unsigned long long* bar, uint32_t bytes) { *bar += bytes; }
+__device__ __forceinline__ void tde_bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    memcpy(dst, src, bytes);
+    *bar -= bytes;
+    if ((uint32_t)*bar == 0u) *bar += 1ull << 32;   // the last byte landed: the phase completes
+    emu::rt().progress++;
+}
+__device__ __forceinline__ void tde_mbar_wait(unsigned long long* bar, uint32_t parity) {
+    emu::wait_phase(bar, parity);
+}
+__device__ __forceinline__ float4 tde_lds_f4(uint32_t a) { return *reinterpret_cast<const float4*>(emu::dyn_smem() + a); }
+__device__ __forceinline__ uint32_t tde_lds_u16(uint32_t a) { return *reinterpret_cast<const uint16_t*>(emu::dyn_smem() + a); }
+__device__ __forceinline__ uint32_t tde_lds_u8(uint32_t a) { return *reinterpret_cast<const uint8_t*>(emu::dyn_smem() + a); }
+#else
+__device__ __forceinline__ uint32_t tde_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tde_mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tde_smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // make the init visible to the async proxy
+}
+__device__ __forceinline__ void tde_mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tde_smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tde_bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tde_smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(tde_smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tde_mbar_wait(unsigned long long* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TDE_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra TDE_MBAR_DONE;\n"
+        "bra TDE_MBAR_WAIT;\n"
+        "TDE_MBAR_DONE:\n"
+        "}\n" ::"r"(tde_smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ float4 tde_lds_f4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t tde_lds_u16(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t tde_lds_u8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+#endif
+
 #define TDE_PI_F 3.14159274101257324219f
 #define TDE_TWO_PI_F 6.28318548202514648438f
 #define FULL_MASK 0xffffffffu
@@ -112,31 +180,33 @@ __device__ __forceinline__ void tde_edge_terms(float ax, float ay, float bx, flo
     d2 = qx * qx + qy * qy;
 }
 
-// Triangle record: 3 float4  [ax ay bx by] [cx cy il_ab il_bc] [il_ca dir_cos dir_sin 0]
-__device__ __forceinline__ float tde_point_tri_dist2(const float4* __restrict__ tri, float px, float py, bool& inside,
-                                                     float& dc, float& ds) {
-    float4 t0 = __ldg(tri), t1 = __ldg(tri + 1), t2 = __ldg(tri + 2);
-    float d0, d1, d2, c0, c1, c2;
-    tde_edge_terms(t0.x, t0.y, t0.z, t0.w, t1.z, px, py, d0, c0);
-    tde_edge_terms(t0.z, t0.w, t1.x, t1.y, t1.w, px, py, d1, c1);
-    tde_edge_terms(t1.x, t1.y, t0.x, t0.y, t2.x, px, py, d2, c2);
-    inside = (c0 >= 0.0f && c1 >= 0.0f && c2 >= 0.0f) || (c0 <= 0.0f && c1 <= 0.0f && c2 <= 0.0f);
-    dc = t2.y; ds = t2.z;
-    return inside ? 0.0f : fminf(fminf(d0, d1), d2);
+// Triangle record: 3 float4  [ax ay bx by] [cx cy il_ab il_bc] [il_ca dir_cos dir_sin 0], read from the global table
+// (read-only path) or from its copy staged in shared memory
+struct Tri3 { float4 t0, t1, t2; };
+template <bool STAGED>
+__device__ __forceinline__ Tri3 tde_load_tri(const float4* __restrict__ g, uint32_t s, int t) {
+    Tri3 r;
+    if (STAGED) {
+        const uint32_t a = s + (uint32_t)t * 48u;
+        r.t0 = tde_lds_f4(a); r.t1 = tde_lds_f4(a + 16u); r.t2 = tde_lds_f4(a + 32u);
+    } else {
+        const float4* q = g + 3 * t;
+        r.t0 = __ldg(q); r.t1 = __ldg(q + 1); r.t2 = __ldg(q + 2);
+    }
+    return r;
 }
-
-// containment only (same edge functions, same operand order as tde_point_tri_dist2)
-__device__ __forceinline__ bool tde_tri_contains(const float4* __restrict__ tri, float px, float py, float& dc, float& ds) {
-    float4 t0 = __ldg(tri), t1 = __ldg(tri + 1), t2 = __ldg(tri + 2);
+// containment (edge functions with a fixed operand order), lane direction of the triangle in (dc, ds)
+__device__ __forceinline__ bool tde_tri_contains(const Tri3& T, float px, float py, float& dc, float& ds) {
+    const float4 t0 = T.t0, t1 = T.t1;
     float c0 = (t0.z - t0.x) * (py - t0.y) - (t0.w - t0.y) * (px - t0.x);
     float c1 = (t1.x - t0.z) * (py - t0.w) - (t1.y - t0.w) * (px - t0.z);
     float c2 = (t0.x - t1.x) * (py - t1.y) - (t0.y - t1.y) * (px - t1.x);
-    dc = t2.y; ds = t2.z;
+    dc = T.t2.y; ds = T.t2.z;
     return (c0 >= 0.0f && c1 >= 0.0f && c2 >= 0.0f) || (c0 <= 0.0f && c1 <= 0.0f && c2 <= 0.0f);
 }
-// min squared distance to the three edges (what tde_point_tri_dist2 returns for a point outside)
-__device__ __forceinline__ float tde_tri_segdist2(const float4* __restrict__ tri, float px, float py) {
-    float4 t0 = __ldg(tri), t1 = __ldg(tri + 1), t2 = __ldg(tri + 2);
+// min squared distance to the three edges (the distance of a point outside the triangle)
+__device__ __forceinline__ float tde_tri_segdist2(const Tri3& T, float px, float py) {
+    const float4 t0 = T.t0, t1 = T.t1, t2 = T.t2;
     float d0, d1, d2, c;
     tde_edge_terms(t0.x, t0.y, t0.z, t0.w, t1.z, px, py, d0, c);
     tde_edge_terms(t0.z, t0.w, t1.x, t1.y, t1.w, px, py, d1, c);

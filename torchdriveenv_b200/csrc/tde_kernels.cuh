@@ -49,6 +49,8 @@ struct MapDev {
     const float* mark_raw;      // [nmark][6] lane-marking triangles as uploaded (recording view, tde_view.cuh)
 };
 
+static_assert(sizeof(MapDev) % 16 == 0, "MapDev rows are copied into shared memory with 16-byte granularity");
+
 struct ScenDev {
     const float2* wp;
     const float4* init;        // [A] x y psi v
@@ -90,6 +92,11 @@ struct StepParams {
     int n_stack;         // frames per env in obs (1 = plain observation)
     uint32_t pal[3][4];  // per channel: 16 class bytes
     float ppm, ppmy;
+    // physics kernel, STAGED launches: the map tables as one blob (16 B header per map: offsets of its triangle records,
+    // stop lines, light schedule and cell summary; then the MapDev array; then the tables), copied to shared memory once
+    // per CTA with bulk-async copies
+    const unsigned char* stage_blob;
+    unsigned int stage_bytes, stage_maps_off;
 };
 
 struct Cam { float ex, ey, ce, se, ppm, ppmy; };
@@ -264,6 +271,15 @@ __device__ __forceinline__ void sat_counts(SatScratch<AH>* ws, const Box (&me)[A
 // every point is provably closer to the road than the offroad threshold are flagged SAFE at upload:
 // there the offroad term is 0 without looking at a triangle.
 #define TDE_CELL_SAFE 0x8000
+#define TDE_CELL16_NONE 0x7fff
+
+// What the physics reads of a map: `g` is the map descriptor (the global one, or its staged copy); with STAGED the
+// triangle records, stop lines, light schedule and the per-cell summary live in shared memory (bulk-async copies made
+// once per CTA, tde_physics_kernel) and tri_s / stop_s / lights_s / cells_s are their shared-window addresses.
+// cells_s: one u16 per grid cell - bit 15 = SAFE, bits 0..14 = the overlapping triangle covering most of the cell
+// (TDE_CELL16_NONE: no triangle overlaps the cell).  The cell records and candidate lists stay in global memory: an
+// agent that drives on its lane needs neither.
+struct MapRef { const MapDev* g; uint32_t tri_s, stop_s, lights_s, cells_s; };
 
 // compute_offroad (gym_env.py:142,415,427): sum over corners of max(dist - threshold, 0), and
 // compute_wrong_way: max(-cos(psi - lane_dir), 0), min over the triangles under the centre.  Called by
@@ -272,26 +288,46 @@ __device__ __forceinline__ void sat_counts(SatScratch<AH>* ws, const Box (&me)[A
 // the cell's overlapping triangles); the corners that still need a distance are taken one at a time by
 // the whole warp, lanes striding over the candidate triangles, min by redux.
 struct MeshInfr { float offroad, wrong_way; };
-template <bool WRONG_WAY>
-__device__ __noinline__ MeshInfr mesh_infractions_warp(const MapDev& M, const Box& b, bool mine, float thr, int lane) {
+template <bool WRONG_WAY, bool STAGED>
+__device__ __noinline__ MeshInfr mesh_infractions_warp(const MapRef R, const Box& b, bool mine, float thr, int lane) {
+    const MapDev& M = *R.g;
     MeshInfr out; out.offroad = 0.0f; out.wrong_way = 0.0f;
     if (M.ntri <= 0) return out;
     int2 rec[5];   // x = first item (-1: off the grid), y = n_items << 16 | SAFE | n_overlapping
+    float cx[4], cy[4];
+    float dc, ds;
+    bool ww_settled = !mine;   // STAGED: the centre's summary triangle contains the centre and the agent follows it
 #pragma unroll
     for (int k = 0; k < (WRONG_WAY ? 5 : 4); ++k) {
         float px = b.x, py = b.y;
-        if (k < 4) tde_box_corner(b, k, px, py);
+        if (k < 4) { tde_box_corner(b, k, px, py); cx[k] = px; cy[k] = py; }
         float fx = floorf((px - M.gx0) * M.inv_cell), fy = floorf((py - M.gy0) * M.inv_cell);
         bool in_grid = fx >= 0.0f && fy >= 0.0f && fx < (float)M.gnx && fy < (float)M.gny;
         rec[k] = make_int2(in_grid ? 0 : -1, in_grid ? TDE_CELL_SAFE : 0);
-        if (mine && in_grid) rec[k] = __ldg(&M.cell_rec[(int)fy * M.gnx + (int)fx]);
+        if (mine && in_grid) {
+            const int cell = (int)fy * M.gnx + (int)fx;
+            bool fetch = true;
+            if (STAGED) {
+                const uint32_t c16 = tde_lds_u16(R.cells_s + 2u * (uint32_t)cell);
+                if (k < 4) fetch = !(c16 & TDE_CELL_SAFE);       // a SAFE corner needs nothing else
+                else {
+                    const int t0 = (int)(c16 & 0x7fffu);
+                    if (t0 == TDE_CELL16_NONE) { ww_settled = true; fetch = false; }   // nothing under the centre: 0
+                    else {
+                        const Tri3 T = tde_load_tri<true>(nullptr, R.tri_s, t0);
+                        if (tde_tri_contains(T, b.x, b.y, dc, ds) && fmaxf(-(b.c * dc + b.s * ds), 0.0f) == 0.0f) { ww_settled = true; fetch = false; }
+                    }
+                }
+            }
+            if (fetch) rec[k] = __ldg(&M.cell_rec[cell]);
+        }
         if (!mine) rec[k] = make_int2(0, TDE_CELL_SAFE);
     }
-    float sum = 0.0f, dc, ds;
+    float sum = 0.0f;
 #pragma unroll 1
     for (int k = 0; k < 4; ++k) {
-        float px, py;
-        tde_box_corner(b, k, px, py);
+        const float px = k == 0 ? cx[0] : k == 1 ? cx[1] : k == 2 ? cx[2] : cx[3];
+        const float py = k == 0 ? cy[0] : k == 1 ? cy[1] : k == 2 ? cy[2] : cy[3];
         const int2 rc = k == 0 ? rec[0] : k == 1 ? rec[1] : k == 2 ? rec[2] : rec[3];
         float d2 = 0.0f;
         int i0 = rc.x, i1 = rc.x + (int)((unsigned)rc.y >> 16);
@@ -302,20 +338,22 @@ __device__ __noinline__ MeshInfr mesh_infractions_warp(const MapDev& M, const Bo
             const int nover = rc.y & 0x7fff;
             need = true;
             for (int i = i0; i < i0 + nover; ++i)
-                if (tde_tri_contains(M.tri + 3 * (int)__ldg(&M.cell_items[i]), px, py, dc, ds)) { need = false; break; }
+                if (tde_tri_contains(tde_load_tri<STAGED>(M.tri, R.tri_s, (int)__ldg(&M.cell_items[i])), px, py, dc, ds)) { need = false; break; }
         }
         unsigned nm = __ballot_sync(FULL_MASK, need);
+        if (nm == 0u) continue;
         if (__popc(nm) > 4) {   // many lanes are off the road (scattered boxes): each walks its own candidates
             if (need) {
                 float best = INFINITY;
                 bool inside = false;
                 if (i1 < 0) {
                     for (int t = 0; t < -i1; ++t) {
-                        inside = inside || tde_tri_contains(M.tri + 3 * t, px, py, dc, ds);
-                        best = fminf(best, tde_tri_segdist2(M.tri + 3 * t, px, py));
+                        const Tri3 T = tde_load_tri<STAGED>(M.tri, R.tri_s, t);
+                        inside = inside || tde_tri_contains(T, px, py, dc, ds);
+                        best = fminf(best, tde_tri_segdist2(T, px, py));
                     }
                 } else {
-                    for (int i = i0; i < i1; ++i) best = fminf(best, tde_tri_segdist2(M.tri + 3 * (int)__ldg(&M.cell_items[i]), px, py));
+                    for (int i = i0; i < i1; ++i) best = fminf(best, tde_tri_segdist2(tde_load_tri<STAGED>(M.tri, R.tri_s, (int)__ldg(&M.cell_items[i])), px, py));
                 }
                 d2 = inside ? 0.0f : best;
             }
@@ -330,12 +368,13 @@ __device__ __noinline__ MeshInfr mesh_infractions_warp(const MapDev& M, const Bo
             bool inside = false;
             if (a1 < 0) {
                 for (int t = lane; t < -a1; t += 32) {
-                    inside = inside || tde_tri_contains(M.tri + 3 * t, qx, qy, dc, ds);
-                    best = fminf(best, tde_tri_segdist2(M.tri + 3 * t, qx, qy));
+                    const Tri3 T = tde_load_tri<STAGED>(M.tri, R.tri_s, t);
+                    inside = inside || tde_tri_contains(T, qx, qy, dc, ds);
+                    best = fminf(best, tde_tri_segdist2(T, qx, qy));
                 }
                 inside = __any_sync(FULL_MASK, inside);
             } else {
-                for (int i = a0 + lane; i < a1; i += 32) best = fminf(best, tde_tri_segdist2(M.tri + 3 * (int)__ldg(&M.cell_items[i]), qx, qy));
+                for (int i = a0 + lane; i < a1; i += 32) best = fminf(best, tde_tri_segdist2(tde_load_tri<STAGED>(M.tri, R.tri_s, (int)__ldg(&M.cell_items[i])), qx, qy));
             }
             // non-negative binary32 values order like their bit patterns
             const unsigned ub = __reduce_min_sync(FULL_MASK, __float_as_uint(best));
@@ -348,17 +387,19 @@ __device__ __noinline__ MeshInfr mesh_infractions_warp(const MapDev& M, const Bo
     if (!WRONG_WAY) return out;
     // wrong way: the triangles under the centre
     float best = INFINITY;
-    if (rec[4].x >= 0) {
-        const int i0 = rec[4].x, nover = rec[4].y & 0x7fff;
-        // the value is a minimum of non-negative terms: a containing triangle the agent follows (term 0) settles it
-        for (int i = i0; i < i0 + nover; ++i)
-            if (tde_tri_contains(M.tri + 3 * (int)__ldg(&M.cell_items[i]), b.x, b.y, dc, ds)) {
-                best = fminf(best, fmaxf(-(b.c * dc + b.s * ds), 0.0f));
-                if (best == 0.0f) break;
-            }
-    } else {
-        for (int t = 0; t < M.ntri; ++t)
-            if (tde_tri_contains(M.tri + 3 * t, b.x, b.y, dc, ds)) best = fminf(best, fmaxf(-(b.c * dc + b.s * ds), 0.0f));
+    if (!ww_settled) {
+        if (rec[4].x >= 0) {
+            const int i0 = rec[4].x, nover = rec[4].y & 0x7fff;
+            // the value is a minimum of non-negative terms: a containing triangle the agent follows (term 0) settles it
+            for (int i = i0; i < i0 + nover; ++i)
+                if (tde_tri_contains(tde_load_tri<STAGED>(M.tri, R.tri_s, (int)__ldg(&M.cell_items[i])), b.x, b.y, dc, ds)) {
+                    best = fminf(best, fmaxf(-(b.c * dc + b.s * ds), 0.0f));
+                    if (best == 0.0f) break;
+                }
+        } else {
+            for (int t = 0; t < M.ntri; ++t)
+                if (tde_tri_contains(tde_load_tri<STAGED>(M.tri, R.tri_s, t), b.x, b.y, dc, ds)) best = fminf(best, fmaxf(-(b.c * dc + b.s * ds), 0.0f));
+        }
     }
     out.wrong_way = best == INFINITY ? 0.0f : best;
     return out;
@@ -370,14 +411,23 @@ __device__ __forceinline__ int light_state_at(const MapDev& M, int step, int pha
     return __ldg(&M.lights[t * M.nstop + l]);
 }
 // bit l set = stop line l shows red at this env time (lane l looks its own light up)
-__device__ __forceinline__ unsigned red_lights_mask(const MapDev& M, int step, int phase, int lane) {
-    bool red = lane < M.nstop && light_state_at(M, step, phase, lane) == TDE_LIGHT_RED;
+template <bool STAGED>
+__device__ __forceinline__ unsigned red_lights_mask(const MapRef R, int step, int phase, int lane) {
+    const MapDev& M = *R.g;
+    bool red = false;
+    if (lane < M.nstop && M.period > 0) {
+        const int t = (step + phase) % M.period;
+        const int st = STAGED ? (int)tde_lds_u8(R.lights_s + (uint32_t)(t * M.nstop + lane)) : (int)__ldg(&M.lights[t * M.nstop + lane]);
+        red = st == TDE_LIGHT_RED;
+    }
     return __ballot_sync(FULL_MASK, red);
 }
 
 // TrafficLightControl.compute_violation: rear strip of the agent box vs the stop lines showing red.
 // Called by the whole warp; a circle test votes before the 4-axis SAT.
-__device__ __noinline__ float tl_violation_warp(const MapDev& M, const Box& b, bool mine, float rear_factor, unsigned red) {
+template <bool STAGED>
+__device__ __noinline__ float tl_violation_warp(const MapRef R, const Box& b, bool mine, float rear_factor, unsigned red) {
+    const MapDev& M = *R.g;
     float length = 2.0f * b.hl;  // exact: hl = 0.5f*length
     float len2 = length * rear_factor;
     float back = 0.5f * (length - len2);
@@ -390,9 +440,11 @@ __device__ __noinline__ float tl_violation_warp(const MapDev& M, const Box& b, b
     while (red) {
         const int l = __ffs(red) - 1;
         red &= red - 1;
-        float4 u = __ldg(&M.stop[2 * l]), v = __ldg(&M.stop[2 * l + 1]);
-        float dx = u.x - rear.x, dy = u.y - rear.y, R = rr + v.z;
-        bool cand = mine && dx * dx + dy * dy <= R * R * 1.001f;
+        float4 u, v;
+        if (STAGED) { u = tde_lds_f4(R.stop_s + 32u * (uint32_t)l); v = tde_lds_f4(R.stop_s + 32u * (uint32_t)l + 16u); }
+        else { u = __ldg(&M.stop[2 * l]); v = __ldg(&M.stop[2 * l + 1]); }
+        float dx = u.x - rear.x, dy = u.y - rear.y, Rr = rr + v.z;
+        bool cand = mine && dx * dx + dy * dy <= Rr * Rr * 1.001f;
         if (__any_sync(FULL_MASK, cand)) {
             Box sb; sb.x = u.x; sb.y = u.y; sb.hl = u.z; sb.hw = u.w; sb.c = v.x; sb.s = v.y; sb.present = 1.0f; sb.r = 0.0f;
             if (cand && tde_overlap(rear, sb)) viol += 1.0f;
@@ -503,8 +555,9 @@ __global__ void __launch_bounds__(256) tde_copy_rows_kernel(const uint8_t* __res
 // WaypointSuiteEnv.step :369-389 minus the observation: bicycle step / NPC replay, all-pairs SAT,
 // offroad / red-light / wrong-way against the lane mesh, reward, termination, truncation, info,
 // waypoint progress, episode statistics and (optionally) the in-kernel auto-reset.
-template <int AH>
-__device__ __forceinline__ void physics_env(const StepParams& p, const int e, const int lane, SatScratch<AH>* ws, double& st_acc, int& n_steps) {
+template <int AH, bool STAGED>
+__device__ __forceinline__ void physics_env(const StepParams& p, const int e, const int lane, SatScratch<AH>* ws, double& st_acc, int& n_steps,
+                                            unsigned char* smem_raw, unsigned long long* mbar, bool& staged_ready) {
     const tde_config& c = p.cfg;
     {
         const EnvVars ev = load_vars<true>(p, e, lane);
@@ -543,20 +596,32 @@ __device__ __forceinline__ void physics_env(const StepParams& p, const int e, co
 
         float4 inf0 = make_float4(0.f, 0.f, 0.f, 0.f);  // ego's infractions, valid on lane 0
         if (p.phases & TDE_PH_INFRACTIONS) {
-            const MapDev& M = p.maps[m];
             Box me[AH];
             float cnt[AH];
 #pragma unroll
             for (int h = 0; h < AH; ++h) me[h] = tde_make_box(st[h].x, st[h].y, st[h].z, at[h].x, at[h].y, at[h].w);
             sat_counts<AH>(ws, me, p.A, lane, cnt);
-            const unsigned red = red_lights_mask(M, step, lphase, lane);
+            MapRef M;
+            if (STAGED) {
+                // the bulk copies were issued when the CTA started; the first env of a warp waits for them here, after
+                // its bicycle step and SAT
+                if (!staged_ready) { tde_mbar_wait(mbar, 0u); staged_ready = true; }
+                const uint4 hd = reinterpret_cast<const uint4*>(smem_raw)[m];
+                const uint32_t base = tde_smem_addr(smem_raw);
+                M.g = reinterpret_cast<const MapDev*>(smem_raw + p.stage_maps_off) + m;
+                M.tri_s = base + hd.x; M.stop_s = base + hd.y; M.lights_s = base + hd.z; M.cells_s = base + hd.w;
+            } else {
+                M.g = &p.maps[m];
+                M.tri_s = M.stop_s = M.lights_s = M.cells_s = 0u;
+            }
+            const unsigned red = red_lights_mask<STAGED>(M, step, lphase, lane);
 #pragma unroll
             for (int h = 0; h < AH; ++h) {
                 int a = h * 32 + lane;
                 bool mine = a < p.A && at[h].w != 0.0f;
                 float4 inf = make_float4(0.f, 0.f, 0.f, 0.f);
-                MeshInfr mi = mesh_infractions_warp<true>(M, me[h], mine, c.offroad_threshold, lane);
-                float tl = tl_violation_warp(M, me[h], mine, c.tl_rear_factor, red);
+                MeshInfr mi = mesh_infractions_warp<true, STAGED>(M, me[h], mine, c.offroad_threshold, lane);
+                float tl = tl_violation_warp<STAGED>(M, me[h], mine, c.tl_rear_factor, red);
                 if (mine) {
                     inf.x = cnt[h];
                     inf.y = mi.offroad;
@@ -639,24 +704,44 @@ __device__ __forceinline__ void physics_env(const StepParams& p, const int e, co
     }
 }
 
-template <int AH>
-__global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32, TDE_PHYS_BLOCKS_PER_SM) tde_physics_kernel(const StepParams p) {
-    __shared__ SatScratch<AH> scratch[TDE_WARPS_PER_BLOCK];
+// Shared memory of the physics kernel: [staged map tables (STAGED only)] [mbarrier, 16 B] [SatScratch per warp].  The
+// number of warps per CTA is the launch's choice (blockDim): 4-warp CTAs when the tables stay in global memory (the rest
+// of the SM is L1 for them), up to 32-warp CTAs when they are staged (one copy per SM).
+#define TDE_PHYS_STAGE_CHUNK 32768u
+template <int AH, bool STAGED>
+__global__ void __launch_bounds__(STAGED ? 1024 : TDE_WARPS_PER_BLOCK * 32, STAGED ? 1 : TDE_PHYS_BLOCKS_PER_SM) tde_physics_kernel(const StepParams p) {
+    TDE_DYN_SMEM(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    SatScratch<AH>* ws = &scratch[warp];
-    const int warps_total = gridDim.x * TDE_WARPS_PER_BLOCK;
+    const int wpb = blockDim.x >> 5;
+    const unsigned int stage_bytes = STAGED ? p.stage_bytes : 0u;
+    unsigned long long* const mbar = reinterpret_cast<unsigned long long*>(smem_raw + stage_bytes);
+    SatScratch<AH>* ws = reinterpret_cast<SatScratch<AH>*>(smem_raw + stage_bytes + 16) + warp;
+    bool staged_ready = !STAGED;
+    if (STAGED) {
+        // per-scenario lane mesh & co staged once per CTA by the TMA engine: cp.async.bulk + mbarrier (complete_tx)
+        if (threadIdx.x == 0) tde_mbar_init(mbar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            tde_mbar_expect_tx(mbar, stage_bytes);
+            for (unsigned int off = 0; off < p.stage_bytes; off += TDE_PHYS_STAGE_CHUNK)
+                tde_bulk_g2s(smem_raw + off, p.stage_blob + off, min(TDE_PHYS_STAGE_CHUNK, p.stage_bytes - off), mbar);
+        }
+    }
+    const int warps_total = gridDim.x * wpb;
     tde_pdl_wait();
     double st_acc = 0.0;  // lane k accumulates statistic k
     int n_steps = 0;      // env steps taken by this warp
 #pragma unroll 1
-    for (int e = p.e_begin + blockIdx.x * TDE_WARPS_PER_BLOCK + warp; e < p.e_end; e += warps_total) {
+    for (int e = p.e_begin + blockIdx.x * wpb + warp; e < p.e_end; e += warps_total) {
         TDE_TRACE_MARK(e, 2);
-        physics_env<AH>(p, e, lane, ws, st_acc, n_steps);
+        physics_env<AH, STAGED>(p, e, lane, ws, st_acc, n_steps, smem_raw, mbar, staged_ready);
         TDE_TRACE_MARK(e, 3);
     }
     tde_pdl_launch_dependents();
     if (lane == TDE_STAT_STEPS) st_acc += (double)n_steps;
     if ((p.phases & TDE_PH_REWARD) && lane < TDE_NUM_STATS && st_acc != 0.0) atomicAdd(&p.stats[lane], st_acc);
+    // a CTA must not exit while its bulk copies are in flight (a warp without envs, or one that skipped the infractions)
+    if (STAGED && !staged_ready) tde_mbar_wait(mbar, 0u);
 }
 
 template <int AH>
@@ -716,7 +801,8 @@ __global__ void __launch_bounds__(256) tde_offroad_kernel(const MapDev* maps, in
         float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), a4 = make_float4(1.f, 1.f, 1.f, 0.f);
         if (i < n) { s4 = state[i]; a4 = attr[i]; }
         Box b = tde_make_box(s4.x, s4.y, s4.z, a4.x, a4.y, a4.w);
-        float val = mesh_infractions_warp<false>(M, b, i < n && a4.w != 0.0f, thr, lane).offroad;
+        MapRef R; R.g = &M; R.tri_s = R.stop_s = R.lights_s = R.cells_s = 0u;
+        float val = mesh_infractions_warp<false, false>(R, b, i < n && a4.w != 0.0f, thr, lane).offroad;
         if (i < n) out[i] = val;
     }
 }
