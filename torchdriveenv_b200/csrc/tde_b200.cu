@@ -642,11 +642,24 @@ extern "C" int tde_upload_scenarios(tde_handle* h, const tde_scenario_set* s) {
             std::vector<float> rp_mark = merge_into_quads(s->mark_tris + 6 * (size_t)k0, nk, 6, max_edge_m);
             const float reach = (0.70710678f * (float)(TDE_OBS_W + TDE_OBS_H) * 0.5f + 2.0f) / ppm;  // as in tde_render_kernel
             StaticIndex si = build_static_index(rp_road, rp_mark, reach);
-            float* rpd = nullptr; uint8_t* clsd = nullptr; int* tsd = nullptr;
+            // bounding circle per primitive (float64, radius rounded up): the render kernel's first culling stage
+            std::vector<float> bound(si.cls.size() * 4);
+            for (size_t k = 0; k < si.cls.size(); ++k) {
+                const float* v = &si.prims[8 * k];
+                double lx = v[0], hx = v[0], ly = v[1], hy = v[1];
+                for (int q = 1; q < 4; ++q) { lx = std::min(lx, (double)v[2 * q]); hx = std::max(hx, (double)v[2 * q]); ly = std::min(ly, (double)v[2 * q + 1]); hy = std::max(hy, (double)v[2 * q + 1]); }
+                const float cx = (float)(0.5 * (lx + hx)), cy = (float)(0.5 * (ly + hy));
+                double r = 0;
+                for (int q = 0; q < 4; ++q) r = std::max(r, std::hypot((double)v[2 * q] - cx, (double)v[2 * q + 1] - cy));
+                bound[4 * k] = cx; bound[4 * k + 1] = cy; bound[4 * k + 2] = (float)(r * 1.0001 + 1e-3);
+                const int32_t c = si.cls[k];
+                std::memcpy(&bound[4 * k + 3], &c, 4);
+            }
+            float* rpd = nullptr; float* bdd = nullptr; int* tsd = nullptr;
             if ((rc = dev_upload(h, &rpd, si.prims.data(), si.prims.size()))) return rc;
-            if ((rc = dev_upload(h, &clsd, si.cls.data(), si.cls.size()))) return rc;
+            if ((rc = dev_upload(h, &bdd, bound.data(), bound.size()))) return rc;
             if ((rc = dev_upload(h, &tsd, si.tile_start.data(), si.tile_start.size()))) return rc;
-            M.rp = (const float4*)rpd; M.rp_cls = clsd; M.tile_start = tsd;
+            M.rp = (const float4*)rpd; M.rp_bound = (const float4*)bdd; M.tile_start = tsd;
             M.n_rp = (int)si.cls.size(); M.n_big = si.n_big;
             M.tgx0 = si.gx0; M.tgy0 = si.gy0; M.tinv = si.inv; M.maxext = si.maxext; M.tnx = si.nx; M.tny = si.ny;
         }

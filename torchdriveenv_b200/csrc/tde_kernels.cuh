@@ -34,7 +34,7 @@ struct MapDev {
     const float4* tri;          // 3 float4 per road triangle (see tde_point_tri_dist2)
     const float4* rp;           // static render primitives (road + lane markings): 2 float4 = 4 vertices (triangle: v3 == v0);
                                 // the n_big oversized ones first, the rest sorted by tile (row-major) of their bbox min corner
-    const uint8_t* rp_cls;      // class of each static render primitive
+    const float4* rp_bound;     // per static render primitive: bounding circle (centre x, y, radius) and the class (int bits in w)
     const int* tile_start;      // [tny*tnx + 1] index into rp of the first primitive of each tile
     const float4* stop;         // 2 float4 per stop line: [x y hl hw] [c s rr 0]
     const uint8_t* lights;      // [period][nstop]
@@ -733,6 +733,17 @@ __global__ void __launch_bounds__(STAGED ? 1024 : TDE_WARPS_PER_BLOCK * 32, STAG
     int n_steps = 0;      // env steps taken by this warp
 #pragma unroll 1
     for (int e = p.e_begin + blockIdx.x * wpb + warp; e < p.e_end; e += warps_total) {
+        {   // the rows of this warp's next env start their way from DRAM now (one lane per 128-byte line)
+            const int en = e + warps_total;
+            if (en < p.e_end) {
+                if (lane * 128 < p.A * 16) {
+                    tde_prefetch_l2(reinterpret_cast<const char*>(p.state + (size_t)en * p.A) + lane * 128);
+                    tde_prefetch_l2(reinterpret_cast<const char*>(p.attr + (size_t)en * p.A) + lane * 128);
+                }
+                if (lane == 31) { tde_prefetch_l2(p.vars + (size_t)en * 8); tde_prefetch_l2(p.ep_return + en); }
+                if (lane == 30 && p.actions) tde_prefetch_l2(p.actions + (size_t)en * 2);
+            }
+        }
         TDE_TRACE_MARK(e, 2);
         physics_env<AH, STAGED>(p, e, lane, ws, st_acc, n_steps, smem_raw, mbar, staged_ready);
         TDE_TRACE_MARK(e, 3);
