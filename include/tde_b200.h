@@ -38,8 +38,13 @@
  *   - Every function returns 0 (TDE_OK) or a negative TDE_E_* code; the message is available through
  *     tde_last_error().  Nothing throws or exits across this boundary.
  *   - tde_step / tde_render / tde_kinematics / ... never allocate, never synchronise with the host and
- *     only enqueue work on `stream`, so they can be captured into a CUDA graph.
- *   - A handle is bound to one GPU and is not thread-safe.
+ *     only enqueue work on `stream`, so they can be captured into a CUDA graph.  The exceptions say so at
+ *     their declaration: tde_step_host (allocates device staging buffers on first use, runs its device-to-host
+ *     copies on an internal second stream and synchronises `stream` before it returns), tde_render_view (may grow
+ *     its scratch), tde_get_episode_stats (synchronises), tde_create / tde_upload_scenarios / tde_clone (allocate).
+ *   - A handle is bound to one GPU and is not thread-safe.  Every call runs on the handle's GPU and restores the
+ *     caller's current CUDA device before it returns.
+ *   - The seed belongs to the handle: tde_reset with env_mask_dev == NULL sets it, a masked reset keeps it.
  */
 #ifndef TDE_B200_H
 #define TDE_B200_H
@@ -153,7 +158,11 @@ typedef struct tde_config {
     float fov;                     /* metres covered by the 64 px birdview, default 35 */
     float start_speed_max;         /* :358 10 */
     float start_heading_sigma;     /* :361 0.1 */
-    int32_t reserved[8];
+    int32_t stage_map_tables;      /* 1: the physics kernel copies the per-map tables (lane-mesh triangle records, stop
+                                      lines, light schedule, per-cell summary) into shared memory once per CTA with
+                                      bulk-async copies (cp.async.bulk + mbarrier) when they fit; 0 (default): it reads
+                                      them through L1.  The environment variable TDE_PHYS_STAGE overrides it. */
+    int32_t reserved[7];
 } tde_config;
 
 /*
@@ -226,7 +235,9 @@ int tde_step(tde_handle* h, const float* actions_dev, uint8_t* obs_dev, float* r
 int tde_step_phases(tde_handle* h, int32_t phases, const float* actions_dev, uint8_t* obs_dev,
                     float* reward_dev, uint8_t* terminated_dev, uint8_t* truncated_dev,
                     float* info_dev, void* stream);
-/* host-buffer variant: copies actions H2D, steps, copies results D2H, synchronises `stream` */
+/* host-buffer variant: copies actions H2D, steps, copies results D2H, synchronises `stream`.  NOT graph-capturable:
+   it allocates device staging buffers on first use and, from 4,096 envs on, steps the envs in chunks whose frames
+   travel back on an internal second stream while the next chunk is computed. */
 int tde_step_host(tde_handle* h, const float* actions_host, uint8_t* obs_host, float* reward_host,
                   uint8_t* terminated_host, uint8_t* truncated_host, float* info_host, void* stream);
 
@@ -289,7 +300,12 @@ int tde_offroad_boxes(tde_handle* h, int32_t map_id, const float* state_dev, con
 int tde_render_view(tde_handle* h, int32_t env, float cam_x, float cam_y, float cam_psi, float fov,
                     int32_t width, int32_t height, uint8_t* out_dev, void* stream);
 
-int tde_clone(tde_handle* h, tde_handle** out);
+/* simulator.copy() :110: a second, independent handle on the same GPU holding a copy of every env (state, attributes,
+   cached infractions, env variables, episode returns, frame-stack restart flags, scenario ranges, seed), made with
+   device-to-device copies on `stream`.  The scenario tables are shared between the two handles (read-only,
+   reference-counted: they are freed when the last handle is destroyed or uploads a new set).  Episode statistics
+   start at zero in the copy. */
+int tde_clone(tde_handle* h, tde_handle** out, void* stream);
 
 /* double[TDE_NUM_STATS]; synchronises `stream`. reset_after != 0 zeroes the accumulators. */
 int tde_get_episode_stats(tde_handle* h, double* out_host, int32_t reset_after, void* stream);

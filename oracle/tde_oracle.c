@@ -392,7 +392,7 @@ static void reset_env(orc_env_set* o, int e) {
 }
 
 void orc_reset(orc_env_set* o, const uint8_t* mask, uint64_t seed) {
-    o->seed = seed;
+    if (!mask) o->seed = seed;   /* the seed belongs to the env set: a masked reset keeps it (tde_reset) */
 #pragma omp parallel for schedule(static)
     for (int e = 0; e < o->E; ++e)
         if (!mask || mask[e]) reset_env(o, e);

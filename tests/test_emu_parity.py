@@ -172,11 +172,13 @@ def test_emu_render_random_triangle_soup(oracle, fov, lh):
         assert np.array_equal(info, oinfo) and np.array_equal(obs, oobs), f"step {k}"
 
 
-def test_emu_physics_global_path_when_staging_is_off(oracle, monkeypatch):
-    """TDE_PHYS_STAGE=0: the physics kernel reads the map tables from global memory (the path taken when they do not
-    fit in shared memory); same results as the staged launch."""
-    monkeypatch.setenv("TDE_PHYS_STAGE", "0")
-    rollout_compare(oracle, S.traffic_lights(16), 40, 16, steps=12, seed=11, auto_reset=1)
+@pytest.mark.parametrize("E,A,ss", [(96, 32, "traffic_lights"), (40, 64, "traffic_lights"), (64, 16, "roundabout"), (30, 16, "mix")])
+def test_emu_physics_with_staged_map_tables(oracle, E, A, ss):
+    """cfg.stage_map_tables = 1: the physics kernel copies the map tables into shared memory with bulk-async copies
+    (emulated as copies gated by the mbarrier) and answers SAFE corners / followed lanes from the per-cell summary; same
+    results as the launch that reads the tables from global memory.  The five-map mix does not fit and falls back."""
+    sets = dict(traffic_lights=lambda: S.traffic_lights(A), roundabout=lambda: S.roundabout(A), mix=lambda: S.validation_mix(12))
+    rollout_compare(oracle, sets[ss](), E, A, steps=12, seed=11, auto_reset=1, stage_map_tables=1)
 
 
 @pytest.mark.parametrize("policy", ["1", "2"])
@@ -189,5 +191,5 @@ def test_emu_is_independent_of_warp_scheduling(policy):
     env = dict(os.environ, TDE_EMU_SCHED=policy)
     here = os.path.dirname(os.path.abspath(__file__))
     r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", os.path.join(here, "test_emu_parity.py"), "-k",
-                        "c3_traffic or stacked or scenario_mix or edge_configurations"], env=env, capture_output=True, text=True)
+                        "c3_traffic or stacked or scenario_mix or edge_configurations or staged"], env=env, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -119,7 +119,16 @@ def test_vec_env_frame_stack_and_auto_reset(oracle):
                 want[have, 3 * slot:3 * slot + 3] = frames[-1 - back][have]
         assert np.array_equal(obs.cpu().numpy(), want), f"step {k}: fused frame stack"
         n_done += int(d.sum())
-        assert set(infos) >= {"offroad", "collision", "traffic_light_violation", "is_success", "terminated", "truncated"}
+        assert set(infos.columns) >= {"offroad", "collision", "traffic_light_violation", "is_success", "terminated", "truncated"}
+        # SB3's contract: a sequence of E dicts; finished envs carry Monitor's episode record and TimeLimit.truncated
+        assert len(infos) == E
+        for e in range(E):
+            row = infos[e]
+            assert row["offroad"] == float(oinfo[e, 0]) and row["is_success"] == bool(otr[e])
+            assert ("episode" in row) == bool(d[e])
+            if d[e]:
+                assert row["episode"]["l"] == int(oinfo[e, 11]) and row["episode"]["r"] == float(oinfo[e, 10])
+                assert row["TimeLimit.truncated"] == bool(otr[e] and not ote[e])
     assert n_done > 0
     stats = venv.episode_statistics()
     assert stats["episodes"] == n_done and stats["steps"] == 25 * E
@@ -268,10 +277,13 @@ def test_vec_env_terminal_observation(oracle, n_stack):
         assert torch.equal(obs, obs2) and torch.equal(rew, rew2) and torch.equal(dones, dones2)
         assert torch.equal(venv.engine.get_state(), twin.engine.get_state())
         assert torch.equal(venv.engine.get_env_vars(), twin.engine.get_env_vars())
-        for key in infos2:
-            assert torch.equal(infos[key], infos2[key]), key
+        for key, col in infos2.columns.items():
+            assert torch.equal(infos.columns[key], col), key
         assert np.array_equal(dones.cpu().numpy(), d) and np.array_equal(obs[:, -3:].cpu().numpy(), oobs)
-        tobs = infos["terminal_observation"].cpu().numpy()
+        tobs = infos.columns["terminal_observation"].cpu().numpy()
+        for e in np.nonzero(d)[0][:3]:      # the per-env dict of a finished env carries its terminal observation
+            assert np.array_equal(infos[int(e)]["terminal_observation"], tobs[e])
+        assert all("terminal_observation" not in infos[int(e)] for e in np.nonzero(~d)[0][:3])
         assert tobs.shape == (E, 3 * n_stack, 64, 64)
         if d.any():
             assert np.array_equal(tobs[d][:, -3:], term_buf[d]), f"step {k}: terminal frame"

@@ -44,7 +44,7 @@ class TdeConfig(C.Structure):
         ("distance_bonus", C.c_float), ("distance_cutoff", C.c_float), ("reach_radius", C.c_float),
         ("offroad_threshold", C.c_float), ("tl_rear_factor", C.c_float), ("fov", C.c_float),
         ("start_speed_max", C.c_float), ("start_heading_sigma", C.c_float),
-        ("reserved", C.c_int32 * 8),
+        ("stage_map_tables", C.c_int32), ("reserved", C.c_int32 * 7),
     ]
 
 
@@ -182,7 +182,7 @@ def bind_signatures(lib: C.CDLL) -> C.CDLL:
         "tde_set_env_vars": ([vp, vp, vp], C.c_int),
         "tde_collision_boxes": ([vp, vp, i32, i32, vp, vp], C.c_int),
         "tde_offroad_boxes": ([vp, i32, vp, vp, i32, i32, vp, vp], C.c_int),
-        "tde_clone": ([vp, C.POINTER(vp)], C.c_int),
+        "tde_clone": ([vp, C.POINTER(vp), vp], C.c_int),
         "tde_get_episode_stats": ([vp, C.POINTER(C.c_double), i32, vp], C.c_int),
         "tde_num_kernel_launches": ([vp, C.POINTER(i64)], C.c_int),
         "tde_device_sm_count": ([vp, C.POINTER(i32)], C.c_int),

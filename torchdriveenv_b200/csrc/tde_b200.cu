@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <array>
 #include <map>
+#include <memory>
 #include <tuple>
 #include <cmath>
 #include <cstdio>
@@ -20,8 +21,34 @@
 
 static thread_local std::string g_create_error;
 
+// Everything tde_upload_scenarios builds on the device.  Handles made by tde_clone share one set (reference-counted).
+struct ScenTables {
+    MapDev* maps_dev = nullptr;
+    ScenDev* scens_dev = nullptr;
+    std::vector<MapDev> maps_host;
+    std::vector<ScenDev> scens_host;
+    std::vector<void*> scenario_allocs;
+    std::vector<std::array<int, 8>> map_info;  // ntri nmark nstop gnx gny items safe_cells render_prims
+    int num_maps = 0, num_scen = 0, device = 0;
+    // the staged blob of map tables (nullptr: they do not fit beside the SAT scratch, or staging is switched off -> the
+    // physics kernel reads them from global memory)
+    unsigned char* stage_blob = nullptr;
+    unsigned int stage_bytes = 0, stage_maps_off = 0;
+    ~ScenTables() {
+        int prev = -1;
+        cudaGetDevice(&prev);
+        cudaSetDevice(device);
+        for (void* p : scenario_allocs) cudaFree(p);
+        if (maps_dev) cudaFree(maps_dev);
+        if (scens_dev) cudaFree(scens_dev);
+        if (stage_blob) cudaFree(stage_blob);
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
 struct tde_handle {
     tde_config cfg;
+    std::shared_ptr<ScenTables> tab;
     int E = 0, A = 0, device = 0, sm_count = 0;
     float4 *state = nullptr, *attr = nullptr, *infr = nullptr;
     int* vars = nullptr;
@@ -31,25 +58,15 @@ struct tde_handle {
     uint8_t* restart = nullptr;
     unsigned int* tickets = nullptr;
     uint8_t* done_mask = nullptr;   // [E] envs that finished in the current tde_step_terminal
-    MapDev* maps_dev = nullptr;
-    ScenDev* scens_dev = nullptr;
-    std::vector<MapDev> maps_host;
-    std::vector<ScenDev> scens_host;
-    std::vector<void*> scenario_allocs;
-    std::vector<std::array<int, 8>> map_info;  // ntri nmark nstop gnx gny items safe_cells overlapping_items
-    int num_maps = 0, num_scen = 0;
     uint8_t palette[TDE_NUM_CLASSES * 3];
     unsigned long long seed = 0;
     bool uploaded = false, was_reset = false;
     long long launches = 0;
     int grid_phys = 0, grid_render = 0;
     size_t smem_render = 0;
-    // physics launch: warps per CTA, CTAs per SM, dynamic shared memory; the staged blob of map tables (nullptr: the
-    // tables do not fit beside the SAT scratch, or staging is switched off -> the kernel reads them from global memory)
+    // physics launch: warps per CTA, CTAs per SM, dynamic shared memory
     int phys_wpb = TDE_WARPS_PER_BLOCK, phys_per_sm = 1;
     size_t smem_phys = 0;
-    unsigned char* stage_blob = nullptr;
-    unsigned int stage_bytes = 0, stage_maps_off = 0;
     // device staging for tde_step_host
     float* h_actions = nullptr; uint8_t* h_obs = nullptr; float* h_reward = nullptr;
     uint8_t *h_term = nullptr, *h_trunc = nullptr; float* h_info = nullptr;
@@ -74,6 +91,24 @@ static int fail(tde_handle* h, int code, const std::string& msg) {
         if (_e != cudaSuccess)                                                                    \
             return fail(h, TDE_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));       \
     } while (0)
+
+// Every export runs on the handle's GPU and leaves the caller's current device as it found it (PyTorch reads the
+// current device through cudaGetDevice: a handle on another GPU must not switch it behind the caller's back).
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = prev == dev || cudaSetDevice(dev) == cudaSuccess;
+        if (prev == dev) prev = -1;   // nothing to restore
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define TDE_ON_DEVICE(h)                                                              \
+    DeviceGuard _guard((h)->device);                                                  \
+    if (!_guard.ok) return fail(h, TDE_E_CUDA, "cudaSetDevice failed for the handle's device")
 
 // ------------------------------------------------------------------ small prep kernels
 
@@ -434,7 +469,7 @@ static int dev_upload(tde_handle* h, T** p, const T* src, size_t n) {
     int rc = dev_alloc(h, p, n);
     if (rc) return rc;
     if (n) CUDA_TRY(h, cudaMemcpy(*p, src, n * sizeof(T), cudaMemcpyHostToDevice));
-    h->scenario_allocs.push_back((void*)*p);
+    h->tab->scenario_allocs.push_back((void*)*p);
     return TDE_OK;
 }
 
@@ -455,13 +490,7 @@ extern "C" int tde_default_config(tde_config* c) {
 }
 
 static void free_scenarios(tde_handle* h) {
-    for (void* p : h->scenario_allocs) cudaFree(p);
-    h->scenario_allocs.clear();
-    if (h->maps_dev) cudaFree(h->maps_dev);
-    if (h->scens_dev) cudaFree(h->scens_dev);
-    if (h->stage_blob) cudaFree(h->stage_blob);
-    h->maps_dev = nullptr; h->scens_dev = nullptr; h->stage_blob = nullptr; h->stage_bytes = 0;
-    h->maps_host.clear(); h->scens_host.clear(); h->map_info.clear();
+    h->tab.reset();   // the tables go when their last handle lets go
     h->uploaded = false;
 }
 
@@ -491,11 +520,11 @@ template <int AH>
 static int configure_physics(tde_handle* h) {
     const size_t scratch = sizeof(SatScratch<AH>);
     const size_t smem_max = 227 * 1024;
-    if (h->stage_blob) {
-        int wpb = 32;
-        while (wpb > 4 && (h->E + wpb - 1) / wpb < h->sm_count) wpb >>= 1;
-        if (const char* v = std::getenv("TDE_PHYS_WARPS")) wpb = std::max(1, std::min(32, std::atoi(v)));
-        const size_t smem = (size_t)h->stage_bytes + 16 + (size_t)wpb * scratch;
+    if (h->tab->stage_blob) {
+        int wpb = TDE_PHYS_STAGED_MAX_WARPS;
+        while (wpb > 4 && (h->E + wpb - 1) / wpb < h->sm_count) wpb = std::max(4, wpb / 2);
+        if (const char* v = std::getenv("TDE_PHYS_WARPS")) wpb = std::max(1, std::min(TDE_PHYS_STAGED_MAX_WARPS, std::atoi(v)));
+        const size_t smem = (size_t)h->tab->stage_bytes + 16 + (size_t)wpb * scratch;
         if (smem <= smem_max) {
             CUDA_TRY(h, cudaFuncSetAttribute(tde_physics_kernel<AH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int per_sm = 0;
@@ -506,7 +535,7 @@ static int configure_physics(tde_handle* h) {
                 return TDE_OK;
             }
         }
-        cudaFree(h->stage_blob); h->stage_blob = nullptr; h->stage_bytes = 0;   // does not fit: global path
+        cudaFree(h->tab->stage_blob); h->tab->stage_blob = nullptr; h->tab->stage_bytes = 0;   // does not fit: global path
     }
     const int wpb = TDE_WARPS_PER_BLOCK;
     const size_t smem = 16 + (size_t)wpb * scratch;
@@ -548,7 +577,8 @@ extern "C" int tde_create(const tde_config* cfg, tde_handle** out) {
     std::memcpy(h->palette, k_default_palette, sizeof(k_default_palette));
     int rc = TDE_OK;
     auto bail = [&](int code) { g_create_error = h->err; tde_destroy(h); return code; };
-    if (cudaSetDevice(h->device) != cudaSuccess) return bail(fail(h, TDE_E_CUDA, "cudaSetDevice failed"));
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return bail(fail(h, TDE_E_CUDA, "cudaSetDevice failed"));
     size_t EA = (size_t)h->E * h->A;
     if ((rc = dev_alloc(h, &h->state, EA)) || (rc = dev_alloc(h, &h->attr, EA)) || (rc = dev_alloc(h, &h->infr, EA)) ||
         (rc = dev_alloc(h, &h->vars, (size_t)h->E * 8)) || (rc = dev_alloc(h, &h->ep_return, (size_t)h->E)) ||
@@ -564,7 +594,7 @@ extern "C" int tde_create(const tde_config* cfg, tde_handle** out) {
 
 extern "C" int tde_destroy(tde_handle* h) {
     if (!h) return TDE_OK;
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     free_scenarios(h);
     cudaFree(h->state); cudaFree(h->attr); cudaFree(h->infr); cudaFree(h->vars); cudaFree(h->ep_return);
     cudaFree(h->scen_lo); cudaFree(h->scen_hi); cudaFree(h->stats); cudaFree(h->restart); cudaFree(h->tickets); cudaFree(h->done_mask);
@@ -586,19 +616,21 @@ extern "C" int tde_set_palette(tde_handle* h, const uint8_t* rgb) {
 extern "C" int tde_upload_scenarios(tde_handle* h, const tde_scenario_set* s) {
     if (!h || !s) return fail(h, TDE_E_INVAL, "tde_upload_scenarios: null argument");
     if (s->num_maps < 1 || s->num_scenarios < 1) return fail(h, TDE_E_INVAL, "tde_upload_scenarios: need >= 1 map and >= 1 scenario");
-    CUDA_TRY(h, cudaSetDevice(h->device));
+    TDE_ON_DEVICE(h);
     free_scenarios(h);
+    h->tab = std::make_shared<ScenTables>();
+    h->tab->device = h->device;
     const int A = h->A;
     const float ppm = (float)TDE_OBS_W / h->cfg.fov;
     const double max_edge_m = 430.0 / (double)ppm;  // keeps snapped vertices of drawn primitives inside +-511 px
-    h->maps_host.resize(s->num_maps);
+    h->tab->maps_host.resize(s->num_maps);
     // pieces of the staged blob (physics kernel): per map the device triangle / stop-line records, the light schedule and
     // the per-cell summary (u16: SAFE flag | the overlapping triangle covering most of the cell)
     struct StagePiece { const float4* tri; int ntri; const float4* stop; int nstop; const uint8_t* lights; size_t nlights; std::vector<uint16_t> cells; };
     std::vector<StagePiece> pieces((size_t)s->num_maps);
     bool stage_ok = true;
     for (int m = 0; m < s->num_maps; ++m) {
-        MapDev& M = h->maps_host[m];
+        MapDev& M = h->tab->maps_host[m];
         std::memset(&M, 0, sizeof(M));
         int t0 = s->map_tri_offset[m], nt = s->map_tri_offset[m + 1] - t0;
         int k0 = s->map_mark_offset[m], nk = s->map_mark_offset[m + 1] - k0;
@@ -629,7 +661,7 @@ extern "C" int tde_upload_scenarios(tde_handle* h, const tde_scenario_set* s) {
         int rc;
         if ((rc = dev_upload(h, &raw, road_sorted.data(), (size_t)nt * 8))) return rc;
         if ((rc = dev_alloc(h, &rec, (size_t)nt * 3))) return rc;
-        h->scenario_allocs.push_back(rec);
+        h->tab->scenario_allocs.push_back(rec);
         if (nt) TDE_LAUNCH((nt + 127) / 128, 128, 0, 0, prep_tris_kernel)(raw, nt, rec);
         M.tri = rec; M.ntri = nt;
         M.nmark = nk;
@@ -642,24 +674,11 @@ extern "C" int tde_upload_scenarios(tde_handle* h, const tde_scenario_set* s) {
             std::vector<float> rp_mark = merge_into_quads(s->mark_tris + 6 * (size_t)k0, nk, 6, max_edge_m);
             const float reach = (0.70710678f * (float)(TDE_OBS_W + TDE_OBS_H) * 0.5f + 2.0f) / ppm;  // as in tde_render_kernel
             StaticIndex si = build_static_index(rp_road, rp_mark, reach);
-            // bounding circle per primitive (float64, radius rounded up): the render kernel's first culling stage
-            std::vector<float> bound(si.cls.size() * 4);
-            for (size_t k = 0; k < si.cls.size(); ++k) {
-                const float* v = &si.prims[8 * k];
-                double lx = v[0], hx = v[0], ly = v[1], hy = v[1];
-                for (int q = 1; q < 4; ++q) { lx = std::min(lx, (double)v[2 * q]); hx = std::max(hx, (double)v[2 * q]); ly = std::min(ly, (double)v[2 * q + 1]); hy = std::max(hy, (double)v[2 * q + 1]); }
-                const float cx = (float)(0.5 * (lx + hx)), cy = (float)(0.5 * (ly + hy));
-                double r = 0;
-                for (int q = 0; q < 4; ++q) r = std::max(r, std::hypot((double)v[2 * q] - cx, (double)v[2 * q + 1] - cy));
-                bound[4 * k] = cx; bound[4 * k + 1] = cy; bound[4 * k + 2] = (float)(r * 1.0001 + 1e-3);
-                const int32_t c = si.cls[k];
-                std::memcpy(&bound[4 * k + 3], &c, 4);
-            }
-            float* rpd = nullptr; float* bdd = nullptr; int* tsd = nullptr;
+            float* rpd = nullptr; uint8_t* clsd = nullptr; int* tsd = nullptr;
             if ((rc = dev_upload(h, &rpd, si.prims.data(), si.prims.size()))) return rc;
-            if ((rc = dev_upload(h, &bdd, bound.data(), bound.size()))) return rc;
+            if ((rc = dev_upload(h, &clsd, si.cls.data(), si.cls.size()))) return rc;
             if ((rc = dev_upload(h, &tsd, si.tile_start.data(), si.tile_start.size()))) return rc;
-            M.rp = (const float4*)rpd; M.rp_bound = (const float4*)bdd; M.tile_start = tsd;
+            M.rp = (const float4*)rpd; M.rp_cls = clsd; M.tile_start = tsd;
             M.n_rp = (int)si.cls.size(); M.n_big = si.n_big;
             M.tgx0 = si.gx0; M.tgy0 = si.gy0; M.tinv = si.inv; M.maxext = si.maxext; M.tnx = si.nx; M.tny = si.ny;
         }
@@ -671,7 +690,7 @@ extern "C" int tde_upload_scenarios(tde_handle* h, const tde_scenario_set* s) {
         float* sraw = nullptr; float4* srec = nullptr;
         if ((rc = dev_upload(h, &sraw, s->stoplines + 5 * (size_t)l0, (size_t)nl * 5))) return rc;
         if ((rc = dev_alloc(h, &srec, (size_t)nl * 2))) return rc;
-        h->scenario_allocs.push_back(srec);
+        h->tab->scenario_allocs.push_back(srec);
         if (nl) TDE_LAUNCH(1, 64, 0, 0, prep_stops_kernel)(sraw, nl, srec);
         M.stop = srec; M.nstop = nl;
         int P = s->map_light_period[m];
@@ -694,7 +713,7 @@ extern "C" int tde_upload_scenarios(tde_handle* h, const tde_scenario_set* s) {
         {
             size_t safe = 0, nover = 0;
             for (uint16_t m : g.meta) { safe += (m & TDE_CELL_SAFE) ? 1 : 0; nover += m & 0x7fff; }
-            h->map_info.push_back({nt, nk, nl, g.nx, g.ny, (int)g.items.size(), (int)safe, M.n_rp});
+            h->tab->map_info.push_back({nt, nk, nl, g.nx, g.ny, (int)g.items.size(), (int)safe, M.n_rp});
         }
         M.gx0 = g.gx0; M.gy0 = g.gy0; M.inv_cell = g.inv_cell; M.gnx = g.nx; M.gny = g.ny;
         {
@@ -710,9 +729,9 @@ extern "C" int tde_upload_scenarios(tde_handle* h, const tde_scenario_set* s) {
             }
         }
     }
-    h->scens_host.resize(s->num_scenarios);
+    h->tab->scens_host.resize(s->num_scenarios);
     for (int k = 0; k < s->num_scenarios; ++k) {
-        ScenDev& S = h->scens_host[k];
+        ScenDev& S = h->tab->scens_host[k];
         std::memset(&S, 0, sizeof(S));
         S.map = s->scen_map[k];
         if (S.map < 0 || S.map >= s->num_maps) return fail(h, TDE_E_INVAL, "tde_upload_scenarios: scen_map out of range");
@@ -743,22 +762,28 @@ extern "C" int tde_upload_scenarios(tde_handle* h, const tde_scenario_set* s) {
         if ((rc = dev_upload(h, &rm, s->replay_mask + (size_t)r0 * A, (size_t)S.rep_T * A))) return rc;
         S.rep_states = rs; S.rep_mask = rm;
     }
-    h->num_maps = s->num_maps; h->num_scen = s->num_scenarios;
-    CUDA_TRY(h, cudaMalloc((void**)&h->maps_dev, sizeof(MapDev) * h->num_maps));
-    CUDA_TRY(h, cudaMemcpy(h->maps_dev, h->maps_host.data(), sizeof(MapDev) * h->num_maps, cudaMemcpyHostToDevice));
-    CUDA_TRY(h, cudaMalloc((void**)&h->scens_dev, sizeof(ScenDev) * h->num_scen));
-    CUDA_TRY(h, cudaMemcpy(h->scens_dev, h->scens_host.data(), sizeof(ScenDev) * h->num_scen, cudaMemcpyHostToDevice));
-    std::vector<int> lo((size_t)h->E, 0), hi((size_t)h->E, h->num_scen);
+    h->tab->num_maps = s->num_maps; h->tab->num_scen = s->num_scenarios;
+    CUDA_TRY(h, cudaMalloc((void**)&h->tab->maps_dev, sizeof(MapDev) * h->tab->num_maps));
+    CUDA_TRY(h, cudaMemcpy(h->tab->maps_dev, h->tab->maps_host.data(), sizeof(MapDev) * h->tab->num_maps, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMalloc((void**)&h->tab->scens_dev, sizeof(ScenDev) * h->tab->num_scen));
+    CUDA_TRY(h, cudaMemcpy(h->tab->scens_dev, h->tab->scens_host.data(), sizeof(ScenDev) * h->tab->num_scen, cudaMemcpyHostToDevice));
+    std::vector<int> lo((size_t)h->E, 0), hi((size_t)h->E, h->tab->num_scen);
     CUDA_TRY(h, cudaMemcpy(h->scen_lo, lo.data(), sizeof(int) * h->E, cudaMemcpyHostToDevice));
     CUDA_TRY(h, cudaMemcpy(h->scen_hi, hi.data(), sizeof(int) * h->E, cudaMemcpyHostToDevice));
     // the staged blob: [16 B header per map] [MapDev per map] [per map: triangle records, stop lines, lights, cell summary]
-    if (const char* v = std::getenv("TDE_PHYS_STAGE")) stage_ok = stage_ok && std::atoi(v) != 0;
+    // Measured at C3 (one map, 85 KB of tables): the staged launch is SLOWER than the one that reads the tables through L1
+    // (57.4 vs 53.7 us at 64 registers), so it is opt-in: TDE_PHYS_STAGE=1 or cfg.stage_map_tables = 1.
+    {
+        const char* v = std::getenv("TDE_PHYS_STAGE");
+        const bool want = v ? std::atoi(v) != 0 : h->cfg.stage_map_tables == 1;
+        stage_ok = stage_ok && want;
+    }
     if (stage_ok) {
         auto al16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
-        std::vector<uint32_t> hdr((size_t)h->num_maps * 4);
-        const size_t maps_off = al16((size_t)h->num_maps * 16);
-        size_t cur = al16(maps_off + sizeof(MapDev) * h->num_maps);
-        for (int m = 0; m < h->num_maps; ++m) {
+        std::vector<uint32_t> hdr((size_t)h->tab->num_maps * 4);
+        const size_t maps_off = al16((size_t)h->tab->num_maps * 16);
+        size_t cur = al16(maps_off + sizeof(MapDev) * h->tab->num_maps);
+        for (int m = 0; m < h->tab->num_maps; ++m) {
             const StagePiece& sp = pieces[(size_t)m];
             hdr[4 * m + 0] = (uint32_t)cur; cur = al16(cur + (size_t)sp.ntri * 48);
             hdr[4 * m + 1] = (uint32_t)cur; cur = al16(cur + (size_t)sp.nstop * 32);
@@ -767,18 +792,18 @@ extern "C" int tde_upload_scenarios(tde_handle* h, const tde_scenario_set* s) {
         }
         const size_t scratch_min = 16 + 4 * sizeof(SatScratch<1>);
         if (cur + scratch_min <= 227 * 1024) {
-            CUDA_TRY(h, cudaMalloc((void**)&h->stage_blob, cur));
-            CUDA_TRY(h, cudaMemset(h->stage_blob, 0, cur));
-            CUDA_TRY(h, cudaMemcpy(h->stage_blob, hdr.data(), hdr.size() * 4, cudaMemcpyHostToDevice));
-            CUDA_TRY(h, cudaMemcpy(h->stage_blob + maps_off, h->maps_host.data(), sizeof(MapDev) * h->num_maps, cudaMemcpyHostToDevice));
-            for (int m = 0; m < h->num_maps; ++m) {
+            CUDA_TRY(h, cudaMalloc((void**)&h->tab->stage_blob, cur));
+            CUDA_TRY(h, cudaMemset(h->tab->stage_blob, 0, cur));
+            CUDA_TRY(h, cudaMemcpy(h->tab->stage_blob, hdr.data(), hdr.size() * 4, cudaMemcpyHostToDevice));
+            CUDA_TRY(h, cudaMemcpy(h->tab->stage_blob + maps_off, h->tab->maps_host.data(), sizeof(MapDev) * h->tab->num_maps, cudaMemcpyHostToDevice));
+            for (int m = 0; m < h->tab->num_maps; ++m) {
                 const StagePiece& sp = pieces[(size_t)m];
-                if (sp.ntri) CUDA_TRY(h, cudaMemcpy(h->stage_blob + hdr[4 * m + 0], sp.tri, (size_t)sp.ntri * 48, cudaMemcpyDeviceToDevice));
-                if (sp.nstop) CUDA_TRY(h, cudaMemcpy(h->stage_blob + hdr[4 * m + 1], sp.stop, (size_t)sp.nstop * 32, cudaMemcpyDeviceToDevice));
-                if (sp.nlights) CUDA_TRY(h, cudaMemcpy(h->stage_blob + hdr[4 * m + 2], sp.lights, sp.nlights, cudaMemcpyHostToDevice));
-                if (!sp.cells.empty()) CUDA_TRY(h, cudaMemcpy(h->stage_blob + hdr[4 * m + 3], sp.cells.data(), sp.cells.size() * 2, cudaMemcpyHostToDevice));
+                if (sp.ntri) CUDA_TRY(h, cudaMemcpy(h->tab->stage_blob + hdr[4 * m + 0], sp.tri, (size_t)sp.ntri * 48, cudaMemcpyDeviceToDevice));
+                if (sp.nstop) CUDA_TRY(h, cudaMemcpy(h->tab->stage_blob + hdr[4 * m + 1], sp.stop, (size_t)sp.nstop * 32, cudaMemcpyDeviceToDevice));
+                if (sp.nlights) CUDA_TRY(h, cudaMemcpy(h->tab->stage_blob + hdr[4 * m + 2], sp.lights, sp.nlights, cudaMemcpyHostToDevice));
+                if (!sp.cells.empty()) CUDA_TRY(h, cudaMemcpy(h->tab->stage_blob + hdr[4 * m + 3], sp.cells.data(), sp.cells.size() * 2, cudaMemcpyHostToDevice));
             }
-            h->stage_bytes = (unsigned int)cur; h->stage_maps_off = (unsigned int)maps_off;
+            h->tab->stage_bytes = (unsigned int)cur; h->tab->stage_maps_off = (unsigned int)maps_off;
         }
     }
     {
@@ -794,8 +819,8 @@ extern "C" int tde_set_env_scenario_range(tde_handle* h, const int32_t* lo, cons
     if (!h || !lo || !hi) return fail(h, TDE_E_INVAL, "tde_set_env_scenario_range: null argument");
     if (!h->uploaded) return fail(h, TDE_E_STATE, "tde_set_env_scenario_range: upload scenarios first");
     for (int e = 0; e < h->E; ++e)
-        if (lo[e] < 0 || hi[e] > h->num_scen || lo[e] >= hi[e]) return fail(h, TDE_E_INVAL, "tde_set_env_scenario_range: need 0 <= lo < hi <= num_scenarios");
-    CUDA_TRY(h, cudaSetDevice(h->device));
+        if (lo[e] < 0 || hi[e] > h->tab->num_scen || lo[e] >= hi[e]) return fail(h, TDE_E_INVAL, "tde_set_env_scenario_range: need 0 <= lo < hi <= num_scenarios");
+    TDE_ON_DEVICE(h);
     CUDA_TRY(h, cudaMemcpy(h->scen_lo, lo, sizeof(int) * h->E, cudaMemcpyHostToDevice));
     CUDA_TRY(h, cudaMemcpy(h->scen_hi, hi, sizeof(int) * h->E, cudaMemcpyHostToDevice));
     return TDE_OK;
@@ -804,12 +829,12 @@ extern "C" int tde_set_env_scenario_range(tde_handle* h, const int32_t* lo, cons
 static StepParams make_params(tde_handle* h) {
     StepParams p;
     std::memset(&p, 0, sizeof(p));
-    p.cfg = h->cfg; p.E = h->E; p.A = h->A; p.num_scen = h->num_scen; p.seed = h->seed;
-    p.maps = h->maps_dev; p.scens = h->scens_dev;
+    p.cfg = h->cfg; p.E = h->E; p.A = h->A; p.num_scen = h->tab->num_scen; p.seed = h->seed;
+    p.maps = h->tab->maps_dev; p.scens = h->tab->scens_dev;
     p.state = h->state; p.attr = h->attr; p.infr = h->infr; p.vars = h->vars; p.ep_return = h->ep_return;
     p.scen_lo = h->scen_lo; p.scen_hi = h->scen_hi; p.stats = h->stats; p.restart = h->restart; p.tickets = h->tickets; p.n_stack = 1;
     p.e_begin = 0; p.e_end = h->E;
-    p.stage_blob = h->stage_blob; p.stage_bytes = h->stage_bytes; p.stage_maps_off = h->stage_maps_off;
+    p.stage_blob = h->tab->stage_blob; p.stage_bytes = h->tab->stage_bytes; p.stage_maps_off = h->tab->stage_maps_off;
     for (int ch = 0; ch < 3; ++ch)
         for (int w = 0; w < 4; ++w) {
             uint32_t v = 0;
@@ -828,8 +853,10 @@ static StepParams make_params(tde_handle* h) {
 extern "C" int tde_reset(tde_handle* h, const uint8_t* env_mask_dev, uint64_t seed, void* stream) {
     if (!h) return TDE_E_INVAL;
     if (!h->uploaded) return fail(h, TDE_E_STATE, "tde_reset: upload scenarios first");
-    CUDA_TRY(h, cudaSetDevice(h->device));
-    h->seed = seed;
+    TDE_ON_DEVICE(h);
+    // the seed belongs to the handle: a full reset sets it, a masked reset keeps it (the in-kernel auto-resets of the
+    // other envs must not change their draw stream because a few envs were reset by hand)
+    if (env_mask_dev == nullptr) h->seed = seed;
     StepParams p = make_params(h);
     p.reset_mask = env_mask_dev;
     cudaStream_t st = (cudaStream_t)stream;
@@ -875,7 +902,7 @@ static int step_impl(tde_handle* h, int32_t phases, const float* actions, uint8_
     if (((uintptr_t)obs | (uintptr_t)obs_prev | (uintptr_t)terminal_obs | (uintptr_t)info) & 15)
         return fail(h, TDE_E_INVAL, "tde_step: obs / terminal_obs / info must be 16-byte aligned");
     if ((uintptr_t)actions & 7) return fail(h, TDE_E_INVAL, "tde_step: actions must be 8-byte aligned");
-    CUDA_TRY(h, cudaSetDevice(h->device));
+    TDE_ON_DEVICE(h);
     StepParams p = make_params(h);
     p.phases = phases; p.actions = actions; p.obs = obs; p.reward = reward; p.terminated = terminated;
     p.truncated = truncated; p.info = info; p.n_stack = n_stack;
@@ -897,7 +924,7 @@ static int step_impl(tde_handle* h, int32_t phases, const float* actions, uint8_
     if (physics) {
         const int wpb = h->phys_wpb, pthreads = wpb * 32;
         const int grid = std::min(h->grid_phys, (p.e_end - p.e_begin + wpb - 1) / wpb);
-        if (h->stage_blob) {
+        if (h->tab->stage_blob) {
             if (h->A <= 32) CUDA_TRY(h, launch_step(tde_physics_kernel<1, true>, grid, pthreads, h->smem_phys, st, p));
             else CUDA_TRY(h, launch_step(tde_physics_kernel<2, true>, grid, pthreads, h->smem_phys, st, p));
         } else {
@@ -997,7 +1024,7 @@ extern "C" int tde_step_host(tde_handle* h, const float* actions, uint8_t* obs, 
                              uint8_t* truncated, float* info, void* stream) {
     if (!h) return TDE_E_INVAL;
     if (!actions || !reward || !terminated || !truncated || !info) return fail(h, TDE_E_INVAL, "tde_step_host: null argument");
-    CUDA_TRY(h, cudaSetDevice(h->device));
+    TDE_ON_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t E = (size_t)h->E, obs_bytes = E * TDE_OBS_C * TDE_OBS_H * TDE_OBS_W;
     if (!h->h_actions) {
@@ -1050,10 +1077,10 @@ extern "C" int tde_render_view(tde_handle* h, int32_t env, float cam_x, float ca
     if (env < 0 || env >= h->E) return fail(h, TDE_E_INVAL, "tde_render_view: env out of range");
     if (width < 1 || height < 1 || width > TDE_VIEW_MAX_RES || height > TDE_VIEW_MAX_RES) return fail(h, TDE_E_INVAL, "tde_render_view: resolution must be in 1..4096");
     if (!(fov > 0.0f)) return fail(h, TDE_E_INVAL, "tde_render_view: fov must be positive");
-    CUDA_TRY(h, cudaSetDevice(h->device));
+    TDE_ON_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     int nmax = 0;   // the env's map is only known on the device: size the scratch for the largest map
-    for (const MapDev& M : h->maps_host) nmax = std::max(nmax, M.ntri + M.nmark + M.nstop);
+    for (const MapDev& M : h->tab->maps_host) nmax = std::max(nmax, M.ntri + M.nmark + M.nstop);
     nmax += 1 + 2 * h->A;
     if (nmax > h->view_cap) {
         CUDA_TRY(h, cudaStreamSynchronize(st));
@@ -1081,7 +1108,7 @@ extern "C" int tde_render_view(tde_handle* h, int32_t env, float cam_x, float ca
 static int copy_dev(tde_handle* h, void* dst, const void* src, size_t bytes, void* stream, const char* what) {
     if (!h) return TDE_E_INVAL;
     if (!dst || !src) return fail(h, TDE_E_INVAL, std::string(what) + ": null argument");
-    CUDA_TRY(h, cudaSetDevice(h->device));
+    TDE_ON_DEVICE(h);
     CUDA_TRY(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return TDE_OK;
 }
@@ -1109,8 +1136,16 @@ extern "C" int tde_set_env_vars(tde_handle* h, const int32_t* in, void* stream) 
 
 extern "C" int tde_collision_boxes(const float* state, const float* attr, int32_t E, int32_t A, float* out, void* stream) {
     if (!state || !attr || !out || E < 1 || A < 1 || A > TDE_MAX_AGENTS) return fail(nullptr, TDE_E_INVAL, "tde_collision_boxes: bad argument");
+    // runs on the GPU that owns the boxes (not on whatever device happens to be current)
     int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, state) != cudaSuccess || pa.type != cudaMemoryTypeDevice) {
+        cudaGetLastError();
+        return fail(nullptr, TDE_E_INVAL, "tde_collision_boxes: state_dev is not a device pointer");
+    }
+    dev = pa.device;
+    DeviceGuard guard(dev);
+    if (!guard.ok || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
         return fail(nullptr, TDE_E_CUDA, "tde_collision_boxes: no CUDA device");
     int grid = std::max(1, std::min((E + TDE_WARPS_PER_BLOCK - 1) / TDE_WARPS_PER_BLOCK, sms * 8));
     cudaStream_t st = (cudaStream_t)stream;
@@ -1125,11 +1160,11 @@ extern "C" int tde_offroad_boxes(tde_handle* h, int32_t map_id, const float* sta
                                  float* out, void* stream) {
     if (!h) return TDE_E_INVAL;
     if (!h->uploaded) return fail(h, TDE_E_STATE, "tde_offroad_boxes: upload scenarios first");
-    if (!state || !attr || !out || E < 1 || A < 1 || map_id < 0 || map_id >= h->num_maps) return fail(h, TDE_E_INVAL, "tde_offroad_boxes: bad argument");
-    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (!state || !attr || !out || E < 1 || A < 1 || map_id < 0 || map_id >= h->tab->num_maps) return fail(h, TDE_E_INVAL, "tde_offroad_boxes: bad argument");
+    TDE_ON_DEVICE(h);
     int n = E * A;
     int grid = std::max(1, std::min((n + 255) / 256, h->sm_count * 8));
-    TDE_LAUNCH(grid, 256, 0, (cudaStream_t)stream, tde_offroad_kernel)(h->maps_dev, map_id, h->cfg.offroad_threshold, (const float4*)state,
+    TDE_LAUNCH(grid, 256, 0, (cudaStream_t)stream, tde_offroad_kernel)(h->tab->maps_dev, map_id, h->cfg.offroad_threshold, (const float4*)state,
                                                                (const float4*)attr, n, out);
     CUDA_TRY(h, cudaGetLastError());
     h->launches++;
@@ -1142,14 +1177,34 @@ extern "C" int tde_debug_set_trace(unsigned long long* dev_ptr) {
 }
 #endif
 
-extern "C" int tde_clone(tde_handle* h, tde_handle** out) {
+// simulator.copy() (gym_env.py:110): an independent handle with the same envs.  The per-env arrays are copied device
+// to device on `stream`; the scenario tables are shared (reference-counted, read-only after the upload).
+extern "C" int tde_clone(tde_handle* h, tde_handle** out, void* stream) {
     if (!h || !out) return fail(h, TDE_E_INVAL, "tde_clone: null argument");
-    return fail(h, TDE_E_STATE, "tde_clone: use the Python-side copy (re-upload + state copy)");
+    if (!h->uploaded) return fail(h, TDE_E_STATE, "tde_clone: upload scenarios first");
+    tde_handle* c = nullptr;
+    int rc = tde_create(&h->cfg, &c);
+    if (rc) return fail(h, rc, std::string("tde_clone: ") + g_create_error);
+    TDE_ON_DEVICE(h);
+    c->tab = h->tab;
+    c->uploaded = true; c->was_reset = h->was_reset; c->seed = h->seed;
+    std::memcpy(c->palette, h->palette, sizeof(h->palette));
+    c->phys_wpb = h->phys_wpb; c->phys_per_sm = h->phys_per_sm; c->smem_phys = h->smem_phys; c->grid_phys = h->grid_phys;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t EA = (size_t)h->E * h->A, E = (size_t)h->E;
+    cudaError_t e = cudaSuccess;
+    auto cp = [&](void* d, const void* s, size_t n) { if (e == cudaSuccess) e = cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, st); };
+    cp(c->state, h->state, EA * 16); cp(c->attr, h->attr, EA * 16); cp(c->infr, h->infr, EA * 16);
+    cp(c->vars, h->vars, E * 32); cp(c->ep_return, h->ep_return, E * 4); cp(c->restart, h->restart, E);
+    cp(c->scen_lo, h->scen_lo, E * 4); cp(c->scen_hi, h->scen_hi, E * 4);
+    if (e != cudaSuccess) { tde_destroy(c); return fail(h, TDE_E_CUDA, std::string("tde_clone: ") + cudaGetErrorString(e)); }
+    *out = c;   // episode statistics start at zero in the copy
+    return TDE_OK;
 }
 
 extern "C" int tde_get_episode_stats(tde_handle* h, double* out, int32_t reset_after, void* stream) {
     if (!h || !out) return fail(h, TDE_E_INVAL, "tde_get_episode_stats: null argument");
-    CUDA_TRY(h, cudaSetDevice(h->device));
+    TDE_ON_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(h, cudaMemcpyAsync(out, h->stats, sizeof(double) * TDE_NUM_STATS, cudaMemcpyDeviceToHost, st));
     if (reset_after) CUDA_TRY(h, cudaMemsetAsync(h->stats, 0, sizeof(double) * TDE_NUM_STATS, st));
@@ -1163,8 +1218,8 @@ extern "C" int tde_num_kernel_launches(const tde_handle* h, int64_t* out) {
     return TDE_OK;
 }
 extern "C" int tde_get_map_info(const tde_handle* h, int32_t map_id, int32_t* out8) {
-    if (!h || !out8 || map_id < 0 || map_id >= (int)h->map_info.size()) return TDE_E_INVAL;
-    for (int k = 0; k < 8; ++k) out8[k] = h->map_info[map_id][k];
+    if (!h || !out8 || !h->tab || map_id < 0 || map_id >= (int)h->tab->map_info.size()) return TDE_E_INVAL;
+    for (int k = 0; k < 8; ++k) out8[k] = h->tab->map_info[map_id][k];
     return TDE_OK;
 }
 extern "C" int tde_device_sm_count(const tde_handle* h, int32_t* out) {

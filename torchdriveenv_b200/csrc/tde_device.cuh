@@ -64,11 +64,6 @@ __device__ __forceinline__ void tde_mbar_wait(unsigned long long* bar, uint32_t 
         "r"(parity)
         : "memory");
 }
-#ifdef TDE_STAGE_GENERIC_LD   // A/B: plain generic loads (schedulable by the compiler) instead of volatile ld.shared
-__device__ __forceinline__ float4 tde_lds_f4(uint32_t a) { return *reinterpret_cast<const float4*>(__cvta_shared_to_generic((size_t)a)); }
-__device__ __forceinline__ uint32_t tde_lds_u16(uint32_t a) { return *reinterpret_cast<const uint16_t*>(__cvta_shared_to_generic((size_t)a)); }
-__device__ __forceinline__ uint32_t tde_lds_u8(uint32_t a) { return *reinterpret_cast<const uint8_t*>(__cvta_shared_to_generic((size_t)a)); }
-#else
 __device__ __forceinline__ float4 tde_lds_f4(uint32_t a) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
@@ -84,13 +79,6 @@ __device__ __forceinline__ uint32_t tde_lds_u8(uint32_t a) {
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
-#endif
-#endif
-
-#ifdef TDE_HOST_EMU
-__device__ __forceinline__ void tde_prefetch_l2(const void*) {}
-#else
-__device__ __forceinline__ void tde_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #endif
 
 #define TDE_PI_F 3.14159274101257324219f

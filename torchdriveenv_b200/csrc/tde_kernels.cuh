@@ -18,23 +18,30 @@
 #define TDE_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
 
-// 32 warps per SM at 64 registers per thread; small blocks, so that the slots of a block are handed to
-// the next launch as soon as its few warps have run dry
+// Small blocks (4 warps), so that the slots of a block are handed to the next launch as soon as its few warps have run
+// dry.  Both step kernels run 6 blocks = 24 warps per SM at up to 80 registers per thread: at the 64 registers that 8 blocks
+// per SM allow both spill (1.3 M local-memory requests per render launch, 1.4 M per physics launch at C3), and the spills
+// cost more than the eight extra warps hide (render 117.9 -> 108.0 us, physics 53.8 -> 51.4 us; 5 blocks / 96 registers:
+// 113.4 / 52.6 us).
 #ifndef TDE_WARPS_PER_BLOCK
 #define TDE_WARPS_PER_BLOCK 4
 #endif
 #ifndef TDE_RENDER_BLOCKS_PER_SM
-#define TDE_RENDER_BLOCKS_PER_SM (32 / TDE_WARPS_PER_BLOCK)
+#define TDE_RENDER_BLOCKS_PER_SM 6
 #endif
 #ifndef TDE_PHYS_BLOCKS_PER_SM
-#define TDE_PHYS_BLOCKS_PER_SM (32 / TDE_WARPS_PER_BLOCK)
+#define TDE_PHYS_BLOCKS_PER_SM 6
+#endif
+// the staged physics launch is one fat CTA per SM: up to 24 warps at the same register budget
+#ifndef TDE_PHYS_STAGED_MAX_WARPS
+#define TDE_PHYS_STAGED_MAX_WARPS 24
 #endif
 
 struct MapDev {
     const float4* tri;          // 3 float4 per road triangle (see tde_point_tri_dist2)
     const float4* rp;           // static render primitives (road + lane markings): 2 float4 = 4 vertices (triangle: v3 == v0);
                                 // the n_big oversized ones first, the rest sorted by tile (row-major) of their bbox min corner
-    const float4* rp_bound;     // per static render primitive: bounding circle (centre x, y, radius) and the class (int bits in w)
+    const uint8_t* rp_cls;      // class of each static render primitive
     const int* tile_start;      // [tny*tnx + 1] index into rp of the first primitive of each tile
     const float4* stop;         // 2 float4 per stop line: [x y hl hw] [c s rr 0]
     const uint8_t* lights;      // [period][nstop]
@@ -709,7 +716,7 @@ __device__ __forceinline__ void physics_env(const StepParams& p, const int e, co
 // of the SM is L1 for them), up to 32-warp CTAs when they are staged (one copy per SM).
 #define TDE_PHYS_STAGE_CHUNK 32768u
 template <int AH, bool STAGED>
-__global__ void __launch_bounds__(STAGED ? 1024 : TDE_WARPS_PER_BLOCK * 32, STAGED ? 1 : TDE_PHYS_BLOCKS_PER_SM) tde_physics_kernel(const StepParams p) {
+__global__ void __launch_bounds__(STAGED ? TDE_PHYS_STAGED_MAX_WARPS * 32 : TDE_WARPS_PER_BLOCK * 32, STAGED ? 1 : TDE_PHYS_BLOCKS_PER_SM) tde_physics_kernel(const StepParams p) {
     TDE_DYN_SMEM(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wpb = blockDim.x >> 5;
@@ -733,17 +740,6 @@ __global__ void __launch_bounds__(STAGED ? 1024 : TDE_WARPS_PER_BLOCK * 32, STAG
     int n_steps = 0;      // env steps taken by this warp
 #pragma unroll 1
     for (int e = p.e_begin + blockIdx.x * wpb + warp; e < p.e_end; e += warps_total) {
-        {   // the rows of this warp's next env start their way from DRAM now (one lane per 128-byte line)
-            const int en = e + warps_total;
-            if (en < p.e_end) {
-                if (lane * 128 < p.A * 16) {
-                    tde_prefetch_l2(reinterpret_cast<const char*>(p.state + (size_t)en * p.A) + lane * 128);
-                    tde_prefetch_l2(reinterpret_cast<const char*>(p.attr + (size_t)en * p.A) + lane * 128);
-                }
-                if (lane == 31) { tde_prefetch_l2(p.vars + (size_t)en * 8); tde_prefetch_l2(p.ep_return + en); }
-                if (lane == 30 && p.actions) tde_prefetch_l2(p.actions + (size_t)en * 2);
-            }
-        }
         TDE_TRACE_MARK(e, 2);
         physics_env<AH, STAGED>(p, e, lane, ws, st_acc, n_steps, smem_raw, mbar, staged_ready);
         TDE_TRACE_MARK(e, 3);

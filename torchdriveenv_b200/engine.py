@@ -51,6 +51,21 @@ class Engine:
         self._host = None
 
     # -- lifetime
+    def clone(self) -> "Engine":
+        """simulator.copy() (gym_env.py:110) at the ABI: tde_clone - an independent engine on the same GPU with a copy of
+        every env (device-to-device), sharing the read-only scenario tables with this one."""
+        other = object.__new__(Engine)
+        other.lib, other.device, other.scenarios = self.lib, self.device, self.scenarios
+        other.E, other.A, other.cfg, other.packed = self.E, self.A, self.cfg, self.packed
+        other.h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            self._check(self.lib.tde_clone(self.h, C.byref(other.h), self._stream()), "tde_clone")
+            other.obs = self.obs.clone()
+            other.reward, other.terminated, other.truncated = self.reward.clone(), self.terminated.clone(), self.truncated.clone()
+            other.info = self.info.clone()
+        other._host = None
+        return other
+
     def close(self):
         if getattr(self, "h", None) is not None and self.h:
             self.lib.tde_destroy(self.h)

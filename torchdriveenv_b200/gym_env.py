@@ -13,6 +13,7 @@ gymnasium / stable-baselines3 are optional: when absent the spaces are small sta
 from __future__ import annotations
 
 import logging
+import time
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
 
@@ -222,8 +223,51 @@ class GymEnv(_Env):
         self.current_action = None
         self.last_birdview = None
 
+    # -- the generic env of the reference (gym_env.py:107-150,159-170): whatever simulator it is given, driven through the
+    #    SimulatorInterface-level surface; WaypointSuiteEnv overrides the per-step part with the fused CUDA step
+    def reset(self, seed: Optional[int] = None, options: Optional[dict] = None):
+        self.simulator = self.start_sim.copy()          # :110 (start_sim is set by the code that builds the env)
+        self.environment_steps = 0
+        self.last_birdview = None
+        return self.get_obs(), {}
+
+    def step(self, action):
+        self.environment_steps += 1
+        self.simulator.step(action)
+        self.last_action = self.current_action if self.current_action is not None else action
+        self.current_action = action
+        return self.get_obs(), self.get_reward(), self.is_terminated(), self.is_truncated(), self.get_info()
+
+    def get_obs(self):
+        return self.simulator.render_egocentric().cpu().numpy().astype(np.uint8)
+
+    def get_reward(self):
+        x = self.simulator.get_state()[..., 0]
+        return np.zeros(tuple(x.shape))
+
+    def is_done(self):
+        return self.is_truncated() or self.is_terminated()
+
     def is_truncated(self):
         return self.environment_steps >= self.max_environment_steps
+
+    def is_terminated(self):
+        return False
+
+    def get_info(self):
+        self.info = dict(
+            offroad=self.simulator.compute_offroad(),
+            collision=self.simulator.compute_collision(),
+            traffic_light_violation=self.simulator.compute_traffic_lights_violations(),
+            is_success=(self.environment_steps >= self.max_environment_steps),
+        )
+        return self.info
+
+    def mock_step(self):
+        obs = np.zeros((1, 3, TDE_OBS_H, TDE_OBS_W))
+        info = dict(offroad=torch.Tensor([[0]]), collision=torch.Tensor([[0]]), traffic_light_violation=torch.Tensor([[0]]),
+                    is_success=False)
+        return obs, 0, False, True, info
 
     def seed(self, seed=None):
         pass
@@ -276,8 +320,13 @@ class WaypointSuiteEnv(GymEnv):
 
     def reset(self, seed: Optional[int] = None, options: Optional[dict] = None):
         if seed is not None:
+            # gymnasium's seeding contract: reset(seed=s) starts a reproducible stream - the same s gives the same
+            # scenario, start pose and light phase.  The draws are keyed by (seed, env, episode counter): restart the counter.
             self._seed = int(seed)
-        self.engine.reset(seed=self._seed)   # the engine's episode counter varies the draw per episode
+            v = self.engine.get_env_vars()
+            v[:, 5] = 0
+            self.engine.set_env_vars(v)
+        self.engine.reset(seed=self._seed)   # without a seed the engine's episode counter varies the draw per episode
         self.environment_steps = 0
         self.reached_waypoint_num = 0
         self.last_obs = self.last_reward = self.last_info = None
@@ -295,7 +344,7 @@ class WaypointSuiteEnv(GymEnv):
     def step(self, action):
         a = torch.as_tensor(np.asarray(action.cpu() if torch.is_tensor(action) else action, dtype=np.float32)).reshape(-1)[:2]
         obs, rew, term, trunc, info = self.engine.step(a.view(1, 2))
-        self.simulator._infractions_valid = True
+        getattr(self.simulator, "simulator", self.simulator)._infractions_valid = True   # on the wrapped simulator in video mode
         if isinstance(self.simulator, BirdviewRecordingWrapper):
             self.simulator._record()
         self.environment_steps += 1
@@ -348,7 +397,71 @@ class SingleAgentWrapper(_Wrapper):
         self.env.close()
 
 
-class TorchDriveVecEnv:
+try:  # pragma: no cover - stable-baselines3 is not installed in the build image
+    from stable_baselines3.common.vec_env import VecEnv as _SB3VecEnv
+except Exception:
+    _SB3VecEnv = None
+
+
+class VecInfos:
+    """SB3's ``infos`` of one vectorised step: a sequence of E dicts, built on demand from the step's arrays.
+
+    ``infos[i]`` is what ``SingleAgentWrapper.step`` returns for one env (get_info gym_env.py:419-437 through
+    transform_out :463-472: ``offroad / collision / traffic_light_violation`` as scalars, ``is_success``,
+    ``reached_waypoint_num``, ``psi_smoothness``, ``psi_reward``, ``dist_reward``, ``speed_smoothness``) - the dict that
+    ``EvalNTimestepsCallback._calc_metrics`` (examples/rl_training.py:39-67) reads - plus what SB3's own wrappers add
+    for an env that finished in this step: ``episode = {r, l, t}`` (``Monitor``, rl_training.py:123),
+    ``TimeLimit.truncated`` and ``terminal_observation`` (``SubprocVecEnv``, :159).  ``infos.columns[name]`` is the
+    whole column as one array (the fast path: no per-env Python objects)."""
+
+    def __init__(self, info, terminated, truncated, terminal_observation=None, elapsed: float = 0.0):
+        self._info, self._term, self._trunc, self._tobs, self._elapsed = info, terminated, truncated, terminal_observation, float(elapsed)
+        self._host = None
+
+    @property
+    def columns(self) -> Dict:
+        cols = {k: self._info[:, i] for k, i in INFO_COLUMNS.items()}
+        cols["terminated"], cols["truncated"] = self._term, self._trunc
+        if self._tobs is not None:
+            cols["terminal_observation"] = self._tobs
+        return cols
+
+    def _arrays(self):
+        if self._host is None:   # one device-to-host copy for the whole step, on first per-env access
+            to_np = lambda t: t.cpu().numpy() if torch.is_tensor(t) else np.asarray(t)
+            self._host = (to_np(self._info), to_np(self._term).astype(bool), to_np(self._trunc).astype(bool))
+        return self._host
+
+    def __len__(self):
+        return int(self._info.shape[0])
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(len(self)))]
+        info, term, trunc = self._arrays()
+        i = int(i)
+        if i < 0:
+            i += len(self)
+        row, c = info[i], INFO_COLUMNS
+        d = dict(offroad=float(row[c["offroad"]]), collision=float(row[c["collision"]]),
+                 traffic_light_violation=float(row[c["traffic_light_violation"]]), is_success=bool(row[c["is_success"]] != 0),
+                 reached_waypoint_num=int(row[c["reached_waypoint_num"]]), psi_smoothness=float(row[c["psi_smoothness"]]),
+                 psi_reward=float(row[c["psi_reward"]]), dist_reward=float(row[c["dist_reward"]]),
+                 speed_smoothness=float(row[c["speed_smoothness"]]), wrong_way=float(row[c["wrong_way"]]))
+        if term[i] or trunc[i]:
+            d["episode"] = dict(r=float(row[c["episode_return"]]), l=int(row[c["episode_length"]]), t=round(self._elapsed, 6))
+            d["TimeLimit.truncated"] = bool(trunc[i] and not term[i])
+            if self._tobs is not None:
+                t = self._tobs[i]
+                d["terminal_observation"] = t.cpu().numpy() if torch.is_tensor(t) else np.asarray(t)
+        return d
+
+
+class TorchDriveVecEnv(*([_SB3VecEnv] if _SB3VecEnv is not None else [])):
+
     """E environments stepped in lockstep on one GPU with the SB3 ``VecEnv`` call shape
     (examples/rl_training.py:159-160: SubprocVecEnv + VecFrameStack(n_stack, channels_order="first")).
 
@@ -356,7 +469,10 @@ class TorchDriveVecEnv:
     finished envs are re-initialised inside the step kernel (auto-reset), their frame stack restarts;
     the stack is shifted and filled by the render kernel itself (no separate roll / copy pass).
     Outputs stay on the GPU as torch tensors (``output="torch"``) or are copied to numpy (``"numpy"``).
-    ``infos`` is a dict of per-env arrays (columns of get_info :419-437), not a list of dicts.
+    ``infos`` is a :class:`VecInfos`: a sequence of per-env dicts as SB3 expects (``infos[i]["terminal_observation"]``,
+    ``["TimeLimit.truncated"]``, ``["episode"]`` for finished envs), materialised lazily, with the whole columns
+    available as ``infos.columns``.  A subclass of SB3's ``VecEnv`` when stable-baselines3 is importable.
+    ``n_stack`` defaults to ``cfg.frame_stack`` (3, as ``VecFrameStack(env, n_stack=3)`` in the reference's trainer).
     """
 
     def __init__(self, cfg: EnvConfig, data, num_envs: int, n_stack: Optional[int] = None, n_background: int = 0,
@@ -364,8 +480,9 @@ class TorchDriveVecEnv:
                  terminal_observation: bool = False):
         self.config = cfg
         self.num_envs = int(num_envs)
-        self.n_stack = int(n_stack if n_stack is not None else 1)
+        self.n_stack = int(n_stack if n_stack is not None else max(1, int(cfg.frame_stack)))
         self.output = output
+        self._t_start = time.time()
         self._seed = int(seed if seed is not None else (cfg.seed if cfg.seed is not None else 0))
         self.scenario_set = data if isinstance(data, ScenarioSet) else scenario_set_from_suite(cfg, data, n_background, self._seed)
         self.engine = Engine(self.scenario_set, self.num_envs, device=device or cfg.device,
@@ -378,11 +495,19 @@ class TorchDriveVecEnv:
         # SB3's VecEnv keeps the last observation of a finished episode in info["terminal_observation"]; here it is
         # one [E, 3*n_stack, 64, 64] tensor whose rows are valid where `dones` is set (tde_step_terminal)
         self._terminal = torch.zeros_like(self._stack) if terminal_observation else None
+        if _SB3VecEnv is not None:   # pragma: no cover
+            _SB3VecEnv.__init__(self, self.num_envs, self.observation_space, self.action_space)
 
     def _out(self, t: torch.Tensor):
         return t.cpu().numpy() if self.output == "numpy" else t
 
-    def reset(self):
+    def reset(self, seed: Optional[int] = None, options: Optional[dict] = None):
+        if seed is not None:   # gymnasium's contract: the same seed restarts the same stream of episodes
+            self._seed = int(seed)
+            v = self.engine.get_env_vars()
+            v[:, 5] = 0
+            self.engine.set_env_vars(v)
+        self._t_start = time.time()
         self.engine.reset(seed=self._seed)
         # the frame stack lives in one [E, 3*n_stack, 64, 64] tensor that the render kernel shifts and
         # fills in place (tde_render_stacked / tde_step_stacked); a reset env restarts with zeros
@@ -399,10 +524,8 @@ class TorchDriveVecEnv:
         else:
             _, rew, term, trunc, info = self.engine.step_stacked(a, self._stack, self.n_stack)
         dones = (term | trunc).bool()
-        infos = {k: self._out(info[:, i]) for k, i in INFO_COLUMNS.items()}
-        if self._terminal is not None:
-            infos["terminal_observation"] = self._out(self._terminal)
-        infos["terminated"], infos["truncated"] = self._out(term.bool()), self._out(trunc.bool())
+        infos = VecInfos(self._out(info), self._out(term.bool()), self._out(trunc.bool()),
+                         None if self._terminal is None else self._out(self._terminal), elapsed=time.time() - self._t_start)
         return self._out(self._stack), self._out(rew), self._out(dones), infos
 
     def step(self, actions):
@@ -420,7 +543,10 @@ class TorchDriveVecEnv:
         return [int(indices)] if isinstance(indices, (int, np.integer)) else [int(i) for i in indices]
 
     def get_attr(self, attr_name: str, indices=None):
-        return [getattr(self, attr_name) for _ in self._indices(indices)]
+        """One value per selected env: row i of a per-env array / tensor attribute, the shared value otherwise."""
+        v = getattr(self, attr_name)
+        per_env = (torch.is_tensor(v) or isinstance(v, np.ndarray)) and v.ndim >= 1 and v.shape[0] == self.num_envs
+        return [v[i] if per_env else v for i in self._indices(indices)]
 
     def set_attr(self, attr_name: str, value, indices=None) -> None:
         setattr(self, attr_name, value)

@@ -103,9 +103,12 @@ class BatchedSimulator:
         return self
 
     def copy(self) -> "BatchedSimulator":
-        a = self._args
-        other = BatchedSimulator(a["scenarios"], a["num_envs"], a["max_agents"], str(self.device), a["expose_npcs"], a["seed"], **a["config"])
-        other._copy_from(self)
+        """simulator.copy() :110 -> tde_clone: device-to-device copy of every env, scenario tables shared."""
+        other = object.__new__(BatchedSimulator)
+        other._args = self._args
+        other.engine = self.engine.clone()
+        other.expose_npcs, other.seed = self.expose_npcs, self.seed
+        other._infractions_valid = self._infractions_valid
         return other
 
     def _copy_from(self, src: "BatchedSimulator") -> None:
