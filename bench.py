@@ -11,7 +11,12 @@ step path (weak scaling: 16,384 envs per GPU); NCCL only reduces the episode sta
   python bench.py --impl reference --gpus N --steps K ...  # CPU oracle port on the host cores
   (N > 1: launched by torch.distributed.run, one rank per GPU)
 
-Prints ONE JSON line (rank 0).
+Prints ONE JSON line (rank 0).  At N = 1 the default line also carries
+  other_configs          the other BASELINE configs (C2, C4, C5) measured the same way on this GPU,
+  pursuit                the C3 step under a pure-pursuit policy (long episodes: junctions, red lights, late waypoints),
+  cpu_baseline           the batched C oracle port on all host cores,
+  cpu_baseline_per_env   BASELINE config C1 the way the reference runs: one process per core, one env each (B = 1),
+                         the reference's call pattern per step (gym_env.py:369-437).
 """
 from __future__ import annotations
 
@@ -50,6 +55,15 @@ def build_scenarios(workload: str):
         return S.training_mix(100, 8), ("C5: rollout collection, 8192 envs x 8 agents per GPU (65,536 over 8 GPUs), mix of 100 synthetic "
                                         "training polylines, 3-frame stack written into a GPU-resident rollout buffer, uniform random policy")
     raise ValueError(workload)
+
+
+def config_dict(workload: str, desc: str, E: int, A: int, render: bool, world: int) -> dict:
+    """The `config` object of the JSON line: the same for the CUDA arm and the reference arm."""
+    return dict(workload=desc, envs_per_gpu=E, agents=A, render=render, global_envs=E * world,
+                parallelism=f"env-sharded x{world}, no collectives on the step path",
+                l2="per-step working set (obs write %.0f MB + state) exceeds the 126 MB L2" % (E * 12288 / 1e6)
+                if render else "inputs smaller than L2 (C2 is latency-bound by design)",
+                actions="U(-1,1) x U(-0.3,0.3), fresh per step, resident in HBM")
 
 
 def make_actions(E: int, n: int, seed: int) -> np.ndarray:
@@ -167,6 +181,7 @@ def cpu_oracle_throughput(workload: str, budget_s: float, seed: int = 0):
     bounded sample of the same workload, all host threads (OpenMP)."""
     from oracle import oracle as O
     from torchdriveenv_b200._capi import default_config
+    O.set_num_threads(os.cpu_count() or 1)     # torch.distributed.run exports OMP_NUM_THREADS=1
     _, A, render = WORKLOADS[workload]
     ss, _ = build_scenarios(workload)
     E = 1024
@@ -188,6 +203,82 @@ def cpu_oracle_throughput(workload: str, budget_s: float, seed: int = 0):
                        f"{threads} threads on {os.cpu_count()} visible cores")
 
 
+def per_env_worker(seconds: float, seed: int) -> None:
+    """One worker of the per-env CPU baseline: ONE env (B = 1, BASELINE config C1: Three Way, ego + 8 NPCs, 64x64
+    birdview) stepped through the oracle with the reference's call pattern (gym_env.py:369-437): per step 12 get_state
+    copies, sim.step, one render, the three infraction metrics evaluated for is_terminated and again for get_info,
+    reward / waypoint arithmetic in Python floats, a reset when the episode ends.  Prints the steps it made."""
+    import math
+    os.environ["OMP_NUM_THREADS"] = "1"
+    from oracle import oracle as O
+    from torchdriveenv_b200 import scenarios as S
+    from torchdriveenv_b200._capi import default_config
+    O.set_num_threads(1)
+    ss = S.three_way(6)
+    A = 9
+    env = O.OracleEnvSet(default_config(num_envs=1, max_agents=A, auto_reset=0), ss.pack(A))
+    wps = np.asarray(ss.scenarios[0].waypoints, np.float64)
+    rng = np.random.default_rng(seed)
+    get_state = lambda: env.state[:, :1].copy()          # simulator.get_state(): B x 1 x 4 (NPCs hidden)
+    episode = 0
+
+    def reset():
+        nonlocal episode
+        env.reset(seed=seed + episode); episode += 1
+        return env.render(), 1, 0
+
+    obs, target, steps_in_ep = reset()
+    n = 0
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        a = np.array([[rng.uniform(-1, 1), rng.uniform(-0.3, 0.3)]], np.float32)
+        st = get_state(); lx, ly, lpsi, lv = (float(st[0, 0, k]) for k in range(4))      # :371-375 (1)
+        env.kinematics(a); steps_in_ep += 1                                              # :117 sim.step
+        obs = env.render()                                                               # :122-124 get_obs
+        x, y, psi = float(get_state()[0, 0, 0]), float(get_state()[0, 0, 1]), float(get_state()[0, 0, 2])   # :397-399 (3)
+        d = math.dist((x, y), (lx, ly))
+        reward = (1.0 if d > 0.5 else 0.0) - 25.0 * (1.0 - math.cos(psi - lpsi))
+        if target < len(wps):                                                            # :391-394 check_reach_target (2)
+            if math.dist((float(get_state()[0, 0, 0]), float(get_state()[0, 0, 1])), tuple(wps[target])) < 3.0:
+                reward += 100.0
+        inf = env.compute_infractions()[0, 0]                                            # :413-417 is_terminated: three metrics
+        terminated = bool(inf[1] > 0 or inf[0] > 0 or inf[2] > 0)
+        truncated = steps_in_ep >= 200                                                   # :134-135
+        s4 = [get_state() for _ in range(4)]                                             # :420-423 get_info (4)
+        inf2 = env.compute_infractions()[0, 0]                                           # :427-429 the metrics again
+        info = dict(offroad=inf2[1], collision=inf2[0], traffic_light_violation=inf2[2],
+                    psi_smoothness=abs(lpsi - float(s4[2][0, 0, 2])) / 0.1, speed_smoothness=abs(lv - float(s4[3][0, 0, 3])) / 0.1)
+        if target < len(wps):                                                            # :378-383 check_reach_target again (2)
+            if math.dist((float(get_state()[0, 0, 0]), float(get_state()[0, 0, 1])), tuple(wps[target])) < 3.0:
+                target += 1
+        n += 1
+        if terminated or truncated:
+            obs, target, steps_in_ep = reset()
+    print(json.dumps(dict(steps=n, seconds=time.perf_counter() - t0, reward=reward, info_keys=len(info))), flush=True)
+
+
+def cpu_per_env_baseline(seconds: float):
+    """BASELINE.md section 3 'CPU-ref (per-env)': one process per host core, one env each; aggregate env-steps/s."""
+    cores = os.cpu_count() or 1
+    procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--per-env-worker", str(seconds), "--seed", str(100 + k)],
+                              stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True) for k in range(cores)]
+    steps, secs = 0, []
+    for pr in procs:
+        out, _ = pr.communicate()
+        try:
+            d = json.loads(out.strip().splitlines()[-1])
+            steps += int(d["steps"]); secs.append(float(d["seconds"]))
+        except Exception:
+            pass
+    if not secs:
+        return None
+    return dict(value=steps / max(secs), unit=UNIT, cores=cores, processes=len(secs), kind="port",
+                config="C1: single env per process, Three Way, ego + 8 NPCs (2 predetermined, 6 log-replay), 64x64 birdview",
+                sample=f"{len(secs)} processes x 1 env, {max(secs):.1f} s each, {steps} env-steps in total; per step the reference's call "
+                       "pattern (gym_env.py:369-437): 12 get_state, sim.step, 1 render, the three infraction metrics twice, "
+                       "Python-float reward; C oracle, OMP_NUM_THREADS=1 per process")
+
+
 def c4_inputs(E: int, A: int, seed: int):
     from torchdriveenv_b200 import scenarios as S
     st, at = S.scatter_boxes(E, A, size=200.0, seed=seed)
@@ -198,6 +289,7 @@ def c4_inputs(E: int, A: int, seed: int):
 def cpu_oracle_c4(budget_s: float, seed: int = 0):
     """CPU oracle on a bounded sample of config C4 (all-pairs SAT + brute-force corner-to-mesh distance)."""
     from oracle import oracle as O
+    O.set_num_threads(os.cpu_count() or 1)
     E, A = 512, 64
     st, at, patch = c4_inputs(E, A, seed)
     O.collision_boxes(st[:8], at[:8])
@@ -224,8 +316,6 @@ def run_c4(args, rank: int, local_rank: int, world: int):
     from torchdriveenv_b200.roofline import c4_bytes_per_env
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     E, A, _ = WORKLOADS["c4"]
     st, at, patch = c4_inputs(E, A, seed=12 + rank)
     eng = Engine(S.ScenarioSet([patch], [S.make_scenario(0, [[5, 5], [50, 5]], 0, 0, "p")]), 1, 1, device=str(dev))
@@ -289,10 +379,8 @@ def run_c4(args, rank: int, local_rank: int, world: int):
                                   avg_launch_ms=ms, peak_source=peak_src,
                                   note="issue-bound by design: ~2,016 pair tests and 256 point-to-mesh queries per env (SURVEY 8d)"),
                     cpu_baseline=cpu)
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        return line
+    return None
 
 
 def run_c5(args, rank: int, local_rank: int, world: int):
@@ -306,8 +394,6 @@ def run_c5(args, rank: int, local_rank: int, world: int):
     from torchdriveenv_b200.roofline import rollout_bytes_per_env_step
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     E, A, _ = WORKLOADS["c5"]
     ss, desc = build_scenarios("c5")
     eng = Engine(ss, E, A, device=str(dev), auto_reset=1, env_index_offset=rank * E)
@@ -387,13 +473,14 @@ def run_c5(args, rank: int, local_rank: int, world: int):
                                   peak=peak, unit="GB/s", frac=achieved / peak, traffic=None, algorithmic_bytes_per_launch=bpe * E,
                                   bytes_per_env_step=bpe, avg_launch_ms=ms, peak_source=peak_src),
                     cpu_baseline=cpu, episode_stats=summarize(stats))
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        return line
+    return None
 
 
 def run_reference(args, rank: int, world: int):
+    """The reference arm: the CPU implementation of the path on the box's host cores - the C oracle port (the reference's
+    own implementation needs torchdrivesim, absent offline), every host thread, rank 0 only.  Each bench "step" is a
+    bounded sample of the workload: a 1,024-env slice stepped for the step's share of ~150 s (at least one oracle step)."""
     if rank != 0:
         return
     workload = args.workload
@@ -406,10 +493,9 @@ def run_reference(args, rank: int, world: int):
         return
     E, A, render = WORKLOADS[workload]
     ss, desc = build_scenarios(workload)
-    # each "step" = one bounded sample of the workload: a 1024-env slice stepped for the step's share of ~150 s (at least
-    # one oracle step), so that any --steps K --warmup W ends within a few minutes; the oracle env is built once
     from oracle import oracle as O
     from torchdriveenv_b200._capi import default_config
+    threads = O.set_num_threads(os.cpu_count() or 1)      # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers
     ES = 1024
     env = O.OracleEnvSet(default_config(num_envs=ES, max_agents=A, auto_reset=1), ss.pack(A))
     env.reset(seed=0)
@@ -429,18 +515,71 @@ def run_reference(args, rank: int, world: int):
         if k >= args.warmup:
             n_total += n; t_total += time.perf_counter() - t0
     value = ES * n_total / t_total
-    threads = O.num_threads()
     cb = dict(value=value, unit=UNIT, cores=threads, kind="port",
-              sample=f"{ES} envs x {n_total} oracle steps over {args.steps} bench steps ({t_total:.1f} s), C oracle with OpenMP over envs, "
-                     f"{threads} threads on {os.cpu_count()} visible cores")
+              sample=f"each of the {args.steps} bench steps = {n_total / max(1, args.steps):.1f} oracle steps of a {ES}-env slice of the workload "
+                     f"({ES * n_total} env-steps in {t_total:.1f} s); C oracle with OpenMP over envs, {threads} threads on {os.cpu_count()} visible cores")
     line = dict(impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=1e3 * E / value, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
-                data="synthetic", config=dict(workload=desc, envs_per_gpu=E, agents=A, render=render,
-                                              note="reference arm = CPU oracle port (the reference itself needs torchdrivesim, absent offline); "
-                                                   "each step is a bounded 1024-env sample of the workload (its share of ~150 s, >= 1 oracle step)"),
+                ms_per_step=1e3 * t_total / max(1, args.steps),           # measured: wall time of one bench step (a bounded sample)
+                oracle_ms_per_step=1e3 * t_total / max(1, n_total), envs_per_oracle_step=ES,
+                ms_per_full_batch=1e3 * E * max(1, args.gpus) / value,    # what one pass over the whole workload would take at this rate
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=config_dict(workload, desc, E, A, render, max(1, args.gpus)),
                 cpu_baseline=cb, e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 wall_s=time.perf_counter() - t_all)
     print(json.dumps(line), flush=True)
+
+
+def pursuit_policy(eng, waypoints, gen, v_want: float = 8.0):
+    """Pure pursuit of each env's current target waypoint, on the GPU (the driver of tests/golden/make_reference_golden.py)."""
+    import torch
+    st = eng.get_state()[:, 0]
+    tgt = eng.get_env_vars()[:, 2].long().clamp_(0, waypoints.shape[0] - 1)
+    w = waypoints[tgt]
+    err = torch.atan2(w[:, 1] - st[:, 1], w[:, 0] - st[:, 0]) - st[:, 2]
+    err = torch.remainder(err + np.pi, 2 * np.pi) - np.pi
+    acc = (0.8 * (v_want - st[:, 3])).clamp_(-1, 1)
+    steer = (0.35 * err + 0.02 * torch.randn(st.shape[0], generator=gen, device=st.device)).clamp_(-0.3, 0.3)
+    return torch.stack([acc, steer], 1).contiguous()
+
+
+def measure_pursuit(eng, ss, E: int, K: int, W: int, dev, stream, seed: int = 77, preroll: int = 150):
+    """The C3 step under a policy that survives: the envs are first rolled out with pure pursuit (untimed) and the actions
+    recorded; then the same seed is replayed - the episodes are deterministic - and the last K steps are timed.  By then
+    the batch is spread along the whole route (junctions, stop lines, late waypoints), not bunched at the start."""
+    import torch
+    from torchdriveenv_b200.distributed import summarize
+    wps = torch.from_numpy(np.asarray(ss.scenarios[0].waypoints, np.float32)).to(dev)
+    gen = torch.Generator(device=dev); gen.manual_seed(seed)
+
+    def restart():
+        v = eng.get_env_vars(); v[:, 5] = 0; eng.set_env_vars(v)      # episode counters: the replay draws the same episodes
+        eng.reset(seed=seed)
+        eng.episode_stats(reset=True)
+
+    restart()
+    tape = torch.empty((preroll + W + K, E, 2), dtype=torch.float32, device=dev)
+    for k in range(tape.shape[0]):
+        tape[k] = pursuit_policy(eng, wps, gen)
+        eng.step(tape[k], render=False)
+    restart()
+    for k in range(preroll):
+        eng.step(tape[k], render=False)
+    for k in range(preroll, preroll + W):
+        eng.step(tape[k])
+    eng.episode_stats(reset=True)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for k in range(preroll + W, preroll + W + K):
+        eng.step(tape[k])
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / K
+    v = eng.get_env_vars()
+    return dict(value=E / (ms * 1e-3), unit=UNIT, ms_per_step=ms, steps=K, policy="pure pursuit of the target waypoint at 8 m/s, "
+                f"recorded then replayed (deterministic episodes), {preroll} untimed steps first",
+                mean_env_step_at_timing=float(v[:, 1].float().mean().item()), mean_target_index=float(v[:, 2].float().mean().item()),
+                episode_stats=summarize(eng.episode_stats()))
 
 
 def run_cuda(args, rank: int, local_rank: int, world: int):
@@ -452,8 +591,6 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     workload = args.workload
     E_total_strong, A, render = WORKLOADS[workload]
     E = E_total_strong if args.scaling == "weak" else max(1, E_total_strong // world)
@@ -521,29 +658,35 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
     # the only collective of this path: episode statistics, after the timed regions
     stats = reduce_episode_stats(eng.episode_stats(), device=dev)
 
-    if rank == 0:
-        peak, peak_src = measured_peak_hbm()
-        bpe = bytes_per_env_step(A, render)
-        achieved = bpe * E / (per_launch_ms * 1e-3) / 1e9
-        roof = dict(bound="hbm", kernel="tde_render_kernel (+ tde_physics_kernel, one launch each per step)" if render else "tde_physics_kernel (one launch per step)", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
-                    traffic=ncu_traffic(workload), algorithmic_bytes_per_launch=bpe * E, bytes_per_env_step=bpe,
-                    avg_launch_ms=per_launch_ms, peak_source=peak_src)
-        cpu = cpu_oracle_throughput(workload, args.cpu_seconds) if world == 1 and not args.no_cpu_baseline else None
-        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=total_ms_max / K,
-                    higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype="f32", data="synthetic",
-                    config=dict(workload=desc, envs_per_gpu=E, agents=A, render=render, global_envs=E * world,
-                                parallelism=f"env-sharded x{world}, no collectives on the step path",
-                                l2="per-step working set (obs write %.0f MB + state) exceeds the 126 MB L2" % (E * 12288 / 1e6)
-                                if render else "inputs smaller than L2 (C2 is latency-bound by design)",
-                                actions="U(-1,1) x U(-0.3,0.3), fresh per step, resident in HBM"),
-                    clocks=clocks, gpu_launches=int(gpu_launches),
-                    e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=K2,
-                             api="tde_step_host (pinned host buffers, copies inside the timed region)"),
-                    roofline=roof, cpu_baseline=cpu, episode_stats=summarize(stats))
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    if rank != 0:
+        return None
+    peak, peak_src = measured_peak_hbm()
+    bpe = bytes_per_env_step(A, render)
+    achieved = bpe * E / (per_launch_ms * 1e-3) / 1e9
+    roof = dict(bound="hbm", kernel="tde_render_kernel (+ tde_physics_kernel, one launch each per step)" if render else "tde_physics_kernel (one launch per step)", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
+                traffic=ncu_traffic(workload), algorithmic_bytes_per_launch=bpe * E, bytes_per_env_step=bpe,
+                avg_launch_ms=per_launch_ms, peak_source=peak_src)
+    cpu = cpu_oracle_throughput(workload, args.cpu_seconds) if world == 1 and not args.no_cpu_baseline else None
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=total_ms_max / K,
+                higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype="f32", data="synthetic",
+                config=config_dict(workload, desc, E, A, render, world),
+                clocks=clocks, gpu_launches=int(gpu_launches),
+                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=K2,
+                         api="tde_step_host (pinned host buffers, copies inside the timed region)",
+                         # the host-buffer number is bound by the bytes that cross PCIe, not by the kernels: its own roofline
+                         pcie_gbs_achieved=(h2d + d2h) * e2e_value / E / 1e9, pcie_note="per GPU; PCIe Gen5 x16 moves ~55 GB/s device to host"),
+                roofline=roof, cpu_baseline=cpu, episode_stats=summarize(stats))
+    if world == 1 and workload == "c3" and args.policy in ("both", "pursuit"):
+        line["pursuit"] = measure_pursuit(eng, ss, E, max(50, min(K, 200)), 10, dev, stream)
+    return line
+
+
+def slim(line):
+    """A sub-line of `other_configs`: the measurement without the nested extras."""
+    if line is None:
+        return None
+    keep = ("metric", "value", "unit", "steps", "warmup", "ms_per_step", "config", "clocks", "gpu_launches", "e2e", "roofline", "episode_stats")
+    return {k: line[k] for k in keep if k in line}
 
 
 def main():
@@ -557,7 +700,15 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--policy", default="both", choices=["random", "pursuit", "both"],
+                    help="C3: the headline value is always the uniform random policy of SURVEY 8d; 'both' / 'pursuit' add the pursuit line")
+    ap.add_argument("--no-other-configs", action="store_true", help="N = 1, C3: skip the C2 / C4 / C5 lines and the per-env CPU baseline")
+    ap.add_argument("--per-env-worker", type=float, default=None, help=argparse.SUPPRESS)
+    ap.add_argument("--seed", type=int, default=0, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.per_env_worker is not None:
+        per_env_worker(args.per_env_worker, args.seed)
+        return
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -570,13 +721,30 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000), os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
-    if args.workload == "c4":
-        run_c4(args, rank, local_rank, world)
-        return
-    if args.workload == "c5":
-        run_c5(args, rank, local_rank, world)
-        return
-    run_cuda(args, rank, local_rank, world)
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    runner = {"c4": run_c4, "c5": run_c5}.get(args.workload, run_cuda)
+    line = runner(args, rank, local_rank, world)
+    if rank == 0 and line is not None and world == 1 and args.workload == "c3" and not args.no_other_configs:
+        # the other BASELINE configs on the same GPU, each long enough for >= 3 clock samples in its timed region
+        others = {}
+        for name, steps, warm in (("c2", 3000, 100), ("c4", 60, 5), ("c5", 128, 32)):
+            sub = argparse.Namespace(**vars(args))
+            sub.workload, sub.steps, sub.warmup, sub.no_cpu_baseline, sub.e2e_steps, sub.policy = name, steps, warm, True, 5, "random"
+            try:
+                others[name] = slim({"c4": run_c4, "c5": run_c5}.get(name, run_cuda)(sub, 0, local_rank, 1))
+            except Exception as ex:      # a failing extra must not take the headline line with it
+                others[name] = dict(error=f"{type(ex).__name__}: {ex}")
+        line["other_configs"] = others
+        line["cpu_baseline_per_env"] = None if args.no_cpu_baseline else cpu_per_env_baseline(min(8.0, args.cpu_seconds))
+    if rank == 0 and line is not None:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

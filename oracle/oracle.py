@@ -60,6 +60,7 @@ def lib() -> C.CDLL:
         L.orc_point_mesh_distance.argtypes, L.orc_point_mesh_distance.restype = [vp, i, f, f], f
         L.orc_wrap_pi.argtypes, L.orc_wrap_pi.restype = [f], f
         L.orc_num_threads.restype = i
+        L.orc_set_num_threads.argtypes = [i]
         L.orc_rng.argtypes, L.orc_rng.restype = [C.c_uint64] * 4, C.c_uint64
         _LIB = L
     return _LIB
@@ -229,3 +230,9 @@ def wrap_pi(x: float) -> float:
 
 def num_threads() -> int:
     return int(lib().orc_num_threads())
+
+
+def set_num_threads(n: int) -> int:
+    """OpenMP threads of the oracle's env loops (overrides OMP_NUM_THREADS, which torchrun sets to 1)."""
+    lib().orc_set_num_threads(int(n))
+    return num_threads()

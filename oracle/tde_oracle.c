@@ -956,3 +956,12 @@ int orc_num_threads(void) {
 #endif
     return n;
 }
+/* torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: the timing legs set the thread count themselves */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    extern void omp_set_num_threads(int);
+    if (n >= 1) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}

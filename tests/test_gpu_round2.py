@@ -1,0 +1,204 @@
+"""GPU parity tests added in round 2: the holes the round-1 review listed (VERDICT "Close the test holes").
+
+(a) collision pile-ups that overflow the compacted pair list (TDE_PAIR_CAP), stateless and inside the step;
+(b) the whole C3 batch (16,384 envs x 32 agents) against the oracle for two steps, every env, bit for bit;
+(c) C5 at its bench size (8,192 envs x 8 agents, 100-map training mix) on env sub-ranges;
+(d) a batch under a pursuit policy that survives > 100 steps: junctions, red lights and late waypoints rendered and scored;
+(e) NaN / inf / huge actions stay inside their env;
+(f) tde_clone: the copy steps bit for bit like the original;
+(g) the physics launch with the map tables staged in shared memory (bulk-async copies) against the default launch."""
+import numpy as np
+import pytest
+import torch
+
+from torchdriveenv_b200 import scenarios as S
+from torchdriveenv_b200._capi import default_config
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(ss, E, A, **cfg):
+    from torchdriveenv_b200.engine import Engine
+    return Engine(ss, E, A, device="cuda:0", **cfg)
+
+
+def pursuit_actions(state, env_vars, waypoints, rng, v_want=8.0):
+    """Pure pursuit of the current target waypoint (the driver of tests/golden/make_reference_golden.py, vectorised)."""
+    x, y, psi, v = (state[:, 0, k] for k in range(4))
+    tgt = np.clip(env_vars[:, 2], 0, len(waypoints) - 1)
+    w = waypoints[tgt]
+    err = np.arctan2(w[:, 1] - y, w[:, 0] - x) - psi
+    err = (err + np.pi) % (2 * np.pi) - np.pi
+    acc = np.clip(0.8 * (v_want - v), -1, 1)
+    steer = np.clip(0.35 * err + rng.normal(0, 0.02, len(x)), -0.3, 0.3)
+    return np.stack([acc, steer], 1).astype(np.float32)
+
+
+def test_collision_pile_up_overflows_the_pair_list(oracle):
+    """64 agents in a 15 m square: hundreds of candidate pairs per env, far beyond the 256 the compacted list holds, so the
+    per-lane fallback of sat_counts runs - stateless (tde_collision_boxes) and inside the step."""
+    st, at = S.scatter_boxes(96, 64, size=15.0, seed=4)
+    want = oracle.collision_boxes(st, at)
+    assert want.max() >= 20 and (want.sum(1) / 2).min() > 256         # more overlapping pairs alone than the list holds
+    patch = S.scatter_patch(60.0, 10.0)
+    sc = S.make_scenario(0, [[5, 5], [50, 5]], 63, 0, "pile")
+    eng = _engine(S.ScenarioSet([patch], [sc]), 96, 64)
+    got = eng.collision_boxes(torch.from_numpy(st).cuda(), torch.from_numpy(at).cuda()).cpu().numpy()
+    assert np.array_equal(got, want)
+    # the same boxes as the env state: the in-step path
+    orc = oracle.OracleEnvSet(default_config(num_envs=96, max_agents=64), eng.packed)
+    eng.reset(seed=1); orc.reset(seed=1)
+    st2 = st.copy(); st2[..., 0] += 20.0; st2[..., 1] += 20.0
+    eng.set_state(torch.from_numpy(st2)); orc.state[...] = st2
+    eng.set_attributes(torch.from_numpy(at)); orc.attr[...] = at
+    assert np.array_equal(eng.compute_infractions().cpu().numpy(), orc.compute_infractions())
+    assert orc.infractions[..., 0].max() >= 20
+
+
+def test_whole_c3_batch_two_steps(oracle):
+    """BASELINE config C3 at its full size: every one of the 16,384 envs against the oracle, reset + two steps."""
+    E, A = 16384, 32
+    eng = _engine(S.traffic_lights(A), E, A, auto_reset=1)
+    orc = oracle.OracleEnvSet(default_config(num_envs=E, max_agents=A, auto_reset=1), eng.packed)
+    eng.reset(seed=21); orc.reset(seed=21)
+    assert np.array_equal(eng.get_state().cpu().numpy(), orc.state)
+    assert np.array_equal(eng.render().cpu().numpy(), orc.render())
+    rng = np.random.default_rng(21)
+    for k in range(2):
+        a = np.stack([rng.uniform(-1, 1, E), rng.uniform(-0.3, 0.3, E)], 1).astype(np.float32)
+        obs, r, te, tr, info = eng.step(torch.from_numpy(a).cuda())
+        oobs, orr, ote, otr, oinfo = orc.step(a)
+        assert np.array_equal(eng.get_state().cpu().numpy(), orc.state), f"step {k}: state"
+        assert np.array_equal(eng.get_infractions().cpu().numpy(), orc.infractions), f"step {k}: infractions"
+        assert np.array_equal(info.cpu().numpy(), oinfo) and np.array_equal(r.cpu().numpy(), orr), f"step {k}: info / reward"
+        assert np.array_equal(te.cpu().numpy(), ote) and np.array_equal(tr.cpu().numpy(), otr), f"step {k}: flags"
+        bad = (obs.cpu().numpy() != oobs).reshape(E, -1).any(1)
+        assert not bad.any(), f"step {k}: {int(bad.sum())} envs render differently"
+
+
+def test_c5_bench_size_on_env_sub_ranges(oracle):
+    """BASELINE config C5's per-GPU shard (8,192 envs x 8 agents, 100 training maps - the physics reads the tables from
+    global memory: they do not fit in shared memory): three windows of 96 envs against the oracle through the stacked step."""
+    E, A, n = 8192, 8, 3
+    ss = S.training_mix(100, A)
+    eng = _engine(ss, E, A, auto_reset=1)
+    eng.reset(seed=9)
+    stack = torch.zeros((E, 3 * n, 64, 64), dtype=torch.uint8, device="cuda")
+    eng.render_stacked(stack, n)
+    windows = [(0, 96), (4000, 4096), (E - 96, E)]
+    orcs = []
+    for lo, hi in windows:
+        o = oracle.OracleEnvSet(default_config(num_envs=hi - lo, max_agents=A, auto_reset=1, env_index_offset=lo), eng.packed)
+        o.reset(seed=9)
+        assert np.array_equal(eng.get_state()[lo:hi].cpu().numpy(), o.state)
+        orcs.append(o)
+    rng = np.random.default_rng(9)
+    for k in range(12):
+        a = np.stack([rng.uniform(-1, 1, E), rng.uniform(-0.3, 0.3, E)], 1).astype(np.float32)
+        eng.step_stacked(torch.from_numpy(a).cuda(), stack, n)
+        st = eng.get_state().cpu().numpy(); info = eng.info.cpu().numpy(); newest = stack[:, -3:].cpu().numpy()
+        for (lo, hi), o in zip(windows, orcs):
+            oobs, orr, ote, otr, oinfo = o.step(a[lo:hi])
+            assert np.array_equal(st[lo:hi], o.state), f"step {k} window {lo}: state"
+            assert np.array_equal(info[lo:hi], oinfo), f"step {k} window {lo}: info"
+            assert np.array_equal(newest[lo:hi], oobs), f"step {k} window {lo}: newest frame"
+    assert len(set(eng.get_env_vars()[:, 0].cpu().numpy().tolist())) > 90      # the shard draws (nearly) all 100 scenarios
+
+
+def test_pursuit_policy_survives_and_is_scored(oracle):
+    """Envs driven by pure pursuit of their target waypoint: most survive > 100 steps, pass the junctions, meet red lights
+    and collect waypoints - the expensive end of the render / scoring distribution, bit for bit against the oracle."""
+    E, A = 128, 16
+    ss = S.traffic_lights(A)
+    cfg = dict(auto_reset=1, terminated_at_infraction=0, distance_cutoff=0.25)
+    eng = _engine(ss, E, A, **cfg)
+    orc = oracle.OracleEnvSet(default_config(num_envs=E, max_agents=A, **cfg), eng.packed)
+    eng.reset(seed=31); orc.reset(seed=31)
+    wps = np.asarray(ss.scenarios[0].waypoints, np.float64)
+    rng = np.random.default_rng(31)
+    reached, red, max_len = 0, 0, 0
+    for k in range(150):
+        a = pursuit_actions(orc.state.astype(np.float64), orc.env_vars, wps, rng)
+        obs, r, te, tr, info = eng.step(torch.from_numpy(a).cuda())
+        oobs, orr, ote, otr, oinfo = orc.step(a)
+        assert np.array_equal(eng.get_state().cpu().numpy(), orc.state), f"step {k}: state"
+        assert np.array_equal(info.cpu().numpy(), oinfo), f"step {k}: info"
+        assert np.array_equal(obs.cpu().numpy(), oobs), f"step {k}: observation"
+        assert np.array_equal(te.cpu().numpy(), ote) and np.array_equal(tr.cpu().numpy(), otr)
+        reached = max(reached, int(oinfo[:, 4].max())); red += int((oinfo[:, 2] > 0).sum())
+        max_len = max(max_len, int(oinfo[:, 11].max()))
+    assert max_len >= 140 and reached >= 5 and red > 0, (max_len, reached, red)
+    np.testing.assert_allclose(eng.episode_stats(), orc.stats, rtol=1e-9)
+
+
+def test_non_finite_actions_stay_inside_their_env(oracle):
+    """NaN, +-inf and huge actions in some envs: those envs may become garbage (as they do in the oracle, bit for bit where
+    the result is defined), the others must be untouched."""
+    E, A = 64, 16
+    eng = _engine(S.traffic_lights(A), E, A, auto_reset=1)
+    orc = oracle.OracleEnvSet(default_config(num_envs=E, max_agents=A, auto_reset=1), eng.packed)
+    eng.reset(seed=5); orc.reset(seed=5)
+    rng = np.random.default_rng(5)
+    bad_envs = np.array([3, 17, 18, 40, 63])
+    good = np.ones(E, bool); good[bad_envs] = False
+    poison = [np.nan, np.inf, -np.inf, 1e30, -1e38]
+    for k in range(10):
+        a = np.stack([rng.uniform(-1, 1, E), rng.uniform(-0.3, 0.3, E)], 1).astype(np.float32)
+        for j, e in enumerate(bad_envs):
+            a[e, (j + k) % 2] = poison[(j + k) % len(poison)]
+        obs, r, te, tr, info = eng.step(torch.from_numpy(a).cuda())
+        oobs, orr, ote, otr, oinfo = orc.step(a)
+        torch.cuda.synchronize()
+        assert np.array_equal(eng.get_state().cpu().numpy()[good], orc.state[good]), f"step {k}"
+        assert np.array_equal(info.cpu().numpy()[good], oinfo[good]) and np.array_equal(obs.cpu().numpy()[good], oobs[good]), f"step {k}"
+        assert np.array_equal(te.cpu().numpy()[good], ote[good]) and np.array_equal(tr.cpu().numpy()[good], otr[good])
+        # the poisoned envs agree too wherever the oracle's value is a number
+        st, ost = eng.get_state().cpu().numpy()[~good], orc.state[~good]
+        fin = np.isfinite(ost)
+        assert np.array_equal(st[fin], ost[fin]) and np.array_equal(np.isnan(st), np.isnan(ost))
+
+
+def test_clone_steps_like_the_original(oracle):
+    """tde_clone (simulator.copy(), gym_env.py:110): device-to-device copy of every env, scenario tables shared."""
+    E, A = 200, 12
+    eng = _engine(S.validation_mix(A), E, A, auto_reset=1)
+    eng.reset(seed=3)
+    rng = np.random.default_rng(3)
+    acts = [torch.from_numpy(np.stack([rng.uniform(-1, 1, E), rng.uniform(-0.3, 0.3, E)], 1).astype(np.float32)).cuda() for _ in range(12)]
+    for a in acts[:4]:
+        eng.step(a)
+    twin = eng.clone()
+    assert torch.equal(twin.get_state(), eng.get_state()) and torch.equal(twin.get_env_vars(), eng.get_env_vars())
+    for a in acts[4:8]:
+        o1, r1, t1, u1, i1 = eng.step(a)
+        o2, r2, t2, u2, i2 = twin.step(a)
+        assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(i1, i2) and torch.equal(t1, t2) and torch.equal(u1, u2)
+        assert torch.equal(twin.get_state(), eng.get_state())
+    keep = eng.get_state().clone()
+    for a in acts[8:]:
+        twin.step(a)                                   # the copy moves on alone ...
+    assert torch.equal(eng.get_state(), keep)          # ... and the original stays where it was
+    eng.close()                                        # the shared tables outlive the first handle
+    twin.step(acts[0])
+    torch.cuda.synchronize()
+    assert torch.cuda.current_device() == 0
+    twin.close()
+
+
+@pytest.mark.parametrize("E,A", [(700, 32), (96, 64), (1, 9)])
+def test_staged_map_tables_match_the_default_launch(oracle, E, A):
+    """cfg.stage_map_tables = 1: the lane-mesh triangle records, stop lines, light schedule and the per-cell summary are
+    copied into shared memory once per CTA (cp.async.bulk + mbarrier); results equal the oracle's, as the default launch's do."""
+    ss = S.three_way(6) if A == 9 else S.traffic_lights(A)
+    cfg = dict(auto_reset=1, stage_map_tables=1)
+    eng = _engine(ss, E, A, **cfg)
+    orc = oracle.OracleEnvSet(default_config(num_envs=E, max_agents=A, auto_reset=1), eng.packed)
+    eng.reset(seed=8); orc.reset(seed=8)
+    rng = np.random.default_rng(8)
+    for k in range(20):
+        a = np.stack([rng.uniform(-1, 1, E), rng.uniform(-0.3, 0.3, E)], 1).astype(np.float32)
+        obs, r, te, tr, info = eng.step(torch.from_numpy(a).cuda())
+        oobs, orr, ote, otr, oinfo = orc.step(a)
+        assert np.array_equal(eng.get_state().cpu().numpy(), orc.state), f"step {k}: state"
+        assert np.array_equal(eng.get_infractions().cpu().numpy(), orc.infractions), f"step {k}: infractions"
+        assert np.array_equal(info.cpu().numpy(), oinfo) and np.array_equal(obs.cpu().numpy(), oobs), f"step {k}"
