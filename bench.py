@@ -52,7 +52,7 @@ def build_scenarios(workload: str):
     if workload == "c2":
         return S.roundabout(16), "C2: 1024 envs x 16 agents, Roundabout, kinematics+collision+offroad+reward, no render"
     if workload == "c5":
-        return S.training_mix(100, 8), ("C5: rollout collection, 8192 envs x 8 agents per GPU (65,536 over 8 GPUs), mix of 100 synthetic "
+        return S.training_mix(100, 8), ("C5: rollout collection, 8192 envs x 8 agents per GPU (65,536 over 8 GPUs), mix of the reference's 100 "
                                         "training polylines, 3-frame stack written into a GPU-resident rollout buffer, uniform random policy")
     raise ValueError(workload)
 
@@ -677,7 +677,14 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
                          pcie_gbs_achieved=(h2d + d2h) * e2e_value / E / 1e9, pcie_note="per GPU; PCIe Gen5 x16 moves ~55 GB/s device to host"),
                 roofline=roof, cpu_baseline=cpu, episode_stats=summarize(stats))
     if world == 1 and workload == "c3" and args.policy in ("both", "pursuit"):
-        line["pursuit"] = measure_pursuit(eng, ss, E, max(50, min(K, 200)), 10, dev, stream)
+        # a second engine that does not end an episode at an infraction (cfg.terminated_at_infraction = False, one of the
+        # reference's own configurations): the pursuit driver runs the red lights, so with termination on it would be back
+        # at the start every ~33 steps; this way the episodes run their 200 steps through every junction of the route
+        eng.close()
+        eng2 = Engine(ss, E, A, device=str(dev), auto_reset=1, env_index_offset=offset, terminated_at_infraction=0)
+        line["pursuit"] = measure_pursuit(eng2, ss, E, max(50, min(K, 200)), 10, dev, stream)
+        line["pursuit"]["config"] = "C3 with terminated_at_infraction = False"
+        eng2.close()
     return line
 
 

@@ -160,8 +160,8 @@ def test_non_finite_actions_stay_inside_their_env(oracle):
 
 def test_clone_steps_like_the_original(oracle):
     """tde_clone (simulator.copy(), gym_env.py:110): device-to-device copy of every env, scenario tables shared."""
-    E, A = 200, 12
-    eng = _engine(S.validation_mix(A), E, A, auto_reset=1)
+    E, A = 200, 16
+    eng = _engine(S.validation_mix(10), E, A, auto_reset=1)
     eng.reset(seed=3)
     rng = np.random.default_rng(3)
     acts = [torch.from_numpy(np.stack([rng.uniform(-1, 1, E), rng.uniform(-0.3, 0.3, E)], 1).astype(np.float32)).cuda() for _ in range(12)]

@@ -189,22 +189,36 @@ def test_background_traffic_loader_and_light_program(tmp_path):
         S.compile_light_program([(1.0, ["green"])], 2)
 
 
-def test_training_mix_statistics_and_rollout_roofline():
-    """Config C5's synthetic scenario mix follows the statistics of the reference's training suite
-     and the rollout roofline formula adds the frame-stack traffic."""
-    from torchdriveenv_b200.roofline import rollout_bytes_per_env_step
+def test_training_mix_uses_the_reference_training_polylines():
+    """Config C5's scenario mix is built on the reference's own 100 training polylines (training_cases.yml, packaged as
+    torchdriveenv_b200/data/training_cases.json); beyond 100, synthetic polylines with the same statistics follow
+    (5-20 waypoints, spacing 12.9-15.0 m)."""
+    import os
+    from torchdriveenv_b200 import env_utils as U
+    polys = S.reference_training_polylines()
+    assert len(polys) == 100 and all(p.shape[1] == 2 and 5 <= len(p) <= 20 for p in polys)
+    assert abs(np.mean([len(p) for p in polys]) - 14.4) < 0.2
+    suite = U.load_default_train_data()
+    assert len(suite.locations) == 100 and [list(map(list, p)) for p in suite.waypoint_suite] == [p.tolist() for p in polys]
+    assert len(U.load_default_validation_data().locations) == 5
+    ref = "/root/reference/torchdriveenv/data/training_cases.yml"
+    if os.path.exists(ref):       # the packaged copy against the reference's file, loaded by the same loader
+        want = U.load_waypoint_suite_data(ref)
+        assert want.locations == suite.locations and want.waypoint_suite == suite.waypoint_suite
+        assert want.car_sequence_suite == suite.car_sequence_suite
+        assert [None if s is None else (s.agent_states, s.agent_attributes) for s in want.scenarios] == \
+               [None if s is None else (s.agent_states, s.agent_attributes) for s in suite.scenarios]
     ss = S.training_mix(12, 5, seed=2)
     assert len(ss.maps) == 12 and len(ss.scenarios) == 12 and ss.max_agents() == 5
-    for sc in ss.scenarios:
-        w = np.asarray(sc.waypoints, np.float64)
-        assert 5 <= len(w) <= 20
-        seg = np.hypot(*np.diff(w, axis=0).T)
-        assert seg.min() > 12.8 and seg.max() < 15.1
+    for sc, p in zip(ss.scenarios, polys):
+        assert np.array_equal(np.asarray(sc.waypoints, np.float32), p.astype(np.float32))
     packed = ss.pack(5)
     assert packed["scen_map"].tolist() == list(range(12))
     again = S.training_mix(12, 5, seed=2).pack(5)
     assert all(np.array_equal(packed[k], again[k]) for k in packed)      # seeded and deterministic
-    assert rollout_bytes_per_env_step(8, 3) == bytes_per_env_step(8, False) + 5 * 12288 + 8
+    extra = S.training_mix(102, 3, seed=1).scenarios[-1]                   # past the 100: synthetic, same statistics
+    seg = np.hypot(*np.diff(np.asarray(extra.waypoints, np.float64), axis=0).T)
+    assert 5 <= len(extra.waypoints) <= 20 and seg.min() > 12.8 and seg.max() < 15.1
 
 
 def test_save_video_writes_the_frames(tmp_path):

@@ -78,15 +78,29 @@ def load_labeled_data(data_dir) -> WaypointSuite:
     return suite
 
 
+def _suite_from_dict(data) -> WaypointSuite:
+    suite = WaypointSuite(locations=data["locations"], waypoint_suite=data["waypoint_suite"],
+                          car_sequence_suite=data["car_sequence_suite"], scenarios=data["scenarios"])
+    if suite.car_sequence_suite is not None:   # JSON object keys are strings; the reference's YAML has int agent slots
+        suite.car_sequence_suite = [None if c is None else {int(k): v for k, v in c.items()} for c in suite.car_sequence_suite]
+    if suite.scenarios is not None:
+        suite.scenarios = [Scenario(agent_states=s["agent_states"], agent_attributes=s["agent_attributes"],
+                                    recurrent_states=s.get("recurrent_states")) if s is not None else None
+                           for s in suite.scenarios]
+    return suite
+
+
 def _load_default_data(file_name) -> Optional[WaypointSuite]:
-    roots = [os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")]
+    """The suites the reference bundles (torchdriveenv/__init__.py:8, env_utils.py:108-123): a YAML of that name under
+    $TORCHDRIVEENV_DATA wins; otherwise the packaged copy torchdriveenv_b200/data/<name>.json (the same content, made by
+    tools/make_packaged_suites.py from the reference's data files)."""
     extra = os.environ.get("TORCHDRIVEENV_DATA")
-    if extra:
-        roots.append(extra)
-    for root in roots:
-        path = os.path.join(root, file_name)
-        if os.path.exists(path):
-            return load_waypoint_suite_data(path)
+    if extra and os.path.exists(os.path.join(extra, file_name)):
+        return load_waypoint_suite_data(os.path.join(extra, file_name))
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", os.path.splitext(file_name)[0] + ".json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return _suite_from_dict(json.load(f))
     return None
 
 

@@ -500,14 +500,27 @@ def synthetic_training_polyline(rng: np.random.Generator) -> np.ndarray:
     return np.round(np.asarray(pts, np.float64), 3)
 
 
+def reference_training_polylines() -> List[np.ndarray]:
+    """The 100 waypoint polylines of the reference's training suite (torchdriveenv/data/training_cases.yml:102-2980),
+    from the packaged copy torchdriveenv_b200/data/training_cases.json (tools/make_packaged_suites.py)."""
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "training_cases.json")
+    with open(path) as f:
+        suite = json.load(f)
+    return [np.asarray(p, np.float64) for p in suite["waypoint_suite"]]
+
+
 def training_mix(n_scenarios: int = 100, n_agents: int = 8, seed: int = 0) -> ScenarioSet:
-    """BASELINE config C5's scenario mix: ``n_scenarios`` synthetic training polylines, one map each
-    (two-lane road, junction arms with stop lines + lights at sharp turns), ego + replay NPCs.  The
-    reference's own training_cases.yml loads through env_utils.load_waypoint_suite_data when present."""
+    """BASELINE config C5's scenario mix: the reference's own training polylines (the first ``n_scenarios`` of the 100 in
+    training_cases.yml; beyond 100 synthetic ones with the same statistics follow), one map each (two-lane road, junction
+    arms with stop lines + lights at sharp turns), ego + constant-speed log-replay NPCs (the offline stand-in for the
+    Inverted AI agents)."""
     rng = np.random.default_rng(seed)
+    polys = reference_training_polylines()
     maps, scen = [], []
     for k in range(n_scenarios):
-        poly = synthetic_training_polyline(rng)
+        poly = polys[k] if k < len(polys) else synthetic_training_polyline(rng)
         maps.append(build_polyline_map(poly, f"train_{k}", with_lights=True))
         scen.append(make_scenario(k, poly, n_agents - 1, seed + 1000 + k, f"train_{k}"))
     return ScenarioSet(maps, scen)
