@@ -53,7 +53,7 @@ def build_scenarios(workload: str):
         return S.roundabout(16), "C2: 1024 envs x 16 agents, Roundabout, kinematics+collision+offroad+reward, no render"
     if workload == "c5":
         return S.training_mix(100, 8), ("C5: rollout collection, 8192 envs x 8 agents per GPU (65,536 over 8 GPUs), mix of the reference's 100 "
-                                        "training polylines, 3-frame stack written into a GPU-resident rollout buffer, uniform random policy")
+                                        "training polylines, 3-frame stack stored (scatter mode, no frame moved) into a GPU-resident rollout buffer, uniform random policy")
     raise ValueError(workload)
 
 
@@ -391,7 +391,7 @@ def run_c5(args, rank: int, local_rank: int, world: int):
     from torchdriveenv_b200.distributed import reduce_episode_stats, summarize
     from torchdriveenv_b200.engine import Engine
     from torchdriveenv_b200.rollout import RolloutCollector, uniform_policy
-    from torchdriveenv_b200.roofline import rollout_bytes_per_env_step
+    from torchdriveenv_b200.roofline import rollout_bytes_per_env_step, rollout_traffic_per_env_step
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     E, A, _ = WORKLOADS["c5"]
@@ -471,7 +471,9 @@ def run_c5(args, rank: int, local_rank: int, world: int):
                                            "every step (observations stay in the GPU rollout buffer)"),
                     roofline=dict(bound="hbm", kernel="tde_render_kernel<stacked> (+ tde_physics_kernel, one launch each per step)", achieved=achieved,
                                   peak=peak, unit="GB/s", frac=achieved / peak, traffic=None, algorithmic_bytes_per_launch=bpe * E,
-                                  bytes_per_env_step=bpe, avg_launch_ms=ms, peak_source=peak_src),
+                                  bytes_per_env_step=bpe, avg_launch_ms=ms, peak_source=peak_src,
+                                  moved_bytes_per_env_step=rollout_traffic_per_env_step(A, C5_N_STACK, col.frame_copy),
+                                  note="algorithmic = one new frame per env-step; the scatter store writes it n_stack times"),
                     cpu_baseline=cpu, episode_stats=summarize(stats))
         return line
     return None

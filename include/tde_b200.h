@@ -16,7 +16,8 @@
  *   tde_step_stacked,
  *   tde_render_stacked           the same with VecFrameStack (examples/rl_training.py:160) fused into the store
  *   tde_step_terminal            the same, keeping info["terminal_observation"] of SB3's VecEnv (the caller's contract)
- *   tde_step_rollout             the same, writing the next slot of a rollout buffer (collect_rollouts of the
+ *   tde_step_rollout,
+ *   tde_step_rollout_scatter     the same, writing the next slot of a rollout buffer (collect_rollouts of the
  *                                  trainer that drives the env, examples/rl_training.py:178-181,200)
  *   tde_get_state/tde_set_state  simulator.get_state() :127,371,392-393,397-399,420-423 / set_state :247
  *   tde_compute_infractions,
@@ -258,6 +259,18 @@ int tde_render_stacked(tde_handle* h, uint8_t* stack_dev, int32_t n_stack, void*
 int tde_step_rollout(tde_handle* h, const float* actions_dev, const uint8_t* stack_prev_dev, uint8_t* stack_next_dev,
                      int32_t n_stack, float* reward_dev, uint8_t* terminated_dev, uint8_t* truncated_dev,
                      float* info_dev, void* stream);
+
+/* Rollout collection without moving frames ("scatter" mode): the rollout buffer holds one stacked observation per
+   time slot, uint8[T + 1][E][3*n_stack][64][64] with `slot_stride_bytes` between slots.  stack_next_dev is slot t + 1.
+   The frame rendered by this step is stored into every stacked observation it belongs to - the newest channel group of
+   slot t + 1 and one group further down in each of the following slots_ahead - 1 slots (slots_ahead = min(n_stack,
+   slots left in the buffer from t + 1 on)) - so that a slot is complete when its own step comes: 3 * n_stack * 4096
+   bytes written per env and step, none read (tde_step_rollout reads (n_stack - 1) frames and writes n_stack).  For an
+   env that restarted, the older groups of slot t + 1 and of the following slots are zeroed.  The caller seeds the
+   older groups of the first n_stack - 1 slots of a new rollout from the observation it carries over (slot 0). */
+int tde_step_rollout_scatter(tde_handle* h, const float* actions_dev, uint8_t* stack_next_dev, int64_t slot_stride_bytes,
+                             int32_t slots_ahead, int32_t n_stack, float* reward_dev, uint8_t* terminated_dev,
+                             uint8_t* truncated_dev, float* info_dev, void* stream);
 
 /* The step with the terminal observation kept (SB3 VecEnv contract of the caller, examples/rl_training.py:159:
    SubprocVecEnv stores the last observation of a finished episode in info["terminal_observation"] before it

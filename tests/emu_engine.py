@@ -131,6 +131,14 @@ class EmuEngine:
                                               _p(self.terminated), _p(self.truncated), _p(self.info), None), "tde_step_rollout")
         return stack_next, self.reward, self.terminated, self.truncated, self.info
 
+    def step_rollout_scatter(self, actions, buffer_obs, t: int, n_stack: int):
+        a = self._act(actions)
+        stride = buffer_obs.strides[0]
+        ahead = min(int(n_stack), buffer_obs.shape[0] - 1 - t)
+        self._check(self.lib.tde_step_rollout_scatter(self.h, _p(a), _p(buffer_obs[t + 1]), stride, ahead, int(n_stack), _p(self.reward),
+                                                      _p(self.terminated), _p(self.truncated), _p(self.info), None), "tde_step_rollout_scatter")
+        return buffer_obs[t + 1], self.reward, self.terminated, self.truncated, self.info
+
     def render_stacked(self, stack, n_stack: int):
         self._check(self.lib.tde_render_stacked(self.h, _p(stack), int(n_stack), None), "tde_render_stacked")
         return stack

@@ -193,3 +193,52 @@ def test_emu_is_independent_of_warp_scheduling(policy):
     r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", os.path.join(here, "test_emu_parity.py"), "-k",
                         "c3_traffic or stacked or scenario_mix or edge_configurations or staged"], env=env, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("NS,T", [(3, 7), (4, 3), (2, 5)])
+def test_emu_rollout_scatter_fills_the_buffer_like_vec_frame_stack(oracle, NS, T):
+    """tde_step_rollout_scatter: every slot of a [T + 1, E, 3 n, 64, 64] rollout buffer must hold what VecFrameStack
+    would have produced (oracle frames stacked oldest first, zeros before a restart), over three rollouts with the
+    carry-over of the last slot - without the kernel ever reading a frame."""
+    from emu_engine import _aligned
+    E, A = 20, 6
+    ss = S.traffic_lights(A)
+    cfg = dict(auto_reset=1, max_environment_steps=9)
+    eng = EmuEngine(ss, E, A, **cfg)
+    orc = oracle.OracleEnvSet(default_config(num_envs=E, max_agents=A, **cfg), eng.packed)
+    eng.reset(seed=13); orc.reset(seed=13)
+    buf = _aligned((T + 1, E, 3 * NS, 64, 64), np.uint8)
+    eng.render_stacked(buf[0], NS)
+    frames, age = [orc.render()], np.zeros(E, np.int64)
+
+    def want_stack():
+        w = np.zeros((E, 3 * NS, 64, 64), np.uint8)
+        for slot in range(NS):
+            back = NS - 1 - slot
+            if back < len(frames):
+                have = age >= back
+                w[have, 3 * slot:3 * slot + 3] = frames[-1 - back][have]
+        return w
+
+    def seed_older():
+        for j in range(1, min(NS, T + 1)):
+            buf[j][:, : 3 * (NS - j)] = buf[0][:, 3 * j:]
+
+    rng = np.random.default_rng(13)
+    n_done = 0
+    for r in range(3):
+        if r:
+            buf[0] = buf[T]
+        assert np.array_equal(buf[0], want_stack())
+        seed_older()
+        for t in range(T):
+            a = np.stack([rng.uniform(-1, 1, E), rng.uniform(-0.3, 0.3, E)], 1).astype(np.float32)
+            eng.step_rollout_scatter(a, buf, t, NS)
+            oobs, orr, ote, otr, oinfo = orc.step(a)
+            d = (ote | otr).astype(bool)
+            frames.append(oobs)
+            age = np.where(d, 0, age + 1)
+            assert np.array_equal(buf[t + 1], want_stack()), f"rollout {r} step {t}"
+            assert np.array_equal(eng.reward, orr) and np.array_equal(eng.info, oinfo)
+            n_done += int(d.sum())
+    assert n_done > 5

@@ -170,7 +170,8 @@ def test_background_traffic_agents_drive_at_constant_velocity(oracle):
     venv.close()
 
 
-def test_rollout_collector_fills_the_buffer_like_vec_frame_stack(oracle):
+@pytest.mark.parametrize("frame_copy", ["scatter", "shift"])
+def test_rollout_collector_fills_the_buffer_like_vec_frame_stack(oracle, frame_copy):
     """Config C5 in small: RolloutCollector on the training-scenario mix.  Every slot of the GPU rollout buffer
     must hold what SubprocVecEnv + VecFrameStack + RolloutBuffer.add would have stored (examples/rl_training.py
     :159-160): oracle frames stacked oldest first, zeros before a restart, rewards / flags / episode starts."""
@@ -181,7 +182,7 @@ def test_rollout_collector_fills_the_buffer_like_vec_frame_stack(oracle):
     eng = Engine(ss, E, A, device="cuda:0", auto_reset=1, max_environment_steps=12)
     orc = oracle.OracleEnvSet(default_config(num_envs=E, max_agents=A, auto_reset=1, max_environment_steps=12), eng.packed)
     orc.reset(seed=11)
-    col = RolloutCollector(eng, T, n_stack=NS, seed=11, with_info=True)
+    col = RolloutCollector(eng, T, n_stack=NS, seed=11, with_info=True, frame_copy=frame_copy)
     rng = np.random.default_rng(11)
     acts = np.stack([rng.uniform(-1, 1, (3 * T, E)), rng.uniform(-0.3, 0.3, (3 * T, E))], -1).astype(np.float32)
     k = [0]

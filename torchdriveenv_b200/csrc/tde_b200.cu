@@ -498,10 +498,11 @@ static void free_scenarios(tde_handle* h) {
 template <int AH>
 static int configure_render(tde_handle* h) {
     size_t smem = TDE_RENDER_SMEM_BYTES;   // groups + warps + the spread and span-mask tables
-    CUDA_TRY(h, cudaFuncSetAttribute(tde_render_kernel<AH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(h, cudaFuncSetAttribute(tde_render_kernel<AH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(h, cudaFuncSetAttribute(tde_render_kernel<AH, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(h, cudaFuncSetAttribute(tde_render_kernel<AH, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(h, cudaFuncSetAttribute(tde_render_kernel<AH, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tde_render_kernel<AH, false>, TDE_WARPS_PER_BLOCK * 32, smem));
+    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tde_render_kernel<AH, 0>, TDE_WARPS_PER_BLOCK * 32, smem));
     if (per_sm < 1) per_sm = 1;
     // tuning knobs for co-residency experiments (tools/coresident.py): cap the resident blocks per SM of either kernel
     if (const char* v = std::getenv("TDE_RENDER_BLOCKS_CAP")) per_sm = std::max(1, std::min(per_sm, std::atoi(v)));
@@ -889,7 +890,7 @@ static cudaError_t launch_step(Kernel k, int grid, int threads, size_t smem, cud
 
 static int step_impl(tde_handle* h, int32_t phases, const float* actions, uint8_t* obs, int32_t n_stack, float* reward,
                      uint8_t* terminated, uint8_t* truncated, float* info, void* stream, const uint8_t* obs_prev = nullptr,
-                     uint8_t* terminal_obs = nullptr, int e_begin = 0, int e_end = -1) {
+                     uint8_t* terminal_obs = nullptr, int e_begin = 0, int e_end = -1, long long slot_stride = 0, int slots_ahead = 0) {
     if (!h) return TDE_E_INVAL;
     if (n_stack < 1 || n_stack > 8) return fail(h, TDE_E_INVAL, "n_stack must be in 1..8");
     if (!h->uploaded || !h->was_reset) return fail(h, TDE_E_STATE, "tde_step: upload scenarios and reset first");
@@ -907,6 +908,8 @@ static int step_impl(tde_handle* h, int32_t phases, const float* actions, uint8_
     p.phases = phases; p.actions = actions; p.obs = obs; p.reward = reward; p.terminated = terminated;
     p.truncated = truncated; p.info = info; p.n_stack = n_stack;
     p.obs_prev = obs_prev ? obs_prev : obs;
+    p.slot_stride = slot_stride; p.slots_ahead = slots_ahead;
+    const bool scatter = slot_stride != 0;
     if (e_end >= 0) { p.e_begin = e_begin; p.e_end = e_end; }   // a slice of the envs (tde_step_host's chunks)
     cudaStream_t st = (cudaStream_t)stream;
     const int threads = TDE_WARPS_PER_BLOCK * 32;
@@ -935,12 +938,15 @@ static int step_impl(tde_handle* h, int32_t phases, const float* actions, uint8_
     }
     if (render) {
         const int grid = std::min(h->grid_render, want_render);
-        if (n_stack > 1) {
-            if (h->A <= 32) CUDA_TRY(h, launch_step(tde_render_kernel<1, true>, grid, threads, h->smem_render, st, p));
-            else CUDA_TRY(h, launch_step(tde_render_kernel<2, true>, grid, threads, h->smem_render, st, p));
+        if (scatter) {
+            if (h->A <= 32) CUDA_TRY(h, launch_step(tde_render_kernel<1, 2>, grid, threads, h->smem_render, st, p));
+            else CUDA_TRY(h, launch_step(tde_render_kernel<2, 2>, grid, threads, h->smem_render, st, p));
+        } else if (n_stack > 1) {
+            if (h->A <= 32) CUDA_TRY(h, launch_step(tde_render_kernel<1, 1>, grid, threads, h->smem_render, st, p));
+            else CUDA_TRY(h, launch_step(tde_render_kernel<2, 1>, grid, threads, h->smem_render, st, p));
         } else {
-            if (h->A <= 32) CUDA_TRY(h, launch_step(tde_render_kernel<1, false>, grid, threads, h->smem_render, st, p));
-            else CUDA_TRY(h, launch_step(tde_render_kernel<2, false>, grid, threads, h->smem_render, st, p));
+            if (h->A <= 32) CUDA_TRY(h, launch_step(tde_render_kernel<1, 0>, grid, threads, h->smem_render, st, p));
+            else CUDA_TRY(h, launch_step(tde_render_kernel<2, 0>, grid, threads, h->smem_render, st, p));
         }
         h->launches++;
     }
@@ -960,11 +966,11 @@ static int step_impl(tde_handle* h, int32_t phases, const float* actions, uint8_
         q.obs_prev = obs;   // the stack was shifted by the first pass; a re-initialised env only keeps zeros anyway
         const int grid = std::min(h->grid_render, want_render);
         if (n_stack > 1) {
-            if (h->A <= 32) TDE_LAUNCH(grid, threads, h->smem_render, st, tde_render_kernel<1, true>)(q);
-            else TDE_LAUNCH(grid, threads, h->smem_render, st, tde_render_kernel<2, true>)(q);
+            if (h->A <= 32) TDE_LAUNCH(grid, threads, h->smem_render, st, tde_render_kernel<1, 1>)(q);
+            else TDE_LAUNCH(grid, threads, h->smem_render, st, tde_render_kernel<2, 1>)(q);
         } else {
-            if (h->A <= 32) TDE_LAUNCH(grid, threads, h->smem_render, st, tde_render_kernel<1, false>)(q);
-            else TDE_LAUNCH(grid, threads, h->smem_render, st, tde_render_kernel<2, false>)(q);
+            if (h->A <= 32) TDE_LAUNCH(grid, threads, h->smem_render, st, tde_render_kernel<1, 0>)(q);
+            else TDE_LAUNCH(grid, threads, h->smem_render, st, tde_render_kernel<2, 0>)(q);
         }
         CUDA_TRY(h, cudaGetLastError());
         h->launches += 3;
@@ -1002,6 +1008,19 @@ extern "C" int tde_step_rollout(tde_handle* h, const float* actions, const uint8
         if (a < b + bytes && b < a + bytes) return fail(h, TDE_E_INVAL, "tde_step_rollout: stack_prev and stack_next overlap");
     }
     return step_impl(h, TDE_PH_ALL, actions, stack_next, n_stack, reward, terminated, truncated, info, stream, stack_prev);
+}
+
+extern "C" int tde_step_rollout_scatter(tde_handle* h, const float* actions, uint8_t* stack_next, int64_t slot_stride_bytes, int32_t slots_ahead,
+                                        int32_t n_stack, float* reward, uint8_t* terminated, uint8_t* truncated, float* info, void* stream) {
+    if (h && !stack_next) return fail(h, TDE_E_INVAL, "tde_step_rollout_scatter: stack_next is null");
+    if (h && n_stack < 2) return fail(h, TDE_E_INVAL, "tde_step_rollout_scatter: n_stack must be in 2..8");
+    if (h && (slots_ahead < 1 || slots_ahead > n_stack)) return fail(h, TDE_E_INVAL, "tde_step_rollout_scatter: slots_ahead must be in 1..n_stack");
+    if (h) {
+        const long long slot = (long long)h->E * n_stack * TDE_OBS_C * TDE_OBS_H * TDE_OBS_W;
+        if (slot_stride_bytes < slot || (slot_stride_bytes & 15)) return fail(h, TDE_E_INVAL, "tde_step_rollout_scatter: slot_stride_bytes must be >= one slot and a multiple of 16");
+    }
+    return step_impl(h, TDE_PH_ALL, actions, stack_next, n_stack, reward, terminated, truncated, info, stream, nullptr, nullptr, 0, -1,
+                     (long long)slot_stride_bytes, slots_ahead);
 }
 
 extern "C" int tde_step(tde_handle* h, const float* actions, uint8_t* obs, float* reward, uint8_t* terminated,

@@ -97,6 +97,8 @@ struct StepParams {
     const uint8_t* render_mask;  // non-null: only envs with a non-zero byte are rendered (strided, no tickets)
     uint8_t* restart;    // [E] 1 = the env was reset since its last stacked frame
     int n_stack;         // frames per env in obs (1 = plain observation)
+    int slots_ahead;     // scatter mode (rollout buffer): slots from the one being written to the end of the buffer, 1..n_stack
+    long long slot_stride;   // scatter mode: bytes between consecutive time slots of the buffer
     uint32_t pal[3][4];  // per channel: 16 class bytes
     float ppm, ppmy;
     // physics kernel, STAGED launches: the map tables as one blob (16 B header per map: offsets of its triangle records,

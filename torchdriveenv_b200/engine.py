@@ -154,6 +154,33 @@ class Engine:
                                               _ptr(outs[1]), _ptr(outs[2]), _ptr(outs[3]), self._stream()), "tde_step_rollout")
         return stack_next, outs[0], outs[1], outs[2], outs[3]
 
+    def step_rollout_scatter(self, actions: torch.Tensor, buffer_obs: torch.Tensor, t: int, n_stack: int,
+                             reward: Optional[torch.Tensor] = None, terminated: Optional[torch.Tensor] = None,
+                             truncated: Optional[torch.Tensor] = None, info: Optional[torch.Tensor] = None):
+        """tde_step_rollout_scatter: step t of a rollout whose stacked observations live in ``buffer_obs``
+        [T + 1, E, 3*n_stack, 64, 64] (contiguous).  The new frame is stored into slot t + 1 and, one channel group further
+        down each, into the following n_stack - 1 slots (as far as the buffer goes); nothing is read or moved."""
+        a = actions.to(device=self.device, dtype=torch.float32).contiguous().view(self.E, 2)
+        T1 = int(buffer_obs.shape[0])
+        if buffer_obs.dim() != 5 or not buffer_obs.is_contiguous() or buffer_obs.dtype != torch.uint8 or buffer_obs.device != self.obs.device:
+            raise ValueError("step_rollout_scatter: buffer_obs must be a contiguous uint8 [T + 1, E, 3*n_stack, 64, 64] tensor on the engine's device")
+        self._check_stack(buffer_obs[0], n_stack)
+        if not 0 <= t < T1 - 1:
+            raise ValueError("step_rollout_scatter: t out of range")
+        outs = []
+        for x, own, shape, dt in ((reward, self.reward, (self.E,), torch.float32), (terminated, self.terminated, (self.E,), torch.uint8),
+                                  (truncated, self.truncated, (self.E,), torch.uint8), (info, self.info, (self.E, TDE_INFO_STRIDE), torch.float32)):
+            if x is None:
+                x = own
+            elif tuple(x.shape) != shape or x.dtype != dt or not x.is_contiguous() or x.device != self.obs.device:
+                raise ValueError(f"step_rollout_scatter: output rows must be contiguous {dt} tensors of shape {shape} on {self.obs.device}")
+            outs.append(x)
+        stride = int(buffer_obs.stride(0)) * buffer_obs.element_size()
+        ahead = min(int(n_stack), T1 - 1 - t)
+        self._check(self.lib.tde_step_rollout_scatter(self.h, _ptr(a), _ptr(buffer_obs[t + 1]), stride, ahead, int(n_stack), _ptr(outs[0]),
+                                                      _ptr(outs[1]), _ptr(outs[2]), _ptr(outs[3]), self._stream()), "tde_step_rollout_scatter")
+        return buffer_obs[t + 1], outs[0], outs[1], outs[2], outs[3]
+
     def render_stacked(self, stack: torch.Tensor, n_stack: int) -> torch.Tensor:
         self._check_stack(stack, n_stack)
         self._check(self.lib.tde_render_stacked(self.h, _ptr(stack), int(n_stack), self._stream()), "tde_render_stacked")

@@ -4,9 +4,11 @@ The reference collects rollouts with stable-baselines3 (examples/rl_training.py:
 ``SubprocVecEnv`` + ``VecFrameStack(n_stack, channels_order="first")`` feeding ``PPO.learn`` ->
 ``collect_rollouts`` -> ``RolloutBuffer.add``): every step the stacked observation, action, reward and
 episode-start flag of every env are copied into the buffer on the host.  Here the buffer lives in HBM
-and the render kernel writes the shifted frame stack of step t + 1 straight into its slot
-(``tde_step_rollout``: older frames read from slot t), so filling the buffer costs no copy pass; reward
-and flags are written by the physics kernel into the buffer's own rows.
+and the render kernel stores every new frame straight into the stacked observations it belongs to
+(``tde_step_rollout_scatter``: the newest channel group of slot t + 1 and one group further down in each
+of the next n_stack - 1 slots), so the buffer is filled without reading or moving a frame; reward and
+flags are written by the physics kernel into the buffer's own rows.  ``frame_copy="shift"`` selects the
+older ``tde_step_rollout`` (older frames read from slot t, shifted stack written to slot t + 1).
 
 Field names and shapes follow SB3's ``RolloutBuffer`` ([n_steps, n_envs, ...]); ``episode_starts[t]``
 is 1 where ``observations[t]`` is the first observation of an episode.  ``returns_and_advantages`` is
@@ -57,9 +59,13 @@ class RolloutCollector:
     episode-start flags over to slot 0 of the next rollout.
     """
 
-    def __init__(self, engine: Engine, n_steps: int, n_stack: int = 3, seed: int = 0, with_info: bool = False):
+    def __init__(self, engine: Engine, n_steps: int, n_stack: int = 3, seed: int = 0, with_info: bool = False,
+                 frame_copy: str = "scatter"):
         if n_stack < 2 or n_stack > 8:
             raise ValueError("n_stack must be in 2..8 (use Engine.step for a plain observation)")
+        if frame_copy not in ("scatter", "shift"):
+            raise ValueError("frame_copy must be 'scatter' or 'shift'")
+        self.frame_copy = frame_copy
         self.engine, self.n_steps, self.n_stack = engine, int(n_steps), int(n_stack)
         self.buffer = RolloutBuffer(n_steps, engine.E, n_stack, engine.device, with_info=with_info)
         self._info = None if with_info else torch.zeros((engine.E, TDE_INFO_STRIDE), dtype=torch.float32, device=engine.device)
@@ -74,7 +80,17 @@ class RolloutCollector:
         self.engine.render_stacked(b.observations[0], self.n_stack)
         b.episode_starts[0].fill_(1)
         self._started = True
+        self._seed_older_groups()
         return b.observations[0]
+
+    def _seed_older_groups(self) -> None:
+        """Scatter mode: the frames of slot 0 also belong to the next n_stack - 1 stacked observations (one channel group
+        further down each); once per rollout they are put there, after that the render kernel keeps the slots complete."""
+        if self.frame_copy != "scatter":
+            return
+        b, n = self.buffer, self.n_stack
+        for j in range(1, min(n, self.n_steps + 1)):
+            b.observations[j][:, : 3 * (n - j)].copy_(b.observations[0][:, 3 * j:])
 
     def collect(self, policy: Policy) -> RolloutBuffer:
         b, eng, T = self.buffer, self.engine, self.n_steps
@@ -83,6 +99,7 @@ class RolloutCollector:
         elif self.num_timesteps:
             b.observations[0].copy_(b.observations[T])      # one slot per rollout: 1/n_steps of the traffic
             b.episode_starts[0].copy_(b.episode_starts[T])
+            self._seed_older_groups()
         for t in range(T):
             out = policy(b.observations[t])
             if isinstance(out, (tuple, list)):
@@ -92,9 +109,14 @@ class RolloutCollector:
             else:
                 act = out
             b.actions[t].copy_(act.reshape(eng.E, 2))
-            eng.step_rollout(b.actions[t], b.observations[t], b.observations[t + 1], self.n_stack,
-                             reward=b.rewards[t], terminated=b.terminated[t], truncated=b.truncated[t],
-                             info=b.infos[t] if b.infos is not None else self._info)
+            if self.frame_copy == "scatter":
+                eng.step_rollout_scatter(b.actions[t], b.observations, t, self.n_stack,
+                                         reward=b.rewards[t], terminated=b.terminated[t], truncated=b.truncated[t],
+                                         info=b.infos[t] if b.infos is not None else self._info)
+            else:
+                eng.step_rollout(b.actions[t], b.observations[t], b.observations[t + 1], self.n_stack,
+                                 reward=b.rewards[t], terminated=b.terminated[t], truncated=b.truncated[t],
+                                 info=b.infos[t] if b.infos is not None else self._info)
             torch.bitwise_or(b.terminated[t], b.truncated[t], out=b.episode_starts[t + 1])
         self.num_timesteps += T * eng.E
         return b

@@ -15,8 +15,15 @@ def c4_bytes_per_env(num_agents: int) -> int:
 
 
 def rollout_bytes_per_env_step(num_agents: int, n_stack: int) -> int:
-    """Rollout collection (config C5, tde_step_rollout): the step without its plain observation, plus the
-    frame stack written into the next buffer slot (n_stack frames) from the previous slot (n_stack - 1
-    frames read), plus the action row kept in the buffer (8 B)."""
+    """Rollout collection (config C5): ALGORITHMIC bytes only - the step with ONE new frame per env (12,288 B) plus the
+    action row kept in the buffer (8 B).  How often the implementation stores that frame (n_stack times in scatter mode;
+    shift mode additionally reads n_stack - 1 frames) is traffic, not algorithm: see rollout_traffic_per_env_step."""
+    return bytes_per_env_step(num_agents, True) + 8
+
+
+def rollout_traffic_per_env_step(num_agents: int, n_stack: int, frame_copy: str = "scatter") -> int:
+    """Bytes the rollout step actually moves per env: scatter mode writes the frame n_stack times; shift mode reads
+    n_stack - 1 frames and writes n_stack."""
     frame = 3 * 64 * 64
-    return bytes_per_env_step(num_agents, False) + (2 * n_stack - 1) * frame + 8
+    frames = n_stack if frame_copy == "scatter" else 2 * n_stack - 1
+    return bytes_per_env_step(num_agents, False) + frames * frame + 8
