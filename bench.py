@@ -398,10 +398,10 @@ def run_c5(args, rank: int, local_rank: int, world: int):
     ss, desc = build_scenarios("c5")
     eng = Engine(ss, E, A, device=str(dev), auto_reset=1, env_index_offset=rank * E)
     T = C5_N_STEPS
-    col = RolloutCollector(eng, T, n_stack=C5_N_STACK, seed=0)
+    col = RolloutCollector(eng, T, n_stack=C5_N_STACK, seed=0, cuda_graph=True)    # a rollout = one CUDA graph replay
     policy = uniform_policy(seed=1000 + rank)
     K = max(T, (args.steps // T) * T)          # whole rollouts
-    W = max(1, -(-args.warmup // T))
+    W = max(3, -(-args.warmup // T))           # >= 3: the eager rollout, the captured one, one replay
     stream = torch.cuda.current_stream(dev)
 
     def barrier():
@@ -437,7 +437,7 @@ def run_c5(args, rank: int, local_rank: int, world: int):
 
     def host_policy_step(t, k):
         a = pin_act[k % 8].to(dev, non_blocking=True)
-        eng.step_rollout(a, b.observations[t], b.observations[t + 1], C5_N_STACK, reward=b.rewards[t], terminated=b.terminated[t], truncated=b.truncated[t])
+        eng.step_rollout_scatter(a, b.observations, t, C5_N_STACK, reward=b.rewards[t], terminated=b.terminated[t], truncated=b.truncated[t])
         host_rew.copy_(b.rewards[t], non_blocking=True)
         host_flags[0].copy_(b.terminated[t], non_blocking=True)
         host_flags[1].copy_(b.truncated[t], non_blocking=True)
@@ -465,9 +465,9 @@ def run_c5(args, rank: int, local_rank: int, world: int):
                                 rollout_steps=T, rollout_buffer_bytes=b.nbytes(),
                                 parallelism=f"env-sharded x{world}, no collectives on the step path",
                                 l2="each step writes a fresh %.0f MB buffer slot: larger than the 126 MB L2" % (E * 9 * 4096 / 1e6)),
-                    clocks=clocks, gpu_launches=int(gpu_launches),
+                    clocks=clocks, gpu_launches=2 * K,      # one physics + one render launch per step (replayed from the captured graph)
                     e2e=dict(value=E * world * K2 / (float(e2e_ms.item()) * 1e-3), unit=UNIT, h2d_bytes_per_step=E * 8, d2h_bytes_per_step=E * 6,
-                             steps=K2, api="Engine.step_rollout with actions from pinned host memory and reward/terminated/truncated read back "
+                             steps=K2, api="Engine.step_rollout_scatter with actions from pinned host memory and reward/terminated/truncated read back "
                                            "every step (observations stay in the GPU rollout buffer)"),
                     roofline=dict(bound="hbm", kernel="tde_render_kernel<stacked> (+ tde_physics_kernel, one launch each per step)", achieved=achieved,
                                   peak=peak, unit="GB/s", frac=achieved / peak, traffic=None, algorithmic_bytes_per_launch=bpe * E,

@@ -202,3 +202,57 @@ def test_staged_map_tables_match_the_default_launch(oracle, E, A):
         assert np.array_equal(eng.get_state().cpu().numpy(), orc.state), f"step {k}: state"
         assert np.array_equal(eng.get_infractions().cpu().numpy(), orc.infractions), f"step {k}: infractions"
         assert np.array_equal(info.cpu().numpy(), oinfo) and np.array_equal(obs.cpu().numpy(), oobs), f"step {k}"
+
+
+def test_rollout_collector_cuda_graph_replay(oracle):
+    """RolloutCollector(cuda_graph=True): the first rollout runs eagerly, the second is captured into one CUDA graph and
+    replayed, the following ones only replay it.  Every buffer slot of five rollouts must hold what the eager collector
+    (and VecFrameStack over the oracle's frames) produces."""
+    from torchdriveenv_b200.engine import Engine
+    from torchdriveenv_b200.rollout import RolloutCollector
+    E, A, T, NS, R = 48, 6, 6, 3, 5
+    ss = S.traffic_lights(A)
+    cfg = dict(auto_reset=1, max_environment_steps=10)
+    eng = Engine(ss, E, A, device="cuda:0", **cfg)
+    orc = oracle.OracleEnvSet(default_config(num_envs=E, max_agents=A, **cfg), eng.packed)
+    orc.reset(seed=19)
+    col = RolloutCollector(eng, T, n_stack=NS, seed=19, cuda_graph=True)
+    rng = np.random.default_rng(19)
+    tape = torch.from_numpy(np.stack([rng.uniform(-1, 1, (R * T, E)), rng.uniform(-0.3, 0.3, (R * T, E))], -1).astype(np.float32)).cuda()
+    cur = torch.zeros((T, E, 2), dtype=torch.float32, device="cuda")
+    state = dict(r=0, t=0)
+
+    def policy(obs, out=None):
+        t = state["t"]; state["t"] += 1
+        return out.copy_(cur[t])
+
+    def before_rollout(n_steps):
+        cur.copy_(tape[state["r"] * T:(state["r"] + 1) * T]); state["r"] += 1; state["t"] = 0
+
+    policy.writes_into, policy.before_rollout = True, before_rollout
+    frames, age = [orc.render()], np.zeros(E, np.int64)
+
+    def want_stack():
+        w = np.zeros((E, 3 * NS, 64, 64), np.uint8)
+        for slot in range(NS):
+            back = NS - 1 - slot
+            if back < len(frames):
+                have = age >= back
+                w[have, 3 * slot:3 * slot + 3] = frames[-1 - back][have]
+        return w
+
+    for r in range(R):
+        b = col.collect(policy)
+        torch.cuda.synchronize()
+        obs = b.observations.cpu().numpy()
+        assert np.array_equal(obs[0], want_stack()), f"rollout {r}: slot 0"
+        for t in range(T):
+            a = tape[r * T + t].cpu().numpy()
+            oobs, orr, ote, otr, oinfo = orc.step(a)
+            d = (ote | otr).astype(bool)
+            frames.append(oobs); age = np.where(d, 0, age + 1)
+            assert np.array_equal(obs[t + 1], want_stack()), f"rollout {r} step {t}"
+            assert np.array_equal(b.rewards[t].cpu().numpy(), orr) and np.array_equal(b.actions[t].cpu().numpy(), a)
+            assert np.array_equal(b.episode_starts[t + 1].cpu().numpy().astype(bool), d)
+    assert col._graph is not None and col.num_timesteps == R * T * E
+    np.testing.assert_allclose(eng.episode_stats(), orc.stats, rtol=1e-9)

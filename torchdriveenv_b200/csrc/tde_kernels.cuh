@@ -316,6 +316,9 @@ __device__ __noinline__ MeshInfr mesh_infractions_warp(const MapRef R, const Box
         if (mine && in_grid) {
             const int cell = (int)fy * M.gnx + (int)fx;
             bool fetch = true;
+            // staged: the per-cell summary (2 bytes in shared memory) settles a SAFE corner and a centre that sits on the lane
+            // the agent follows without touching the 8-byte cell records.  (The same summary as a 64 KB global table for the
+            // launch that does not stage was measured and dropped: physics 56.0 vs 54.2 us, C4 offroad 366 vs 347 us.)
             if (STAGED) {
                 const uint32_t c16 = tde_lds_u16(R.cells_s + 2u * (uint32_t)cell);
                 if (k < 4) fetch = !(c16 & TDE_CELL_SAFE);       // a SAFE corner needs nothing else
@@ -323,7 +326,7 @@ __device__ __noinline__ MeshInfr mesh_infractions_warp(const MapRef R, const Box
                     const int t0 = (int)(c16 & 0x7fffu);
                     if (t0 == TDE_CELL16_NONE) { ww_settled = true; fetch = false; }   // nothing under the centre: 0
                     else {
-                        const Tri3 T = tde_load_tri<true>(nullptr, R.tri_s, t0);
+                        const Tri3 T = tde_load_tri<STAGED>(M.tri, R.tri_s, t0);
                         if (tde_tri_contains(T, b.x, b.y, dc, ds) && fmaxf(-(b.c * dc + b.s * ds), 0.0f) == 0.0f) { ww_settled = true; fetch = false; }
                     }
                 }

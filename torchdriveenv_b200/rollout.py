@@ -60,12 +60,19 @@ class RolloutCollector:
     """
 
     def __init__(self, engine: Engine, n_steps: int, n_stack: int = 3, seed: int = 0, with_info: bool = False,
-                 frame_copy: str = "scatter"):
+                 frame_copy: str = "scatter", cuda_graph: bool = False):
         if n_stack < 2 or n_stack > 8:
             raise ValueError("n_stack must be in 2..8 (use Engine.step for a plain observation)")
         if frame_copy not in ("scatter", "shift"):
             raise ValueError("frame_copy must be 'scatter' or 'shift'")
         self.frame_copy = frame_copy
+        # cuda_graph=True: from the third rollout on, collect() replays one captured CUDA graph of the whole rollout (the
+        # tde_* calls only enqueue work on the current stream, so they capture).  For policies made of static-shape GPU ops
+        # that read their inputs from fixed tensors; a policy's `before_rollout(n_steps)` hook runs outside the graph (the
+        # place for anything that cannot be captured, e.g. drawing random numbers from a torch.Generator).
+        self.cuda_graph = bool(cuda_graph)
+        self._graph = None
+        self._graph_policy = None
         self.engine, self.n_steps, self.n_stack = engine, int(n_steps), int(n_stack)
         self.buffer = RolloutBuffer(n_steps, engine.E, n_stack, engine.device, with_info=with_info)
         self._info = None if with_info else torch.zeros((engine.E, TDE_INFO_STRIDE), dtype=torch.float32, device=engine.device)
@@ -93,22 +100,43 @@ class RolloutCollector:
             b.observations[j][:, : 3 * (n - j)].copy_(b.observations[0][:, 3 * j:])
 
     def collect(self, policy: Policy) -> RolloutBuffer:
-        b, eng, T = self.buffer, self.engine, self.n_steps
         if not self._started:
             self.reset()
-        elif self.num_timesteps:
+        hook = getattr(policy, "before_rollout", None)
+        if hook is not None:
+            hook(self.n_steps)
+        if not (self.cuda_graph and self.num_timesteps):
+            self._collect_body(policy, carry=self.num_timesteps > 0)      # first rollout (no carry-over) / plain mode
+        else:
+            if self._graph is None or self._graph_policy is not policy:
+                torch.cuda.synchronize(self.engine.device)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._collect_body(policy, carry=True)
+                self._graph, self._graph_policy = g, policy              # the capture does not run the work: replay it now
+            self._graph.replay()
+        self.num_timesteps += self.n_steps * self.engine.E
+        return self.buffer
+
+    def _collect_body(self, policy: Policy, carry: bool) -> None:
+        b, eng, T = self.buffer, self.engine, self.n_steps
+        if carry:
             b.observations[0].copy_(b.observations[T])      # one slot per rollout: 1/n_steps of the traffic
             b.episode_starts[0].copy_(b.episode_starts[T])
             self._seed_older_groups()
+        into = bool(getattr(policy, "writes_into", False))   # the policy stores its actions in the buffer row itself
         for t in range(T):
-            out = policy(b.observations[t])
-            if isinstance(out, (tuple, list)):
-                act, val, logp = out
-                b.values[t].copy_(val.reshape(-1))
-                b.log_probs[t].copy_(logp.reshape(-1))
+            if into:
+                policy(b.observations[t], out=b.actions[t])
             else:
-                act = out
-            b.actions[t].copy_(act.reshape(eng.E, 2))
+                out = policy(b.observations[t])
+                if isinstance(out, (tuple, list)):
+                    act, val, logp = out
+                    b.values[t].copy_(val.reshape(-1))
+                    b.log_probs[t].copy_(logp.reshape(-1))
+                else:
+                    act = out
+                b.actions[t].copy_(act.reshape(eng.E, 2))
             if self.frame_copy == "scatter":
                 eng.step_rollout_scatter(b.actions[t], b.observations, t, self.n_stack,
                                          reward=b.rewards[t], terminated=b.terminated[t], truncated=b.truncated[t],
@@ -117,9 +145,7 @@ class RolloutCollector:
                 eng.step_rollout(b.actions[t], b.observations[t], b.observations[t + 1], self.n_stack,
                                  reward=b.rewards[t], terminated=b.terminated[t], truncated=b.truncated[t],
                                  info=b.infos[t] if b.infos is not None else self._info)
-            torch.bitwise_or(b.terminated[t], b.truncated[t], out=b.episode_starts[t + 1])
-        self.num_timesteps += T * eng.E
-        return b
+        torch.bitwise_or(b.terminated, b.truncated, out=b.episode_starts[1:])     # one launch per rollout, not per step
 
     def last_observation(self) -> torch.Tensor:
         return self.buffer.observations[self.n_steps]
@@ -147,16 +173,36 @@ class RolloutCollector:
 
 def uniform_policy(action_low=(-1.0, -0.3), action_high=(1.0, 0.3), seed: int = 0) -> Policy:
     """U(low, high) actions drawn on the GPU (the reference action space, gym_env.py:83-84): the stand-in
-    for the CnnPolicy of examples/rl_training.py when no trainer is attached."""
-    state: Dict[str, Optional[torch.Generator]] = {"gen": None}
+    for the CnnPolicy of examples/rl_training.py when no trainer is attached.  The uniforms of a whole rollout are drawn in
+    `before_rollout` (outside a CUDA graph) into one fixed tensor; a step scales its slice straight into the caller's row
+    (`writes_into`): one small launch per step, capturable."""
+    state: Dict[str, object] = {"gen": None, "u": None, "k": 0}
 
-    def policy(obs: torch.Tensor) -> torch.Tensor:
+    def setup(device):
+        state["gen"] = torch.Generator(device=device)
+        state["gen"].manual_seed(seed)
+        state["lo"] = torch.tensor(action_low, dtype=torch.float32, device=device)
+        state["span"] = torch.tensor(action_high, dtype=torch.float32, device=device) - state["lo"]
+
+    def before_rollout(n_steps: int, num_envs: Optional[int] = None, device=None) -> None:
+        if state["u"] is not None:
+            torch.rand(state["u"].shape, generator=state["gen"], device=state["u"].device, out=state["u"])
+            state["k"] = 0
+        state["want"] = int(n_steps)
+
+    def policy(obs: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         if state["gen"] is None:
-            state["gen"] = torch.Generator(device=obs.device)
-            state["gen"].manual_seed(seed)
-            state["lo"] = torch.tensor(action_low, dtype=torch.float32, device=obs.device)
-            state["span"] = torch.tensor(action_high, dtype=torch.float32, device=obs.device) - state["lo"]
-        u = torch.rand((obs.shape[0], 2), generator=state["gen"], device=obs.device)
-        return state["lo"] + u * state["span"]
+            setup(obs.device)
+        if state["u"] is None or state["k"] >= state["u"].shape[0]:
+            n = max(int(state.get("want", 64)), 1)
+            state["u"] = torch.rand((n, obs.shape[0], 2), generator=state["gen"], device=obs.device)
+            state["k"] = 0
+        k = state["k"]
+        state["k"] += 1
+        if out is None:
+            return torch.addcmul(state["lo"], state["u"][k], state["span"])
+        return torch.addcmul(state["lo"], state["u"][k], state["span"], out=out)
 
+    policy.writes_into = True
+    policy.before_rollout = before_rollout
     return policy
