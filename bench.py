@@ -641,21 +641,32 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
     # end to end through the host-buffer C-ABI call: H2D actions + D2H obs/reward/flags/info every step
     K2 = max(3, min(K, args.e2e_steps))
     host_acts = make_actions(E, 8, seed=2000 + rank)
-    for k in range(2):
-        eng.step_host(host_acts[k], render=render)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for k in range(K2):
-        eng.step_host(host_acts[k % 8], render=render)
-    e1.record(stream)
-    barrier()
-    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = E * world * K2 / (float(e2e_ms.item()) * 1e-3)
+
+    def host_steps(mode):
+        """env-steps/s of the whole job through tde_step_host; mode = what crosses PCIe for the observation
+        ("rgb": the 12 KB planes; "classes": the 2 KB class image, expanded to the same planes by host threads)"""
+        os.environ["TDE_HOST_OBS"] = mode
+        for k in range(2):
+            eng.step_host(host_acts[k], render=render)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for k in range(K2):
+            eng.step_host(host_acts[k % 8], render=render)
+        e1.record(stream)     # tde_step_host returns with the host buffers filled: the host-side expansion is inside
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return E * world * K2 / (float(ms.item()) * 1e-3)
+
     h2d = E * 2 * 4
-    d2h = E * ((3 * 64 * 64 if render else 0) + 4 + 1 + 1 + 16 * 4)
+    small = 4 + 1 + 1 + 16 * 4
+    host_modes = {m: host_steps(m) for m in (("rgb", "classes") if render else ("rgb",))}
+    e2e_mode = args.host_obs if render else "rgb"
+    os.environ["TDE_HOST_OBS"] = e2e_mode
+    e2e_value = host_modes[e2e_mode]
+    d2h = E * ((3 * 64 * 64 if render and e2e_mode == "rgb" else 64 * 32 if render else 0) + small)
 
     # the only collective of this path: episode statistics, after the timed regions
     stats = reduce_episode_stats(eng.episode_stats(), device=dev)
@@ -675,8 +686,11 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
                 clocks=clocks, gpu_launches=int(gpu_launches),
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=K2,
                          api="tde_step_host (pinned host buffers, copies inside the timed region)",
+                         observation_over_pcie=e2e_mode, by_mode=host_modes,
                          # the host-buffer number is bound by the bytes that cross PCIe, not by the kernels: its own roofline
-                         pcie_gbs_achieved=(h2d + d2h) * e2e_value / E / 1e9, pcie_note="per GPU; PCIe Gen5 x16 moves ~55 GB/s device to host"),
+                         pcie_gbs_achieved=(h2d + d2h) * e2e_value / E / world / 1e9, pcie_note="per GPU; PCIe Gen5 x16 moves ~55 GB/s device to host",
+                         # what bounds the class-image mode: the 12 KB per env the host threads write into the caller's planes
+                         host_fill_gbs=(3 * 64 * 64 if render else 0) * e2e_value / 1e9, host_fill_note="whole box, bytes written into the callers' observation buffers"),
                 roofline=roof, cpu_baseline=cpu, episode_stats=summarize(stats))
     if world == 1 and workload == "c3" and args.policy in ("both", "pursuit"):
         # a second engine that does not end an episode at an infraction (cfg.terminated_at_infraction = False, one of the
@@ -707,6 +721,8 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--host-obs", choices=("rgb", "classes"), default="classes",
+                    help="what tde_step_host sends over PCIe for the observation in the e2e leg (both are timed, this one is e2e.value)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--policy", default="both", choices=["random", "pursuit", "both"],

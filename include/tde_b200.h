@@ -163,7 +163,13 @@ typedef struct tde_config {
                                       lines, light schedule, per-cell summary) into shared memory once per CTA with
                                       bulk-async copies (cp.async.bulk + mbarrier) when they fit; 0 (default): it reads
                                       them through L1.  The environment variable TDE_PHYS_STAGE overrides it. */
-    int32_t reserved[7];
+    int32_t host_obs_rgb;          /* tde_step_host only.  0 (default): the frames cross PCIe as the 4-bit class image (2 KB
+                                      per env) and host threads (TDE_HOST_THREADS; default: the CPUs of the process /
+                                      LOCAL_WORLD_SIZE, at most 16) expand them to the caller's RGB planes with the
+                                      palette; 1: the RGB planes (12 KB per env) cross PCIe and no host thread is
+                                      started.  Same bytes in the caller's buffer either way.  The environment variable
+                                      TDE_HOST_OBS=classes|rgb overrides it. */
+    int32_t reserved[6];
 } tde_config;
 
 /*
@@ -284,6 +290,12 @@ int tde_step_terminal(tde_handle* h, const float* actions_dev, uint8_t* obs_dev,
 
 int tde_kinematics(tde_handle* h, const float* actions_dev, void* stream);
 int tde_render(tde_handle* h, uint8_t* obs_dev, void* stream);
+/* The birdview as class indices, before the palette (reference: the per-class masks that
+   torchdrivesim's renderer composites into RGB; torchdriveenv/gym_env.py:123 consumes only the composite).
+   nibbles_dev is uint8[E][64][32]: 4 bits per pixel, pixel (row, 2 b) in the low and (row, 2 b + 1) in the high nibble
+   of byte b of the row; tde_render's RGB planes are palette[class] of exactly these classes.  It is what
+   tde_step_host sends over PCIe unless cfg.host_obs_rgb = 1. */
+int tde_render_classes(tde_handle* h, uint8_t* nibbles_dev, void* stream);
 int tde_compute_infractions(tde_handle* h, void* stream);
 
 /* state float[E][A][4] = x y psi v; attr float[E][A][4] = length width lr present */

@@ -157,6 +157,11 @@ class EmuEngine:
         self._check(self.lib.tde_render(self.h, _p(out), None), "tde_render")
         return out
 
+    def render_classes(self):
+        nib = _aligned((self.E, TDE_OBS_H, TDE_OBS_W // 2), np.uint8)
+        self._check(self.lib.tde_render_classes(self.h, _p(nib), None), "tde_render_classes")
+        return np.stack((nib & 15, nib >> 4), axis=-1).reshape(self.E, TDE_OBS_H, TDE_OBS_W)
+
     def render_view(self, env, cam_x, cam_y, cam_psi, fov, width, height):
         out = _aligned((3, int(height), int(width)), np.uint8)
         self._check(self.lib.tde_render_view(self.h, int(env), float(cam_x), float(cam_y), float(cam_psi), float(fov), int(width),

@@ -242,3 +242,38 @@ def test_emu_rollout_scatter_fills_the_buffer_like_vec_frame_stack(oracle, NS, T
             assert np.array_equal(eng.reward, orr) and np.array_equal(eng.info, oinfo)
             n_done += int(d.sum())
     assert n_done > 5
+
+
+def test_emu_class_image_and_compact_host_step(oracle, monkeypatch):
+    """tde_render_classes is the oracle's class image, nibble-packed; tde_step_host's default path (the class
+    image crosses PCIe, host threads apply the palette) fills the caller's buffer with the same bytes as cfg.host_obs_rgb = 1,
+    with one chunk and with several, with the default and with a caller-set palette."""
+    E, A = 37, 16
+    ss = S.validation_mix(12)
+    cfg = dict(auto_reset=1)
+    rgb = EmuEngine(ss, E, A, host_obs_rgb=1, **cfg)
+    cmp_ = EmuEngine(ss, E, A, **cfg)
+    orc = oracle.OracleEnvSet(default_config(num_envs=E, max_agents=A, **cfg), rgb.packed)
+    pal = np.random.default_rng(5).integers(0, 256, (11, 3)).astype(np.uint8)
+    rng = np.random.default_rng(9)
+    for eng in (rgb, cmp_):
+        eng.reset(seed=4)
+    orc.reset(seed=4)
+    assert np.array_equal(cmp_.render_classes(), orc.render_classes())
+    for k in range(12):
+        if k == 6:
+            for eng in (rgb, cmp_, orc):
+                eng.set_palette(pal)
+        monkeypatch.setenv("TDE_HOST_CHUNKS", "1" if k % 2 else "5")
+        if k in (3, 4, 8):
+            monkeypatch.setenv("TDE_HOST_NO_SIMD", "1")     # the scalar expansion loop
+        else:
+            monkeypatch.delenv("TDE_HOST_NO_SIMD", raising=False)
+        a = np.stack([rng.uniform(-1, 1, E), rng.uniform(-0.3, 0.3, E)], 1).astype(np.float32)
+        want = [np.array(x, copy=True) for x in rgb.step_host(a)]
+        got = cmp_.step_host(a)
+        ref = orc.step(a)
+        for name, w, g, o in zip(("obs", "reward", "terminated", "truncated", "info"), want, got, ref):
+            assert np.array_equal(w, g), f"step {k}: {name} differs between the RGB and the compact host step"
+            assert np.array_equal(g, o), f"step {k}: {name} differs from the oracle"
+        assert np.array_equal(cmp_.render_classes(), orc.render_classes()), f"step {k}: class image"

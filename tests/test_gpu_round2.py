@@ -256,3 +256,30 @@ def test_rollout_collector_cuda_graph_replay(oracle):
             assert np.array_equal(b.episode_starts[t + 1].cpu().numpy().astype(bool), d)
     assert col._graph is not None and col.num_timesteps == R * T * E
     np.testing.assert_allclose(eng.episode_stats(), orc.stats, rtol=1e-9)
+
+
+def test_compact_host_step_fills_the_same_bytes_as_the_rgb_host_step(oracle, monkeypatch):
+    """tde_step_host by default: the frames cross PCIe as the 4-bit class image and host threads apply the palette; the
+    caller's buffers must hold the same bytes as with cfg.host_obs_rgb = 1 (the planes cross PCIe) and as the oracle's, chunked (4,608 envs -> 8 chunks)
+    and unchunked, and tde_render_classes must be the oracle's class image."""
+    E, A = 4608, 16
+    ss = S.validation_mix(12)
+    cfg = dict(auto_reset=1)
+    rgb = _engine(ss, E, A, host_obs_rgb=1, **cfg)
+    cmp_ = _engine(ss, E, A, **cfg)
+    orc = oracle.OracleEnvSet(default_config(num_envs=E, max_agents=A, **cfg), rgb.packed)
+    for eng in (rgb, cmp_, orc):
+        eng.reset(seed=12)
+    assert np.array_equal(cmp_.render_classes().cpu().numpy(), orc.render_classes())
+    rng = np.random.default_rng(3)
+    for k in range(6):
+        if k == 4:
+            monkeypatch.setenv("TDE_HOST_CHUNKS", "1")
+        a = np.stack([rng.uniform(-1, 1, E), rng.uniform(-0.3, 0.3, E)], 1).astype(np.float32)
+        want = [np.array(x, copy=True) for x in rgb.step_host(a)]
+        got = cmp_.step_host(a)
+        ref = orc.step(a)
+        for name, w, g, o in zip(("obs", "reward", "terminated", "truncated", "info"), want, got, ref):
+            assert np.array_equal(w, g), f"step {k}: {name} differs between the RGB and the compact host step"
+            assert np.array_equal(g, o), f"step {k}: {name} differs from the oracle"
+    assert np.array_equal(cmp_.render_classes().cpu().numpy(), orc.render_classes())

@@ -44,7 +44,7 @@ class TdeConfig(C.Structure):
         ("distance_bonus", C.c_float), ("distance_cutoff", C.c_float), ("reach_radius", C.c_float),
         ("offroad_threshold", C.c_float), ("tl_rear_factor", C.c_float), ("fov", C.c_float),
         ("start_speed_max", C.c_float), ("start_heading_sigma", C.c_float),
-        ("stage_map_tables", C.c_int32), ("reserved", C.c_int32 * 7),
+        ("stage_map_tables", C.c_int32), ("host_obs_rgb", C.c_int32), ("reserved", C.c_int32 * 6),
     ]
 
 
@@ -123,7 +123,7 @@ _LIB_PATH = os.environ.get("TDE_B200_LIB") or os.path.join(os.path.dirname(os.pa
 EXPORTS = [
     "tde_version", "tde_last_error", "tde_create", "tde_destroy", "tde_default_config",
     "tde_upload_scenarios", "tde_set_env_scenario_range", "tde_set_palette", "tde_reset", "tde_step",
-    "tde_step_phases", "tde_step_host", "tde_step_stacked", "tde_render_stacked", "tde_step_rollout", "tde_step_rollout_scatter", "tde_step_terminal", "tde_kinematics", "tde_render",
+    "tde_step_phases", "tde_step_host", "tde_step_stacked", "tde_render_stacked", "tde_step_rollout", "tde_step_rollout_scatter", "tde_step_terminal", "tde_kinematics", "tde_render", "tde_render_classes",
     "tde_compute_infractions",
     "tde_get_state", "tde_set_state", "tde_get_attributes", "tde_set_attributes", "tde_get_infractions",
     "tde_get_env_vars", "tde_set_env_vars", "tde_collision_boxes", "tde_offroad_boxes", "tde_clone",
@@ -173,6 +173,7 @@ def bind_signatures(lib: C.CDLL) -> C.CDLL:
         "tde_step_rollout_scatter": ([vp, vp, vp, i64, i32, i32, vp, vp, vp, vp, vp], C.c_int),
         "tde_kinematics": ([vp, vp, vp], C.c_int),
         "tde_render": ([vp, vp, vp], C.c_int),
+        "tde_render_classes": ([vp, vp, vp], C.c_int),
         "tde_compute_infractions": ([vp, vp], C.c_int),
         "tde_get_state": ([vp, vp, vp], C.c_int),
         "tde_set_state": ([vp, vp, vp], C.c_int),

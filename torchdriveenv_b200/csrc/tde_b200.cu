@@ -13,8 +13,16 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
+#include <immintrin.h>
+#ifdef __linux__
+#include <sched.h>
+#endif
 
 #include "tde_kernels.cuh"
 #include "tde_view.cuh"
@@ -46,6 +54,9 @@ struct ScenTables {
     }
 };
 
+struct ExpandPool;
+static void delete_pool(ExpandPool* pool);
+
 struct tde_handle {
     tde_config cfg;
     std::shared_ptr<ScenTables> tab;
@@ -73,6 +84,10 @@ struct tde_handle {
     ViewPrim* view_prims = nullptr; int view_cap = 0;   // tde_render_view scratch
     cudaStream_t copy_stream = nullptr;          // tde_step_host: observation chunks go back while later chunks are computed
     cudaEvent_t chunk_done[16] = {}, copies_done = nullptr;
+    // tde_step_host, compact mode: the 4-bit class image crosses PCIe and is expanded to RGB planes by host threads
+    uint8_t *h_nib = nullptr, *pin_nib = nullptr;   // [E][64][32] on the device / in pinned host memory
+    cudaEvent_t chunk_copied[16] = {};
+    ExpandPool* pool = nullptr;
     std::string err;
 };
 
@@ -501,6 +516,7 @@ static int configure_render(tde_handle* h) {
     CUDA_TRY(h, cudaFuncSetAttribute(tde_render_kernel<AH, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_TRY(h, cudaFuncSetAttribute(tde_render_kernel<AH, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_TRY(h, cudaFuncSetAttribute(tde_render_kernel<AH, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(h, cudaFuncSetAttribute(tde_render_kernel<AH, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tde_render_kernel<AH, 0>, TDE_WARPS_PER_BLOCK * 32, smem));
     if (per_sm < 1) per_sm = 1;
@@ -603,6 +619,9 @@ extern "C" int tde_destroy(tde_handle* h) {
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (cudaEvent_t ev : h->chunk_done) if (ev) cudaEventDestroy(ev);
     if (h->copies_done) cudaEventDestroy(h->copies_done);
+    for (cudaEvent_t ev : h->chunk_copied) if (ev) cudaEventDestroy(ev);
+    delete_pool(h->pool);
+    cudaFree(h->h_nib); if (h->pin_nib) cudaFreeHost(h->pin_nib);
     cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_reward); cudaFree(h->h_term); cudaFree(h->h_trunc); cudaFree(h->h_info);
     delete h;
     return TDE_OK;
@@ -890,7 +909,8 @@ static cudaError_t launch_step(Kernel k, int grid, int threads, size_t smem, cud
 
 static int step_impl(tde_handle* h, int32_t phases, const float* actions, uint8_t* obs, int32_t n_stack, float* reward,
                      uint8_t* terminated, uint8_t* truncated, float* info, void* stream, const uint8_t* obs_prev = nullptr,
-                     uint8_t* terminal_obs = nullptr, int e_begin = 0, int e_end = -1, long long slot_stride = 0, int slots_ahead = 0) {
+                     uint8_t* terminal_obs = nullptr, int e_begin = 0, int e_end = -1, long long slot_stride = 0, int slots_ahead = 0,
+                     bool class_nibbles = false) {
     if (!h) return TDE_E_INVAL;
     if (n_stack < 1 || n_stack > 8) return fail(h, TDE_E_INVAL, "n_stack must be in 1..8");
     if (!h->uploaded || !h->was_reset) return fail(h, TDE_E_STATE, "tde_step: upload scenarios and reset first");
@@ -938,7 +958,10 @@ static int step_impl(tde_handle* h, int32_t phases, const float* actions, uint8_
     }
     if (render) {
         const int grid = std::min(h->grid_render, want_render);
-        if (scatter) {
+        if (class_nibbles) {   // obs is the 4-bit class image [E][64][32]
+            if (h->A <= 32) CUDA_TRY(h, launch_step(tde_render_kernel<1, 3>, grid, threads, h->smem_render, st, p));
+            else CUDA_TRY(h, launch_step(tde_render_kernel<2, 3>, grid, threads, h->smem_render, st, p));
+        } else if (scatter) {
             if (h->A <= 32) CUDA_TRY(h, launch_step(tde_render_kernel<1, 2>, grid, threads, h->smem_render, st, p));
             else CUDA_TRY(h, launch_step(tde_render_kernel<2, 2>, grid, threads, h->smem_render, st, p));
         } else if (n_stack > 1) {
@@ -1035,8 +1058,186 @@ extern "C" int tde_kinematics(tde_handle* h, const float* actions, void* stream)
 extern "C" int tde_render(tde_handle* h, uint8_t* obs, void* stream) {
     return tde_step_phases(h, TDE_PH_RENDER, nullptr, obs, nullptr, nullptr, nullptr, nullptr, stream);
 }
+extern "C" int tde_render_classes(tde_handle* h, uint8_t* nibbles, void* stream) {
+    return step_impl(h, TDE_PH_RENDER, nullptr, nibbles, 1, nullptr, nullptr, nullptr, nullptr, stream, nullptr, nullptr, 0, -1, 0, 0, true);
+}
 extern "C" int tde_compute_infractions(tde_handle* h, void* stream) {
     return tde_step_phases(h, TDE_PH_INFRACTIONS, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+// ---- tde_step_host, compact mode: the frames cross PCIe as the 4-bit class image (2 KB per env instead of 12 KB) and
+// host threads expand them to the caller's RGB planes with the handle's palette while later chunks are on their way.
+static void expand_env_scalar(const uint8_t* nib, uint8_t* rgb, const uint8_t* lut) {
+    constexpr int PX = TDE_OBS_H * TDE_OBS_W;
+    for (int b = 0; b < PX / 2; ++b) {
+        const int c0 = nib[b] & 15, c1 = nib[b] >> 4;
+        for (int ch = 0; ch < 3; ++ch) {
+            rgb[ch * PX + 2 * b] = lut[16 * ch + c0];
+            rgb[ch * PX + 2 * b + 1] = lut[16 * ch + c1];
+        }
+    }
+}
+__attribute__((target("avx2"))) static void expand_env_avx2(const uint8_t* nib, uint8_t* rgb, const uint8_t* lut) {
+    constexpr int PX = TDE_OBS_H * TDE_OBS_W;
+    const __m256i low4 = _mm256_set1_epi8(0x0f);
+    __m256i L[3];
+    for (int ch = 0; ch < 3; ++ch) L[ch] = _mm256_broadcastsi128_si256(_mm_loadu_si128((const __m128i*)(lut + 16 * ch)));
+    const bool aligned = ((uintptr_t)rgb & 31) == 0;   // non-temporal stores: the planes are not read again by these threads
+    for (int r = 0; r < TDE_OBS_H; ++r) {
+        const __m256i v = _mm256_loadu_si256((const __m256i*)(nib + 32 * r));
+        const __m256i lo = _mm256_and_si256(v, low4), hi = _mm256_and_si256(_mm256_srli_epi16(v, 4), low4);
+        const __m256i a = _mm256_unpacklo_epi8(lo, hi), b = _mm256_unpackhi_epi8(lo, hi);
+        const __m256i px0 = _mm256_permute2x128_si256(a, b, 0x20), px1 = _mm256_permute2x128_si256(a, b, 0x31);   // pixels 0..31, 32..63
+        for (int ch = 0; ch < 3; ++ch) {
+            __m256i* o = (__m256i*)(rgb + ch * PX + r * TDE_OBS_W);
+            const __m256i w0 = _mm256_shuffle_epi8(L[ch], px0), w1 = _mm256_shuffle_epi8(L[ch], px1);
+            if (aligned) { _mm256_stream_si256(o, w0); _mm256_stream_si256(o + 1, w1); }
+            else { _mm256_storeu_si256(o, w0); _mm256_storeu_si256(o + 1, w1); }
+        }
+    }
+}
+// The host threads of the expansion.  One job per step: the threads take blocks of envs in order and wait (yielding,
+// never spinning hard) until the chunk a block belongs to has landed in pinned memory; between steps they sleep on a
+// condition variable.  The calling thread works too, so `threads` = 1 means no pool at all.
+struct ExpandPool {
+    static constexpr int BLOCK = 8;   // envs per grab: 16 KB read, 96 KB written
+    std::vector<std::thread> workers;
+    std::mutex m;
+    std::condition_variable cv_job, cv_done;
+    unsigned long long job = 0;
+    int pending = 0;
+    bool stop = false;
+    // the job
+    const uint8_t* nib = nullptr; uint8_t* rgb = nullptr; int E = 0; bool avx2 = false;
+    uint8_t lut[48] = {};
+    std::atomic<int> next{0}, ready{0};
+
+    explicit ExpandPool(int threads) {
+        for (int t = 1; t < threads; ++t) workers.emplace_back([this] { loop(); });
+    }
+    ~ExpandPool() {
+        { std::lock_guard<std::mutex> lk(m); stop = true; }
+        cv_job.notify_all();
+        for (std::thread& t : workers) t.join();
+    }
+    void work() {
+        constexpr int PX = TDE_OBS_H * TDE_OBS_W;
+        for (;;) {
+            const int b0 = next.fetch_add(BLOCK, std::memory_order_relaxed);
+            if (b0 >= E) break;
+            const int b1 = std::min(E, b0 + BLOCK);
+            while (ready.load(std::memory_order_acquire) < b1) std::this_thread::yield();
+            for (int e = b0; e < b1; ++e) {
+                if (avx2) expand_env_avx2(nib + (size_t)e * (PX / 2), rgb + (size_t)e * 3 * PX, lut);
+                else expand_env_scalar(nib + (size_t)e * (PX / 2), rgb + (size_t)e * 3 * PX, lut);
+            }
+        }
+        if (avx2) _mm_sfence();
+    }
+    void loop() {
+        unsigned long long seen = 0;
+        std::unique_lock<std::mutex> lk(m);
+        for (;;) {
+            cv_job.wait(lk, [&] { return stop || job != seen; });
+            if (stop) return;
+            seen = job;
+            lk.unlock();
+            work();
+            lk.lock();
+            if (--pending == 0) cv_done.notify_one();
+        }
+    }
+    // post the job; the caller then publishes `ready` as the chunks arrive and finally calls finish()
+    void begin(const uint8_t* nib_, uint8_t* rgb_, const uint8_t* palette, int E_) {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            nib = nib_; rgb = rgb_; E = E_;
+            avx2 = __builtin_cpu_supports("avx2") && !std::getenv("TDE_HOST_NO_SIMD");   // the scalar loop stays testable
+            std::memset(lut, 0, sizeof(lut));
+            for (int ch = 0; ch < 3; ++ch)
+                for (int c = 0; c < TDE_NUM_CLASSES; ++c) lut[16 * ch + c] = palette[3 * c + ch];
+            next.store(0); ready.store(0);
+            pending = (int)workers.size();
+            ++job;
+        }
+        cv_job.notify_all();
+    }
+    void arrived(int envs) { ready.store(envs, std::memory_order_release); }
+    void finish() {
+        work();
+        std::unique_lock<std::mutex> lk(m);
+        cv_done.wait(lk, [&] { return pending == 0; });
+    }
+};
+
+static void delete_pool(ExpandPool* pool) { delete pool; }
+
+// threads of the expansion: TDE_HOST_THREADS, else the CPUs this process may run on shared between the ranks of the
+// box (torchrun's LOCAL_WORLD_SIZE), at most 16 (one GPU's frames saturate the host memory well before that)
+static int host_thread_count() {
+    if (const char* v = std::getenv("TDE_HOST_THREADS")) return std::max(1, std::min(64, std::atoi(v)));
+    int cpus = (int)std::max(1u, std::thread::hardware_concurrency());
+#ifdef __linux__
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) cpus = std::max(1, CPU_COUNT(&set));
+#endif
+    int ranks = 1;
+    if (const char* w = std::getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, std::atoi(w));
+    return std::max(1, std::min(cpus / ranks, 16));
+}
+
+static int ensure_copy_stream(tde_handle* h) {
+    if (h->copy_stream) return TDE_OK;
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t& ev : h->chunk_done) CUDA_TRY(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (cudaEvent_t& ev : h->chunk_copied) CUDA_TRY(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->copies_done, cudaEventDisableTiming));
+    return TDE_OK;
+}
+
+// chunks of envs whose frames travel while later chunks are computed (TDE_HOST_CHUNKS overrides the choice, 1..16)
+static inline int host_chunks(const tde_handle* h, int few, int some) {
+    int n = h->E < few ? 1 : h->E < some ? 8 : 16;
+    if (const char* v = std::getenv("TDE_HOST_CHUNKS")) n = std::max(1, std::min(16, std::atoi(v)));
+    return std::min(n, h->E);
+}
+static inline int compact_chunks(const tde_handle* h) { return host_chunks(h, 2048, 8192); }
+
+static int step_host_compact_launch(tde_handle* h, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t E = (size_t)h->E, nib_env = TDE_OBS_H * TDE_OBS_W / 2;
+    if (!h->h_nib) {
+        CUDA_TRY(h, cudaMalloc((void**)&h->h_nib, E * nib_env));
+        CUDA_TRY(h, cudaMallocHost((void**)&h->pin_nib, E * nib_env));
+        h->pool = new ExpandPool(host_thread_count());
+    }
+    if (int rc = ensure_copy_stream(h)) return rc;
+    const int chunks = compact_chunks(h);
+    for (int c = 0; c < chunks; ++c) {
+        const int e0 = (int)((long long)h->E * c / chunks), e1 = (int)((long long)h->E * (c + 1) / chunks);
+        int rc = step_impl(h, TDE_PH_ALL, h->h_actions, h->h_nib, 1, h->h_reward, h->h_term, h->h_trunc, h->h_info, stream, nullptr, nullptr,
+                           e0, e1, 0, 0, true);
+        if (rc) return rc;
+        CUDA_TRY(h, cudaEventRecord(h->chunk_done[c], st));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->chunk_done[c], 0));
+        CUDA_TRY(h, cudaMemcpyAsync(h->pin_nib + e0 * nib_env, h->h_nib + e0 * nib_env, (size_t)(e1 - e0) * nib_env, cudaMemcpyDeviceToHost, h->copy_stream));
+        CUDA_TRY(h, cudaEventRecord(h->chunk_copied[c], h->copy_stream));
+    }
+    return TDE_OK;
+}
+
+static int step_host_compact_expand(tde_handle* h, uint8_t* obs) {
+    const int chunks = compact_chunks(h);
+    h->pool->begin(h->pin_nib, obs, h->palette, h->E);
+    cudaError_t err = cudaSuccess;
+    for (int c = 0; c < chunks && err == cudaSuccess; ++c) {
+        err = cudaEventSynchronize(h->chunk_copied[c]);
+        if (err == cudaSuccess) h->pool->arrived((int)((long long)h->E * (c + 1) / chunks));
+    }
+    if (err != cudaSuccess) h->pool->arrived(h->E);   // release the threads; the caller gets the error, not the frames
+    h->pool->finish();
+    CUDA_TRY(h, err);
+    return TDE_OK;
 }
 
 extern "C" int tde_step_host(tde_handle* h, const float* actions, uint8_t* obs, float* reward, uint8_t* terminated,
@@ -1053,21 +1254,33 @@ extern "C" int tde_step_host(tde_handle* h, const float* actions, uint8_t* obs, 
         CUDA_TRY(h, cudaMalloc((void**)&h->h_trunc, E));
         CUDA_TRY(h, cudaMalloc((void**)&h->h_info, E * TDE_INFO_STRIDE * sizeof(float)));
     }
-    if (obs && !h->h_obs) CUDA_TRY(h, cudaMalloc((void**)&h->h_obs, obs_bytes));
+    // the observation crosses PCIe as the class image unless cfg.host_obs_rgb / TDE_HOST_OBS=rgb asks for the planes
+    const char* mode = std::getenv("TDE_HOST_OBS");
+    const bool compact = obs && (mode ? std::strcmp(mode, "rgb") != 0 : h->cfg.host_obs_rgb == 0);
+    if (obs && !compact && !h->h_obs) CUDA_TRY(h, cudaMalloc((void**)&h->h_obs, obs_bytes));
     CUDA_TRY(h, cudaMemcpyAsync(h->h_actions, actions, E * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (compact) {
+        // the small rows travel while the host threads expand the frames
+        int rc = step_host_compact_launch(h, stream);
+        if (rc) return rc;
+        CUDA_TRY(h, cudaMemcpyAsync(reward, h->h_reward, E * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(h, cudaMemcpyAsync(terminated, h->h_term, E, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(h, cudaMemcpyAsync(truncated, h->h_trunc, E, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(h, cudaMemcpyAsync(info, h->h_info, E * TDE_INFO_STRIDE * sizeof(float), cudaMemcpyDeviceToHost, st));
+        rc = step_host_compact_expand(h, obs);
+        if (rc) return rc;
+        CUDA_TRY(h, cudaStreamSynchronize(st));
+        return TDE_OK;
+    }
     // With observations the step is bound by the 12 KB per env that cross PCIe: the envs are stepped in
     // chunks, and the frames of a finished chunk travel on a second stream while the next chunk is computed.
-    const int chunks = !obs || h->E < 4096 ? 1 : h->E < 8192 ? 8 : 16;   // only the first chunk's compute is not hidden behind the copies
+    const int chunks = !obs ? 1 : host_chunks(h, 4096, 8192);   // only the first chunk's compute is not hidden behind the copies
     if (chunks == 1) {
         int rc = tde_step(h, h->h_actions, obs ? h->h_obs : nullptr, h->h_reward, h->h_term, h->h_trunc, h->h_info, stream);
         if (rc) return rc;
         if (obs) CUDA_TRY(h, cudaMemcpyAsync(obs, h->h_obs, obs_bytes, cudaMemcpyDeviceToHost, st));
     } else {
-        if (!h->copy_stream) {
-            CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-            for (cudaEvent_t& ev : h->chunk_done) CUDA_TRY(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-            CUDA_TRY(h, cudaEventCreateWithFlags(&h->copies_done, cudaEventDisableTiming));
-        }
+        if (int rc = ensure_copy_stream(h)) return rc;
         const size_t frame = (size_t)TDE_OBS_C * TDE_OBS_H * TDE_OBS_W;
         for (int c = 0; c < chunks; ++c) {
             const int e0 = (int)((long long)h->E * c / chunks), e1 = (int)((long long)h->E * (c + 1) / chunks);

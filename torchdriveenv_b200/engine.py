@@ -213,6 +213,16 @@ class Engine:
         self._check(self.lib.tde_render(self.h, _ptr(out), self._stream()), "tde_render")
         return out
 
+    def render_classes(self, out: Optional[torch.Tensor] = None, unpack: bool = True) -> torch.Tensor:
+        """tde_render_classes: the class-index birdview.  The kernel writes uint8[E, 64, 32] (4 bits per pixel, even
+        pixel in the low nibble); unpack=True returns uint8[E, 64, 64] class indices (two torch ops on that result)."""
+        if out is None:
+            out = torch.empty((self.E, TDE_OBS_H, TDE_OBS_W // 2), dtype=torch.uint8, device=self.device)
+        self._check(self.lib.tde_render_classes(self.h, _ptr(out), self._stream()), "tde_render_classes")
+        if not unpack:
+            return out
+        return torch.stack((out & 15, out >> 4), dim=-1).reshape(self.E, TDE_OBS_H, TDE_OBS_W)
+
     def render_view(self, env: int = 0, camera_xy=None, camera_psi: float = 0.0, fov: float = 500.0, res=(1024, 1024),
                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Recording view (tde_render_view): env `env` as a uint8[3, H, W] frame from a free camera.  camera_xy = None
