@@ -398,7 +398,9 @@ def run_c5(args, rank: int, local_rank: int, world: int):
     ss, desc = build_scenarios("c5")
     eng = Engine(ss, E, A, device=str(dev), auto_reset=1, env_index_offset=rank * E)
     T = C5_N_STEPS
-    col = RolloutCollector(eng, T, n_stack=C5_N_STACK, seed=0, cuda_graph=True)    # a rollout = one CUDA graph replay
+    # a rollout = one CUDA graph replay; frames kept once each in a ring (the consumer gathers the stack), or scattered into
+    # the n_stack stacked observations they belong to (--c5-frame-copy scatter)
+    col = RolloutCollector(eng, T, n_stack=C5_N_STACK, seed=0, cuda_graph=True, frame_copy=args.c5_frame_copy)
     policy = uniform_policy(seed=1000 + rank)
     K = max(T, (args.steps // T) * T)          # whole rollouts
     W = max(3, -(-args.warmup // T))           # >= 3: the eager rollout, the captured one, one replay
@@ -437,7 +439,10 @@ def run_c5(args, rank: int, local_rank: int, world: int):
 
     def host_policy_step(t, k):
         a = pin_act[k % 8].to(dev, non_blocking=True)
-        eng.step_rollout_scatter(a, b.observations, t, C5_N_STACK, reward=b.rewards[t], terminated=b.terminated[t], truncated=b.truncated[t])
+        if col.frame_copy == "ring":
+            eng.step_into(a, b.frames[t + C5_N_STACK], reward=b.rewards[t], terminated=b.terminated[t], truncated=b.truncated[t])
+        else:
+            eng.step_rollout_scatter(a, b.observations, t, C5_N_STACK, reward=b.rewards[t], terminated=b.terminated[t], truncated=b.truncated[t])
         host_rew.copy_(b.rewards[t], non_blocking=True)
         host_flags[0].copy_(b.terminated[t], non_blocking=True)
         host_flags[1].copy_(b.truncated[t], non_blocking=True)
@@ -462,18 +467,18 @@ def run_c5(args, rank: int, local_rank: int, world: int):
         line = dict(metric=METRIC, value=E * world / (ms * 1e-3), unit=UNIT, n_gpus=world, steps=K, warmup=W * T, ms_per_step=ms,
                     higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                     config=dict(workload=desc, envs_per_gpu=E, agents=A, render=True, global_envs=E * world, n_stack=C5_N_STACK,
-                                rollout_steps=T, rollout_buffer_bytes=b.nbytes(),
+                                rollout_steps=T, rollout_buffer_bytes=b.nbytes(), frame_copy=col.frame_copy,
                                 parallelism=f"env-sharded x{world}, no collectives on the step path",
                                 l2="each step writes a fresh %.0f MB buffer slot: larger than the 126 MB L2" % (E * 9 * 4096 / 1e6)),
                     clocks=clocks, gpu_launches=2 * K,      # one physics + one render launch per step (replayed from the captured graph)
                     e2e=dict(value=E * world * K2 / (float(e2e_ms.item()) * 1e-3), unit=UNIT, h2d_bytes_per_step=E * 8, d2h_bytes_per_step=E * 6,
-                             steps=K2, api="Engine.step_rollout_scatter with actions from pinned host memory and reward/terminated/truncated read back "
+                             steps=K2, api="Engine.step_into / step_rollout_scatter with actions from pinned host memory and reward/terminated/truncated read back "
                                            "every step (observations stay in the GPU rollout buffer)"),
-                    roofline=dict(bound="hbm", kernel="tde_render_kernel<stacked> (+ tde_physics_kernel, one launch each per step)", achieved=achieved,
+                    roofline=dict(bound="hbm", kernel="tde_render_kernel (+ tde_physics_kernel, one launch each per step)", achieved=achieved,
                                   peak=peak, unit="GB/s", frac=achieved / peak, traffic=None, algorithmic_bytes_per_launch=bpe * E,
                                   bytes_per_env_step=bpe, avg_launch_ms=ms, peak_source=peak_src,
                                   moved_bytes_per_env_step=rollout_traffic_per_env_step(A, C5_N_STACK, col.frame_copy),
-                                  note="algorithmic = one new frame per env-step; the scatter store writes it n_stack times"),
+                                  note="algorithmic = one new frame per env-step; the ring stores it once, the scatter store n_stack times"),
                     cpu_baseline=cpu, episode_stats=summarize(stats))
         return line
     return None
@@ -721,6 +726,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--c5-frame-copy", choices=("ring", "scatter", "shift"), default="ring", help="how the C5 rollout buffer keeps the frame stack")
     ap.add_argument("--host-obs", choices=("rgb", "classes"), default="classes",
                     help="what tde_step_host sends over PCIe for the observation in the e2e leg (both are timed, this one is e2e.value)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

@@ -283,3 +283,36 @@ def test_compact_host_step_fills_the_same_bytes_as_the_rgb_host_step(oracle, mon
             assert np.array_equal(w, g), f"step {k}: {name} differs between the RGB and the compact host step"
             assert np.array_equal(g, o), f"step {k}: {name} differs from the oracle"
     assert np.array_equal(cmp_.render_classes().cpu().numpy(), orc.render_classes())
+
+
+def test_ring_of_frames_rollout_equals_the_scatter_rollout():
+    """RolloutCollector(frame_copy="ring") keeps every frame once; what RolloutBuffer.stacked hands out must be the stacked
+    observations the scatter collector stores, over several rollouts (carry-over, CUDA graph replay from the third on), for
+    a policy that ignores the observation and for one that reads it at every step."""
+    from torchdriveenv_b200.engine import Engine
+    from torchdriveenv_b200.rollout import RolloutCollector, uniform_policy
+    E, A, T, NS = 96, 6, 5, 3
+    ss = S.traffic_lights(A)
+    cfg = dict(auto_reset=1, max_environment_steps=9)
+
+    def brightness_policy(obs):     # depends on every channel group of the stacked observation
+        m = obs.view(obs.shape[0], -1).float().mean(1) / 255.0
+        return torch.stack((torch.cos(40.0 * m), 0.3 * torch.sin(55.0 * m)), 1)
+
+    for make_policy, graph in ((lambda: uniform_policy(seed=3), True), (lambda: brightness_policy, False)):
+        cols = []
+        for mode in ("scatter", "ring"):
+            eng = Engine(ss, E, A, device="cuda:0", **cfg)
+            cols.append(RolloutCollector(eng, T, n_stack=NS, seed=21, frame_copy=mode, cuda_graph=graph))
+        pols = [make_policy(), make_policy()]
+        n_done = 0
+        for r in range(5):
+            bs, br = cols[0].collect(pols[0]), cols[1].collect(pols[1])
+            torch.cuda.synchronize()
+            for t in range(T + 1):
+                assert torch.equal(br.stacked(t), bs.observations[t]), f"rollout {r} observation {t}"
+            for name in ("actions", "rewards", "terminated", "truncated", "episode_starts"):
+                assert torch.equal(getattr(br, name), getattr(bs, name)), name
+            n_done += int(bs.episode_starts[1:].sum())
+        assert n_done > 20
+        assert torch.equal(cols[1].last_observation(), cols[0].last_observation())

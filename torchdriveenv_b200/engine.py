@@ -108,6 +108,25 @@ class Engine:
                                              _ptr(self.info), self._stream()), "tde_step")
         return (self.obs if render else None), self.reward, self.terminated, self.truncated, self.info
 
+    def step_into(self, actions: torch.Tensor, obs: torch.Tensor, reward: Optional[torch.Tensor] = None,
+                  terminated: Optional[torch.Tensor] = None, truncated: Optional[torch.Tensor] = None,
+                  info: Optional[torch.Tensor] = None):
+        """tde_step with the caller's rows: the new frame goes to `obs` uint8[E, 3, 64, 64] (e.g. one slot of a ring of
+        frames), the per-env results to the given rows (contiguous, on this device) or to the engine's own tensors."""
+        a = actions.to(device=self.device, dtype=torch.float32).contiguous().view(self.E, 2)
+        self._check_stack(obs, 1)
+        outs = []
+        for x, own, shape, dt in ((reward, self.reward, (self.E,), torch.float32), (terminated, self.terminated, (self.E,), torch.uint8),
+                                  (truncated, self.truncated, (self.E,), torch.uint8), (info, self.info, (self.E, TDE_INFO_STRIDE), torch.float32)):
+            if x is None:
+                x = own
+            elif tuple(x.shape) != shape or x.dtype != dt or not x.is_contiguous() or x.device != self.obs.device:
+                raise ValueError(f"step_into: output rows must be contiguous {dt} tensors of shape {shape} on {self.obs.device}")
+            outs.append(x)
+        self._check(self.lib.tde_step(self.h, _ptr(a), _ptr(obs), _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _ptr(outs[3]),
+                                      self._stream()), "tde_step")
+        return obs, outs[0], outs[1], outs[2], outs[3]
+
     def _check_stack(self, stack: torch.Tensor, n_stack: int):
         want = (self.E, 3 * n_stack, TDE_OBS_H, TDE_OBS_W)
         if tuple(stack.shape) != want or stack.dtype != torch.uint8 or not stack.is_contiguous() or stack.device != self.obs.device:

@@ -9,6 +9,10 @@ and the render kernel stores every new frame straight into the stacked observati
 of the next n_stack - 1 slots), so the buffer is filled without reading or moving a frame; reward and
 flags are written by the physics kernel into the buffer's own rows.  ``frame_copy="shift"`` selects the
 older ``tde_step_rollout`` (older frames read from slot t, shifted stack written to slot t + 1).
+``frame_copy="ring"`` stores every frame exactly once: the buffer keeps single frames ([T + n_stack, E, 3, 64, 64],
+observation t = frames t .. t + n_stack - 1) and an age per observation (how many of the older frames belong to the
+running episode); ``RolloutBuffer.stacked(t, envs)`` gathers the VecFrameStack observation where it is consumed, so a
+rollout step writes 12 KB per env instead of 36.
 
 Field names and shapes follow SB3's ``RolloutBuffer`` ([n_steps, n_envs, ...]); ``episode_starts[t]``
 is 1 where ``observations[t]`` is the first observation of an episode.  ``returns_and_advantages`` is
@@ -28,11 +32,19 @@ from .engine import Engine
 class RolloutBuffer:
     """[n_steps (+1 for observations / episode_starts), E, ...] tensors on the engine's GPU."""
 
-    def __init__(self, n_steps: int, num_envs: int, n_stack: int, device, with_info: bool = False):
+    def __init__(self, n_steps: int, num_envs: int, n_stack: int, device, with_info: bool = False, ring: bool = False):
         T, E = int(n_steps), int(num_envs)
         self.n_steps, self.num_envs, self.n_stack = T, E, int(n_stack)
         z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=device)
-        self.observations = z((T + 1, E, 3 * self.n_stack, TDE_OBS_H, TDE_OBS_W), torch.uint8)
+        if ring:
+            # single frames: observation t is frames[t : t + n_stack] (oldest first); ages[t, e] = how many of the older
+            # frames of observation t belong to env e's running episode (the others read as zeros, as VecFrameStack has them)
+            self.observations = None
+            self.frames = z((T + self.n_stack, E, 3, TDE_OBS_H, TDE_OBS_W), torch.uint8)
+            self.ages = z((T + 1, E), torch.uint8)
+        else:
+            self.observations = z((T + 1, E, 3 * self.n_stack, TDE_OBS_H, TDE_OBS_W), torch.uint8)
+            self.frames = self.ages = None
         self.actions = z((T, E, 2), torch.float32)
         self.rewards = z((T, E), torch.float32)
         self.terminated = z((T, E), torch.uint8)
@@ -45,6 +57,24 @@ class RolloutBuffer:
 
     def nbytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in vars(self).values() if isinstance(t, torch.Tensor))
+
+    def stacked(self, t: int, envs: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Observation t as VecFrameStack hands it out, uint8[E or len(envs), 3 * n_stack, 64, 64]: a view of the stored
+        stack, or (ring of frames) gathered from the n_stack frames with the ones from before the episode zeroed."""
+        if self.observations is not None:
+            o = self.observations[t]
+            return o if envs is None else o[envs]
+        n = self.n_stack
+        age = self.ages[t] if envs is None else self.ages[t][envs]
+        rows = age.shape[0]
+        if out is None:
+            out = torch.empty((rows, 3 * n, TDE_OBS_H, TDE_OBS_W), dtype=torch.uint8, device=self.frames.device)
+        groups = out.view(rows, n, 3, TDE_OBS_H, TDE_OBS_W)
+        for j in range(n):
+            f = self.frames[t + j] if envs is None else self.frames[t + j][envs]
+            keep = (age >= n - 1 - j).to(torch.uint8).view(rows, 1, 1, 1)      # frame j is n - 1 - j steps old
+            torch.mul(f, keep, out=groups[:, j])
+        return out
 
 
 Policy = Callable[[torch.Tensor], object]
@@ -63,8 +93,8 @@ class RolloutCollector:
                  frame_copy: str = "scatter", cuda_graph: bool = False):
         if n_stack < 2 or n_stack > 8:
             raise ValueError("n_stack must be in 2..8 (use Engine.step for a plain observation)")
-        if frame_copy not in ("scatter", "shift"):
-            raise ValueError("frame_copy must be 'scatter' or 'shift'")
+        if frame_copy not in ("scatter", "shift", "ring"):
+            raise ValueError("frame_copy must be 'scatter', 'shift' or 'ring'")
         self.frame_copy = frame_copy
         # cuda_graph=True: from the third rollout on, collect() replays one captured CUDA graph of the whole rollout (the
         # tde_* calls only enqueue work on the current stream, so they capture).  For policies made of static-shape GPU ops
@@ -74,7 +104,10 @@ class RolloutCollector:
         self._graph = None
         self._graph_policy = None
         self.engine, self.n_steps, self.n_stack = engine, int(n_steps), int(n_stack)
-        self.buffer = RolloutBuffer(n_steps, engine.E, n_stack, engine.device, with_info=with_info)
+        self.buffer = RolloutBuffer(n_steps, engine.E, n_stack, engine.device, with_info=with_info, ring=frame_copy == "ring")
+        if frame_copy == "ring":
+            self._slots = torch.arange(self.n_steps + 1, dtype=torch.int32, device=engine.device).view(-1, 1)
+            self._stack_now = None      # scratch for policies that read the observation while the rollout is collected
         self._info = None if with_info else torch.zeros((engine.E, TDE_INFO_STRIDE), dtype=torch.float32, device=engine.device)
         self._seed = int(seed)
         self._started = False
@@ -83,6 +116,13 @@ class RolloutCollector:
     def reset(self) -> torch.Tensor:
         b = self.buffer
         self.engine.reset(seed=self._seed)
+        if self.frame_copy == "ring":
+            b.frames[: self.n_stack].zero_()
+            self.engine.render(out=b.frames[self.n_stack - 1])
+            b.episode_starts[0].fill_(1)
+            b.ages[0].zero_()
+            self._started = True
+            return b.stacked(0)
         b.observations[0].zero_()
         self.engine.render_stacked(b.observations[0], self.n_stack)
         b.episode_starts[0].fill_(1)
@@ -118,7 +158,51 @@ class RolloutCollector:
         self.num_timesteps += self.n_steps * self.engine.E
         return self.buffer
 
+    def _collect_ring(self, policy: Policy, carry: bool) -> None:
+        """One rollout into the ring of frames: step t stores its frame once, in slot t + n_stack."""
+        b, eng, T, n = self.buffer, self.engine, self.n_steps, self.n_stack
+        if carry:
+            for j in range(n):                               # n_stack frames per rollout: 1 / n_steps of the traffic
+                b.frames[j].copy_(b.frames[T + j])           # (ascending: a source slot is read before it is a destination)
+            b.episode_starts[0].copy_(b.episode_starts[T])
+            b.ages[0].copy_(b.ages[T])
+        into = bool(getattr(policy, "writes_into", False))
+        reads = bool(getattr(policy, "needs_observation", True))
+        for t in range(T):
+            if reads:
+                if self._stack_now is None:
+                    self._stack_now = torch.empty((eng.E, 3 * n, TDE_OBS_H, TDE_OBS_W), dtype=torch.uint8, device=b.frames.device)
+                obs = b.stacked(t, out=self._stack_now)
+            else:
+                obs = b.frames[t + n - 1]                    # the policy only looks at shape and device
+            if into:
+                policy(obs, out=b.actions[t])
+            else:
+                out = policy(obs)
+                if isinstance(out, (tuple, list)):
+                    act, val, logp = out
+                    b.values[t].copy_(val.reshape(-1))
+                    b.log_probs[t].copy_(logp.reshape(-1))
+                else:
+                    act = out
+                b.actions[t].copy_(act.reshape(eng.E, 2))
+            eng.step_into(b.actions[t], b.frames[t + n], reward=b.rewards[t], terminated=b.terminated[t], truncated=b.truncated[t],
+                          info=b.infos[t] if b.infos is not None else self._info)
+            if reads:   # the next observation's age is needed before the rollout ends
+                running = 1 - torch.bitwise_or(b.terminated[t], b.truncated[t])
+                torch.mul(torch.clamp(b.ages[t] + 1, max=n - 1), running, out=b.ages[t + 1])
+        torch.bitwise_or(b.terminated, b.truncated, out=b.episode_starts[1:])
+        if not reads:
+            # all ages of the rollout at once: age[t] = min(n - 1, t - slot of the last episode start at or before t), the
+            # episode running in slot 0 having started ages[0] slots before it
+            first = torch.where(b.episode_starts[:1].bool(), 0, -b.ages[:1].to(torch.int32))
+            begun = torch.where(b.episode_starts[1:].bool(), self._slots[1:], -(1 << 20))
+            last = torch.cummax(torch.cat((first, begun), 0), dim=0).values
+            b.ages.copy_(torch.clamp(self._slots - last, max=n - 1))
+
     def _collect_body(self, policy: Policy, carry: bool) -> None:
+        if self.frame_copy == "ring":
+            return self._collect_ring(policy, carry)
         b, eng, T = self.buffer, self.engine, self.n_steps
         if carry:
             b.observations[0].copy_(b.observations[T])      # one slot per rollout: 1/n_steps of the traffic
@@ -148,7 +232,7 @@ class RolloutCollector:
         torch.bitwise_or(b.terminated, b.truncated, out=b.episode_starts[1:])     # one launch per rollout, not per step
 
     def last_observation(self) -> torch.Tensor:
-        return self.buffer.observations[self.n_steps]
+        return self.buffer.stacked(self.n_steps)
 
     def returns_and_advantages(self, last_values: torch.Tensor, gamma: float = 0.99, gae_lambda: float = 0.95) -> Tuple[torch.Tensor, torch.Tensor]:
         """GAE(lambda) over the collected rollout (SB3 RolloutBuffer.compute_returns_and_advantage):
@@ -204,5 +288,6 @@ def uniform_policy(action_low=(-1.0, -0.3), action_high=(1.0, 0.3), seed: int = 
         return torch.addcmul(state["lo"], state["u"][k], state["span"], out=out)
 
     policy.writes_into = True
+    policy.needs_observation = False     # a ring-of-frames collector does not have to gather the stack for it
     policy.before_rollout = before_rollout
     return policy

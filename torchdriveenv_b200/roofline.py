@@ -22,8 +22,8 @@ def rollout_bytes_per_env_step(num_agents: int, n_stack: int) -> int:
 
 
 def rollout_traffic_per_env_step(num_agents: int, n_stack: int, frame_copy: str = "scatter") -> int:
-    """Bytes the rollout step actually moves per env: scatter mode writes the frame n_stack times; shift mode reads
-    n_stack - 1 frames and writes n_stack."""
+    """Bytes the rollout step actually moves per env: the ring of frames writes the frame once; scatter mode writes it
+    n_stack times; shift mode reads n_stack - 1 frames and writes n_stack."""
     frame = 3 * 64 * 64
-    frames = n_stack if frame_copy == "scatter" else 2 * n_stack - 1
+    frames = 1 if frame_copy == "ring" else n_stack if frame_copy == "scatter" else 2 * n_stack - 1
     return bytes_per_env_step(num_agents, False) + frames * frame + 8
