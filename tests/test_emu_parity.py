@@ -104,6 +104,10 @@ def test_emu_collision_and_offroad_boxes(oracle):
     eng = EmuEngine(S.ScenarioSet([patch], [S.make_scenario(0, [[5, 5], [50, 5]], 0, 0, "p")]), 1, 1)
     assert np.array_equal(eng.collision_boxes(st, at), oracle.collision_boxes(st, at))
     assert np.array_equal(eng.offroad_boxes(0, st, at), oracle.offroad_boxes(patch.road_tris, 0.5, st, at))
+    # boxes off the grid (every triangle is a candidate), absent agents, a ragged count (35 boxes: 3 lanes of the second round)
+    st3, at3 = S.scatter_boxes(5, 7, size=140.0, seed=8, present_p=0.7)
+    st3[..., :2] -= 40.0
+    assert np.array_equal(eng.offroad_boxes(0, st3, at3), oracle.offroad_boxes(patch.road_tris, 0.5, st3, at3))
     # a pile-up: more candidate pairs than the compacted pair list holds
     st2, at2 = S.scatter_boxes(6, 64, size=15.0, seed=4)
     got, want = eng.collision_boxes(st2, at2), oracle.collision_boxes(st2, at2)

@@ -165,14 +165,15 @@ __device__ __forceinline__ Box sat_ld(const SatScratch<AH>* ws, int a) {
 // box overlaps its own.  Broad phase: lane = agent a, box j broadcast from shared memory, circle test
 // with the circumradius bounds (+1 cm, +0.1 %), only pairs a < j are kept as a bit per lane.  The
 // surviving pairs are compacted into a list and the exact 4-axis SAT (bitwise symmetric in its
-// arguments) runs once per pair with all lanes busy; a hit counts for both agents.
+// arguments) runs once per pair with all lanes busy; a hit counts for both agents.  The broad phase only
+// has to be conservative, not reproducible: it uses fused multiply-adds and radii scaled by sqrt(1.001) up front.
 template <int AH>
 __device__ __forceinline__ void sat_counts(SatScratch<AH>* ws, const Box (&me)[AH], int A, int lane, float (&cnt_out)[AH]) {
     float rr[AH];
 #pragma unroll
     for (int h = 0; h < AH; ++h) {
         int a = h * 32 + lane;
-        rr[h] = (a < A && me[h].present != 0.0f) ? me[h].r + 0.005f : __int_as_float(0x7fc00000);
+        rr[h] = (a < A && me[h].present != 0.0f) ? (me[h].r + 0.005f) * 1.0005f : __int_as_float(0x7fc00000);   // 1.0005^2 > 1.001
         if (a < A) {
             ws->pos[a] = make_float4(me[h].x, me[h].y, rr[h], 0.0f);
             ws->ext[a] = make_float4(me[h].c, me[h].s, me[h].hl, me[h].hw);
@@ -188,18 +189,17 @@ __device__ __forceinline__ void sat_counts(SatScratch<AH>* ws, const Box (&me)[A
     if (AH == 1) {
         // one slot per lane: rotate instead of broadcasting.  At step r lane a meets lane (a + r) mod 32, so
         // r = 1..15 visits every unordered pair once and r = 16 twice (kept for a < 16): half the tests.
-        unsigned m = 0u;
+        unsigned m = 0u;   // bit r: the agent r lanes further on (mod 32) is a candidate
 #pragma unroll 4
         for (int r = 1; r <= 16; ++r) {
             const int src = (lane + r) & 31;
             const float ox = __shfl_sync(FULL_MASK, me[0].x, src), oy = __shfl_sync(FULL_MASK, me[0].y, src);
             const float orr = __shfl_sync(FULL_MASK, rr[0], src);
-            float dx = ox - me[0].x, dy = oy - me[0].y;
-            float R = rr[0] + orr;
-            bool cand = (dx * dx + dy * dy <= R * R * 1.001f) && (r < 16 || lane < 16);  // NaN radius: never
-            if (cand) m |= 1u << src;
+            const float dx = ox - me[0].x, dy = oy - me[0].y, R = rr[0] + orr;
+            if (__fmaf_rn(dx, dx, dy * dy) <= R * R) m |= 1u << r;   // NaN radius: never
         }
-        cm[0][0] = m;
+        if (lane >= 16) m &= 0xffffu;                          // r = 16 meets every pair twice
+        cm[0][0] = __funnelshift_l(m, m, lane);                // bit r -> bit (lane + r) mod 32
     } else
 #pragma unroll
     for (int g = 0; g < AH; ++g) {
@@ -210,12 +210,11 @@ __device__ __forceinline__ void sat_counts(SatScratch<AH>* ws, const Box (&me)[A
 #pragma unroll
             for (int h = 0; h < AH; ++h) {
                 if (h > g) continue;  // only pairs a < j
-                float dx = o.x - me[h].x, dy = o.y - me[h].y;
-                float R = rr[h] + o.z;
-                bool cand = (dx * dx + dy * dy <= R * R * 1.001f) && (h < g || jj > lane);  // NaN radius: never
-                if (cand) cm[h][g] |= 1u << jj;
+                const float dx = o.x - me[h].x, dy = o.y - me[h].y, R = rr[h] + o.z;
+                if (__fmaf_rn(dx, dx, dy * dy) <= R * R) cm[h][g] |= 1u << jj;   // NaN radius: never
             }
         }
+        cm[g][g] &= ~((2u << lane) - 1u);   // within a group of 32 only j > a (the test above also met j <= a)
     }
     int n = 0;
 #pragma unroll
@@ -802,19 +801,99 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32) tde_collision_kernel
     }
 }
 
-__global__ void __launch_bounds__(256) tde_offroad_kernel(const MapDev* maps, int map_id, float thr,
-                                                          const float4* __restrict__ state, const float4* __restrict__ attr,
-                                                          int n, float* __restrict__ out) {
+// Stateless offroad (config C4: scattered boxes, half of the corners off the road).  Walking each corner's candidate
+// list in its own lane leaves 12 of 32 lanes busy (the lists differ in length and half the lanes have none), so the
+// (corner, candidate) pairs of a warp's 32 boxes are numbered consecutively and taken 32 at a time with every lane
+// busy, the way the rasteriser takes (primitive, row) items: a scan over the list lengths, a binary search for the
+// corner an item belongs to, a shared-memory atomicMin per corner (non-negative binary32 values order like their bit
+// patterns).  Same candidates, same per-candidate arithmetic, a minimum and a sum in the same order: same bits as
+// mesh_infractions_warp.
+struct OffroadScratch {        // per warp; corner c = 4 * lane + k
+    uint32_t start[128];       // candidates before corner c
+    int base[128];             // first item of the corner's list, or -1: every triangle of the map, containment included
+    float px[128], py[128];
+    uint32_t best[128];        // min squared distance so far (bit pattern)
+    unsigned short nover[128]; // the first nover candidates of the corner overlap its cell: the ones that can contain it
+    uint32_t inside[4];        // corners found inside a triangle
+};
+#define TDE_OFFROAD_WARPS 8
+__global__ void __launch_bounds__(TDE_OFFROAD_WARPS * 32) tde_offroad_kernel(const MapDev* maps, int map_id, float thr,
+                                                                              const float4* __restrict__ state, const float4* __restrict__ attr,
+                                                                              int n, float* __restrict__ out) {
+    __shared__ OffroadScratch scratch[TDE_OFFROAD_WARPS];
     const MapDev& M = maps[map_id];
     const int lane = threadIdx.x & 31;
+    OffroadScratch* ws = &scratch[threadIdx.x >> 5];
     const int stride = gridDim.x * blockDim.x;
-    for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < n; base += stride) {  // warp-uniform trip count
-        int i = base + lane;
+    for (int first = blockIdx.x * blockDim.x + (threadIdx.x & ~31); first < n; first += stride) {  // warp-uniform trip count
+        const int i = first + lane;
         float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), a4 = make_float4(1.f, 1.f, 1.f, 0.f);
         if (i < n) { s4 = state[i]; a4 = attr[i]; }
-        Box b = tde_make_box(s4.x, s4.y, s4.z, a4.x, a4.y, a4.w);
-        MapRef R; R.g = &M; R.tri_s = R.stop_s = R.lights_s = R.cells_s = 0u;
-        float val = mesh_infractions_warp<false, false>(R, b, i < n && a4.w != 0.0f, thr, lane).offroad;
-        if (i < n) out[i] = val;
+        const Box b = tde_make_box(s4.x, s4.y, s4.z, a4.x, a4.y, a4.w);
+        const bool mine = i < n && a4.w != 0.0f && M.ntri > 0;
+        uint32_t cnt[4];
+        unsigned need = 0u;
+        if (lane < 4) ws->inside[lane] = 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float px, py;
+            tde_box_corner(b, k, px, py);
+            cnt[k] = 0u;
+            int bs = 0, nov = 0;
+            if (mine) {
+                const float fx = floorf((px - M.gx0) * M.inv_cell), fy = floorf((py - M.gy0) * M.inv_cell);
+                if (!(fx >= 0.0f && fy >= 0.0f && fx < (float)M.gnx && fy < (float)M.gny)) {
+                    need |= 1u << k; cnt[k] = (uint32_t)M.ntri; bs = -1;     // off the grid: every triangle, containment included
+                } else {
+                    const int2 rec = __ldg(&M.cell_rec[(int)fy * M.gnx + (int)fx]);
+                    // a cell that is not SAFE: all its candidates become items; the overlapping ones (listed first) are
+                    // also tested for containment, and a corner found inside ignores its distance
+                    if (!(rec.y & TDE_CELL_SAFE)) { need |= 1u << k; cnt[k] = (uint32_t)rec.y >> 16; bs = rec.x; nov = rec.y & 0x7fff; }
+                }
+            }
+            const int c = 4 * lane + k;
+            ws->base[c] = bs; ws->px[c] = px; ws->py[c] = py; ws->best[c] = 0x7f800000u; ws->nover[c] = (unsigned short)nov;
+        }
+        const uint32_t mine_total = cnt[0] + cnt[1] + cnt[2] + cnt[3];
+        uint32_t incl = mine_total;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL_MASK, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const uint32_t total = __shfl_sync(FULL_MASK, incl, 31);
+        const uint32_t excl = incl - mine_total;
+        *reinterpret_cast<uint4*>(&ws->start[4 * lane]) = make_uint4(excl, excl + cnt[0], excl + cnt[0] + cnt[1], excl + cnt[0] + cnt[1] + cnt[2]);
+        __syncwarp();
+        for (uint32_t w0 = 0; w0 < total; w0 += 32) {   // warp-uniform trip count: the search shuffles
+            const uint32_t w = min(w0 + lane, total - 1u);   // surplus lanes of the last pass repeat its last item (min is idempotent)
+            // the last corner that starts at or before item w (corners without candidates share their start with the next
+            // one): the box by a binary search over the lanes' running totals, then one of its four corners
+            int o = 0;
+#pragma unroll
+            for (int st = 16; st >= 1; st >>= 1) {
+                const uint32_t v = __shfl_sync(FULL_MASK, excl, (o + st) & 31);
+                if (v <= w) o += st;
+            }
+            const uint4 s4c = *reinterpret_cast<const uint4*>(&ws->start[4 * o]);
+            const int c = 4 * o + (w >= s4c.y) + (w >= s4c.z) + (w >= s4c.w);
+            const int j = (int)(w - ws->start[c]), bs = ws->base[c];
+            const float qx = ws->px[c], qy = ws->py[c];
+            const Tri3 T = tde_load_tri<false>(M.tri, 0u, bs < 0 ? j : (int)__ldg(&M.cell_items[bs + j]));
+            float dc, ds;
+            if ((bs < 0 || j < (int)ws->nover[c]) && tde_tri_contains(T, qx, qy, dc, ds)) atomicOr(&ws->inside[c >> 5], 1u << (c & 31));
+            atomicMin(&ws->best[c], __float_as_uint(tde_tri_segdist2(T, qx, qy)));
+        }
+        __syncwarp();
+        float sum = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = 4 * lane + k;
+            float d2 = 0.0f;
+            if (need & (1u << k)) d2 = (ws->inside[c >> 5] >> (c & 31)) & 1u ? 0.0f : __uint_as_float(ws->best[c]);
+            sum = sum + fmaxf(sqrtf(d2) - thr, 0.0f);
+        }
+        if (i < n) out[i] = mine ? sum : 0.0f;
+        __syncwarp();   // the scratch is rewritten by the next round
     }
 }
