@@ -623,20 +623,46 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
     # CUDA events on the launching stream bracket the timed region; inside it one more event every EV steps gives
     # the per-launch durations (an event record between every pair of launches costs about 1 % of a C3 step)
     EV = 10
+    # the timed steps are replayed from CUDA graphs of 50 steps each (Engine.capture_steps): a small batch (C2: 1,024 envs)
+    # steps in less time than the host needs to issue a launch, and on C3 the replay closes most of the gap between the two
+    # kernels of a step.  `eager_ms_per_step` (one tde_step call per step from Python) is reported beside it.
+    use_graph = args.cuda_graph != "off"
+    if use_graph:
+        EV = 50
+        K = max(EV, K // EV * EV)
+        graph = eng.capture_steps(acts[(torch.arange(EV) + W) % n_act], render=render)
+        per_step_launches = (eng.num_kernel_launches() - launches0) // EV
+        graph.replay()          # the capture itself ran nothing
+        barrier()
     marks = sorted(set(range(0, K, EV)) | {K})
     evs = {k: torch.cuda.Event(enable_timing=True) for k in marks}
     t0 = time.time()
     evs[0].record(stream)
-    for k in range(K):
-        eng.step(acts[(W + k) % n_act], render=render)
-        if (k + 1) in evs:
-            evs[k + 1].record(stream)
+    if use_graph:
+        for k in range(0, K, EV):
+            graph.replay()
+            evs[k + EV].record(stream)
+    else:
+        for k in range(K):
+            eng.step(acts[(W + k) % n_act], render=render)
+            if (k + 1) in evs:
+                evs[k + 1].record(stream)
     barrier()
     t1 = time.time()
     clocks = sampler.stop(t0, t1) if sampler else None
     total_ms = evs[0].elapsed_time(evs[K])
     per_launch_ms = float(np.sum([evs[a].elapsed_time(evs[b]) for a, b in zip(marks[:-1], marks[1:])]) / K)
-    gpu_launches = eng.num_kernel_launches() - launches0
+    gpu_launches = per_step_launches * K if use_graph else eng.num_kernel_launches() - launches0
+    eager_ms = None
+    if use_graph:
+        n_eager = min(K, 200)
+        ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ee0.record(stream)
+        for k in range(n_eager):
+            eng.step(acts[k % n_act], render=render)
+        ee1.record(stream)
+        barrier()
+        eager_ms = ee0.elapsed_time(ee1) / n_eager
     tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -686,6 +712,8 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
                 avg_launch_ms=per_launch_ms, peak_source=peak_src)
     cpu = cpu_oracle_throughput(workload, args.cpu_seconds) if world == 1 and not args.no_cpu_baseline else None
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=total_ms_max / K,
+                launch_mode="CUDA graphs of %d steps (Engine.capture_steps)" % EV if use_graph else "one tde_step call per step",
+                eager_ms_per_step=eager_ms,
                 higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype="f32", data="synthetic",
                 config=config_dict(workload, desc, E, A, render, world),
                 clocks=clocks, gpu_launches=int(gpu_launches),
@@ -713,7 +741,7 @@ def slim(line):
     """A sub-line of `other_configs`: the measurement without the nested extras."""
     if line is None:
         return None
-    keep = ("metric", "value", "unit", "steps", "warmup", "ms_per_step", "config", "clocks", "gpu_launches", "e2e", "roofline", "episode_stats")
+    keep = ("metric", "value", "unit", "steps", "warmup", "ms_per_step", "launch_mode", "eager_ms_per_step", "config", "clocks", "gpu_launches", "e2e", "roofline", "episode_stats")
     return {k: line[k] for k in keep if k in line}
 
 
@@ -726,6 +754,8 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--cuda-graph", choices=("auto", "on", "off"), default="auto",
+                    help="replay the timed steps from CUDA graphs of 50 steps (auto = on)")
     ap.add_argument("--c5-frame-copy", choices=("ring", "scatter", "shift"), default="ring", help="how the C5 rollout buffer keeps the frame stack")
     ap.add_argument("--host-obs", choices=("rgb", "classes"), default="classes",
                     help="what tde_step_host sends over PCIe for the observation in the e2e leg (both are timed, this one is e2e.value)")

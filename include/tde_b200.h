@@ -40,9 +40,12 @@
  *     tde_last_error().  Nothing throws or exits across this boundary.
  *   - tde_step / tde_render / tde_kinematics / ... never allocate, never synchronise with the host and
  *     only enqueue work on `stream`, so they can be captured into a CUDA graph.  The exceptions say so at
- *     their declaration: tde_step_host (allocates device staging buffers on first use, runs its device-to-host
- *     copies on an internal second stream and synchronises `stream` before it returns), tde_render_view (may grow
+ *     their declaration: tde_step_host (allocates device and pinned staging buffers on first use, runs its device-to-host
+ *     copies on an internal second stream, expands the frames on a pool of host threads it owns and synchronises
+ *     `stream` before it returns), tde_render_view (may grow
  *     its scratch), tde_get_episode_stats (synchronises), tde_create / tde_upload_scenarios / tde_clone (allocate).
+ *     A step without observations (obs_dev == NULL) is launched with programmatic stream serialization unless `stream`
+ *     is capturing: it may be scheduled while the previous kernel on the stream drains and waits for it on the device.
  *   - A handle is bound to one GPU and is not thread-safe.  Every call runs on the handle's GPU and restores the
  *     caller's current CUDA device before it returns.
  *   - The seed belongs to the handle: tde_reset with env_mask_dev == NULL sets it, a masked reset keeps it.

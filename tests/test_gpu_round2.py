@@ -316,3 +316,30 @@ def test_ring_of_frames_rollout_equals_the_scatter_rollout():
             n_done += int(bs.episode_starts[1:].sum())
         assert n_done > 20
         assert torch.equal(cols[1].last_observation(), cols[0].last_observation())
+
+
+def test_capture_steps_replays_the_eager_steps(oracle):
+    """Engine.capture_steps: a CUDA graph of G consecutive steps leaves the envs exactly where G eager steps (and the
+    oracle) leave them, replay after replay."""
+    E, A, G = 200, 16, 7
+    ss = S.roundabout(A)
+    cfg = dict(auto_reset=1)
+    eager, graphed = _engine(ss, E, A, **cfg), _engine(ss, E, A, **cfg)
+    orc = oracle.OracleEnvSet(default_config(num_envs=E, max_agents=A, **cfg), eager.packed)
+    for eng in (eager, graphed, orc):
+        eng.reset(seed=6)
+    rng = np.random.default_rng(2)
+    seq = torch.zeros((G, E, 2), dtype=torch.float32, device="cuda:0")
+    graph = graphed.capture_steps(seq, render=True)
+    for r in range(4):
+        a = np.stack([rng.uniform(-1, 1, (G, E)), rng.uniform(-0.3, 0.3, (G, E))], -1).astype(np.float32)
+        seq.copy_(torch.from_numpy(a))          # the graph reads the actions at replay time
+        graph.replay()
+        for j in range(G):
+            eager.step(torch.from_numpy(a[j]).cuda())
+            want = orc.step(a[j])
+        torch.cuda.synchronize()
+        assert torch.equal(graphed.get_state(), eager.get_state()), f"replay {r}"
+        assert torch.equal(graphed.obs, eager.obs) and torch.equal(graphed.reward, eager.reward)
+        assert torch.equal(graphed.get_env_vars(), eager.get_env_vars())
+        assert np.array_equal(graphed.obs.cpu().numpy(), want[0]) and np.array_equal(graphed.get_state().cpu().numpy(), orc.state)

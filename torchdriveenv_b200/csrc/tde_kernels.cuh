@@ -118,10 +118,12 @@ __device__ __forceinline__ unsigned long long tde_now() { unsigned long long t; 
 #define TDE_TRACE_MARK(e, k) do { } while (0)
 #endif
 
-// Programmatic dependent launch (experiment, -DTDE_PDL): a step kernel lets the next kernel on the stream be
-// scheduled once all its warps have run dry, and itself waits for the previous kernel's completion and memory
-// flush before it reads anything that kernel may have written.  No-ops without the launch attribute.
-#ifdef TDE_PDL
+// Programmatic dependent launch: a step kernel lets the next kernel on the stream be scheduled once all its warps have
+// run dry, and itself waits for the previous kernel's completion and memory flush before it reads anything that
+// kernel may have written.  No-ops unless the next kernel is launched with the attribute: the physics kernel of a step
+// without observations is (small batches step in 10 us, the gap between two launches is 2 of them); between the physics
+// and the render kernel of a full step it loses (different shared-memory carve-outs).
+#ifndef TDE_HOST_EMU
 __device__ __forceinline__ void tde_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void tde_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 #else
