@@ -118,7 +118,8 @@ class Engine:
             raise ValueError(f"actions_seq must have shape [G, {self.E}, 2]")
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.device(self.device), torch.cuda.graph(graph):
+        # thread_local: CUDA calls of other threads (a NCCL watchdog, a clock sampler) must not abort the capture
+        with torch.cuda.device(self.device), torch.cuda.graph(graph, capture_error_mode="thread_local"):
             for j in range(seq.shape[0]):
                 self.step(seq[j], render=render)
         graph._tde_actions = seq      # the graph reads this tensor at every replay: keep it alive with the graph

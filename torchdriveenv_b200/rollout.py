@@ -151,7 +151,7 @@ class RolloutCollector:
             if self._graph is None or self._graph_policy is not policy:
                 torch.cuda.synchronize(self.engine.device)
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
                     self._collect_body(policy, carry=True)
                 self._graph, self._graph_policy = g, policy              # the capture does not run the work: replay it now
             self._graph.replay()
