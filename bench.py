@@ -623,13 +623,16 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
     # CUDA events on the launching stream bracket the timed region; inside it one more event every EV steps gives
     # the per-launch durations (an event record between every pair of launches costs about 1 % of a C3 step)
     EV = 10
-    # the timed steps are replayed from CUDA graphs of 50 steps each (Engine.capture_steps): a small batch (C2: 1,024 envs)
+    # the timed steps are replayed from CUDA graphs of up to 50 steps each (Engine.capture_steps): a small batch (C2: 1,024 envs)
     # steps in less time than the host needs to issue a launch, and on C3 the replay closes most of the gap between the two
     # kernels of a step.  `eager_ms_per_step` (one tde_step call per step from Python) is reported beside it.
     use_graph = args.cuda_graph != "off"
+    if use_graph:   # exactly K steps are timed: the block length is the largest divisor of K up to 50
+        EV = max(d for d in range(1, 51) if K % d == 0)
+        use_graph = EV >= 5
+        if not use_graph:
+            EV = 10
     if use_graph:
-        EV = 50
-        K = max(EV, K // EV * EV)
         graph = eng.capture_steps(acts[(torch.arange(EV) + W) % n_act], render=render)
         per_step_launches = (eng.num_kernel_launches() - launches0) // EV
         graph.replay()          # the capture itself ran nothing
