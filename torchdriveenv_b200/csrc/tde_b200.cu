@@ -419,10 +419,13 @@ StaticIndex build_static_index(const std::vector<float>& road, const std::vector
     add(road, TDE_CLS_ROAD);
     add(mark, TDE_CLS_LANE_MARKING);
     if (items.empty()) { si.tile_start.assign(2, 0); return si; }
-    // tile size: 8 m unless the viewport is large; primitives longer than two tiles stay out of the tiles
-    double T = std::max(8.0, (2.0 * reach + 16.0) / 20.0);
+    // tile size: 4 m unless the viewport is large (measured at fov 35: 8 / 6 / 4 / 3 / 2 m -> render 106.8 / 105.7 / 105.4 /
+    // 104.9 / 105.0 us); primitives longer than 16 m (and than two tiles) stay out of the tiles.  TDE_TILE_M overrides.
+    double T0 = 4.0;
+    if (const char* v = std::getenv("TDE_TILE_M")) T0 = std::max(0.5, std::atof(v));
+    double T = std::max(T0, (2.0 * reach + 16.0) / 20.0 * (T0 / 8.0));
     for (int attempt = 0; attempt < 8; ++attempt) {
-        const float big = (float)(2.0 * T);
+        const float big = (float)std::max(2.0 * T, 16.0);
         float lox = INFINITY, loy = INFINITY, hix = -INFINITY, hiy = -INFINITY, maxext = 0.f;
         for (auto& it : items)
             if (it.ext <= big) { lox = std::min(lox, it.lox); loy = std::min(loy, it.loy); hix = std::max(hix, it.lox); hiy = std::max(hiy, it.loy); maxext = std::max(maxext, it.ext); }
@@ -435,7 +438,7 @@ StaticIndex build_static_index(const std::vector<float>& road, const std::vector
         if ((double)si.nx * si.ny <= 4.0e6 && rows <= 24.0) break;
         T *= 1.5;
     }
-    const float big = (float)(2.0 / (double)si.inv);
+    const float big = (float)std::max(2.0 / (double)si.inv, 16.0);
     for (auto& it : items) {
         if (it.ext > big) { it.tile = -1; continue; }
         int tx = (int)std::floor((it.lox - si.gx0) * si.inv), ty = (int)std::floor((it.loy - si.gy0) * si.inv);
