@@ -89,7 +89,6 @@ struct tde_handle {
     cudaEvent_t chunk_copied[16] = {};
     ExpandPool* pool = nullptr;
     bool pdl_physics = true;  // TDE_PDL_PHYSICS=0 switches the programmatic dependent launch of render-less steps off
-    int offroad_per_sm = 0;   // tde_offroad_boxes: resident CTAs per SM the kernel's carve-out was set for
     std::string err;
 };
 
@@ -1413,16 +1412,10 @@ extern "C" int tde_offroad_boxes(tde_handle* h, int32_t map_id, const float* sta
     if (!state || !attr || !out || E < 1 || A < 1 || map_id < 0 || map_id >= h->tab->num_maps) return fail(h, TDE_E_INVAL, "tde_offroad_boxes: bad argument");
     TDE_ON_DEVICE(h);
     int n = E * A;
-    // 6 CTAs of 8 warps per SM: the kernel lives on L1 hits of the cell records and triangle tables, so it asks for no more
-    // shared memory than its resident CTAs use (measured: 232 us against 266 us with 8 CTAs per SM)
+    // 6 CTAs of 8 warps per SM: the kernel lives on L1 hits of the cell records and triangle tables, and every resident
+    // CTA takes 22 KB of shared memory away from L1 (measured: 232 us against 266 us with 8 CTAs per SM, 243 with 4)
     int per_sm = 6;
     if (const char* v = std::getenv("TDE_OFFROAD_CTAS")) per_sm = std::max(1, std::min(8, std::atoi(v)));
-    if (h->offroad_per_sm != per_sm) {
-        int carve = (int)((per_sm * (sizeof(OffroadScratch) * TDE_OFFROAD_WARPS + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
-        if (const char* v = std::getenv("TDE_OFFROAD_CARVE")) carve = std::atoi(v);
-        if (carve >= 0) CUDA_TRY(h, cudaFuncSetAttribute(tde_offroad_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, std::min(carve, 100)));
-        h->offroad_per_sm = per_sm;
-    }
     int grid = std::max(1, std::min((n + 255) / 256, h->sm_count * per_sm));
     TDE_LAUNCH(grid, TDE_OFFROAD_WARPS * 32, 0, (cudaStream_t)stream, tde_offroad_kernel)(h->tab->maps_dev, map_id, h->cfg.offroad_threshold, (const float4*)state,
                                                                (const float4*)attr, n, out);
