@@ -162,10 +162,11 @@ typedef struct tde_config {
     float fov;                     /* metres covered by the 64 px birdview, default 35 */
     float start_speed_max;         /* :358 10 */
     float start_heading_sigma;     /* :361 0.1 */
-    int32_t stage_map_tables;      /* 1: the physics kernel copies the per-map tables (lane-mesh triangle records, stop
-                                      lines, light schedule, per-cell summary) into shared memory once per CTA with
-                                      bulk-async copies (cp.async.bulk + mbarrier) when they fit; 0 (default): it reads
-                                      them through L1.  The environment variable TDE_PHYS_STAGE overrides it. */
+    int32_t stage_map_tables;      /* the physics kernel can copy the per-map tables (lane-mesh triangle records, stop lines,
+                                      light schedule, per-cell summary) into shared memory once per CTA with bulk-async
+                                      copies (cp.async.bulk + mbarrier) when they fit, instead of reading them through L1.
+                                      0 (default): it does for handles of at most 8 envs per SM (small batches start every
+                                      launch with a cold L1), 1: always, 2: never.  TDE_PHYS_STAGE=0|1 overrides it. */
     int32_t host_obs_rgb;          /* tde_step_host only.  0 (default): the frames cross PCIe as the 4-bit class image (2 KB
                                       per env) and host threads (TDE_HOST_THREADS; default: the CPUs of the process /
                                       LOCAL_WORLD_SIZE, at most 16) expand them to the caller's RGB planes with the

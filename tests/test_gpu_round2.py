@@ -185,12 +185,14 @@ def test_clone_steps_like_the_original(oracle):
     twin.close()
 
 
-@pytest.mark.parametrize("E,A", [(700, 32), (96, 64), (1, 9)])
-def test_staged_map_tables_match_the_default_launch(oracle, E, A):
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("E,A", [(700, 32), (96, 64), (1, 9), (1500, 16)])
+def test_staged_map_tables_match_the_default_launch(oracle, E, A, mode):
     """cfg.stage_map_tables = 1: the lane-mesh triangle records, stop lines, light schedule and the per-cell summary are
-    copied into shared memory once per CTA (cp.async.bulk + mbarrier); results equal the oracle's, as the default launch's do."""
+    copied into shared memory once per CTA (cp.async.bulk + mbarrier); 2: they are read through L1 (what a large batch does
+    by default; small batches are staged by default).  Results equal the oracle's either way."""
     ss = S.three_way(6) if A == 9 else S.traffic_lights(A)
-    cfg = dict(auto_reset=1, stage_map_tables=1)
+    cfg = dict(auto_reset=1, stage_map_tables=mode)
     eng = _engine(ss, E, A, **cfg)
     orc = oracle.OracleEnvSet(default_config(num_envs=E, max_agents=A, auto_reset=1), eng.packed)
     eng.reset(seed=8); orc.reset(seed=8)

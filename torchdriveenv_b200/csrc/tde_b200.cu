@@ -797,10 +797,15 @@ extern "C" int tde_upload_scenarios(tde_handle* h, const tde_scenario_set* s) {
     CUDA_TRY(h, cudaMemcpy(h->scen_hi, hi.data(), sizeof(int) * h->E, cudaMemcpyHostToDevice));
     // the staged blob: [16 B header per map] [MapDev per map] [per map: triangle records, stop lines, lights, cell summary]
     // Measured at C3 (one map, 85 KB of tables): the staged launch is SLOWER than the one that reads the tables through L1
-    // (57.4 vs 53.7 us at 64 registers), so it is opt-in: TDE_PHYS_STAGE=1 or cfg.stage_map_tables = 1.
+    // (57.4 vs 53.7 us at 64 registers): after the first wave of envs the tables are L1-resident
+    // anyway.  A small batch never gets there - at most 8 envs per SM, every launch starts with a cold L1 and the table walks
+    // of a lone warp go to L2 one after the other - and there staging wins (C2: 11.5 vs 12.0 us per step).  So:
+    // cfg.stage_map_tables 0 = staged for handles of at most 8 envs per SM, 1 = always (when the tables fit), 2 = never;
+    // TDE_PHYS_STAGE=0|1 overrides.
     {
         const char* v = std::getenv("TDE_PHYS_STAGE");
-        const bool want = v ? std::atoi(v) != 0 : h->cfg.stage_map_tables == 1;
+        const bool small_batch = h->E <= 8 * h->sm_count;
+        const bool want = v ? std::atoi(v) != 0 : h->cfg.stage_map_tables == 1 || (h->cfg.stage_map_tables == 0 && small_batch);
         stage_ok = stage_ok && want;
     }
     if (stage_ok) {
