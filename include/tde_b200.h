@@ -282,6 +282,17 @@ int tde_step_rollout_scatter(tde_handle* h, const float* actions_dev, uint8_t* s
                              int32_t slots_ahead, int32_t n_stack, float* reward_dev, uint8_t* terminated_dev,
                              uint8_t* truncated_dev, float* info_dev, void* stream);
 
+/* VecFrameStack without moving a frame, for a stepping loop (TorchDriveVecEnv): `ring_dev` is uint8[ring_slots][E][3*n_stack][64][64],
+   n_stack <= ring_slots <= 64.  The step's stacked observation is slot `ring_pos`; the caller advances ring_pos by one
+   (modulo ring_slots) per step.  The new frame is stored into the newest channel group of slot ring_pos and, one group
+   further down each, into the following n_stack - 1 slots of the ring, so every slot is complete when its step comes
+   (tde_step_rollout_scatter on a ring).  The slot of step t stays intact for ring_slots - n_stack further steps: with
+   ring_slots = n_stack + 1 the previous observation survives the next step (what an on-policy trainer needs, which
+   stores the observation it acted on after stepping: examples/rl_training.py:178-181 via collect_rollouts).  Before the
+   first step: tde_render_stacked into slot 0 and its frames copied one group further down into slots 1 .. n_stack - 1. */
+int tde_step_stacked_ring(tde_handle* h, const float* actions_dev, uint8_t* ring_dev, int32_t ring_slots, int32_t ring_pos, int32_t n_stack,
+                          float* reward_dev, uint8_t* terminated_dev, uint8_t* truncated_dev, float* info_dev, void* stream);
+
 /* The step with the terminal observation kept (SB3 VecEnv contract of the caller, examples/rl_training.py:159:
    SubprocVecEnv stores the last observation of a finished episode in info["terminal_observation"] before it
    resets the env; off-policy trainers use it as next_obs, PPO for the time-limit bootstrap).  obs_dev and

@@ -139,6 +139,13 @@ class EmuEngine:
                                                       _p(self.terminated), _p(self.truncated), _p(self.info), None), "tde_step_rollout_scatter")
         return buffer_obs[t + 1], self.reward, self.terminated, self.truncated, self.info
 
+    def step_stacked_ring(self, actions, ring, pos: int, n_stack: int):
+        a = self._act(actions)
+        R = ring.shape[0]
+        self._check(self.lib.tde_step_stacked_ring(self.h, _p(a), _p(ring), int(R), int(pos) % R, int(n_stack), _p(self.reward),
+                                                   _p(self.terminated), _p(self.truncated), _p(self.info), None), "tde_step_stacked_ring")
+        return ring[int(pos) % R], self.reward, self.terminated, self.truncated, self.info
+
     def render_stacked(self, stack, n_stack: int):
         self._check(self.lib.tde_render_stacked(self.h, _p(stack), int(n_stack), None), "tde_render_stacked")
         return stack

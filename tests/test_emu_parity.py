@@ -281,3 +281,41 @@ def test_emu_class_image_and_compact_host_step(oracle, monkeypatch):
             assert np.array_equal(w, g), f"step {k}: {name} differs between the RGB and the compact host step"
             assert np.array_equal(g, o), f"step {k}: {name} differs from the oracle"
         assert np.array_equal(cmp_.render_classes(), orc.render_classes()), f"step {k}: class image"
+
+
+@pytest.mark.parametrize("NS,R", [(3, 4), (2, 2), (4, 7)])
+def test_emu_stacked_ring_is_vec_frame_stack(oracle, NS, R):
+    """tde_step_stacked_ring: slot pos of the ring is VecFrameStack's observation of the step (the oracle's frames stacked,
+    zeros before an episode's first frame), and the slots of the last R - NS steps are still intact."""
+    from emu_engine import _aligned
+    E, A = 21, 6
+    ss = S.traffic_lights(A)
+    cfg = dict(auto_reset=1, max_environment_steps=7)
+    eng = EmuEngine(ss, E, A, **cfg)
+    orc = oracle.OracleEnvSet(default_config(num_envs=E, max_agents=A, **cfg), eng.packed)
+    eng.reset(seed=5); orc.reset(seed=5)
+    ring = _aligned((R, E, 3 * NS, 64, 64), np.uint8)
+    eng.render_stacked(ring[0], NS)
+    for j in range(1, min(NS, R)):
+        ring[j][:, : 3 * (NS - j)] = ring[0][:, 3 * j:]
+    stack = np.zeros((E, 3 * NS, 64, 64), np.uint8)
+    stack[:, -3:] = orc.render()
+    assert np.array_equal(ring[0], stack)
+    history = [stack.copy()]
+    rng = np.random.default_rng(1)
+    n_done = 0
+    for k in range(1, 40):
+        a = np.stack([rng.uniform(-1, 1, E), rng.uniform(-0.3, 0.3, E)], 1).astype(np.float32)
+        obs, r, te, tr, info = eng.step_stacked_ring(a, ring, k, NS)
+        oobs, orr, ote, otr, oinfo = orc.step(a)
+        done = (ote | otr).astype(bool)
+        n_done += int(done.sum())
+        stack = np.concatenate((stack[:, 3:], oobs), 1)
+        stack[done, : 3 * (NS - 1)] = 0
+        history.append(stack.copy())
+        assert np.array_equal(obs, stack), f"step {k}"
+        assert np.array_equal(r, orr) and np.array_equal(info, oinfo)
+        for back in range(1, R - NS + 1):       # older observations that must have survived
+            if k - back >= 0:
+                assert np.array_equal(ring[(k - back) % R], history[k - back]), f"step {k}: the observation of step {k - back} was overwritten"
+    assert n_done > 10

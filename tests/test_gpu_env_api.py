@@ -82,11 +82,15 @@ def test_simulator_interface_surface(oracle):
     assert full.get_state().shape == (4, 12, 4) and full.compute_collision().shape == (4, 12)
 
 
-def test_vec_env_frame_stack_and_auto_reset(oracle):
+@pytest.mark.parametrize("frame_ring", [None, 0, 3])
+def test_vec_env_frame_stack_and_auto_reset(oracle, frame_ring):
+    """frame_ring=None: the default ring of n_stack + 1 stacked observations (no frame is moved; the tensor a step returns
+    survives the next step); 0: one tensor shifted in place by the kernel; 3: a ring without a spare slot."""
     from torchdriveenv_b200.gym_env import EnvConfig, TorchDriveVecEnv
     E = 48
     cfg = EnvConfig(seed=8, device="cuda:0", max_environment_steps=15)
-    venv = TorchDriveVecEnv(cfg, S.traffic_lights(8), num_envs=E, n_stack=3)
+    venv = TorchDriveVecEnv(cfg, S.traffic_lights(8), num_envs=E, n_stack=3, frame_ring=frame_ring)
+    last_obs, last_want = None, None
     obs = venv.reset()
     assert obs.shape == (E, 9, 64, 64) and obs.dtype == torch.uint8
     assert bool((obs[:, :6] == 0).all()) and bool((obs[:, 6:] != 0).any())
@@ -118,6 +122,9 @@ def test_vec_env_frame_stack_and_auto_reset(oracle):
                 have = age >= back
                 want[have, 3 * slot:3 * slot + 3] = frames[-1 - back][have]
         assert np.array_equal(obs.cpu().numpy(), want), f"step {k}: fused frame stack"
+        if frame_ring is None and last_obs is not None:   # the observation the policy acted on is still there after the step
+            assert np.array_equal(last_obs.cpu().numpy(), last_want), f"step {k}: the previous observation was overwritten"
+        last_obs, last_want = obs, want
         n_done += int(d.sum())
         assert set(infos.columns) >= {"offroad", "collision", "traffic_light_violation", "is_success", "terminated", "truncated"}
         # SB3's contract: a sequence of E dicts; finished envs carry Monitor's episode record and TimeLimit.truncated

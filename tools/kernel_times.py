@@ -25,5 +25,8 @@ t_rend = timed(lambda k: eng.render(out=obs))
 t_both = timed(lambda k: eng.step(acts[k % 64]))
 stack = torch.zeros((E, 9, 64, 64), dtype=torch.uint8, device="cuda")
 t_stack = timed(lambda k: eng.step_stacked(acts[k % 64], stack, 3))
-print(f"E={E} A={A} physics {t_phys:.1f} us  render {t_rend:.1f} us  step {t_both:.1f} us  ({E / t_both:.1f} M env-steps/s)  step with fused 3-frame stack {t_stack:.1f} us")
+ring = eng.new_stack_ring(3)
+eng.render_stacked_ring(ring, 3)
+t_ring = timed(lambda k: eng.step_stacked_ring(acts[k % 64], ring, k + 1, 3))
+print(f"E={E} A={A} physics {t_phys:.1f} us  render {t_rend:.1f} us  step {t_both:.1f} us  ({E / t_both:.1f} M env-steps/s)  step with fused 3-frame stack {t_stack:.1f} us  with the ring of stacks {t_ring:.1f} us")
 print("map", eng.map_info(0))

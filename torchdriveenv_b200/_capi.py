@@ -123,7 +123,7 @@ _LIB_PATH = os.environ.get("TDE_B200_LIB") or os.path.join(os.path.dirname(os.pa
 EXPORTS = [
     "tde_version", "tde_last_error", "tde_create", "tde_destroy", "tde_default_config",
     "tde_upload_scenarios", "tde_set_env_scenario_range", "tde_set_palette", "tde_reset", "tde_step",
-    "tde_step_phases", "tde_step_host", "tde_step_stacked", "tde_render_stacked", "tde_step_rollout", "tde_step_rollout_scatter", "tde_step_terminal", "tde_kinematics", "tde_render", "tde_render_classes",
+    "tde_step_phases", "tde_step_host", "tde_step_stacked", "tde_render_stacked", "tde_step_rollout", "tde_step_rollout_scatter", "tde_step_stacked_ring", "tde_step_terminal", "tde_kinematics", "tde_render", "tde_render_classes",
     "tde_compute_infractions",
     "tde_get_state", "tde_set_state", "tde_get_attributes", "tde_set_attributes", "tde_get_infractions",
     "tde_get_env_vars", "tde_set_env_vars", "tde_collision_boxes", "tde_offroad_boxes", "tde_clone",
@@ -171,6 +171,7 @@ def bind_signatures(lib: C.CDLL) -> C.CDLL:
         "tde_step_rollout": ([vp, vp, vp, vp, i32, vp, vp, vp, vp, vp], C.c_int),
         "tde_step_terminal": ([vp, vp, vp, i32, vp, vp, vp, vp, vp, vp], C.c_int),
         "tde_step_rollout_scatter": ([vp, vp, vp, i64, i32, i32, vp, vp, vp, vp, vp], C.c_int),
+        "tde_step_stacked_ring": ([vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp], C.c_int),
         "tde_kinematics": ([vp, vp, vp], C.c_int),
         "tde_render": ([vp, vp, vp], C.c_int),
         "tde_render_classes": ([vp, vp, vp], C.c_int),

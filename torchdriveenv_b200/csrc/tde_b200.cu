@@ -921,7 +921,7 @@ static cudaError_t launch_step(Kernel k, int grid, int threads, size_t smem, cud
 static int step_impl(tde_handle* h, int32_t phases, const float* actions, uint8_t* obs, int32_t n_stack, float* reward,
                      uint8_t* terminated, uint8_t* truncated, float* info, void* stream, const uint8_t* obs_prev = nullptr,
                      uint8_t* terminal_obs = nullptr, int e_begin = 0, int e_end = -1, long long slot_stride = 0, int slots_ahead = 0,
-                     bool class_nibbles = false) {
+                     bool class_nibbles = false, int ring_slots = 0, int ring_pos = 0) {
     if (!h) return TDE_E_INVAL;
     if (n_stack < 1 || n_stack > 8) return fail(h, TDE_E_INVAL, "n_stack must be in 1..8");
     if (!h->uploaded || !h->was_reset) return fail(h, TDE_E_STATE, "tde_step: upload scenarios and reset first");
@@ -940,6 +940,10 @@ static int step_impl(tde_handle* h, int32_t phases, const float* actions, uint8_
     p.truncated = truncated; p.info = info; p.n_stack = n_stack;
     p.obs_prev = obs_prev ? obs_prev : obs;
     p.slot_stride = slot_stride; p.slots_ahead = slots_ahead;
+    for (int j = 0; j < 8; ++j) {   // copy j of the new frame: j slots ahead (modulo the ring size in a ring of slots), one channel group down
+        const long long slots = ring_slots > 0 ? (long long)((ring_pos + j) % ring_slots) - ring_pos : (long long)j;
+        p.copy_off[j] = slots * slot_stride - (long long)j * (TDE_OBS_C * TDE_OBS_H * TDE_OBS_W);
+    }
     const bool scatter = slot_stride != 0;
     if (e_end >= 0) { p.e_begin = e_begin; p.e_end = e_end; }   // a slice of the envs (tde_step_host's chunks)
     cudaStream_t st = (cudaStream_t)stream;
@@ -1062,6 +1066,18 @@ extern "C" int tde_step_rollout_scatter(tde_handle* h, const float* actions, uin
     }
     return step_impl(h, TDE_PH_ALL, actions, stack_next, n_stack, reward, terminated, truncated, info, stream, nullptr, nullptr, 0, -1,
                      (long long)slot_stride_bytes, slots_ahead);
+}
+
+extern "C" int tde_step_stacked_ring(tde_handle* h, const float* actions, uint8_t* ring, int32_t ring_slots, int32_t ring_pos, int32_t n_stack,
+                                     float* reward, uint8_t* terminated, uint8_t* truncated, float* info, void* stream) {
+    if (h && !ring) return fail(h, TDE_E_INVAL, "tde_step_stacked_ring: ring is null");
+    if (h && (n_stack < 2 || n_stack > 8)) return fail(h, TDE_E_INVAL, "tde_step_stacked_ring: n_stack must be in 2..8");
+    if (h && (ring_slots < n_stack || ring_slots > 64)) return fail(h, TDE_E_INVAL, "tde_step_stacked_ring: ring_slots must be in n_stack..64");
+    if (h && (ring_pos < 0 || ring_pos >= ring_slots)) return fail(h, TDE_E_INVAL, "tde_step_stacked_ring: ring_pos out of range");
+    if (!h) return TDE_E_INVAL;
+    const long long slot = (long long)h->E * n_stack * TDE_OBS_C * TDE_OBS_H * TDE_OBS_W;
+    return step_impl(h, TDE_PH_ALL, actions, ring + (size_t)ring_pos * (size_t)slot, n_stack, reward, terminated, truncated, info, stream, nullptr, nullptr,
+                     0, -1, slot, n_stack, false, ring_slots, ring_pos);
 }
 
 extern "C" int tde_step(tde_handle* h, const float* actions, uint8_t* obs, float* reward, uint8_t* terminated,

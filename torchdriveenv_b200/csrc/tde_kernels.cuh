@@ -99,6 +99,8 @@ struct StepParams {
     int n_stack;         // frames per env in obs (1 = plain observation)
     int slots_ahead;     // scatter mode (rollout buffer): slots from the one being written to the end of the buffer, 1..n_stack
     long long slot_stride;   // scatter mode: bytes between consecutive time slots of the buffer
+    long long copy_off[8];   // scatter mode: where copy j of the new frame goes, in bytes from copy 0 (one slot ahead and one
+                             // channel group down per copy; the slots are consecutive in a rollout buffer, modulo the ring size in a ring)
     uint32_t pal[3][4];  // per channel: 16 class bytes
     float ppm, ppmy;
     // physics kernel, STAGED launches: the map tables as one blob (16 B header per map: offsets of its triangle records,

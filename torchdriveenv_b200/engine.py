@@ -217,6 +217,35 @@ class Engine:
                                                       _ptr(outs[1]), _ptr(outs[2]), _ptr(outs[3]), self._stream()), "tde_step_rollout_scatter")
         return buffer_obs[t + 1], outs[0], outs[1], outs[2], outs[3]
 
+    def new_stack_ring(self, n_stack: int, ring_slots: Optional[int] = None) -> torch.Tensor:
+        """uint8[ring_slots, E, 3*n_stack, 64, 64] for step_stacked_ring (default: n_stack + 1 slots)."""
+        R = int(ring_slots if ring_slots is not None else n_stack + 1)
+        return torch.zeros((R, self.E, 3 * int(n_stack), TDE_OBS_H, TDE_OBS_W), dtype=torch.uint8, device=self.device)
+
+    def render_stacked_ring(self, ring: torch.Tensor, n_stack: int) -> torch.Tensor:
+        """The reset observation (zeros + the first frame) into slot 0 of the ring, and its frames one channel group further
+        down into the following n_stack - 1 slots, as step_stacked_ring keeps them from then on."""
+        self._check_stack(ring[0], n_stack)
+        ring[0].zero_()
+        self.render_stacked(ring[0], n_stack)
+        for j in range(1, min(int(n_stack), ring.shape[0])):
+            ring[j][:, : 3 * (n_stack - j)].copy_(ring[0][:, 3 * j:])
+        return ring[0]
+
+    def step_stacked_ring(self, actions: torch.Tensor, ring: torch.Tensor, pos: int, n_stack: int):
+        """tde_step_stacked_ring: VecFrameStack without moving a frame.  The step's stacked observation is ``ring[pos]``; the
+        caller advances pos by one (modulo the ring size) per step.  ``ring[pos]`` stays intact for
+        ``ring.shape[0] - n_stack`` further steps."""
+        a = actions.to(device=self.device, dtype=torch.float32).contiguous().view(self.E, 2)
+        if ring.dim() != 5 or not ring.is_contiguous() or ring.dtype != torch.uint8 or ring.device != self.obs.device:
+            raise ValueError("step_stacked_ring: ring must be a contiguous uint8 [R, E, 3*n_stack, 64, 64] tensor on the engine's device")
+        self._check_stack(ring[0], n_stack)
+        R = int(ring.shape[0])
+        self._check(self.lib.tde_step_stacked_ring(self.h, _ptr(a), _ptr(ring), R, int(pos) % R, int(n_stack), _ptr(self.reward),
+                                                   _ptr(self.terminated), _ptr(self.truncated), _ptr(self.info), self._stream()),
+                    "tde_step_stacked_ring")
+        return ring[int(pos) % R], self.reward, self.terminated, self.truncated, self.info
+
     def render_stacked(self, stack: torch.Tensor, n_stack: int) -> torch.Tensor:
         self._check_stack(stack, n_stack)
         self._check(self.lib.tde_render_stacked(self.h, _ptr(stack), int(n_stack), self._stream()), "tde_render_stacked")

@@ -477,7 +477,7 @@ class TorchDriveVecEnv(*([_SB3VecEnv] if _SB3VecEnv is not None else [])):
 
     def __init__(self, cfg: EnvConfig, data, num_envs: int, n_stack: Optional[int] = None, n_background: int = 0,
                  device: Optional[str] = None, output: str = "torch", env_index_offset: int = 0, seed: Optional[int] = None,
-                 terminal_observation: bool = False):
+                 terminal_observation: bool = False, frame_ring: Optional[int] = None):
         self.config = cfg
         self.num_envs = int(num_envs)
         self.n_stack = int(n_stack if n_stack is not None else max(1, int(cfg.frame_stack)))
@@ -490,11 +490,22 @@ class TorchDriveVecEnv(*([_SB3VecEnv] if _SB3VecEnv is not None else [])):
         self.device = self.engine.device
         self.action_space = _Box(low=np.array([-1.0, -0.3], np.float32), high=np.array([1.0, 0.3], np.float32), dtype=np.float32)
         self.observation_space = _Box(low=0, high=255, shape=(3 * self.n_stack, TDE_OBS_H, TDE_OBS_W), dtype=np.uint8)
-        self._stack = torch.zeros((self.num_envs, 3 * self.n_stack, TDE_OBS_H, TDE_OBS_W), dtype=torch.uint8, device=self.device)
+        # The frame stack.  Default (n_stack > 1, no terminal observations): a ring of n_stack + 1 stacked observations that
+        # the render kernel fills without moving a frame (tde_step_stacked_ring: the new frame goes into the observation of
+        # this step and, one channel group further down each, into those of the next n_stack - 1 steps).  The tensor a step
+        # returns is a slot of the ring: it stays as it is through the NEXT step (what an on-policy trainer needs, which
+        # stores the observation it acted on after stepping) and is rewritten after that.  frame_ring=0 selects the single
+        # tensor shifted in place by the kernel (VecFrameStack's roll-and-copy; the returned tensor is the same every step).
+        ring = (self.n_stack + 1 if self.n_stack > 1 and not terminal_observation else 0) if frame_ring is None else int(frame_ring)
+        if ring and (self.n_stack < 2 or terminal_observation or ring < self.n_stack):
+            raise ValueError("frame_ring needs n_stack >= 2, at least n_stack slots and terminal_observation=False")
+        self._ring = self.engine.new_stack_ring(self.n_stack, ring) if ring else None
+        self._pos = 0
+        self._stack = self._ring[0] if ring else torch.zeros((self.num_envs, 3 * self.n_stack, TDE_OBS_H, TDE_OBS_W), dtype=torch.uint8, device=self.device)
         self._actions = None
         # SB3's VecEnv keeps the last observation of a finished episode in info["terminal_observation"]; here it is
         # one [E, 3*n_stack, 64, 64] tensor whose rows are valid where `dones` is set (tde_step_terminal)
-        self._terminal = torch.zeros_like(self._stack) if terminal_observation else None
+        self._terminal = torch.zeros((self.num_envs, 3 * self.n_stack, TDE_OBS_H, TDE_OBS_W), dtype=torch.uint8, device=self.device) if terminal_observation else None
         if _SB3VecEnv is not None:   # pragma: no cover
             _SB3VecEnv.__init__(self, self.num_envs, self.observation_space, self.action_space)
 
@@ -509,9 +520,13 @@ class TorchDriveVecEnv(*([_SB3VecEnv] if _SB3VecEnv is not None else [])):
             self.engine.set_env_vars(v)
         self._t_start = time.time()
         self.engine.reset(seed=self._seed)
-        # the frame stack lives in one [E, 3*n_stack, 64, 64] tensor that the render kernel shifts and
-        # fills in place (tde_render_stacked / tde_step_stacked); a reset env restarts with zeros
-        self.engine.render_stacked(self._stack, self.n_stack)
+        # a reset env restarts with zeros and its first frame
+        if self._ring is not None:
+            self._pos = 0
+            self._stack = self.engine.render_stacked_ring(self._ring, self.n_stack)
+        else:
+            self._stack.zero_()
+            self.engine.render_stacked(self._stack, self.n_stack)
         return self._out(self._stack)
 
     def step_async(self, actions):
@@ -519,7 +534,10 @@ class TorchDriveVecEnv(*([_SB3VecEnv] if _SB3VecEnv is not None else [])):
 
     def step_wait(self):
         a = torch.as_tensor(self._actions, dtype=torch.float32)
-        if self._terminal is not None:
+        if self._ring is not None:
+            self._pos = (self._pos + 1) % self._ring.shape[0]
+            self._stack, rew, term, trunc, info = self.engine.step_stacked_ring(a, self._ring, self._pos, self.n_stack)
+        elif self._terminal is not None:
             _, rew, term, trunc, info = self.engine.step_terminal(a, self._stack, self._terminal, self.n_stack)
         else:
             _, rew, term, trunc, info = self.engine.step_stacked(a, self._stack, self.n_stack)
