@@ -170,7 +170,7 @@ typedef struct tde_config {
     int32_t host_obs_rgb;          /* tde_step_host only.  0 (default): the frames cross PCIe as the 4-bit class image (2 KB
                                       per env) and host threads (TDE_HOST_THREADS; default: the CPUs of the process /
                                       LOCAL_WORLD_SIZE, at most 16) expand them to the caller's RGB planes with the
-                                      palette; 1: the RGB planes (12 KB per env) cross PCIe and no host thread is
+                                      palette (AVX-512 / AVX2 / scalar, whatever the CPU has); 1: the RGB planes (12 KB per env) cross PCIe and no host thread is
                                       started.  Same bytes in the caller's buffer either way.  The environment variable
                                       TDE_HOST_OBS=classes|rgb overrides it. */
     int32_t reserved[6];

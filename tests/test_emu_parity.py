@@ -269,10 +269,7 @@ def test_emu_class_image_and_compact_host_step(oracle, monkeypatch):
             for eng in (rgb, cmp_, orc):
                 eng.set_palette(pal)
         monkeypatch.setenv("TDE_HOST_CHUNKS", "1" if k % 2 else "5")
-        if k in (3, 4, 8):
-            monkeypatch.setenv("TDE_HOST_NO_SIMD", "1")     # the scalar expansion loop
-        else:
-            monkeypatch.delenv("TDE_HOST_NO_SIMD", raising=False)
+        monkeypatch.setenv("TDE_HOST_SIMD", ("scalar", "avx2", "avx512")[k % 3])   # every expansion loop the CPU has
         a = np.stack([rng.uniform(-1, 1, E), rng.uniform(-0.3, 0.3, E)], 1).astype(np.float32)
         want = [np.array(x, copy=True) for x in rgb.step_host(a)]
         got = cmp_.step_host(a)

@@ -18,8 +18,12 @@ from torchdriveenv_b200 import scenarios as S          # noqa: E402
 from torchdriveenv_b200.engine import Engine           # noqa: E402
 
 
-def run_arm(ss, E, A, steps, mode, threads, chunks, acts):
+def run_arm(ss, E, A, steps, mode, threads, chunks, acts, simd=""):
     os.environ["TDE_HOST_OBS"] = mode
+    if simd:
+        os.environ["TDE_HOST_SIMD"] = simd
+    else:
+        os.environ.pop("TDE_HOST_SIMD", None)
     if threads:
         os.environ["TDE_HOST_THREADS"] = str(threads)
     if chunks:
@@ -38,7 +42,7 @@ def run_arm(ss, E, A, steps, mode, threads, chunks, acts):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     eng.close()
-    return dict(mode=mode, host_threads=threads or "default", chunks=chunks or "default", envs=E, steps=steps,
+    return dict(mode=mode, simd=simd or "widest", host_threads=threads or "default", chunks=chunks or "default", envs=E, steps=steps,
                 env_steps_per_s=E * steps / dt, ms_per_step=dt / steps * 1e3,
                 pcie_gbs=E * ((12288 if mode == "rgb" else 2048) + 82) * steps / dt / 1e9, obs_digest_after_3_steps=digest)
 
@@ -49,6 +53,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--threads", default="2,4,8,16")
     ap.add_argument("--chunks", default="0")
+    ap.add_argument("--simd", default="widest", help="comma list of scalar|avx2|avx512|widest for the class-image arms")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     E, A = args.envs, 32
@@ -58,7 +63,8 @@ def main():
     rows = [run_arm(ss, E, A, args.steps, "rgb", 0, 0, acts)]
     for ch in [int(c) for c in args.chunks.split(",")]:
         for th in [int(t) for t in args.threads.split(",")]:
-            rows.append(run_arm(ss, E, A, args.steps, "classes", th, ch, acts))
+            for simd in args.simd.split(","):
+                rows.append(run_arm(ss, E, A, args.steps, "classes", th, ch, acts, simd if simd != "widest" else ""))
     assert len({r["obs_digest_after_3_steps"] for r in rows}) == 1, "the arms disagree on the observation bytes"
     for r in rows:
         print(json.dumps(r), flush=True)

@@ -1130,6 +1130,31 @@ __attribute__((target("avx2"))) static void expand_env_avx2(const uint8_t* nib, 
         }
     }
 }
+__attribute__((target("avx512f,avx512bw"))) static void expand_env_avx512(const uint8_t* nib, uint8_t* rgb, const uint8_t* lut) {
+    constexpr int PX = TDE_OBS_H * TDE_OBS_W;
+    const __m512i low4 = _mm512_set1_epi16(0x0f0f);
+    __m512i L[3];
+    for (int ch = 0; ch < 3; ++ch) L[ch] = _mm512_broadcast_i32x4(_mm_loadu_si128((const __m128i*)(lut + 16 * ch)));
+    const bool aligned = ((uintptr_t)rgb & 63) == 0;   // a row of a plane is one cache line: one non-temporal store each
+    for (int r = 0; r < TDE_OBS_H; ++r) {
+        // byte b of the row = pixels 2 b (low nibble) and 2 b + 1 (high nibble): widen to 16 bits and pull the high nibble up
+        const __m512i x = _mm512_cvtepu8_epi16(_mm256_loadu_si256((const __m256i*)(nib + 32 * r)));
+        const __m512i px = _mm512_and_si512(_mm512_or_si512(x, _mm512_slli_epi16(x, 4)), low4);
+        for (int ch = 0; ch < 3; ++ch) {
+            __m512i* o = (__m512i*)(rgb + ch * PX + r * TDE_OBS_W);
+            const __m512i w = _mm512_shuffle_epi8(L[ch], px);
+            if (aligned) _mm512_stream_si512(o, w); else _mm512_storeu_si512(o, w);
+        }
+    }
+}
+// widest instruction set the expansion may use: what the CPU has, capped by TDE_HOST_SIMD=scalar|avx2|avx512 (TDE_HOST_NO_SIMD=1 = scalar)
+static int host_simd_level() {
+    int level = __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512f") ? 2 : __builtin_cpu_supports("avx2") ? 1 : 0;
+    if (std::getenv("TDE_HOST_NO_SIMD")) level = 0;
+    if (const char* v = std::getenv("TDE_HOST_SIMD")) level = std::min(level, !std::strcmp(v, "scalar") ? 0 : !std::strcmp(v, "avx2") ? 1 : 2);
+    return level;
+}
+
 // The host threads of the expansion.  One job per step: the threads take blocks of envs in order and wait (yielding,
 // never spinning hard) until the chunk a block belongs to has landed in pinned memory; between steps they sleep on a
 // condition variable.  The calling thread works too, so `threads` = 1 means no pool at all.
@@ -1142,7 +1167,7 @@ struct ExpandPool {
     int pending = 0;
     bool stop = false;
     // the job
-    const uint8_t* nib = nullptr; uint8_t* rgb = nullptr; int E = 0; bool avx2 = false;
+    const uint8_t* nib = nullptr; uint8_t* rgb = nullptr; int E = 0; int simd = 0;
     uint8_t lut[48] = {};
     std::atomic<int> next{0}, ready{0};
 
@@ -1162,11 +1187,12 @@ struct ExpandPool {
             const int b1 = std::min(E, b0 + BLOCK);
             while (ready.load(std::memory_order_acquire) < b1) std::this_thread::yield();
             for (int e = b0; e < b1; ++e) {
-                if (avx2) expand_env_avx2(nib + (size_t)e * (PX / 2), rgb + (size_t)e * 3 * PX, lut);
+                if (simd == 2) expand_env_avx512(nib + (size_t)e * (PX / 2), rgb + (size_t)e * 3 * PX, lut);
+                else if (simd == 1) expand_env_avx2(nib + (size_t)e * (PX / 2), rgb + (size_t)e * 3 * PX, lut);
                 else expand_env_scalar(nib + (size_t)e * (PX / 2), rgb + (size_t)e * 3 * PX, lut);
             }
         }
-        if (avx2) _mm_sfence();
+        if (simd) _mm_sfence();
     }
     void loop() {
         unsigned long long seen = 0;
@@ -1186,7 +1212,7 @@ struct ExpandPool {
         {
             std::lock_guard<std::mutex> lk(m);
             nib = nib_; rgb = rgb_; E = E_;
-            avx2 = __builtin_cpu_supports("avx2") && !std::getenv("TDE_HOST_NO_SIMD");   // the scalar loop stays testable
+            simd = host_simd_level();   // read per step: the narrower loops stay testable
             std::memset(lut, 0, sizeof(lut));
             for (int ch = 0; ch < 3; ++ch)
                 for (int c = 0; c < TDE_NUM_CLASSES; ++c) lut[16 * ch + c] = palette[3 * c + ch];
