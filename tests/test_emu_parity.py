@@ -316,3 +316,24 @@ def test_emu_stacked_ring_is_vec_frame_stack(oracle, NS, R):
             if k - back >= 0:
                 assert np.array_equal(ring[(k - back) % R], history[k - back]), f"step {k}: the observation of step {k - back} was overwritten"
     assert n_done > 10
+
+
+@pytest.mark.parametrize("thr", [0.5, 0.0])
+def test_emu_offroad_boxes_on_a_random_triangle_soup(oracle, thr):
+    """The stateless offroad kernel (flat list of (corner, candidate) pairs) on an adversarial mesh - overlapping triangles
+    from slivers of 5 cm to 40 m, so cells list many candidates and several containing triangles - with boxes on, near, far
+    from and off the grid, some absent, in a count that is not a multiple of 32: every value equals the oracle's brute
+    force over all triangles."""
+    rng = np.random.default_rng(int(thr * 10) + 3)
+    road = S.subdivide_long_triangles(_triangle_soup(rng, 300, [0.05, 0.5, 3.0, 12.0, 40.0], 80.0, 8), 200.0)
+    m = S.MapData(road_tris=road.astype(np.float32), name="soup")
+    eng = EmuEngine(S.ScenarioSet([m], [S.make_scenario(0, [[5, 5], [50, 5]], 0, 0, "p")]), 1, 1, offroad_threshold=thr)
+    E, A = 7, 19
+    st = np.zeros((E, A, 4), np.float32); at = np.zeros((E, A, 4), np.float32)
+    st[..., 0:2] = rng.uniform(-130, 130, (E, A, 2)); st[..., 2] = rng.uniform(-np.pi, np.pi, (E, A))
+    st[0, :, 0:2] = rng.uniform(-400, 400, (A, 2))                      # far off the grid
+    at[..., 0] = rng.uniform(3, 9, (E, A)); at[..., 1] = rng.uniform(1.5, 2.6, (E, A)); at[..., 2] = 1.0
+    at[..., 3] = (rng.uniform(0, 1, (E, A)) < 0.85).astype(np.float32)
+    got, want = eng.offroad_boxes(0, st, at), oracle.offroad_boxes(m.road_tris, thr, st, at)
+    assert (want > 0).mean() > 0.2 and (want == 0).mean() > 0.2
+    assert np.array_equal(got, want), f"{int((got != want).sum())} of {got.size} differ"

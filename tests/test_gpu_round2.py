@@ -345,3 +345,29 @@ def test_capture_steps_replays_the_eager_steps(oracle):
         assert torch.equal(graphed.obs, eager.obs) and torch.equal(graphed.reward, eager.reward)
         assert torch.equal(graphed.get_env_vars(), eager.get_env_vars())
         assert np.array_equal(graphed.obs.cpu().numpy(), want[0]) and np.array_equal(graphed.get_state().cpu().numpy(), orc.state)
+
+
+@pytest.mark.parametrize("thr", [0.5, 0.0])
+def test_offroad_boxes_on_a_random_triangle_soup(oracle, thr):
+    """tde_offroad_boxes (flat list of (corner, candidate) pairs) on an adversarial mesh: overlapping triangles from slivers of
+    5 cm to 40 m, boxes on, near, far from and off the grid, some absent, a count that is not a multiple of 32 - every value
+    equals the oracle's brute force over all triangles."""
+    rng = np.random.default_rng(int(thr * 10) + 3)
+    n = 300
+    c = rng.uniform(-80, 80, (n, 1, 2)); sc = rng.choice([0.05, 0.5, 3.0, 12.0, 40.0], (n, 1, 1))
+    v = c + rng.normal(0, 1, (n, 3, 2)) * sc
+    road = np.zeros((n, 8), np.float32); road[:, :6] = v.reshape(n, 6)
+    ang = rng.uniform(-np.pi, np.pi, n); road[:, 6], road[:, 7] = np.cos(ang), np.sin(ang)
+    road = S.subdivide_long_triangles(road, 200.0)
+    m = S.MapData(road_tris=road.astype(np.float32), name="soup")
+    eng = _engine(S.ScenarioSet([m], [S.make_scenario(0, [[5, 5], [50, 5]], 0, 0, "p")]), 1, 1, offroad_threshold=thr)
+    E, A = 301, 19
+    st = np.zeros((E, A, 4), np.float32); at = np.zeros((E, A, 4), np.float32)
+    st[..., 0:2] = rng.uniform(-130, 130, (E, A, 2)); st[..., 2] = rng.uniform(-np.pi, np.pi, (E, A))
+    st[:9, :, 0:2] = rng.uniform(-400, 400, (9, A, 2))                  # far off the grid
+    at[..., 0] = rng.uniform(3, 9, (E, A)); at[..., 1] = rng.uniform(1.5, 2.6, (E, A)); at[..., 2] = 1.0
+    at[..., 3] = (rng.uniform(0, 1, (E, A)) < 0.85).astype(np.float32)
+    got = eng.offroad_boxes(0, torch.from_numpy(st).cuda(), torch.from_numpy(at).cuda()).cpu().numpy()
+    want = oracle.offroad_boxes(m.road_tris, thr, st, at)
+    assert (want > 0).mean() > 0.2 and (want == 0).mean() > 0.2
+    assert np.array_equal(got, want), f"{int((got != want).sum())} of {got.size} differ"
