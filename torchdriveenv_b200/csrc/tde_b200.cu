@@ -1247,10 +1247,10 @@ static int host_thread_count() {
 }
 
 static int ensure_copy_stream(tde_handle* h) {
-    if (h->copy_stream) return TDE_OK;
-    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-    for (cudaEvent_t& ev : h->chunk_done) CUDA_TRY(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    for (cudaEvent_t& ev : h->chunk_copied) CUDA_TRY(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    if (h->copy_stream && h->copies_done) return TDE_OK;   // copies_done is created last: everything else exists then
+    if (!h->copy_stream) CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t& ev : h->chunk_done) if (!ev) CUDA_TRY(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (cudaEvent_t& ev : h->chunk_copied) if (!ev) CUDA_TRY(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CUDA_TRY(h, cudaEventCreateWithFlags(&h->copies_done, cudaEventDisableTiming));
     return TDE_OK;
 }
@@ -1266,11 +1266,10 @@ static inline int compact_chunks(const tde_handle* h) { return host_chunks(h, 20
 static int step_host_compact_launch(tde_handle* h, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const size_t E = (size_t)h->E, nib_env = TDE_OBS_H * TDE_OBS_W / 2;
-    if (!h->h_nib) {
-        CUDA_TRY(h, cudaMalloc((void**)&h->h_nib, E * nib_env));
-        CUDA_TRY(h, cudaMallocHost((void**)&h->pin_nib, E * nib_env));
-        h->pool = new ExpandPool(host_thread_count());
-    }
+    // each piece on its own: a failed allocation leaves the others to be retried by the next call
+    if (!h->h_nib) CUDA_TRY(h, cudaMalloc((void**)&h->h_nib, E * nib_env));
+    if (!h->pin_nib) CUDA_TRY(h, cudaMallocHost((void**)&h->pin_nib, E * nib_env));
+    if (!h->pool) h->pool = new ExpandPool(host_thread_count());
     if (int rc = ensure_copy_stream(h)) return rc;
     const int chunks = compact_chunks(h);
     for (int c = 0; c < chunks; ++c) {
@@ -1307,13 +1306,11 @@ extern "C" int tde_step_host(tde_handle* h, const float* actions, uint8_t* obs, 
     TDE_ON_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t E = (size_t)h->E, obs_bytes = E * TDE_OBS_C * TDE_OBS_H * TDE_OBS_W;
-    if (!h->h_actions) {
-        CUDA_TRY(h, cudaMalloc((void**)&h->h_actions, E * 2 * sizeof(float)));
-        CUDA_TRY(h, cudaMalloc((void**)&h->h_reward, E * sizeof(float)));
-        CUDA_TRY(h, cudaMalloc((void**)&h->h_term, E));
-        CUDA_TRY(h, cudaMalloc((void**)&h->h_trunc, E));
-        CUDA_TRY(h, cudaMalloc((void**)&h->h_info, E * TDE_INFO_STRIDE * sizeof(float)));
-    }
+    if (!h->h_actions) CUDA_TRY(h, cudaMalloc((void**)&h->h_actions, E * 2 * sizeof(float)));
+    if (!h->h_reward) CUDA_TRY(h, cudaMalloc((void**)&h->h_reward, E * sizeof(float)));
+    if (!h->h_term) CUDA_TRY(h, cudaMalloc((void**)&h->h_term, E));
+    if (!h->h_trunc) CUDA_TRY(h, cudaMalloc((void**)&h->h_trunc, E));
+    if (!h->h_info) CUDA_TRY(h, cudaMalloc((void**)&h->h_info, E * TDE_INFO_STRIDE * sizeof(float)));
     // the observation crosses PCIe as the class image unless cfg.host_obs_rgb / TDE_HOST_OBS=rgb asks for the planes
     const char* mode = std::getenv("TDE_HOST_OBS");
     const bool compact = obs && (mode ? std::strcmp(mode, "rgb") != 0 : h->cfg.host_obs_rgb == 0);
