@@ -812,13 +812,13 @@ __global__ void __launch_bounds__(TDE_WARPS_PER_BLOCK * 32) tde_collision_kernel
 // corner an item belongs to, a shared-memory atomicMin per corner (non-negative binary32 values order like their bit
 // patterns).  Same candidates, same per-candidate arithmetic, a minimum and a sum in the same order: same bits as
 // mesh_infractions_warp.
-struct OffroadScratch {        // per warp; corner c = 4 * lane + k
-    uint32_t start[128];       // candidates before corner c
+struct OffroadScratch {        // per warp; corner k of lane l: start[4 l + k] (one 128-bit row per lane), the other arrays [32 k + l] (bank = lane)
+    uint32_t start[128];       // candidates before the corner
     int base[128];             // first item of the corner's list, or -1: every triangle of the map, containment included
     float px[128], py[128];
     uint32_t best[128];        // min squared distance so far (bit pattern)
     unsigned short nover[128]; // the first nover candidates of the corner overlap its cell: the ones that can contain it
-    uint32_t inside[4];        // corners found inside a triangle
+    uint32_t inside[4];        // corners found inside a triangle, bit l of word k
 };
 #define TDE_OFFROAD_WARPS 8
 __global__ void __launch_bounds__(TDE_OFFROAD_WARPS * 32) tde_offroad_kernel(const MapDev* maps, int map_id, float thr,
@@ -855,7 +855,7 @@ __global__ void __launch_bounds__(TDE_OFFROAD_WARPS * 32) tde_offroad_kernel(con
                     if (!(rec.y & TDE_CELL_SAFE)) { need |= 1u << k; cnt[k] = (uint32_t)rec.y >> 16; bs = rec.x; nov = rec.y & 0x7fff; }
                 }
             }
-            const int c = 4 * lane + k;
+            const int c = 32 * k + lane;
             ws->base[c] = bs; ws->px[c] = px; ws->py[c] = py; ws->best[c] = 0x7f800000u; ws->nover[c] = (unsigned short)nov;
         }
         const uint32_t mine_total = cnt[0] + cnt[1] + cnt[2] + cnt[3];
@@ -880,8 +880,9 @@ __global__ void __launch_bounds__(TDE_OFFROAD_WARPS * 32) tde_offroad_kernel(con
                 if (v <= w) o += st;
             }
             const uint4 s4c = *reinterpret_cast<const uint4*>(&ws->start[4 * o]);
-            const int c = 4 * o + (w >= s4c.y) + (w >= s4c.z) + (w >= s4c.w);
-            const int j = (int)(w - ws->start[c]), bs = ws->base[c];
+            const int kk = (w >= s4c.y) + (w >= s4c.z) + (w >= s4c.w);
+            const int c = 32 * kk + o;
+            const int j = (int)(w - (kk == 0 ? s4c.x : kk == 1 ? s4c.y : kk == 2 ? s4c.z : s4c.w)), bs = ws->base[c];
             const float qx = ws->px[c], qy = ws->py[c];
             const Tri3 T = tde_load_tri<false>(M.tri, 0u, bs < 0 ? j : (int)__ldg(&M.cell_items[bs + j]));
             float dc, ds;
@@ -892,7 +893,7 @@ __global__ void __launch_bounds__(TDE_OFFROAD_WARPS * 32) tde_offroad_kernel(con
         float sum = 0.0f;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int c = 4 * lane + k;
+            const int c = 32 * k + lane;
             float d2 = 0.0f;
             if (need & (1u << k)) d2 = (ws->inside[c >> 5] >> (c & 31)) & 1u ? 0.0f : __uint_as_float(ws->best[c]);
             sum = sum + fmaxf(sqrtf(d2) - thr, 0.0f);
