@@ -12,7 +12,7 @@ step path (weak scaling: 16,384 envs per GPU); NCCL only reduces the episode sta
   (N > 1: launched by torch.distributed.run, one rank per GPU)
 
 Prints ONE JSON line (rank 0).  At N = 1 the default line also carries
-  other_configs          the other BASELINE configs (C2, C4, C5) measured the same way on this GPU,
+  other_configs          the other BASELINE configs (C2, C4, C5; C1 as the latency of one env behind the gym.Env API) measured the same way on this GPU,
   pursuit                the C3 step under a pure-pursuit policy (long episodes: junctions, red lights, late waypoints),
   cpu_baseline           the batched C oracle port on all host cores,
   cpu_baseline_per_env   BASELINE config C1 the way the reference runs: one process per core, one env each (B = 1),
@@ -740,6 +740,35 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
     return line
 
 
+def run_c1_gym_api(local_rank: int, steps: int = 400):
+    """Config C1 the way a user of the reference runs it, on the GPU: ONE env behind the reference's gym.Env API
+    (SingleAgentWrapper(WaypointSuiteEnv), gym_env.py:440-487), numpy observation / float reward / bool flags / info dict back
+    on the host every step.  One env cannot fill a GPU: this is the latency of the drop-in call, reported beside the
+    per-env CPU baseline (`cpu_baseline_per_env`) that runs the same call pattern on the host cores."""
+    from torchdriveenv_b200 import gym_env as G, scenarios as S
+    cfg = G.EnvConfig(device=f"cuda:{local_rank}", seed=0)
+    env = G.SingleAgentWrapper(G.WaypointSuiteEnv(cfg, S.three_way(6)))
+    rng = np.random.default_rng(0)
+    env.reset(seed=0)
+    acts = np.stack([rng.uniform(-1, 1, steps + 20), rng.uniform(-0.3, 0.3, steps + 20)], 1).astype(np.float32)
+    n_done = 0
+    for k in range(20):
+        _, _, te, tr, _ = env.step(acts[k])
+        if te or tr:
+            env.reset()
+    t0 = time.perf_counter()
+    for k in range(steps):
+        obs, r, te, tr, info = env.step(acts[20 + k])
+        if te or tr:
+            n_done += 1
+            env.reset()
+    dt = time.perf_counter() - t0
+    env.close()
+    return dict(metric="env_steps_per_sec_single_env_gym_api", value=steps / dt, unit="env-steps/s", steps=steps, us_per_step=dt / steps * 1e6,
+                episodes_finished=n_done, config="C1: one env (Three Way, 6 agents) behind SingleAgentWrapper(WaypointSuiteEnv).step, host numpy outputs, "
+                                                 "resets included; wall clock (the call synchronises)")
+
+
 def slim(line):
     """A sub-line of `other_configs`: the measurement without the nested extras."""
     if line is None:
@@ -802,6 +831,10 @@ def main():
                 others[name] = slim({"c4": run_c4, "c5": run_c5}.get(name, run_cuda)(sub, 0, local_rank, 1))
             except Exception as ex:      # a failing extra must not take the headline line with it
                 others[name] = dict(error=f"{type(ex).__name__}: {ex}")
+        try:
+            others["c1_gym_api"] = run_c1_gym_api(local_rank)
+        except Exception as ex:
+            others["c1_gym_api"] = dict(error=f"{type(ex).__name__}: {ex}")
         line["other_configs"] = others
         line["cpu_baseline_per_env"] = None if args.no_cpu_baseline else cpu_per_env_baseline(min(8.0, args.cpu_seconds))
     if rank == 0 and line is not None:

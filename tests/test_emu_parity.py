@@ -248,11 +248,13 @@ def test_emu_rollout_scatter_fills_the_buffer_like_vec_frame_stack(oracle, NS, T
     assert n_done > 5
 
 
-def test_emu_class_image_and_compact_host_step(oracle, monkeypatch):
+@pytest.mark.parametrize("E,steps", [(37, 12), (300, 4)])
+def test_emu_class_image_and_compact_host_step(oracle, monkeypatch, E, steps):
     """tde_render_classes is the oracle's class image, nibble-packed; tde_step_host's default path (the class
     image crosses PCIe, host threads apply the palette) fills the caller's buffer with the same bytes as cfg.host_obs_rgb = 1,
-    with one chunk and with several, with the default and with a caller-set palette."""
-    E, A = 37, 16
+    with one chunk and with several, with the default and with a caller-set palette; a handful of envs is expanded by the
+    calling thread, 300 by the pool of host threads."""
+    A = 16
     ss = S.validation_mix(12)
     cfg = dict(auto_reset=1)
     rgb = EmuEngine(ss, E, A, host_obs_rgb=1, **cfg)
@@ -264,8 +266,8 @@ def test_emu_class_image_and_compact_host_step(oracle, monkeypatch):
         eng.reset(seed=4)
     orc.reset(seed=4)
     assert np.array_equal(cmp_.render_classes(), orc.render_classes())
-    for k in range(12):
-        if k == 6:
+    for k in range(steps):
+        if k == steps // 2:
             for eng in (rgb, cmp_, orc):
                 eng.set_palette(pal)
         monkeypatch.setenv("TDE_HOST_CHUNKS", "1" if k % 2 else "5")

@@ -1223,6 +1223,17 @@ struct ExpandPool {
         cv_job.notify_all();
     }
     void arrived(int envs) { ready.store(envs, std::memory_order_release); }
+    // the caller expands everything itself (all of it has arrived): no worker is woken
+    void begin_serial(const uint8_t* nib_, uint8_t* rgb_, const uint8_t* palette, int E_) {
+        std::lock_guard<std::mutex> lk(m);
+        nib = nib_; rgb = rgb_; E = E_;
+        simd = host_simd_level();
+        std::memset(lut, 0, sizeof(lut));
+        for (int ch = 0; ch < 3; ++ch)
+            for (int c = 0; c < TDE_NUM_CLASSES; ++c) lut[16 * ch + c] = palette[3 * c + ch];
+        next.store(0); ready.store(E_);
+        work();
+    }
     void finish() {
         work();
         std::unique_lock<std::mutex> lk(m);
@@ -1287,6 +1298,11 @@ static int step_host_compact_launch(tde_handle* h, void* stream) {
 
 static int step_host_compact_expand(tde_handle* h, uint8_t* obs) {
     const int chunks = compact_chunks(h);
+    if (h->E < 256) {   // a handful of envs (one, behind the gym.Env API): waking the pool costs more than expanding them here
+        for (int c = 0; c < chunks; ++c) CUDA_TRY(h, cudaEventSynchronize(h->chunk_copied[c]));
+        h->pool->begin_serial(h->pin_nib, obs, h->palette, h->E);
+        return TDE_OK;
+    }
     h->pool->begin(h->pin_nib, obs, h->palette, h->E);
     cudaError_t err = cudaSuccess;
     for (int c = 0; c < chunks && err == cudaSuccess; ++c) {

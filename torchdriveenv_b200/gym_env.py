@@ -341,18 +341,24 @@ class WaypointSuiteEnv(GymEnv):
     def get_obs(self):
         return self.simulator.render_egocentric().cpu().numpy().astype(np.uint8)
 
+    # get_info's infraction entries are B x A tensors (gym_env.py:419-437).  They are made on the host by default: one env
+    # behind this API is a latency path, and every tensor moved to the GPU and back (SingleAgentWrapper.transform_out) is a
+    # synchronisation.  True puts them on the simulator's device, as the reference's simulator returns them.
+    info_tensors_on_device = False
+
     def step(self, action):
-        a = torch.as_tensor(np.asarray(action.cpu() if torch.is_tensor(action) else action, dtype=np.float32)).reshape(-1)[:2]
-        obs, rew, term, trunc, info = self.engine.step(a.view(1, 2))
+        a = np.asarray(action.cpu() if torch.is_tensor(action) else action, dtype=np.float32).reshape(-1)[:2]
+        # tde_step_host: actions up, one step, observation / reward / flags / info row down, ONE synchronisation
+        obs, rew, term, trunc, info = self.engine.step_host(a.reshape(1, 2))
         getattr(self.simulator, "simulator", self.simulator)._infractions_valid = True   # on the wrapped simulator in video mode
         if isinstance(self.simulator, BirdviewRecordingWrapper):
             self.simulator._record()
         self.environment_steps += 1
-        obs_np = obs.unsqueeze(1).cpu().numpy()
-        row = info[0].cpu().numpy()
-        reward = float(rew[0].item())
-        terminated, truncated = bool(term[0].item()), bool(trunc[0].item())
-        info_d = _info_from_row(row, self.torch_device)
+        obs_np = obs.reshape(1, 1, 3, TDE_OBS_H, TDE_OBS_W).copy()       # the engine's pinned buffers are reused by the next call
+        row = info[0].copy()
+        reward = float(rew[0])
+        terminated, truncated = bool(term[0]), bool(trunc[0])
+        info_d = _info_from_row(row, self.torch_device if self.info_tensors_on_device else None)
         self.reached_waypoint_num = info_d["reached_waypoint_num"]
         self.last_obs, self.last_reward, self.last_info = obs_np, reward, info_d
         return obs_np, reward, terminated, truncated, info_d
